@@ -1,0 +1,19 @@
+"""conditional_ude_b200 — B200-native hot path of Computational-Biology-TUe/conditional-ude:
+the batched forward solve and gradient of the c-peptide conditional-UDE loss.
+
+Host side mirrors the reference's constructors and loss entry points; all numerics run in the
+hand-written sm_100a CUDA kernels of csrc/ through the C ABI in include/cude_b200.h.
+There is no CPU fallback.
+"""
+from .models import (Chain, chain, softplus, van_cauter_parameters, CPeptideConditionalUDEModel,
+                     CPeptideConditionalCovariateUDEModel, pack_models)
+from .population import Context, Population, SolverOptions, default_context
+from .losses import loss, loss_sigma, loss_and_gradient, ComponentVector
+from .profiles import likelihood_profile, likelihood_profile_population, find_confidence_intervals
+
+__all__ = [
+    "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel",
+    "CPeptideConditionalCovariateUDEModel", "pack_models", "Context", "Population", "SolverOptions",
+    "default_context", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",
+    "likelihood_profile", "likelihood_profile_population", "find_confidence_intervals",
+]

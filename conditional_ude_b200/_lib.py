@@ -1,0 +1,90 @@
+"""ctypes binding of libcude_b200.so (C ABI declared in include/cude_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing, or no CUDA device is usable, every
+compute entry point raises.  The library is built in-tree by `__graft_entry__.build()` or
+`make -C conditional_ude_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcude_b200.so")
+
+CUDE_OK = 0
+CUDE_EINVAL, CUDE_ENODEVICE, CUDE_ECUDA, CUDE_ENOMEM, CUDE_EUNSUPPORTED = -1, -2, -3, -4, -5
+
+
+class CudeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cude_b200 error {code}: {msg}")
+        self.code = code
+
+
+class cude_net(C.Structure):
+    _fields_ = [("n_in", C.c_int), ("depth", C.c_int), ("width", C.c_int)]
+
+
+class cude_opts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiters", C.c_int),
+                ("precision", C.c_int), ("block", C.c_int)]
+
+
+class cude_stats(C.Structure):
+    _fields_ = [("n_traj", C.c_ulonglong), ("n_acc", C.c_ulonglong), ("n_rej", C.c_ulonglong),
+                ("n_rhs", C.c_ulonglong), ("n_fail", C.c_ulonglong), ("kernel_ms", C.c_float),
+                ("launches", C.c_int)]
+
+
+# every symbol include/cude_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int)
+SYMBOLS = {
+    "cude_abi_version": (C.c_int, []),
+    "cude_default_opts": (None, [C.POINTER(cude_opts)]),
+    "cude_net_nparams": (C.c_int, [C.POINTER(cude_net)]),
+    "cude_van_cauter_parameters": (None, [C.c_double, C.c_int, _D, _D, _D]),
+    "cude_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "cude_ctx_destroy": (C.c_int, [_P]),
+    "cude_last_error": (C.c_char_p, [_P]),
+    "cude_sync": (C.c_int, [_P]),
+    "cude_get_stats": (C.c_int, [_P, C.POINTER(cude_stats)]),
+    "cude_ctx_stream": (_P, [_P]),
+    "cude_population_create": (C.c_int, [_P, C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.POINTER(_P)]),
+    "cude_population_destroy": (C.c_int, [_P]),
+    "cude_population_size": (C.c_int, [_P]),
+    "cude_loss": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, _D, _D]),
+    "cude_loss_grad": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
+                                 C.c_int, _D, _D, _D, _D]),
+    "cude_eval_dev": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _P, C.c_longlong, _P,
+                                C.c_int, C.c_double, _P, _P, _P]),
+    "cude_measure_fp64_peak": (C.c_int, [_P, _D]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C conditional_ude_b200/csrc`.  conditional_ude_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.cude_abi_version() != 1:
+        raise ImportError("libcude_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, ctx=None):
+    if rc != CUDE_OK:
+        msg = load().cude_last_error(ctx)
+        raise CudeError(rc, msg.decode() if msg else "?")

@@ -1,0 +1,474 @@
+// =====================================================================================
+// cude_api.cu — C ABI (include/cude_b200.h) over the sm_100a kernels in cude_kernels.cuh.
+// No CPU fallback: every compute entry point requires a CUDA device.
+// =====================================================================================
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/cude_b200.h"
+#include "cude_kernels.cuh"
+
+using namespace cude;
+
+// ---------------------------------------------------------------- handles
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct cude_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    cude_stats stats{};
+    bool stats_pending = false;
+    DevBuf neural, cond, sse, partials, sums, gcond, counters, scratch;
+    double* h_sums = nullptr;   // pinned
+    size_t h_sums_cap = 0;
+    unsigned long long* h_counters = nullptr;  // pinned [3]
+};
+
+struct cude_population {
+    cude_ctx* ctx = nullptr;
+    int n_ind = 0, max_knots = 0, max_obs = 0;
+    int* n_knots = nullptr;
+    int* n_obs = nullptr;
+    double* block = nullptr;   // one allocation holding all double arrays
+    PopDev dev{};
+};
+
+static thread_local std::string g_err;
+
+static int fail(cude_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return fail(ctx, (e__ == cudaErrorMemoryAllocation) ? CUDE_ENOMEM : CUDE_ECUDA, b__);  \
+        }                                                                                          \
+    } while (0)
+
+static int ensure(cude_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return CUDE_OK;
+    if (b.p) { CU_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    CU_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return CUDE_OK;
+}
+
+// ---------------------------------------------------------------- small host-side entry points
+extern "C" int cude_abi_version(void) { return CUDE_B200_ABI_VERSION; }
+
+extern "C" void cude_default_opts(cude_opts* o) {
+    if (!o) return;
+    o->abstol = 1e-6;   // OrdinaryDiffEq defaults used by parameter-estimation.jl:59
+    o->reltol = 1e-3;
+    o->maxiters = 100000;
+    o->precision = 0;
+    o->block = 0;
+}
+
+extern "C" int cude_net_nparams(const cude_net* net) {
+    if (!net || net->n_in < 1 || net->depth < 1 || net->width < 1) return CUDE_EINVAL;
+    int p = 0, in = net->n_in;
+    for (int l = 0; l < net->depth; ++l) { p += net->width * (in + 1); in = net->width; }
+    return p + in + 1;
+}
+
+extern "C" void cude_van_cauter_parameters(double age, int t2dm, double* k0, double* k1, double* k2) {
+    // src/c-peptide-models.jl:30-42
+    const double ln2 = std::log(2.0);
+    const double short_half_life = t2dm ? 4.52 : 4.95;
+    const double fraction = t2dm ? 0.78 : 0.76;
+    const double long_half_life = 0.14 * age + 29.2;
+    const double kk1 = fraction * (ln2 / long_half_life) + (1 - fraction) * (ln2 / short_half_life);
+    const double kk0 = (ln2 / short_half_life) * (ln2 / long_half_life) / kk1;
+    const double kk2 = (ln2 / short_half_life) + (ln2 / long_half_life) - kk0 - kk1;
+    if (k0) *k0 = kk0;
+    if (k1) *k1 = kk1;
+    if (k2) *k2 = kk2;
+}
+
+extern "C" const char* cude_last_error(const cude_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+// ---------------------------------------------------------------- context
+extern "C" int cude_ctx_create(int device, cude_ctx** out) {
+    if (!out) return fail(nullptr, CUDE_EINVAL, "cude_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, CUDE_ENODEVICE, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, CUDE_EINVAL, "cude_ctx_create: bad device index");
+    cude_ctx* ctx = new (std::nothrow) cude_ctx();
+    if (!ctx) return fail(nullptr, CUDE_ENOMEM, "out of host memory");
+    ctx->device = device;
+    CU_TRY(ctx, cudaSetDevice(device));
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
+    CU_TRY(ctx, cudaMallocHost(&ctx->h_counters, 3 * sizeof(unsigned long long)));
+    *out = ctx;
+    return CUDE_OK;
+}
+
+extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
+    if (!ctx) return CUDE_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CUDE_OK;
+}
+
+extern "C" void* cude_ctx_stream(cude_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+static int collect_stats(cude_ctx* ctx) {
+    if (!ctx->stats_pending) return CUDE_OK;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.n_acc = ctx->h_counters[0];
+    ctx->stats.n_rej = ctx->h_counters[1];
+    ctx->stats.n_fail = ctx->h_counters[2];
+    ctx->stats.n_rhs = 6ull * (ctx->stats.n_acc + ctx->stats.n_rej) + 2ull * ctx->stats.n_traj;
+    ctx->stats.kernel_ms = ms;
+    ctx->stats_pending = false;
+    return CUDE_OK;
+}
+
+extern "C" int cude_sync(cude_ctx* ctx) {
+    if (!ctx) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CUDE_OK;
+}
+
+extern "C" int cude_get_stats(cude_ctx* ctx, cude_stats* out) {
+    if (!ctx || !out) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = collect_stats(ctx);
+    if (rc) return rc;
+    *out = ctx->stats;
+    return CUDE_OK;
+}
+
+// ---------------------------------------------------------------- population
+extern "C" int cude_population_create(cude_ctx* ctx, int n_ind,
+                                      int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                                      int max_obs, const int* n_obs, const double* obs_t, const double* obs_y,
+                                      const double* kin, const double* covariate, cude_population** out) {
+    if (!ctx || !out) return fail(ctx, CUDE_EINVAL, "cude_population_create: NULL ctx/out");
+    *out = nullptr;
+    if (n_ind < 1 || max_knots < 2 || max_obs < 1 || !n_knots || !knot_t || !knot_g || !n_obs || !obs_t || !obs_y || !kin)
+        return fail(ctx, CUDE_EINVAL, "cude_population_create: bad argument");
+    const size_t N = (size_t)n_ind, K = (size_t)max_knots, M = (size_t)max_obs;
+    // validate + transpose to struct-of-arrays (individual index fastest)
+    std::vector<double> h((3 * K + 2 * M + 5) * N, 0.0);
+    double* hkt = h.data();
+    double* hkg = hkt + K * N;
+    double* hsl = hkg + K * N;
+    double* hot = hsl + K * N;
+    double* hoy = hot + M * N;
+    double* hk0 = hoy + M * N;
+    double* hk1 = hk0 + N;
+    double* hk2 = hk1 + N;
+    double* hc0 = hk2 + N;
+    double* hcv = hc0 + N;
+    for (size_t i = 0; i < N; ++i) {
+        const int nk = n_knots[i], no = n_obs[i];
+        if (nk < 2 || nk > max_knots || no < 0 || no > max_obs) return fail(ctx, CUDE_EINVAL, "cude_population_create: n_knots/n_obs out of range");
+        for (int k = 0; k < max_knots; ++k) {
+            // pad with the last knot so that stray reads stay finite
+            const int kk = k < nk ? k : nk - 1;
+            hkt[k * N + i] = knot_t[i * K + kk];
+            hkg[k * N + i] = knot_g[i * K + kk];
+            if (k + 1 < nk) {
+                const double dtk = knot_t[i * K + k + 1] - knot_t[i * K + k];
+                if (!(dtk > 0.0)) return fail(ctx, CUDE_EINVAL, "cude_population_create: knot times must be strictly increasing");
+                hsl[k * N + i] = (knot_g[i * K + k + 1] - knot_g[i * K + k]) / dtk;   // DataInterpolations slope
+            }
+        }
+        const double t0 = knot_t[i * K], t1 = knot_t[i * K + nk - 1];
+        for (int k = 0; k < max_obs; ++k) {
+            const int kk = k < no ? k : (no > 0 ? no - 1 : 0);
+            hot[k * N + i] = no > 0 ? obs_t[i * M + kk] : 0.0;
+            hoy[k * N + i] = no > 0 ? obs_y[i * M + kk] : 0.0;
+            if (k < no) {
+                const double ts = obs_t[i * M + k];
+                if (!(ts >= t0 && ts <= t1)) return fail(ctx, CUDE_EINVAL, "cude_population_create: observation time outside the glucose time span");
+                if (k > 0 && !(ts > obs_t[i * M + k - 1])) return fail(ctx, CUDE_EINVAL, "cude_population_create: observation times must be strictly increasing");
+            }
+        }
+        hk0[i] = kin[4 * i + 0]; hk1[i] = kin[4 * i + 1]; hk2[i] = kin[4 * i + 2]; hc0[i] = kin[4 * i + 3];
+        hcv[i] = covariate ? covariate[i] : 0.0;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cude_population* pop = new (std::nothrow) cude_population();
+    if (!pop) return fail(ctx, CUDE_ENOMEM, "out of host memory");
+    pop->ctx = ctx; pop->n_ind = n_ind; pop->max_knots = max_knots; pop->max_obs = max_obs;
+    cudaError_t e;
+    if ((e = cudaMalloc(&pop->block, h.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&pop->n_knots, N * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&pop->n_obs, N * sizeof(int))) != cudaSuccess) {
+        cude_population_destroy(pop);
+        return fail(ctx, CUDE_ENOMEM, std::string("cude_population_create: cudaMalloc failed: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(pop->block, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pop->n_knots, n_knots, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pop->n_obs, n_obs, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    PopDev& d = pop->dev;
+    d.n_ind = n_ind; d.max_knots = max_knots; d.max_obs = max_obs;
+    d.n_knots = pop->n_knots; d.n_obs = pop->n_obs;
+    d.knot_t = pop->block; d.knot_g = d.knot_t + K * N; d.slope = d.knot_g + K * N;
+    d.obs_t = d.slope + K * N; d.obs_y = d.obs_t + M * N;
+    d.k0 = d.obs_y + M * N; d.k1 = d.k0 + N; d.k2 = d.k1 + N; d.c0 = d.k2 + N;
+    d.cov = covariate ? d.c0 + N : nullptr;
+    *out = pop;
+    return CUDE_OK;
+}
+
+extern "C" int cude_population_destroy(cude_population* pop) {
+    if (!pop) return CUDE_OK;
+    if (pop->ctx) cudaSetDevice(pop->ctx->device);
+    if (pop->block) cudaFree(pop->block);
+    if (pop->n_knots) cudaFree(pop->n_knots);
+    if (pop->n_obs) cudaFree(pop->n_obs);
+    delete pop;
+    return CUDE_OK;
+}
+
+extern "C" int cude_population_size(const cude_population* pop) { return pop ? pop->n_ind : CUDE_EINVAL; }
+
+// ---------------------------------------------------------------- launch
+typedef void (*eval_kernel_t)(const EvalArgs);
+
+template <class NS>
+static eval_kernel_t pick(bool grad) { return grad ? cude_eval_kernel<NS, true> : cude_eval_kernel<NS, false>; }
+
+static eval_kernel_t select_kernel(const cude_net* net, bool grad) {
+    if (net->depth == 2 && net->width == 4) {
+        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad);   // chain(4, 2, tanh), 02-conditional.jl:22
+        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad);   // covariate net, 07-covariate-inclusion.jl:32
+    }
+    return nullptr;
+}
+
+static int choose_block(const cude_opts* o, int n_ind, bool flat) {
+    if (o->block > 0) return o->block;
+    if (flat) return 128;
+    if (n_ind > 64) return 128;
+    if (n_ind > 32) return 64;
+    return 32;
+}
+
+extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
+                             int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
+                             int want_grad, double cond_scale,
+                             double* d_sse_out, double* d_sums_out, double* d_g_cond) {
+    if (!ctx || !pop || !net || !d_neural || !d_cond) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: NULL argument");
+    if (pop->ctx != ctx) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: population belongs to another context");
+    if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: n_starts < 1");
+    cude_opts o;
+    if (opts_in) o = *opts_in; else cude_default_opts(&o);
+    if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad solver options");
+    if (o.precision != 0) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: only precision 0 (FP64) is available");
+    const int P = cude_net_nparams(net);
+    if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad network description");
+    if (net->n_in == 3 && !pop->dev.cov) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: 3-input network needs a population with a covariate");
+    const bool grad = want_grad != 0;
+    eval_kernel_t kern = select_kernel(net, grad);
+    if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
+    if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+
+    const int N = pop->n_ind, np1 = P + 1;
+    // flat indexing when every trajectory shares one network and no per-start network gradient is needed
+    const bool want_neural_grad = grad && (want_grad & 2);
+    const bool flat = (neural_stride == 0) && !want_neural_grad;
+    const int B = choose_block(&o, N, flat);
+    if (B < 32 || B > 128 || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: block must be 32, 64, 96 or 128");
+    const long long ntraj = (long long)N * n_starts;
+    const int nchunks = (N + B - 1) / B;
+    const long long nblocks = flat ? (ntraj + B - 1) / B : (long long)n_starts * nchunks;
+    if (nblocks > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many blocks; split the call");
+
+    int rc;
+    if ((rc = ensure(ctx, ctx->counters, 3 * sizeof(unsigned long long)))) return rc;
+    double* d_partials = nullptr;
+    if (!flat && d_sums_out) {
+        if ((rc = ensure(ctx, ctx->partials, (size_t)nblocks * np1 * sizeof(double)))) return rc;
+        d_partials = (double*)ctx->partials.p;
+    }
+    double* d_sse = d_sse_out;
+    if (flat && d_sums_out && !d_sse) {
+        if ((rc = ensure(ctx, ctx->scratch, (size_t)ntraj * sizeof(double)))) return rc;
+        d_sse = (double*)ctx->scratch.p;
+    }
+
+    EvalArgs a{};
+    a.pop = pop->dev;
+    a.n_starts = n_starts;
+    a.neural = d_neural;
+    a.neural_stride = neural_stride;
+    a.cond = d_cond;
+    a.abstol = o.abstol; a.reltol = o.reltol; a.maxiters = o.maxiters;
+    a.flat = flat ? 1 : 0;
+    a.nchunks = nchunks;
+    a.cond_scale = cond_scale;
+    a.sse_out = d_sse;
+    a.partials = d_partials;
+    a.g_cond = grad ? d_g_cond : nullptr;
+    a.counters = (unsigned long long*)ctx->counters.p;
+
+    const int K = pop->max_knots, M = pop->max_obs, nw = B / 32;
+    const size_t smem = sizeof(double) * (((P + 1) & ~1) + (size_t)3 * K * B + (grad ? (size_t)M * B : 0) + (size_t)nw * np1);
+    if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
+    if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (d_sums_out && (flat || !want_neural_grad))
+        CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
+    CU_TRY(ctx, cudaGetLastError());
+    int launches = 1;
+    if (d_sums_out) {
+        if (flat) {
+            const int wpb = 8;
+            cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);
+        } else {
+            const int wpb = 8;
+            const long long nwarps = (long long)n_starts * np1;
+            cude_reduce_partials<<<(unsigned)((nwarps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+                d_partials, nchunks, n_starts, np1, want_neural_grad ? np1 : 1, d_sums_out);
+        }
+        CU_TRY(ctx, cudaGetLastError());
+        ++launches;
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->stats = cude_stats{};
+    ctx->stats.n_traj = (unsigned long long)ntraj;
+    ctx->stats.launches = launches;
+    ctx->stats_pending = true;
+    return CUDE_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                     int n_starts, const double* neural, long long neural_stride, const double* cond,
+                     int want_grad, int mean_over_individuals,
+                     double* sse_out, double* loss_out, double* g_neural, double* g_cond) {
+    if (!ctx || !pop || !net || !neural || !cond) return fail(ctx, CUDE_EINVAL, "cude_loss: NULL argument");
+    if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_loss: n_starts < 1");
+    const int P = cude_net_nparams(net);
+    if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_loss: bad network description");
+    if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_loss: neural_stride < n_params");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int N = pop->n_ind, np1 = P + 1;
+    const size_t ntraj = (size_t)N * n_starts;
+    const size_t n_neural = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
+    int rc;
+    if ((rc = ensure(ctx, ctx->neural, n_neural * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->cond, ntraj * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->sums, (size_t)np1 * n_starts * sizeof(double)))) return rc;
+    if (sse_out && (rc = ensure(ctx, ctx->sse, ntraj * sizeof(double)))) return rc;
+    if (g_cond && (rc = ensure(ctx, ctx->gcond, ntraj * sizeof(double)))) return rc;
+    if (ctx->h_sums_cap < (size_t)np1 * n_starts) {
+        if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+        ctx->h_sums = nullptr; ctx->h_sums_cap = 0;
+        CU_TRY(ctx, cudaMallocHost(&ctx->h_sums, (size_t)np1 * n_starts * sizeof(double)));
+        ctx->h_sums_cap = (size_t)np1 * n_starts;
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->neural.p, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cond.p, cond, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int wg = 0;
+    if (want_grad) wg = (g_neural ? 2 : 0) | 1;
+    const double scale = mean_over_individuals ? 1.0 / N : 1.0;
+    rc = cude_eval_dev(ctx, pop, net, opts, n_starts, (const double*)ctx->neural.p, neural_stride, (const double*)ctx->cond.p,
+                       wg, scale, sse_out ? (double*)ctx->sse.p : nullptr, (double*)ctx->sums.p,
+                       g_cond ? (double*)ctx->gcond.p : nullptr);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, ctx->sse.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond, ctx->gcond.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, CUDE_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(e));
+    }
+    for (int s = 0; s < n_starts; ++s) {
+        const double* row = ctx->h_sums + (size_t)s * np1;
+        const bool ok = std::isfinite(row[0]);
+        if (loss_out) loss_out[s] = row[0] * scale;   // Inf stays Inf (parameter-estimation.jl:134-136)
+        if (g_neural) for (int p = 0; p < P; ++p) g_neural[(size_t)s * P + p] = ok ? row[1 + p] * scale : 0.0;
+        if (g_cond && !ok) for (int i = 0; i < N; ++i) g_cond[(size_t)s * N + i] = 0.0;
+    }
+    return CUDE_OK;
+}
+
+extern "C" int cude_loss(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                         int n_starts, const double* neural, long long neural_stride, const double* cond,
+                         double* sse_out, double* loss_out) {
+    return eval_host(ctx, pop, net, opts, n_starts, neural, neural_stride, cond, 0, 1, sse_out, loss_out, nullptr, nullptr);
+}
+
+extern "C" int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                              int n_starts, const double* neural, long long neural_stride, const double* cond,
+                              int mean_over_individuals,
+                              double* sse_out, double* loss_out, double* g_neural, double* g_cond) {
+    return eval_host(ctx, pop, net, opts, n_starts, neural, neural_stride, cond, 1, mean_over_individuals,
+                     sse_out, loss_out, g_neural, g_cond);
+}
+
+// ---------------------------------------------------------------- FP64 peak
+extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    int rc = ensure(ctx, ctx->scratch, (size_t)threads * blocks * sizeof(double));
+    if (rc) return rc;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        cude_dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch.p, iters, 0.999999, 1e-9);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->stats_pending = false;
+    *tflops = best;
+    return CUDE_OK;
+}

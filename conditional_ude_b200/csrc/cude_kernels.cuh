@@ -1,0 +1,648 @@
+// =====================================================================================
+// cude_kernels.cuh — sm_100a kernels for the c-peptide conditional-UDE loss and its gradient.
+//
+// One thread integrates one trajectory (individual i, start s) with an in-kernel adaptive Tsit5
+// (the scheme OrdinaryDiffEq's default algorithm runs for `solve(model.problem, p=theta,
+// saveat=timepoints, save_idxs=1)`, reference src/parameter-estimation.jl:59), evaluates the SSE of
+// :67 and — in the GRAD instantiation — the exact derivative of that discrete solve w.r.t. the MLP
+// weights and the conditional parameter by a discrete adjoint over the recorded accepted steps.
+//
+// Structure exploited (reference src/c-peptide-models.jl:7-14, :86-94, :108-114):
+//   u' = A u + b + e1 * prod(t),   prod(t) = NN([dG(t); beta]) - NN([0; beta]),  beta = exp(cond)
+// The production term does not depend on the state, so
+//   * the forward pass needs only 5 network evaluations per step (c6 = c7 = 1 and FSAL share the
+//     node t+dt with the next step's first stage),
+//   * the adjoint needs no stored states or stages: only (t_n, dt_n) of the accepted steps; the
+//     2-vector adjoint is propagated backwards through the linear stage recursion and the network
+//     is re-evaluated (forward + backward) at the 5 nodes of each step with a scalar seed.
+//
+// Data layout in HBM (struct-of-arrays, individual index fastest => coalesced per warp):
+//   knot_t/knot_g/slope [K][N], obs_t/obs_y [M][N], k0,k1,k2,c0,cov [N], cond/sse/g_cond [N x S].
+// Per block: the start's MLP weights are staged once in shared memory (block-uniform broadcast
+// reads), each thread's glucose knots are staged in shared memory ([k][tid], conflict-free), state,
+// stages, adjoint and the gradient accumulators live in registers.
+// Reduction: per-thread gradients -> warp shuffles -> one partial row per block ->
+// deterministic second-stage kernel (no atomics on the data path).
+// =====================================================================================
+#pragma once
+#ifndef CUDE_HOST_EMU   // tests/emu compiles this file with g++ behind a shim (CI without a GPU)
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#endif
+#include "cude_math.cuh"
+
+#ifndef CUDE_TRACE_STEP   // host-emulation test hook; compiles to nothing in the CUDA build
+#define CUDE_TRACE_STEP(t, dt, eest)
+#endif
+
+namespace cude {
+
+// ---------------------------------------------------------------- Tsit5 tableau
+// Published coefficients of Tsitouras' 5(4) pair as used by OrdinaryDiffEq.Tsit5.
+namespace tab {
+constexpr double c2 = 0.161, c3 = 0.327, c4 = 0.9, c5 = 0.9800255409045097;
+constexpr double a21 = 0.161;
+constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
+constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383;
+constexpr double b1 = 0.09646076681806523, b2 = 0.01, b3 = 0.4798896504144996, b4 = 1.379008574103742, b5 = -3.290069515436081, b6 = 2.324710524099774;
+constexpr double e1 = -0.00178001105222577714, e2 = -0.0008164344596567469, e3 = 0.007880878010261995, e4 = -0.1447110071732629,
+                 e5 = 0.5823571654525552, e6 = -0.45808210592918697, e7 = 0.015151515151515152;
+constexpr double r11 = 1.0, r12 = -2.763706197274826, r13 = 2.9132554618219126, r14 = -1.0530884977290216;
+constexpr double r22 = 0.13169999999999998, r23 = -0.2234, r24 = 0.1017;
+constexpr double r32 = 3.9302962368947516, r33 = -5.941033872131505, r34 = 2.490627285651253;
+constexpr double r42 = -12.411077166933676, r43 = 30.33818863028232, r44 = -16.548102889244902;
+constexpr double r52 = 37.50931341651104, r53 = -88.1789048947664, r54 = 47.37952196281928;
+constexpr double r62 = -27.896526289197286, r63 = 65.09189467479366, r64 = -34.87065786149661;
+constexpr double r72 = 1.5, r73 = -4.0, r74 = 2.5;
+// PI controller defaults of OrdinaryDiffEq for Tsit5
+constexpr double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0, qoldinit = 1e-4;
+}  // namespace tab
+
+// dense-output weights b_j(theta)
+__device__ __forceinline__ void dense_weights(double th, double (&bw)[7]) {
+    using namespace tab;
+    const double th2 = th * th;
+    bw[0] = th * fma(th, fma(th, fma(th, r14, r13), r12), r11);
+    bw[1] = th2 * fma(th, fma(th, r24, r23), r22);
+    bw[2] = th2 * fma(th, fma(th, r34, r33), r32);
+    bw[3] = th2 * fma(th, fma(th, r44, r43), r42);
+    bw[4] = th2 * fma(th, fma(th, r54, r53), r52);
+    bw[5] = th2 * fma(th, fma(th, r64, r63), r62);
+    bw[6] = th2 * fma(th, fma(th, r74, r73), r72);
+}
+
+// ---------------------------------------------------------------- device-side problem description
+struct PopDev {
+    int n_ind, max_knots, max_obs;
+    const int* n_knots;
+    const double* knot_t;  // [K][N]
+    const double* knot_g;  // [K][N]
+    const double* slope;   // [K-1][N]  (g[k+1]-g[k])/(t[k+1]-t[k]), DataInterpolations' cached parameter
+    const int* n_obs;
+    const double* obs_t;   // [M][N]
+    const double* obs_y;   // [M][N]
+    const double* k0;
+    const double* k1;
+    const double* k2;
+    const double* c0;
+    const double* cov;     // [N] or nullptr
+};
+
+struct EvalArgs {
+    PopDev pop;
+    int n_starts;
+    const double* neural;       // start s: neural + s*neural_stride
+    long long neural_stride;
+    const double* cond;         // [N x S]
+    double abstol, reltol;
+    int maxiters;
+    int flat;                   // 1: shared network, trajectories flattened over (i,s)
+    int nchunks;                // tiles per start (tile mode)
+    double cond_scale;          // g_cond = cond_scale * d sse / d cond
+    double* sse_out;            // [N x S] or nullptr
+    double* partials;           // [n_blocks][P+1]: {sum sse, sum d sse/d neural} per block (GRAD or loss sums) or nullptr
+    double* g_cond;             // [N x S] or nullptr
+    unsigned long long* counters;  // {n_acc, n_rej, n_fail}
+};
+
+// ---------------------------------------------------------------- network shape
+template <int NIN_, int DEPTH_, int WIDTH_>
+struct NetShape {
+    static constexpr int NIN = NIN_, DEPTH = DEPTH_, W = WIDTH_;
+    static constexpr int L1 = W * (NIN + 1);               // first layer block
+    static constexpr int LH = W * (W + 1);                 // hidden W->W layer block
+    static constexpr int OFF_OUT = L1 + (DEPTH - 1) * LH;  // output layer offset
+    static constexpr int P = OFF_OUT + W + 1;
+    // compressed accumulator count: first layer keeps only dW1[:,0] and the sum of dz1
+    static constexpr int NACC = 2 * W + (DEPTH - 1) * LH + W + 1;
+};
+
+#ifndef CUDE_REC_CAP
+#define CUDE_REC_CAP 48
+#endif
+constexpr int REC_CAP = CUDE_REC_CAP;  // ring of accepted-step records kept per thread (local memory)
+
+// per-thread view of the staged glucose knots in shared memory, layout [k][tid]
+struct Knots {
+    const double* t;
+    const double* g;
+    const double* sl;
+    int nk;
+    int stride;
+    double g0;
+    // DataInterpolations LinearInterpolation: idx = clamp(searchsortedlast(t, tau), 1, n-1)
+    __device__ __forceinline__ double dG(double tau) const {
+        int idx = 0;
+        for (int k = 1; k < nk - 1; ++k) idx = (t[k * stride] <= tau) ? k : idx;
+        const double v = fma(sl[idx * stride], tau - t[idx * stride], g[idx * stride]);
+        return v - g0;
+    }
+};
+
+// ---------------------------------------------------------------- MLP
+// forward: returns softplus(z_out) for input dG; c[] = first-layer pre-activation constant part
+template <class NS>
+__device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, const double (&c)[NS::W], double dG) {
+    constexpr int W = NS::W;
+    double a[W], b[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[j], dG, c[j]));
+    int off = NS::L1;
+#pragma unroll
+    for (int l = 1; l < NS::DEPTH; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            double z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
+            b[j] = m_tanh(z);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) a[j] = b[j];
+        off += NS::LH;
+    }
+    double z = sW[off + W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
+    return m_softplus(z);
+}
+
+// forward + backward at one time node with scalar seed w: acc += w * d softplus(z_out)/d(params)
+// accumulator layout: [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
+template <class NS>
+__device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, const double (&c)[NS::W], double dG, double w,
+                                             double (&acc)[NS::NACC]) {
+    constexpr int W = NS::W, D = NS::DEPTH;
+    double a[D][W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[j], dG, c[j]));
+    int off = NS::L1;
+#pragma unroll
+    for (int l = 1; l < D; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            double z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
+            a[l][j] = m_tanh(z);
+        }
+        off += NS::LH;
+    }
+    double z = sW[off + W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
+    // d softplus = sigmoid
+    const double dz = w * m_sigmoid(z);
+    double da[W];
+    int aoff = 2 * W + (D - 1) * NS::LH;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        acc[aoff + i] = fma(dz, a[D - 1][i], acc[aoff + i]);
+        da[i] = dz * sW[off + i];
+    }
+    acc[aoff + W] += dz;
+#pragma unroll
+    for (int l = D - 1; l >= 1; --l) {
+        off -= NS::LH;
+        aoff -= NS::LH;
+        double dzl[W], dprev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], 1.0);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                acc[aoff + i * W + j] = fma(dzl[j], a[l - 1][i], acc[aoff + i * W + j]);
+                s = fma(sW[off + i * W + j], dzl[j], s);
+            }
+            dprev[i] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) { acc[aoff + W * W + j] += dzl[j]; da[j] = dprev[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const double dz1 = da[j] * fma(-a[0][j], a[0][j], 1.0);
+        acc[j] = fma(dz1, dG, acc[j]);
+        acc[W + j] += dz1;
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+struct Kin { double k0, k1, k2, c0, d00, kc; };  // d00 = -(k0+k2), kc = k0*c0
+
+__device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, double p, double& f0, double& f1) {
+    // c_peptide_kinetics! + production on the plasma compartment
+    f0 = fma(K.d00, u0, fma(K.k1, u1, K.kc)) + p;
+    f1 = fma(-K.k1, u1, K.k2 * u0);
+}
+
+template <class NS, bool GRAD>
+__global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
+    using namespace tab;
+    constexpr int W = NS::W, P = NS::P;
+    extern __shared__ double smem[];
+    const int B = blockDim.x, tid = threadIdx.x;
+    const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
+
+    // ---- shared memory carve-up ----
+    double* sW = smem;                               // [P] (padded to even)
+    double* sKt = sW + ((P + 1) & ~1);               // [K][B]
+    double* sKg = sKt + (size_t)K * B;               // [K][B]
+    double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
+    double* sRes = sSl + (size_t)K * B;              // [M][B] residuals (GRAD)
+    double* sRed = sRes + (GRAD ? (size_t)M * B : 0);  // [nwarps][P+1]
+
+    // ---- which trajectory ----
+    long long j;
+    int i, s;
+    bool active;
+    if (A.flat) {
+        j = (long long)blockIdx.x * B + tid;
+        active = j < (long long)N * A.n_starts;
+        i = active ? (int)(j % N) : 0;
+        s = active ? (int)(j / N) : 0;
+    } else {
+        s = blockIdx.x / A.nchunks;
+        const int c = blockIdx.x - s * A.nchunks;
+        i = c * B + tid;
+        active = i < N;
+        j = (long long)s * N + i;
+        if (!active) i = 0;
+    }
+    // ---- stage the start's weights (block-uniform) ----
+    {
+        const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
+        for (int p = tid; p < P; p += B) sW[p] = gW[p];
+    }
+    // ---- stage this thread's knots ----
+    const int nk = A.pop.n_knots[i];
+    for (int k = 0; k < nk; ++k) {
+        sKt[k * B + tid] = A.pop.knot_t[(size_t)k * N + i];
+        sKg[k * B + tid] = A.pop.knot_g[(size_t)k * N + i];
+        if (k < nk - 1) sSl[k * B + tid] = A.pop.slope[(size_t)k * N + i];
+    }
+    __syncthreads();
+
+    double sse = 0.0, gcond = 0.0;
+    int nacc = 0, nrej = 0;
+    bool failed = false;
+    double acc[GRAD ? NS::NACC : 1];
+#pragma unroll
+    for (int q = 0; q < (GRAD ? NS::NACC : 1); ++q) acc[q] = 0.0;
+    double beta = 0.0, covv = 0.0;
+
+    if (active) {
+        Kin Kc;
+        Kc.k0 = A.pop.k0[i]; Kc.k1 = A.pop.k1[i]; Kc.k2 = A.pop.k2[i]; Kc.c0 = A.pop.c0[i];
+        Kc.d00 = -(Kc.k0 + Kc.k2); Kc.kc = Kc.k0 * Kc.c0;
+        Knots kn;
+        kn.t = sKt + tid; kn.g = sKg + tid; kn.sl = sSl + tid; kn.nk = nk; kn.stride = B;
+        kn.g0 = kn.g[0];
+        const double t0 = kn.t[0], tend = kn.t[(nk - 1) * B];
+        const int nobs = A.pop.n_obs[i];
+        const double* obs_t = A.pop.obs_t + i;
+        const double* obs_y = A.pop.obs_y + i;
+
+        // conditional_production: beta = exp(cond); first-layer constant part
+        beta = m_exp(A.cond[j]);
+        covv = (NS::NIN > 2 && A.pop.cov) ? A.pop.cov[i] : 0.0;
+        double c[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            double z = fma(sW[W + q], beta, sW[NS::NIN * W + q]);
+            if (NS::NIN > 2) z = fma(sW[2 * W + q], covv, z);
+            c[q] = z;
+        }
+        const double nn0 = mlp_forward<NS>(sW, c, 0.0);   // network([0; beta]) — identical at every call
+
+        const double abstol = A.abstol, reltol = A.reltol;
+        const double dtmax = tend - t0;
+        const double at0 = fabs(t0), at1 = fabs(tend);
+        const double dtmin = fmax(nextafter(at0, CUDART_INF) - at0, nextafter(at1, CUDART_INF) - at1);
+        const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
+
+        double2 rec[GRAD ? REC_CAP : 1];
+        int stop_at = 0x7fffffff;   // replay limit (GRAD)
+        int N_steps = 0;
+        // adjoint carry
+        double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
+        int kobs_top = nobs - 1;
+        bool first_pass = true;
+
+        do {
+            // =================== forward pass (or replay up to stop_at accepted steps) ===================
+            double u0 = Kc.c0, u1 = (Kc.k2 / Kc.k1) * Kc.c0;   // c-peptide-models.jl:185
+            double t = t0;
+            int iobs = 0, na = 0, nr = 0;
+            double fsse = 0.0;
+            double next_ot = (nobs > 0) ? obs_t[0] : CUDART_INF;
+            // save_start: observations at (or before) t0 see u0
+            while (iobs < nobs && next_ot <= t0) {
+                const double r = u0 - obs_y[(size_t)iobs * N];
+                if (GRAD) sRes[iobs * B + tid] = r;
+                fsse = fma(r, r, fsse);
+                ++iobs;
+                next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
+            }
+            double p1 = mlp_forward<NS>(sW, c, kn.dG(t0)) - nn0;   // production at t0 (dG = 0 -> 0)
+            double k10, k11;
+            kinetics(Kc, u0, u1, p1, k10, k11);
+            // ---- Hairer initial step (ode_determine_initdt) ----
+            double dt;
+            {
+                const double sk0 = fma(fabs(u0), reltol, abstol), sk1 = fma(fabs(u1), reltol, abstol);
+                const double isk0 = 1.0 / sk0, isk1 = 1.0 / sk1;
+                double x0 = u0 * isk0, x1 = u1 * isk1;
+                const double d0 = sqrt((x0 * x0 + x1 * x1) * 0.5);
+                x0 = k10 * isk0; x1 = k11 * isk1;
+                const double d1 = sqrt((x0 * x0 + x1 * x1) * 0.5);
+                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+                dt0 = fmin(dt0, dtmax);
+                const double pe = mlp_forward<NS>(sW, c, kn.dG(t0 + dt0)) - nn0;
+                double f0, f1;
+                kinetics(Kc, fma(dt0, k10, u0), fma(dt0, k11, u1), pe, f0, f1);
+                x0 = (f0 - k10) * isk0; x1 = (f1 - k11) * isk1;
+                const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
+                const double dm = fmax(d1, d2);
+                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0);
+                dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
+            }
+            int ret = 0;
+            if (!(isfinite(dt) && isfinite(k10) && isfinite(k11))) ret = 3;
+            double qold = qoldinit;
+            int iter = 0;
+            while (ret == 0 && t < tend && na < stop_at) {
+                if (++iter > A.maxiters) { ret = 1; break; }
+                dt = fmin(dt, tend - t);                       // modify_dt_for_tstops!
+                if (!(dt > dtmin)) { ret = (dt != dt) ? 3 : 2; break; }
+                // ---- stages: production at the 5 new nodes, kinetics is linear ----
+                double f0, f1, g0, g1;
+                const double p2 = mlp_forward<NS>(sW, c, kn.dG(fma(c2, dt, t))) - nn0;
+                g0 = fma(dt * a21, k10, u0); g1 = fma(dt * a21, k11, u1);
+                double k20, k21; kinetics(Kc, g0, g1, p2, k20, k21);
+                const double p3 = mlp_forward<NS>(sW, c, kn.dG(fma(c3, dt, t))) - nn0;
+                g0 = fma(dt, fma(a31, k10, a32 * k20), u0); g1 = fma(dt, fma(a31, k11, a32 * k21), u1);
+                double k30, k31; kinetics(Kc, g0, g1, p3, k30, k31);
+                const double p4 = mlp_forward<NS>(sW, c, kn.dG(fma(c4, dt, t))) - nn0;
+                g0 = fma(dt, fma(a41, k10, fma(a42, k20, a43 * k30)), u0); g1 = fma(dt, fma(a41, k11, fma(a42, k21, a43 * k31)), u1);
+                double k40, k41; kinetics(Kc, g0, g1, p4, k40, k41);
+                const double p5 = mlp_forward<NS>(sW, c, kn.dG(fma(c5, dt, t))) - nn0;
+                g0 = fma(dt, fma(a51, k10, fma(a52, k20, fma(a53, k30, a54 * k40))), u0);
+                g1 = fma(dt, fma(a51, k11, fma(a52, k21, fma(a53, k31, a54 * k41))), u1);
+                double k50, k51; kinetics(Kc, g0, g1, p5, k50, k51);
+                const double p6 = mlp_forward<NS>(sW, c, kn.dG(t + dt)) - nn0;   // shared by stages 6, 7 and the next k1
+                g0 = fma(dt, fma(a61, k10, fma(a62, k20, fma(a63, k30, fma(a64, k40, a65 * k50)))), u0);
+                g1 = fma(dt, fma(a61, k11, fma(a62, k21, fma(a63, k31, fma(a64, k41, a65 * k51)))), u1);
+                double k60, k61; kinetics(Kc, g0, g1, p6, k60, k61);
+                const double un0 = fma(dt, fma(b1, k10, fma(b2, k20, fma(b3, k30, fma(b4, k40, fma(b5, k50, b6 * k60))))), u0);
+                const double un1 = fma(dt, fma(b1, k11, fma(b2, k21, fma(b3, k31, fma(b4, k41, fma(b5, k51, b6 * k61))))), u1);
+                double k70, k71; kinetics(Kc, un0, un1, p6, k70, k71);
+                // ---- error estimate ----
+                f0 = dt * fma(e1, k10, fma(e2, k20, fma(e3, k30, fma(e4, k40, fma(e5, k50, fma(e6, k60, e7 * k70))))));
+                f1 = dt * fma(e1, k11, fma(e2, k21, fma(e3, k31, fma(e4, k41, fma(e5, k51, fma(e6, k61, e7 * k71))))));
+                f0 = f0 / fma(fmax(fabs(u0), fabs(un0)), reltol, abstol);
+                f1 = f1 / fma(fmax(fabs(u1), fabs(un1)), reltol, abstol);
+                const double EEst = sqrt((f0 * f0 + f1 * f1) * 0.5);
+                if (!(EEst == EEst) || !isfinite(un0) || !isfinite(un1)) { ret = 3; break; }
+                CUDE_TRACE_STEP(t, dt, EEst)
+                // ---- PI controller ----
+                double q, q11 = 0.0;
+                if (EEst == 0.0) q = 1.0 / qmax;
+                else {
+                    q11 = m_pow(EEst, beta1);
+                    q = q11 / m_pow(qold, beta2);
+                    q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
+                }
+                if (EEst <= 1.0) {
+                    double tnew = t + dt;
+                    if (fabs(tnew - tend) < snap) tnew = tend;
+                    // saveat by dense output: observation times in (t, tnew]
+                    while (iobs < nobs && next_ot <= tnew) {
+                        double y;
+                        if (next_ot == tnew) y = un0;
+                        else {
+                            double bw[7];
+                            dense_weights((next_ot - t) / dt, bw);
+                            const double sdo = fma(bw[0], k10, fma(bw[1], k20, fma(bw[2], k30, fma(bw[3], k40, fma(bw[4], k50, fma(bw[5], k60, bw[6] * k70))))));
+                            y = fma(dt, sdo, u0);
+                        }
+                        const double r = y - obs_y[(size_t)iobs * N];
+                        if (GRAD) sRes[iobs * B + tid] = r;
+                        fsse = fma(r, r, fsse);
+                        ++iobs;
+                        next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
+                    }
+                    if (GRAD) rec[na % REC_CAP] = make_double2(t, dt);
+                    ++na;
+                    qold = fmax(EEst, qoldinit);
+                    dt = fmin(dt / q, dtmax);
+                    t = tnew; u0 = un0; u1 = un1; k10 = k70; k11 = k71;   // FSAL
+                } else {
+                    ++nr;
+                    dt = dt / fmin(1.0 / qmin, q11 / gamma);
+                }
+            }
+            if (first_pass) {
+                if (ret == 0 && iobs < nobs) ret = 3;   // observation beyond tend: not produced by saveat
+                nacc = na; nrej = nr; N_steps = na;
+                failed = (ret != 0);
+                sse = failed ? CUDART_INF : fsse;
+                stop_at = na;
+                first_pass = false;
+            }
+            if (!GRAD || failed) break;
+            if constexpr (GRAD) {
+            // =================== adjoint over steps [lo, stop_at) held in the ring ===================
+            const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
+            for (int n = stop_at - 1; n >= lo; --n) {
+                const double2 r2 = rec[n % REC_CAP];
+                const double tn = r2.x, h = r2.y;
+                double kb[7][2];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
+                double ub0 = 0.0, ub1 = 0.0;
+                // observations in (tn, t_next]
+                while (kobs_top >= 0) {
+                    const double ts = obs_t[(size_t)kobs_top * N];
+                    if (!(ts > tn)) break;
+                    const double wr = 2.0 * sRes[kobs_top * B + tid];
+                    if (ts == t_next) lam0 += wr;
+                    else {
+                        double bw[7];
+                        dense_weights((ts - tn) / h, bw);
+                        ub0 += wr;
+                        const double wh = wr * h;
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
+                    }
+                    --kobs_top;
+                }
+                // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
+                const double pb7 = kb[6][0];
+                lam0 = fma(Kc.d00, kb[6][0], lam0);   // kb7[1] == 0
+                lam1 = fma(Kc.k1, kb[6][0], lam1);
+                // un = u + h sum b_j k_j
+                ub0 += lam0; ub1 += lam1;
+                {
+                    const double hl0 = h * lam0, hl1 = h * lam1;
+                    kb[0][0] = fma(b1, hl0, kb[0][0]); kb[0][1] = fma(b1, hl1, kb[0][1]);
+                    kb[1][0] = fma(b2, hl0, kb[1][0]); kb[1][1] = fma(b2, hl1, kb[1][1]);
+                    kb[2][0] = fma(b3, hl0, kb[2][0]); kb[2][1] = fma(b3, hl1, kb[2][1]);
+                    kb[3][0] = fma(b4, hl0, kb[3][0]); kb[3][1] = fma(b4, hl1, kb[3][1]);
+                    kb[4][0] = fma(b5, hl0, kb[4][0]); kb[4][1] = fma(b5, hl1, kb[4][1]);
+                    kb[5][0] = fma(b6, hl0, kb[5][0]); kb[5][1] = fma(b6, hl1, kb[5][1]);
+                }
+                // stage i: k_i = A g_i + b + e1 p_i, g_i = u + h sum_{j<i} a_ij k_j
+                // gb = A^T kb_i = [d00*kb0 + k2*kb1, k1*kb0 - k1*kb1]
+                double gb0, gb1, hg0, hg1;
+#define CUDE_STAGE_BACK(I)                                                    \
+    gb0 = fma(Kc.d00, kb[I][0], Kc.k2 * kb[I][1]);                            \
+    gb1 = Kc.k1 * (kb[I][0] - kb[I][1]);                                      \
+    ub0 += gb0; ub1 += gb1; hg0 = h * gb0; hg1 = h * gb1;
+#define CUDE_PUSH(J, COEF) kb[J][0] = fma(COEF, hg0, kb[J][0]); kb[J][1] = fma(COEF, hg1, kb[J][1]);
+                const double pb6 = kb[5][0];
+                CUDE_STAGE_BACK(5) CUDE_PUSH(0, a61) CUDE_PUSH(1, a62) CUDE_PUSH(2, a63) CUDE_PUSH(3, a64) CUDE_PUSH(4, a65)
+                const double pb5 = kb[4][0];
+                CUDE_STAGE_BACK(4) CUDE_PUSH(0, a51) CUDE_PUSH(1, a52) CUDE_PUSH(2, a53) CUDE_PUSH(3, a54)
+                const double pb4 = kb[3][0];
+                CUDE_STAGE_BACK(3) CUDE_PUSH(0, a41) CUDE_PUSH(1, a42) CUDE_PUSH(2, a43)
+                const double pb3 = kb[2][0];
+                CUDE_STAGE_BACK(2) CUDE_PUSH(0, a31) CUDE_PUSH(1, a32)
+                const double pb2 = kb[1][0];
+                CUDE_STAGE_BACK(1) CUDE_PUSH(0, a21)
+                const double pb1 = kb[0][0];
+                CUDE_STAGE_BACK(0)
+#undef CUDE_STAGE_BACK
+#undef CUDE_PUSH
+                // ---- network gradient at the 5 nodes of this step ----
+                const double w6 = pb6 + pb7 + wnode;   // node tn+h: stages 6, 7 and the next step's stage 1
+                mlp_backward<NS>(sW, c, kn.dG(tn + h), w6, acc);
+                mlp_backward<NS>(sW, c, kn.dG(fma(c5, h, tn)), pb5, acc);
+                mlp_backward<NS>(sW, c, kn.dG(fma(c4, h, tn)), pb4, acc);
+                mlp_backward<NS>(sW, c, kn.dG(fma(c3, h, tn)), pb3, acc);
+                mlp_backward<NS>(sW, c, kn.dG(fma(c2, h, tn)), pb2, acc);
+                wsum += w6 + pb5 + pb4 + pb3 + pb2;
+                wnode = pb1;
+                lam0 = ub0; lam1 = ub1;
+                t_next = tn;
+            }
+            stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
+            }  // if constexpr (GRAD)
+        } while (stop_at > 0);
+
+        if constexpr (GRAD) if (!failed) {
+            // node t0 carries weight wnode; NN([0;beta]) is subtracted at every node
+            mlp_backward<NS>(sW, c, kn.dG(t0), wnode, acc);
+            wsum += wnode;
+            mlp_backward<NS>(sW, c, 0.0, -wsum, acc);
+            // d sse / d cond = (sum_q dz1_q * W1[q,1]) * beta      (beta = exp(cond))
+            double db = 0.0;
+#pragma unroll
+            for (int q = 0; q < W; ++q) db = fma(acc[W + q], sW[W + q], db);
+            gcond = db * beta;
+        }
+        (void)N_steps;
+    }
+
+    // ---- outputs ----
+    if (active) {
+        if (A.sse_out) A.sse_out[j] = sse;
+        if (GRAD && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
+    }
+    // ---- block reduction: {sse, d sse/d neural[0..P)} and the step counters ----
+    const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
+    if (A.partials) {
+        constexpr int nred = GRAD ? P + 1 : 1;
+#pragma unroll
+        for (int q = 0; q < nred; ++q) {   // fully unrolled: acc[] must only see compile-time indices
+            double v = 0.0;
+            if (active) {
+                if (q == 0) v = sse;
+                else if constexpr (GRAD) { if (!failed) {
+                    // expand the compressed accumulators to the SimpleChains layout
+                    const int p = q - 1;
+                    if (p < W) v = acc[p];                                   // W1[:,0]  (dG column)
+                    else if (p < 2 * W) v = acc[W + (p - W)] * beta;         // W1[:,1]  (beta column)
+                    else if (NS::NIN > 2 && p < 3 * W) v = acc[W + (p - 2 * W)] * covv;   // W1[:,2] (covariate)
+                    else if (p < NS::L1) v = acc[W + (p - NS::NIN * W)];     // b1
+                    else v = acc[2 * W + (p - NS::L1)];                      // hidden + output layers
+                } }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sRed[wid * (P + 1) + q] = v;
+        }
+        __syncthreads();
+        for (int q = tid; q < nred; q += B) {
+            double v = 0.0;
+            for (int w2 = 0; w2 < nw; ++w2) v += sRed[w2 * (P + 1) + q];
+            A.partials[(size_t)blockIdx.x * (P + 1) + q] = v;
+        }
+    }
+    if (A.counters) {
+        unsigned int ca = active ? (unsigned)nacc : 0u, cr = active ? (unsigned)nrej : 0u, cf = (active && failed) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ca += __shfl_xor_sync(0xffffffffu, ca, o);
+            cr += __shfl_xor_sync(0xffffffffu, cr, o);
+            cf += __shfl_xor_sync(0xffffffffu, cf, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&A.counters[0], (unsigned long long)ca);
+            atomicAdd(&A.counters[1], (unsigned long long)cr);
+            if (cf) atomicAdd(&A.counters[2], (unsigned long long)cf);
+        }
+    }
+}
+
+// Second stage (tile mode): sums[(P+1) x S] column-major, sums[q + (P+1)*s] = sum over the start's
+// chunks of partials[(s*nchunks + c)*(P+1) + q], in fixed chunk order (deterministic).
+// One warp per (start, q-group); lanes stride over chunks then shuffle.
+__global__ void cude_reduce_partials(const double* __restrict__ partials, int nchunks, int n_starts, int np1,
+                                     int nred, double* __restrict__ sums) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)n_starts * np1) return;
+    const int s = (int)(gw / np1), q = (int)(gw % np1);
+    double v = 0.0;
+    if (q < nred) {
+        const double* base = partials + (size_t)s * nchunks * np1 + q;
+        for (int c = lane; c < nchunks; c += 32) v += base[(size_t)c * np1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    if (lane == 0) sums[(size_t)s * np1 + q] = v;
+}
+
+// flat mode: per-start sse sums from the per-trajectory sse array (loss-only / beta-only calls)
+__global__ void cude_sum_sse(const double* __restrict__ sse, int n_ind, int n_starts, int np1, double* __restrict__ sums) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long s = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (s >= n_starts) return;
+    double v = 0.0;
+    for (int i = lane; i < n_ind; i += 32) v += sse[(size_t)s * n_ind + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sums[(size_t)s * np1] = v;
+}
+
+// FP64 FMA peak micro-benchmark: 8 independent DFMA chains per thread.
+__global__ void cude_dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace cude

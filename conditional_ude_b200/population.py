@@ -1,0 +1,175 @@
+"""Device-resident population + batched loss / gradient calls through the C ABI.
+
+`Population` is the batched seam the reference does not have: the reference loops
+`for (i, model) in enumerate(models)` on one CPU thread (src/parameter-estimation.jl:129-138,
+:224-228, :362-366; src/likelihood-profiles.jl:11-14); here every (individual, start) pair is one
+GPU thread.  All arithmetic happens in conditional_ude_b200/csrc (CUDA); this file only marshals.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .models import pack_models, Chain
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class SolverOptions:
+    """abstol / reltol / maxiters of the reference's `solve` call (OrdinaryDiffEq defaults)."""
+
+    def __init__(self, abstol=1e-6, reltol=1e-3, maxiters=100000, block=0):
+        self.abstol, self.reltol, self.maxiters, self.block = abstol, reltol, maxiters, block
+
+    def c(self):
+        return _lib.cude_opts(self.abstol, self.reltol, int(self.maxiters), 0, int(self.block))
+
+
+class Context:
+    """One CUDA device + stream.  Raises if no device is present (no CPU fallback)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.cude_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, self._lib.cude_ctx_destroy, h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        _lib.check(self._lib.cude_sync(self._h), self._h)
+
+    def stats(self):
+        st = _lib.cude_stats()
+        _lib.check(self._lib.cude_get_stats(self._h, C.byref(st)), self._h)
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def stream(self):
+        return self._lib.cude_ctx_stream(self._h)
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        _lib.check(self._lib.cude_measure_fp64_peak(self._h, C.byref(v)), self._h)
+        return v.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class Population:
+    """Vector of CPeptideConditionalUDEModel + observations, uploaded once to HBM."""
+
+    def __init__(self, models=None, timepoints=None, cpeptide_data=None, ctx=None, packed=None):
+        self.ctx = ctx or default_context()
+        self._lib = self.ctx._lib
+        pk = packed if packed is not None else pack_models(models, timepoints, cpeptide_data)
+        self.chain = pk["chain"]
+        self.n_ind = int(pk["n_ind"])
+        self.net = _lib.cude_net(self.chain.input_dims, self.chain.depth, self.chain.width)
+        self.n_params = self.chain.n_params
+        arrs = {k: np.ascontiguousarray(pk[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
+        nk = np.ascontiguousarray(pk["n_knots"], dtype=np.int32)
+        no = np.ascontiguousarray(pk["n_obs"], dtype=np.int32)
+        cov = None if pk.get("cov") is None else np.ascontiguousarray(pk["cov"], dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(self._lib.cude_population_create(
+            self.ctx.handle, self.n_ind, int(pk["max_knots"]), _iptr(nk), _dptr(arrs["knot_t"]), _dptr(arrs["knot_g"]),
+            int(pk["max_obs"]), _iptr(no), _dptr(arrs["obs_t"]), _dptr(arrs["obs_y"]), _dptr(arrs["kin"]), _dptr(cov),
+            C.byref(h)), self.ctx.handle)
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.cude_population_destroy, h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- argument marshalling -------------------------------------------------------------
+    def _prep(self, neural, cond):
+        neural = np.asarray(neural, dtype=np.float64)
+        cond = np.asarray(cond, dtype=np.float64)
+        P, N = self.n_params, self.n_ind
+        if cond.ndim == 1:
+            cond = cond.reshape(1, N) if cond.size == N else None
+        if cond is None or cond.ndim != 2 or cond.shape[1] != N:
+            raise ValueError(f"cond must be [n_starts x {N}] (row s = start s)")
+        S = cond.shape[0]
+        if neural.ndim == 1:
+            if neural.size != P:
+                raise ValueError(f"neural must have {P} entries")
+            stride = 0
+        else:
+            if neural.shape != (S, P):
+                raise ValueError(f"neural must be [{S} x {P}] or [{P}]")
+            stride = P
+        # row-major [S x N] / [S x P] == the ABI's column-major [N x S] / [P x S]
+        return np.ascontiguousarray(neural), stride, np.ascontiguousarray(cond), S
+
+    def loss(self, neural, cond, opts=None, return_sse=False):
+        """Loss-only evaluation of S starts.  neural: [P] (shared) or [S x P]; cond: [S x N].
+        Returns loss[S] = mean_i sse (Inf when a trajectory failed), optionally sse[S x N]."""
+        neural, stride, cond, S = self._prep(neural, cond)
+        o = (opts or SolverOptions()).c()
+        loss = np.empty(S)
+        sse = np.empty((S, self.n_ind)) if return_sse else None
+        _lib.check(self._lib.cude_loss(self.ctx.handle, self._h, C.byref(self.net), C.byref(o), S, _dptr(neural), stride,
+                                       _dptr(cond), _dptr(sse), _dptr(loss)), self.ctx.handle)
+        return (loss, sse) if return_sse else loss
+
+    def loss_grad(self, neural, cond, opts=None, neural_grad=True, mean=True, return_sse=False):
+        """Loss and gradient.  Returns (loss[S], g_neural[S x P] or None, g_cond[S x N])
+        (+ sse[S x N] when return_sse).  mean=False gives sums / per-trajectory derivatives."""
+        neural, stride, cond, S = self._prep(neural, cond)
+        o = (opts or SolverOptions()).c()
+        loss = np.empty(S)
+        gn = np.empty((S, self.n_params)) if neural_grad else None
+        gc = np.empty((S, self.n_ind))
+        sse = np.empty((S, self.n_ind)) if return_sse else None
+        _lib.check(self._lib.cude_loss_grad(self.ctx.handle, self._h, C.byref(self.net), C.byref(o), S, _dptr(neural), stride,
+                                            _dptr(cond), 1 if mean else 0, _dptr(sse), _dptr(loss), _dptr(gn), _dptr(gc)),
+                   self.ctx.handle)
+        return (loss, gn, gc, sse) if return_sse else (loss, gn, gc)
+
+    def eval_dev(self, n_starts, d_neural, neural_stride, d_cond, want_grad, cond_scale, d_sse, d_sums, d_g_cond, opts=None):
+        """Asynchronous device-pointer call (ints are raw device addresses)."""
+        o = (opts or SolverOptions()).c()
+        _lib.check(self._lib.cude_eval_dev(self.ctx.handle, self._h, C.byref(self.net), C.byref(o), int(n_starts),
+                                           C.c_void_p(d_neural), int(neural_stride), C.c_void_p(d_cond), int(want_grad),
+                                           float(cond_scale), C.c_void_p(d_sse or 0) if d_sse else None,
+                                           C.c_void_p(d_sums) if d_sums else None,
+                                           C.c_void_p(d_g_cond) if d_g_cond else None), self.ctx.handle)
+
+
+_pop_cache = {}
+
+
+def cached_population(models, timepoints, cpeptide_data, ctx=None):
+    """Population for a (models, timepoints, data) triple, cached on object identity + data bytes so
+    that reference-style per-call `loss(theta, (models, t, Y))` does not re-upload every call."""
+    ts = np.ascontiguousarray(timepoints, dtype=np.float64)
+    ys = np.ascontiguousarray(cpeptide_data, dtype=np.float64)
+    key = (tuple(id(m) for m in models), ts.tobytes(), ys.tobytes(), id(ctx))
+    pop = _pop_cache.get(key)
+    if pop is None:
+        if len(_pop_cache) > 64:
+            _pop_cache.clear()
+        pop = Population(list(models), ts, ys, ctx=ctx)
+        _pop_cache[key] = (pop, list(models))   # keep the models alive so ids stay unique
+        return pop
+    return pop[0]

@@ -1,0 +1,62 @@
+"""Likelihood profiles (src/likelihood-profiles.jl), with the grid evaluated as ONE GPU batch.
+
+  likelihood_profile(beta, nn, model, t, y, lb, ub, sigma; steps)   :4-17
+  likelihood_profile_population(...)   batched over individuals (the loop at 02-conditional.jl:371-377)
+  find_confidence_intervals(loss_values, loss_minimum, parameter_values; target)   :34-59
+"""
+import numpy as np
+
+from .population import Population, cached_population
+
+CHISQ1_095 = 3.841458820694124  # quantile(Chisq(1), 0.95)
+
+
+def likelihood_profile(beta, neural_network_parameters, model, timepoints, cpeptide_data, lower_bound, upper_bound, sigma,
+                       steps=1000, opts=None):
+    """Returns (nll_values[steps], nll_minimum, parameter_values[steps]) like the reference: the loss at
+    `beta` and on range(lower_bound, upper_bound, length=steps), each scaled by 1/(2 sigma^2)."""
+    pop = cached_population([model], np.asarray(timepoints, dtype=np.float64),
+                            np.asarray(cpeptide_data, dtype=np.float64).reshape(1, -1))
+    parameter_values = np.linspace(lower_bound, upper_bound, steps)
+    b0 = float(np.asarray(beta, dtype=np.float64).reshape(-1)[0])
+    cond = np.concatenate([[b0], parameter_values]).reshape(-1, 1)
+    sse = pop.loss(np.asarray(neural_network_parameters, dtype=np.float64), cond, opts)
+    scale = 1.0 / (2.0 * sigma ** 2)
+    return scale * sse[1:], scale * sse[0], parameter_values
+
+
+def likelihood_profile_population(betas, neural_network_parameters, population, lower_bounds, upper_bounds, sigmas,
+                                  steps=1000, opts=None):
+    """All individuals' profiles in one launch: grid[s, i] = lower_i + s (upper_i - lower_i)/(steps-1).
+    Returns (nll[steps x N], nll_minimum[N], parameter_values[steps x N])."""
+    if not isinstance(population, Population):
+        raise TypeError("population must be a Population")
+    n = population.n_ind
+    lb = np.broadcast_to(np.asarray(lower_bounds, dtype=np.float64), (n,))
+    ub = np.broadcast_to(np.asarray(upper_bounds, dtype=np.float64), (n,))
+    sig = np.broadcast_to(np.asarray(sigmas, dtype=np.float64), (n,))
+    grid = np.linspace(lb, ub, steps)                       # [steps x N]
+    cond = np.vstack([np.asarray(betas, dtype=np.float64).reshape(1, n), grid])
+    _, sse = population.loss(np.asarray(neural_network_parameters, dtype=np.float64), cond, opts, return_sse=True)
+    scale = 1.0 / (2.0 * sig ** 2)
+    return sse[1:] * scale, sse[0] * scale, grid
+
+
+def find_confidence_intervals(loss_values, loss_minimum, parameter_values, target="cantelli95"):
+    """src/likelihood-profiles.jl:34-59 (host-side bookkeeping, identical thresholds)."""
+    if target == "cantelli95":
+        threshold = loss_minimum + 7.16
+    elif target == "cantelli90":
+        threshold = loss_minimum + 5.24
+    else:
+        if target != "raue95":
+            print(f"Unknown target {target}. Using raue 95%")
+        threshold = loss_minimum + CHISQ1_095
+    loss_values = np.asarray(loss_values)
+    idx = np.flatnonzero(loss_values <= threshold)
+    if idx.size == 0:
+        raise ValueError("no profile value below the threshold")   # Julia: minimum of an empty collection throws
+    lo, hi = idx.min(), idx.max()
+    lo_v = -np.inf if lo == 0 else parameter_values[lo]
+    hi_v = np.inf if hi == len(parameter_values) - 1 else parameter_values[hi]
+    return lo_v, hi_v

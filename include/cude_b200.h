@@ -1,0 +1,144 @@
+/* =====================================================================================
+ * cude_b200.h — C ABI of the B200-native c-peptide conditional-UDE loss / gradient path.
+ *
+ * The reference (Computational-Biology-TUe/conditional-ude) has no FFI: its seam is the Julia
+ * method table.  Each entry point below replaces the reference interface cited beside it; the
+ * Julia `ccall` stubs a maintainer would add are in INTEGRATION.md and julia/CUDEB200.jl.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CUDE_E* code on error; the message is
+ *     available from cude_last_error().  No exceptions cross the boundary.
+ *   - the caller owns all host buffers; the library owns device memory behind opaque handles.
+ *   - matrices are column-major (Julia): cond[i + n_ind*s], neural[p + neural_stride*s].
+ *   - FP64 host interface.  A context is bound to one CUDA device and one host thread at a time.
+ *   - there is NO CPU fallback: without a CUDA device cude_ctx_create fails with CUDE_ENODEVICE.
+ *   - a trajectory whose integrator fails (maxiters, dt underflow, NaN) has sse = +Inf and zero
+ *     gradient; a start containing such a trajectory has loss = +Inf
+ *     (src/parameter-estimation.jl:61-64, :134-136).
+ * ===================================================================================== */
+#ifndef CUDE_B200_H
+#define CUDE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUDE_B200_ABI_VERSION 1
+
+enum {
+    CUDE_OK = 0,
+    CUDE_EINVAL = -1,     /* bad argument */
+    CUDE_ENODEVICE = -2,  /* no usable CUDA device (no CPU fallback) */
+    CUDE_ECUDA = -3,      /* CUDA runtime error, see cude_last_error */
+    CUDE_ENOMEM = -4,
+    CUDE_EUNSUPPORTED = -5 /* network shape / option not compiled in */
+};
+
+typedef struct cude_ctx cude_ctx;
+typedef struct cude_population cude_population;
+
+/* Network of src/neural-network.jl:42-58 `chain(width, depth, tanh; input_dims)`:
+ * n_in inputs -> `depth` hidden tanh layers of `width` -> 1 softplus output.
+ * Parameter layout = SimpleChains TurboDense{true}: per layer W[out x in] column-major, then
+ * bias[out].  Input order [dG; beta] (c-peptide-models.jl:91) or [dG; beta; covariate] (:101). */
+typedef struct {
+    int n_in;   /* 2 (cUDE) or 3 (covariate cUDE) */
+    int depth;  /* hidden layers */
+    int width;  /* hidden width */
+} cude_net;
+
+/* Solver options of `solve(model.problem, p=theta, saveat=timepoints, save_idxs=1)`
+ * (src/parameter-estimation.jl:59): OrdinaryDiffEq defaults -> Tsit5, abstol 1e-6, reltol 1e-3,
+ * maxiters 1e5.  cude_default_opts() fills these. */
+typedef struct {
+    double abstol;
+    double reltol;
+    int maxiters;
+    int precision; /* 0 = FP64 (the only parity-gated mode) */
+    int block;     /* threads per block (individuals per tile); 0 = library default */
+} cude_opts;
+
+typedef struct {
+    unsigned long long n_traj;  /* trajectories evaluated by the last call            */
+    unsigned long long n_acc;   /* accepted Tsit5 steps, summed over trajectories     */
+    unsigned long long n_rej;   /* rejected steps                                     */
+    unsigned long long n_rhs;   /* RHS evaluations the reference scheme would perform */
+    unsigned long long n_fail;  /* trajectories that returned +Inf                    */
+    float kernel_ms;            /* device time of the last call's kernels (CUDA events) */
+    int launches;               /* kernels launched by the last call                  */
+} cude_stats;
+
+int cude_abi_version(void);
+void cude_default_opts(cude_opts* o);
+/* number of MLP parameters: 37 for (2,2,4), 41 for (3,2,4) */
+int cude_net_nparams(const cude_net* net);
+
+/* van_cauter_parameters(age, t2dm) -> (k0,k1,k2), src/c-peptide-models.jl:30-42 (host arithmetic) */
+void cude_van_cauter_parameters(double age, int t2dm, double* k0, double* k1, double* k2);
+
+/* ---- context ---- */
+int cude_ctx_create(int device, cude_ctx** out);
+int cude_ctx_destroy(cude_ctx* ctx);
+/* message of the last error on this context (ctx may be NULL for creation errors) */
+const char* cude_last_error(const cude_ctx* ctx);
+int cude_sync(cude_ctx* ctx);
+int cude_get_stats(cude_ctx* ctx, cude_stats* out);
+/* the CUDA stream (cudaStream_t) the context launches on, for interop / event timing */
+void* cude_ctx_stream(cude_ctx* ctx);
+
+/* ---- population: the device-resident image of a vector of CPeptideConditionalUDEModel
+ * (ctor src/c-peptide-models.jl:170-194; covariate variant :196-220) plus its data
+ * (timepoints, cpeptide_data rows of the loss tuple, parameter-estimation.jl:126).
+ *   knot_t, knot_g : [n_ind x max_knots] row-major (one row per individual), n_knots[i] used
+ *   obs_t, obs_y   : [n_ind x max_obs]   row-major, n_obs[i] used; obs_t must lie in
+ *                    [knot_t[0], knot_t[n_knots-1]] and be increasing
+ *   kin            : [n_ind x 4] rows k0,k1,k2,c0   (u0 = [c0, k2/k1*c0], tspan = knot range)
+ *   covariate      : [n_ind] third network input (age) or NULL
+ * Uploaded once; re-used by every loss / gradient / profile call. */
+int cude_population_create(cude_ctx* ctx, int n_ind,
+                           int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                           int max_obs, const int* n_obs, const double* obs_t, const double* obs_y,
+                           const double* kin, const double* covariate, cude_population** out);
+int cude_population_destroy(cude_population* pop);
+int cude_population_size(const cude_population* pop);
+
+/* ---- loss only: replaces loss(theta, (model,t,y)) :56-68, loss(theta, (model,t,y,nn)) :93-99,
+ * the population loss :126-140, the screening loop :362-366 and likelihood_profile
+ * (src/likelihood-profiles.jl:4-17).
+ *   start s uses network  neural + s*neural_stride   (neural_stride 0 = one shared network, i.e.
+ *   the fixed-NN / profile case) and conditional parameters cond[i + n_ind*s].
+ *   sse_out [n_ind x n_starts] (may be NULL): per-trajectory sum of squared errors
+ *   loss_out[n_starts]         (may be NULL): mean over individuals (:139), Inf if any failed */
+int cude_loss(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+              int n_starts, const double* neural, long long neural_stride, const double* cond,
+              double* sse_out, double* loss_out);
+
+/* ---- loss + gradient: replaces OptimizationFunction(loss, AutoForwardDiff()) :231,:281,:299,:370.
+ *   g_neural[P x n_starts] (may be NULL: beta-only estimation, :272-288): d loss[s] / d neural
+ *   g_cond  [n_ind x n_starts] (may be NULL): d loss[s] / d cond[i,s]   (= (1/N) d sse_i / d cond)
+ *   With mean_over_individuals = 0 the outputs are per-trajectory sums instead:
+ *   loss_out[s] = sum_i sse, g_neural = sum_i d sse_i, g_cond = d sse_i / d cond (beta-only fits). */
+int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                   int n_starts, const double* neural, long long neural_stride, const double* cond,
+                   int mean_over_individuals,
+                   double* sse_out, double* loss_out, double* g_neural, double* g_cond);
+
+/* ---- device-resident variants (asynchronous on the context stream; all pointers are device
+ * pointers on the context's device).  Used by multi-GPU population training: each rank holds a
+ * shard of the individuals, `sums_out` [(P+1) x n_starts] receives for every start
+ * { sum_i sse_i, sum_i d sse_i / d neural[0..P) } so that it can be all-reduced in place (NCCL)
+ * and divided by the global N; g_cond receives d sse_i / d cond scaled by cond_scale
+ * (pass 1/N_global).  want_grad = 0 computes only the sse sums (rows 1..P are zeroed). */
+int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                  int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
+                  int want_grad, double cond_scale,
+                  double* d_sse_out, double* d_sums_out, double* d_g_cond);
+
+/* Measured FP64 FMA peak of the context's device (dependent-chain-free DFMA micro-benchmark),
+ * the denominator of the roofline.  Returns TFLOP/s in *tflops. */
+int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDE_B200_H */

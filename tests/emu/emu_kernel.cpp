@@ -1,0 +1,82 @@
+// Host emulation of conditional_ude_b200/csrc/cude_kernels.cuh — TEST TOOL ONLY.
+// Compiles the *same kernel source* with g++ behind a minimal CUDA shim and runs it one
+// "thread" per block (blockDim = 1), so that the kernel's integrator / adjoint logic can be
+// checked against the oracle in the CPU-only test tier (pytest -m "not gpu").  It is never
+// loaded by the package; the product path is the CUDA library and has no CPU fallback.
+#define CUDE_HOST_EMU 1
+#include <math.h>
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <vector>
+using std::isfinite;
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__
+#define CUDART_INF INFINITY
+struct emu_dim3 { int x, y, z; };
+static emu_dim3 blockIdx, threadIdx, blockDim;
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+static inline void __syncthreads() {}
+template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }   // lanes 1..31 are empty
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+namespace cude { double smem[1 << 16]; }   // the kernel's `extern __shared__ double smem[]`
+
+static double* g_trace_buf = nullptr; static int g_trace_cap = 0, g_trace_n = 0;
+#define CUDE_TRACE_STEP(t, dt, eest) if (g_trace_buf && g_trace_n < g_trace_cap) { double* r_ = g_trace_buf + 4 * g_trace_n++; r_[0] = t; r_[1] = dt; r_[2] = eest; r_[3] = (eest <= 1.0) ? 1.0 : 0.0; }
+#include "../../conditional_ude_b200/csrc/cude_kernels.cuh"
+
+using namespace cude;
+
+extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                        int max_obs, const int* n_obs, const double* obs_t, const double* obs_y,
+                        const double* kin, const double* cov,
+                        int n_in, int n_starts, const double* neural, long long neural_stride, const double* cond,
+                        double abstol, double reltol, int maxiters, int grad, int flat,
+                        double* sse, double* g_neural_traj, double* g_cond, unsigned long long* counters) {
+    const size_t N = n_ind, K = max_knots, M = max_obs;
+    std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N), cv(N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+        const int nk = n_knots[i], no = n_obs[i];
+        for (int k = 0; k < max_knots; ++k) {
+            const int kk = k < nk ? k : nk - 1;
+            kt[k * N + i] = knot_t[i * K + kk]; kg[k * N + i] = knot_g[i * K + kk];
+            if (k + 1 < nk) sl[k * N + i] = (knot_g[i * K + k + 1] - knot_g[i * K + k]) / (knot_t[i * K + k + 1] - knot_t[i * K + k]);
+        }
+        for (int k = 0; k < max_obs; ++k) { const int kk = k < no ? k : no - 1; ot[k * N + i] = obs_t[i * M + kk]; oy[k * N + i] = obs_y[i * M + kk]; }
+        k0[i] = kin[4 * i]; k1[i] = kin[4 * i + 1]; k2[i] = kin[4 * i + 2]; c0[i] = kin[4 * i + 3];
+        if (cov) cv[i] = cov[i];
+    }
+    EvalArgs a{};
+    a.pop.n_ind = n_ind; a.pop.max_knots = max_knots; a.pop.max_obs = max_obs;
+    a.pop.n_knots = n_knots; a.pop.knot_t = kt.data(); a.pop.knot_g = kg.data(); a.pop.slope = sl.data();
+    a.pop.n_obs = n_obs; a.pop.obs_t = ot.data(); a.pop.obs_y = oy.data();
+    a.pop.k0 = k0.data(); a.pop.k1 = k1.data(); a.pop.k2 = k2.data(); a.pop.c0 = c0.data(); a.pop.cov = cov ? cv.data() : nullptr;
+    a.n_starts = n_starts; a.neural = neural; a.neural_stride = neural_stride; a.cond = cond;
+    a.abstol = abstol; a.reltol = reltol; a.maxiters = maxiters;
+    a.flat = flat; a.nchunks = n_ind; a.cond_scale = 1.0;
+    a.sse_out = sse; a.g_cond = g_cond; a.counters = counters;
+    const int P = (n_in == 2) ? NetShape<2, 2, 4>::P : NetShape<3, 2, 4>::P;
+    const long long nblocks = (long long)n_ind * n_starts;
+    std::vector<double> partials((size_t)nblocks * (P + 1), 0.0);
+    a.partials = flat ? nullptr : partials.data();
+    blockDim.x = 1; threadIdx.x = 0;
+    for (long long b = 0; b < nblocks; ++b) {
+        blockIdx.x = (int)b;
+        if (n_in == 2) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false>(a); }
+        else { if (grad) cude_eval_kernel<NetShape<3, 2, 4>, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false>(a); }
+    }
+    if (!flat && grad && g_neural_traj)
+        for (long long b = 0; b < nblocks; ++b)   // block b = s*N + i = trajectory index
+            for (int p = 0; p < P; ++p) g_neural_traj[b * P + p] = partials[b * (P + 1) + 1 + p];
+    return 0;
+}
+
+extern "C" void emu_set_trace(double* buf, int cap) { g_trace_buf = buf; g_trace_cap = cap; g_trace_n = 0; }
+extern "C" int emu_trace_count(void) { return g_trace_n; }
+extern "C" int emu_rec_cap(void) { return REC_CAP; }

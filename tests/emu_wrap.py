@@ -1,0 +1,50 @@
+"""ctypes wrapper for tests/emu/libcude_emu.so — the kernel source compiled for the host (test tool)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+LIB = os.path.join(_HERE, "libcude_emu.so")
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int)
+
+
+def build():
+    src = [os.path.join(_HERE, "emu_kernel.cpp")] + [
+        os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f) for f in ("cude_kernels.cuh", "cude_math.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-o", LIB, src[0]])
+    return LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(_D) if a is not None else None
+
+
+def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, grad=True, flat=False):
+    L = C.CDLL(build())
+    L.emu_eval.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.c_int, C.c_int, _D, C.c_longlong, _D,
+                           C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.POINTER(C.c_ulonglong)]
+    ch = packed["chain"]
+    N, P = int(packed["n_ind"]), ch.n_params
+    a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
+    nk = np.ascontiguousarray(packed["n_knots"], dtype=np.int32)
+    no = np.ascontiguousarray(packed["n_obs"], dtype=np.int32)
+    cov = None if packed.get("cov") is None else np.ascontiguousarray(packed["cov"], dtype=np.float64)
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float64).reshape(-1, N))
+    S = cond.shape[0]
+    stride = 0 if neural.ndim == 1 else P
+    sse = np.empty((S, N))
+    gn = np.zeros((S, N, P))
+    gc = np.zeros((S, N))
+    cnt = (C.c_ulonglong * 3)()
+    rc = L.emu_eval(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
+                    int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]), _dp(cov),
+                    ch.input_dims, S, _dp(neural), stride, _dp(cond), abstol, reltol, maxiters, int(grad), int(flat),
+                    _dp(sse), _dp(gn), _dp(gc), cnt)
+    assert rc == 0
+    return dict(sse=sse, g_neural=gn, g_cond=gc, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])

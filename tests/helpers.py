@@ -1,0 +1,46 @@
+"""Shared builders for the tests: reference-style model vectors from the golden fixtures."""
+import numpy as np
+
+import conditional_ude_b200 as cu
+
+
+def ohashi_models(fx, split="train", covariate=False):
+    net = cu.chain(4, 2, "tanh", input_dims=3 if covariate else 2)
+    ctor = cu.CPeptideConditionalCovariateUDEModel if covariate else cu.CPeptideConditionalUDEModel
+    g, c = fx[f"ohashi_{split}_glucose"], fx[f"ohashi_{split}_cpeptide"]
+    ages, t2dm, t = fx[f"ohashi_{split}_ages"], fx[f"ohashi_{split}_t2dm"], fx["ohashi_timepoints"]
+    # 02-conditional.jl:26-28
+    models = [ctor(g[i], t, float(ages[i]), net, c[i], bool(t2dm[i])) for i in range(g.shape[0])]
+    return models, t, c
+
+
+def fujita_models(fx):
+    net = cu.chain(4, 2, "tanh")
+    g, c, t = fx["fujita_glucose"], fx["fujita_cpeptide"], fx["fujita_timepoints"]
+    models = [cu.CPeptideConditionalUDEModel(g[i], t, 29.0, net, c[i], False) for i in range(g.shape[0])]
+    return models, t, c
+
+
+def train57(fx):
+    """The 57-individual training split with stored weights 14 and betas (config 1)."""
+    models, t, c = ohashi_models(fx, "train")
+    idx = fx["train_split_idx"]
+    best = int(fx["cude_best_model_index"]) - 1
+    return [models[i] for i in idx], t, c[idx], fx["cude_neural"][best], fx["cude_betas"][best]
+
+
+def mixed_population(fx):
+    """Ohashi train+test (5 knots) and Fujita (14 knots, t0 = -10): ragged knots and observations."""
+    m1, t1, c1 = ohashi_models(fx, "train")
+    m2, t2, c2 = ohashi_models(fx, "test")
+    m3, t3, c3 = fujita_models(fx)
+    models = m1 + m2 + m3
+    ts = [t1] * len(m1) + [t2] * len(m2) + [t3] * len(m3)
+    ys = [c1[i] for i in range(len(m1))] + [c2[i] for i in range(len(m2))] + [c3[i] for i in range(len(m3))]
+    return models, ts, ys
+
+
+def random_starts(rng, chain, n_ind, n_starts, scale=1.0):
+    neural = np.stack([chain.init_params(rng) * scale for _ in range(n_starts)])
+    cond = rng.uniform(-2.0, 0.0, size=(n_starts, n_ind))
+    return neural, cond
