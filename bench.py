@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — cUDE trajectory loss+gradient evaluations / second (BASELINE.json metric).
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): a synthetic virtual
+population of 1,000,000 individuals x 64 starts; one "step" = one loss+gradient evaluation of all
+64 M trajectories (adaptive Tsit5 solve at the reference's default tolerances, SSE, d/d(37 NN weights,
+beta)), the global NN gradient [38 x 64] all-reduced over NCCL when N > 1.  Individuals are sharded
+over the ranks (strong scaling: the population size is fixed).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # CPU restatement of the reference path (oracle)
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cUDE trajectory loss+grad evals/sec"
+UNIT = "evals/s"
+LN2 = float(np.log(2.0))
+
+
+# ----------------------------------------------------------------------------- synthetic population
+def synthetic_population(n, seed):
+    """Ohashi-like OGTT individuals (5 knots on [0,120] min)."""
+    from conditional_ude_b200 import chain
+    rng = np.random.default_rng(seed)
+    age = rng.uniform(20.0, 80.0, n)
+    t2dm = rng.random(n) < 0.44
+    short = np.where(t2dm, 4.52, 4.95)
+    frac = np.where(t2dm, 0.78, 0.76)
+    long_ = 0.14 * age + 29.2
+    k1 = frac * (LN2 / long_) + (1 - frac) * (LN2 / short)      # van_cauter_parameters, c-peptide-models.jl:30-42
+    k0 = (LN2 / short) * (LN2 / long_) / k1
+    k2 = (LN2 / short) + (LN2 / long_) - k0 - k1
+    c0 = np.clip(rng.lognormal(np.log(0.6), 0.4, n), 0.2, 1.5)
+    t = np.array([0.0, 30.0, 60.0, 90.0, 120.0])
+    g0 = rng.uniform(4.0, 8.0, n)
+    peak = rng.uniform(1.0, 15.0, n)
+    shape = np.stack([np.zeros(n), 0.6 + 0.4 * rng.random(n), 0.8 + 0.2 * rng.random(n),
+                      0.4 + 0.5 * rng.random(n), 0.1 + 0.4 * rng.random(n)], axis=1)
+    glucose = g0[:, None] + peak[:, None] * shape
+    gain = rng.uniform(1.0, 4.0, n)
+    y = c0[:, None] * (1.0 + gain[:, None] * shape * (peak[:, None] / 8.0)) + rng.normal(0.0, 0.1, (n, 5))
+    y = np.maximum(y, 0.05)
+    y[:, 0] = c0                                                  # c0 = cpeptide_data[1], c-peptide-models.jl:174
+    return dict(n_ind=n, max_knots=5, max_obs=5, n_knots=np.full(n, 5, np.int32), knot_t=np.tile(t, (n, 1)),
+                knot_g=glucose, n_obs=np.full(n, 5, np.int32), obs_t=np.tile(t, (n, 1)), obs_y=y,
+                kin=np.stack([k0, k1, k2, c0], axis=1), cov=None, chain=chain(4, 2, "tanh"))
+
+
+def synthetic_starts(n_ind, n_starts, seed_shared, seed_rank):
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz"))
+    nn = fx["cude_neural"][int(fx["cude_best_model_index"]) - 1]
+    neural = nn[None, :] + 0.1 * np.random.default_rng(seed_shared).standard_normal((n_starts, nn.size))
+    cond = np.random.default_rng(seed_rank).uniform(-2.0, 0.0, (n_starts, n_ind))   # LHS range, parameter-estimation.jl:343-344
+    return np.ascontiguousarray(neural), np.ascontiguousarray(cond)
+
+
+def alg_flops(n_traj, n_acc, n_rej, grad=True):
+    """Algorithmic work of SURVEY.md 8(d) (MAC = 2 flops; each tanh/exp/log/pow counted once, separately)."""
+    steps = n_acc + n_rej
+    fl = 79.0 * (6 * steps + 2 * n_traj) + 170.0 * steps + 315.0 * n_traj
+    tr = 10.0 * (6 * steps + 2 * n_traj) + 4.0 * steps
+    if grad:
+        fl += 6 * 240.0 * n_acc + 170.0 * n_acc + 240.0 * n_traj
+        tr += 60.0 * n_acc + 10.0 * n_traj
+    return fl, tr
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_baseline(n_ind, n_starts, threads, seed=7):
+    """Times the oracle (C++ restatement of the reference path, forward-mode gradient like the reference's
+    AutoForwardDiff) on a bounded sample of the same synthetic workload."""
+    from oracle import oracle
+    pk = synthetic_population(n_ind, seed)
+    neural, cond = synthetic_starts(n_ind, n_starts, 11, seed + 1)
+    op = oracle.OraclePopulation(pk)
+    op.population_loss(neural[:1], cond[:1], with_grad=True, n_threads=threads)   # warm-up
+    t0 = time.perf_counter()
+    r = op.population_loss(neural, cond, with_grad=True, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_ind * n_starts / dt, dt, r
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation cannot run (Julia is absent from the image),
+    so this arm times the oracle port of it on all host cores; each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    threads = oracle.max_threads()
+    n_ind, n_starts = args.ref_individuals, args.ref_starts
+    pk = synthetic_population(n_ind, 7)
+    neural, cond = synthetic_starts(n_ind, n_starts, 11, 8)
+    op = oracle.OraclePopulation(pk)
+    for _ in range(args.warmup):
+        op.population_loss(neural, cond, with_grad=True, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        op.population_loss(neural, cond, with_grad=True, n_threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n_ind * n_starts / dt
+    sample = f"{n_ind} individuals x {n_starts} starts per step (same generator as the GPU workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "sample": sample,
+                   "note": "Julia is not installed: the oracle (C++ port of the reference algorithm, forward-mode "
+                           "gradient, OpenMP over trajectories) is timed instead of the Julia code"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+WORKLOAD_NAME = "configs[4]: synthetic virtual population, 1M individuals x 64 starts, loss+grad, NN gradient all-reduced"
+
+
+# ----------------------------------------------------------------------------- this repo's arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import conditional_ude_b200 as cu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — conditional_ude_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N_total, S = args.individuals, args.starts
+    n_lo = rank * N_total // world
+    n_hi = (rank + 1) * N_total // world
+    n_loc = n_hi - n_lo
+
+    ctx = cu.Context(local)
+    # one explicit (non-default) stream for everything: kernels, copies, NCCL and the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    pk = synthetic_population(n_loc, 1000 + rank)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    P = pop.n_params
+    neural_h, cond_h = synthetic_starts(n_loc, S, 11, 2000 + rank)
+    # pinned host buffers for the end-to-end arm
+    neural_p = torch.from_numpy(neural_h).pin_memory()
+    cond_p = torch.from_numpy(cond_h).pin_memory()
+    gcond_p = torch.empty((S, n_loc), dtype=torch.float64).pin_memory()
+    sums_p = torch.empty((S, P + 1), dtype=torch.float64).pin_memory()
+    d_neural = neural_p.to(dev)
+    d_cond = cond_p.to(dev)
+    d_sums = torch.zeros((S, P + 1), dtype=torch.float64, device=dev)
+    d_gcond = torch.empty((S, n_loc), dtype=torch.float64, device=dev)
+    opts = cu.SolverOptions(block=args.block)
+
+    def step_resident():
+        pop.eval_dev(S, d_neural.data_ptr(), P, d_cond.data_ptr(), 3, 1.0 / N_total, 0, d_sums.data_ptr(), d_gcond.data_ptr(), opts)
+        if world > 1:
+            dist.all_reduce(d_sums)           # {sum sse, sum d sse/d neural} over ranks: 64 x 38 doubles
+
+    def step_e2e():
+        d_neural.copy_(neural_p, non_blocking=True)
+        d_cond.copy_(cond_p, non_blocking=True)
+        step_resident()
+        sums_p.copy_(d_sums, non_blocking=True)
+        gcond_p.copy_(d_gcond, non_blocking=True)
+        stream.synchronize()
+        return sums_p[:, 0].numpy() / N_total   # the step's result: loss per start
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms_total = timed(step_resident, args.steps)
+    ms_step = ms_total / args.steps
+    value = N_total * S / (ms_step * 1e-3)
+
+    # stats of one step (outside the timed region: reading them synchronises)
+    step_resident()
+    st = ctx.stats()
+    cnt = torch.tensor([st["n_acc"], st["n_rej"], st["n_fail"], st["n_traj"]], dtype=torch.float64, device=dev)
+    kms = torch.tensor([st["kernel_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    n_acc, n_rej, n_fail, n_traj = [float(x) for x in cnt.tolist()]
+    loss0 = (d_sums[:, 0] / N_total).cpu().numpy()
+
+    # end-to-end through host buffers (pinned): H2D of the step's inputs + D2H of its results every step
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    e2e_value = N_total * S / (ms_e2e * 1e-3)
+    h2d = (neural_p.numel() + cond_p.numel()) * 8
+    d2h = (sums_p.numel() + gcond_p.numel()) * 8
+
+    # roofline of the dominant kernel (cude_eval_kernel<..., GRAD>): FP64 CUDA-core pipe
+    peak = ctx.fp64_peak_tflops()
+    fl, tr = alg_flops(n_traj / world, n_acc / world, n_rej / world, grad=True)   # per launch (one rank)
+    kernel_s = float(kms.item()) * 1e-3
+    achieved = (fl + tr) / kernel_s / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "cude_eval_kernel<NetShape<2,2,4>,GRAD>", "kernel_ms": float(kms.item()),
+                "alg_flops_per_traj": fl / (n_traj / world), "alg_transcendentals_per_traj": tr / (n_traj / world),
+                "peak_source": "measured live: DFMA micro-benchmark (cude_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "n_acc_per_traj": n_acc / n_traj, "n_rej_per_traj": n_rej / n_traj}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "individuals": N_total, "starts": S, "trajectories_per_step": N_total * S,
+                       "abstol": opts.abstol, "reltol": opts.reltol, "network": "chain(4,2,tanh): 37 parameters",
+                       "sharding": f"individuals over {world} rank(s); all-reduce of {S}x{P + 1} f64",
+                       "l2": "inputs larger than L2 (cond + g_cond = %.0f MB per rank)" % (2 * S * n_loc * 8 / 1e6),
+                       "n_fail": n_fail, "mean_loss_start0": float(loss0[0])},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": 2 * args.steps,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle
+            threads = oracle.max_threads()
+            v, secs, _ = cpu_baseline(args.cpu_individuals, args.cpu_starts, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{args.cpu_individuals} individuals x {args.cpu_starts} starts, {secs:.1f} s "
+                                             "(oracle: C++ port of the reference algorithm, forward-mode gradient)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--individuals", type=int, default=1_000_000)
+    ap.add_argument("--starts", type=int, default=64)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-individuals", type=int, default=4000)
+    ap.add_argument("--cpu-starts", type=int, default=64)
+    ap.add_argument("--ref-individuals", type=int, default=2000)
+    ap.add_argument("--ref-starts", type=int, default=64)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,7 @@ SYMBOLS = {
     "cude_sync": (C.c_int, [_P]),
     "cude_get_stats": (C.c_int, [_P, C.POINTER(cude_stats)]),
     "cude_ctx_stream": (_P, [_P]),
+    "cude_ctx_set_stream": (C.c_int, [_P, _P]),
     "cude_population_create": (C.c_int, [_P, C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.POINTER(_P)]),
     "cude_population_destroy": (C.c_int, [_P]),
     "cude_population_size": (C.c_int, [_P]),

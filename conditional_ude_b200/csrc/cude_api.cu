@@ -23,7 +23,8 @@ struct DevBuf {
 
 struct cude_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream in use
+    cudaStream_t own_stream = nullptr;   // stream created by the context
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     cude_stats stats{};
@@ -121,7 +122,8 @@ extern "C" int cude_ctx_create(int device, cude_ctx** out) {
     if (!ctx) return fail(nullptr, CUDE_ENOMEM, "out of host memory");
     ctx->device = device;
     CU_TRY(ctx, cudaSetDevice(device));
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
     CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
     CU_TRY(ctx, cudaMallocHost(&ctx->h_counters, 3 * sizeof(unsigned long long)));
@@ -139,12 +141,20 @@ extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return CUDE_OK;
 }
 
 extern "C" void* cude_ctx_stream(cude_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int cude_ctx_set_stream(cude_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return CUDE_OK;
+}
 
 static int collect_stats(cude_ctx* ctx) {
     if (!ctx->stats_pending) return CUDE_OK;

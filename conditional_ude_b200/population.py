@@ -58,6 +58,10 @@ class Context:
     def stream(self):
         return self._lib.cude_ctx_stream(self._h)
 
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned cudaStream_t (int address), e.g. torch.cuda.current_stream().cuda_stream."""
+        _lib.check(self._lib.cude_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None), self._h)
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         _lib.check(self._lib.cude_measure_fp64_peak(self._h, C.byref(v)), self._h)

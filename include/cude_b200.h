@@ -85,6 +85,9 @@ int cude_sync(cude_ctx* ctx);
 int cude_get_stats(cude_ctx* ctx, cude_stats* out);
 /* the CUDA stream (cudaStream_t) the context launches on, for interop / event timing */
 void* cude_ctx_stream(cude_ctx* ctx);
+/* make the context launch on a caller-owned stream (e.g. the one NCCL all-reduces on);
+ * NULL restores the context's own stream */
+int cude_ctx_set_stream(cude_ctx* ctx, void* cuda_stream);
 
 /* ---- population: the device-resident image of a vector of CPeptideConditionalUDEModel
  * (ctor src/c-peptide-models.jl:170-194; covariate variant :196-220) plus its data

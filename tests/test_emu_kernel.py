@@ -1,0 +1,105 @@
+"""CPU tier: the CUDA kernel *source* (conditional_ude_b200/csrc/cude_kernels.cuh) compiled for the host
+behind a CUDA shim (tests/emu) and run one thread per block, against the oracle.
+
+This is a test tool, not a product path: it lets the CPU-only test tier exercise the kernel's
+integrator, dense output, discrete adjoint, step-ring replay and gradient expansion.  The GPU tier
+(test_gpu_parity.py) runs the same comparisons on the real device through the C ABI.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import conditional_ude_b200 as cu
+from oracle import oracle
+from helpers import train57, mixed_population, ohashi_models, random_starts
+import emu_wrap
+
+DET = dict(abstol=1e3, reltol=1e3)
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_deterministic_regime_exact(fx):
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    rng = np.random.default_rng(0)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 3)
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    e = emu_wrap.emu_eval(pk, neural, cond, **DET)
+    assert relmax(e["sse"], g["sse"]) < 1e-10
+    assert relmax(e["g_cond"], g["g_cond"]) < 1e-9
+    assert relmax(e["g_neural"], g["g_neural"]) < 1e-9
+    assert e["n_acc"] == g["stats"][..., 0].sum() and e["n_rej"] == g["stats"][..., 1].sum() and e["n_fail"] == 0
+    # flat indexing (shared network) gives the same per-trajectory results
+    e1 = emu_wrap.emu_eval(pk, neural[0], cond, flat=True, **DET)
+    e2 = emu_wrap.emu_eval(pk, neural[0], cond, flat=False, **DET)
+    assert np.array_equal(e1["sse"], e2["sse"]) and np.array_equal(e1["g_cond"], e2["g_cond"])
+    # loss-only instantiation == forward pass of the gradient instantiation
+    e3 = emu_wrap.emu_eval(pk, neural, cond, grad=False, **DET)
+    assert np.array_equal(e3["sse"], e["sse"])
+
+
+def test_default_tolerance_within_noise_floor(fx):
+    models, t, c, nn, betas = train57(fx)
+    pk = cu.pack_models(models, t, c)
+    g = oracle.OraclePopulation(pk).eval(nn, betas, grad_mode=0)
+    e = emu_wrap.emu_eval(pk, nn, betas)
+    d = np.abs(e["sse"] - g["sse"]) / g["sse"]
+    assert np.median(d) < 1e-8 and d.max() < 1e-5
+    assert relmax(e["g_cond"], g["g_cond"]) < 1e-4 and relmax(e["g_neural"], g["g_neural"]) < 1e-4
+    assert abs(e["sse"].mean() - 0.4281389) < 1e-6
+
+
+def test_covariate_network(fx):
+    models, t, c = ohashi_models(fx, "train", covariate=True)
+    idx = fx["train_split_idx"][:20]
+    pk = cu.pack_models([models[i] for i in idx], t, c[idx])
+    nn, betas = fx["cov_neural"][1], fx["cov_betas"][1][:20]
+    g = oracle.OraclePopulation(pk).eval(nn, betas, grad_mode=0, **DET)
+    e = emu_wrap.emu_eval(pk, nn, betas, **DET)
+    assert e["g_neural"].shape[-1] == 41
+    assert relmax(e["sse"], g["sse"]) < 1e-10 and relmax(e["g_neural"], g["g_neural"]) < 1e-9
+    assert relmax(e["g_cond"], g["g_cond"]) < 1e-9
+
+
+def test_step_ring_replay(fx, tmp_path):
+    """Rebuild the emulation with a 4-entry step ring: the 9-step deterministic solve then needs three
+    replays of the forward pass; the gradient must not change."""
+    lib = str(tmp_path / "libcude_emu_cap4.so")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                           "-DCUDE_REC_CAP=4", "-o", lib, os.path.join(emu_wrap._HERE, "emu_kernel.cpp")])
+    models, ts, ys = mixed_population(fx)
+    pick = [0, 50, 100, 120, 130]
+    pk = cu.pack_models([models[i] for i in pick], [ts[i] for i in pick], [ys[i] for i in pick])
+    rng = np.random.default_rng(4)
+    neural, cond = random_starts(rng, pk["chain"], len(pick), 2)
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    assert g["stats"][..., 0].min() > 4
+    old = emu_wrap.LIB
+    try:
+        emu_wrap.LIB = lib
+        emu_wrap.build = lambda: lib
+        assert C.CDLL(lib).emu_rec_cap() == 4
+        e = emu_wrap.emu_eval(pk, neural, cond, **DET)
+    finally:
+        emu_wrap.LIB = old
+        import importlib
+        importlib.reload(emu_wrap)
+    assert relmax(e["sse"], g["sse"]) < 1e-10
+    assert relmax(e["g_cond"], g["g_cond"]) < 1e-9 and relmax(e["g_neural"], g["g_neural"]) < 1e-9
+
+
+def test_failures(fx):
+    models, t, c, nn, betas = train57(fx)
+    pk = cu.pack_models(models, t, c)
+    b = betas.copy()
+    b[5] = np.nan
+    e = emu_wrap.emu_eval(pk, nn, b)
+    assert np.isinf(e["sse"][0, 5]) and e["g_cond"][0, 5] == 0 and np.all(e["g_neural"][0, 5] == 0) and e["n_fail"] == 1
+    e = emu_wrap.emu_eval(pk, nn, betas, maxiters=5)
+    assert np.isinf(e["sse"]).all() and e["n_fail"] == 57

