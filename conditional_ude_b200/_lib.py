@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcude_b200.so")
+# CUDE_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("CUDE_B200_LIB") or os.path.join(_HERE, "csrc", "libcude_b200.so")
 
 CUDE_OK = 0
 CUDE_EINVAL, CUDE_ENODEVICE, CUDE_ECUDA, CUDE_ENOMEM, CUDE_EUNSUPPORTED = -1, -2, -3, -4, -5

@@ -356,8 +356,9 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     a.g_cond = grad ? d_g_cond : nullptr;
     a.counters = (unsigned long long*)ctx->counters.p;
 
-    const int K = pop->max_knots, M = pop->max_obs, nw = B / 32;
-    const size_t smem = sizeof(double) * (((P + 1) & ~1) + (size_t)3 * K * B + (grad ? (size_t)M * B : 0) + (size_t)nw * np1);
+    const int K = pop->max_knots, M = pop->max_obs;
+    const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
+    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, grad);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 

@@ -119,6 +119,17 @@ struct NetShape {
     static constexpr int NACC = 2 * W + (DEPTH - 1) * LH + W + 1;
 };
 
+#ifndef CUDE_MIN_BLOCKS
+#define CUDE_MIN_BLOCKS 3   // resident 128-thread blocks per SM the register allocation is tuned for
+#endif
+#ifndef CUDE_FWD_UNROLL
+#define CUDE_FWD_UNROLL 1   // unroll factor of the forward network-evaluation loop over a step's 5 nodes
+#endif
+#ifndef CUDE_BWD_UNROLL
+#define CUDE_BWD_UNROLL 1   // same for the adjoint's forward+backward evaluation loop
+#endif
+#define CUDE_PRAGMA(x) _Pragma(#x)
+#define CUDE_UNROLL(n) CUDE_PRAGMA(unroll n)
 #ifndef CUDE_REC_CAP
 #define CUDE_REC_CAP 48
 #endif
@@ -139,9 +150,30 @@ struct Knots {
         const double v = fma(sl[idx * stride], tau - t[idx * stride], g[idx * stride]);
         return v - g0;
     }
+    // the 5 node times of a step at once: one pass over the knots, 5 independent select chains, then
+    // 15 independent shared-memory loads (a per-node search serialised on the LDS latency, ncu v4)
+    __device__ __forceinline__ void dG5(const double (&tau)[5], double* out, int ostride) const {
+        int idx[5] = {0, 0, 0, 0, 0};
+        for (int k = 1; k < nk - 1; ++k) {
+            const double tk = t[k * stride];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) idx[q] = (tk <= tau[q]) ? k : idx[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const double v = fma(sl[idx[q] * stride], tau[q] - t[idx[q] * stride], g[idx[q] * stride]);
+            out[q * ostride] = v - g0;
+        }
+    }
 };
 
 // ---------------------------------------------------------------- MLP
+// Node-time coefficient tables: a step evaluates the network at t + c*dt for the 5 new nodes
+// (c6 = c7 = 1 share one node with the next step's first stage); the init phase evaluates the two
+// nodes t0 (-> NN([0;beta])) and t0 + dt0 (Hairer's probe).
+__constant__ double CN_STEP[5] = {0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
+__constant__ double CN_INIT[5] = {0.0, 1.0, 1.0, 1.0, 1.0};
+
 // forward: returns softplus(z_out) for input dG; c[] = first-layer pre-activation constant part
 template <class NS>
 __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, const double (&c)[NS::W], double dG) {
@@ -169,11 +201,17 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
     return m_softplus(z);
 }
 
-// forward + backward at one time node with scalar seed w: acc += w * d softplus(z_out)/d(params)
-// accumulator layout: [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
+// forward + backward at one time node with scalar seed w: acc += w * d softplus(z_out)/d(params).
+// The activations are recomputed: keeping them from the forward pass (9 doubles per node, ~7 KB per
+// trajectory in local memory) was measured slower on B200 (1.05e8 vs 1.30e8 evals/s) — the footprint of
+// all resident threads exceeds L2 and the kernel has too few warps to hide the HBM latency.
+// The accumulators g[] stay in registers during the adjoint sweep (updating them in shared memory
+// serialised on the LDS latency: ncu v2 short_scoreboard); they are parked in shared memory only around a
+// forward replay and for the final block reduction.  Layout:
+// [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
 template <class NS>
 __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, const double (&c)[NS::W], double dG, double w,
-                                             double (&acc)[NS::NACC]) {
+                                             double (&g)[NS::NACC]) {
     constexpr int W = NS::W, D = NS::DEPTH;
     double a[D][W];
 #pragma unroll
@@ -193,16 +231,15 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
     double z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
-    // d softplus = sigmoid
-    const double dz = w * m_sigmoid(z);
+    const double dz = w * m_sigmoid(z);   // d softplus = sigmoid
     double da[W];
     int aoff = 2 * W + (D - 1) * NS::LH;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        acc[aoff + i] = fma(dz, a[D - 1][i], acc[aoff + i]);
+        g[aoff + i] = fma(dz, a[D - 1][i], g[aoff + i]);
         da[i] = dz * sW[off + i];
     }
-    acc[aoff + W] += dz;
+    g[aoff + W] += dz;
 #pragma unroll
     for (int l = D - 1; l >= 1; --l) {
         off -= NS::LH;
@@ -215,19 +252,19 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                acc[aoff + i * W + j] = fma(dzl[j], a[l - 1][i], acc[aoff + i * W + j]);
+                g[aoff + i * W + j] = fma(dzl[j], a[l - 1][i], g[aoff + i * W + j]);
                 s = fma(sW[off + i * W + j], dzl[j], s);
             }
             dprev[i] = s;
         }
 #pragma unroll
-        for (int j = 0; j < W; ++j) { acc[aoff + W * W + j] += dzl[j]; da[j] = dprev[j]; }
+        for (int j = 0; j < W; ++j) { g[aoff + W * W + j] += dzl[j]; da[j] = dprev[j]; }
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         const double dz1 = da[j] * fma(-a[0][j], a[0][j], 1.0);
-        acc[j] = fma(dz1, dG, acc[j]);
-        acc[W + j] += dz1;
+        g[j] = fma(dz1, dG, g[j]);
+        g[W + j] += dz1;
     }
 }
 
@@ -240,8 +277,14 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
     f1 = fma(-K.k1, u1, K.k2 * u0);
 }
 
+// dynamic shared memory (doubles) needed by cude_eval_kernel
+__host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad) {
+    return (size_t)((P + 1) & ~1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
+           (size_t)((B + 31) / 32) * (P + 1);
+}
+
 template <class NS, bool GRAD>
-__global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
+__global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const EvalArgs A) {
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
     extern __shared__ double smem[];
@@ -253,8 +296,11 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
     double* sKt = sW + ((P + 1) & ~1);               // [K][B]
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
-    double* sRes = sSl + (size_t)K * B;              // [M][B] residuals (GRAD)
-    double* sRed = sRes + (GRAD ? (size_t)M * B : 0);  // [nwarps][P+1]
+    double* sNode = sSl + (size_t)K * B;             // [5][B] network outputs (forward) / node weights (adjoint)
+    double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD)
+    double* sRes = sDG + (GRAD ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
+    double* sAcc = sRes + (GRAD ? (size_t)M * B : 0);           // [NACC][B] gradient accumulators (GRAD)
+    double* sRed = sAcc + (GRAD ? (size_t)NS::NACC * B : 0);    // [nwarps][P+1]
 
     // ---- which trajectory ----
     long long j;
@@ -290,10 +336,10 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
     double sse = 0.0, gcond = 0.0;
     int nacc = 0, nrej = 0;
     bool failed = false;
-    double acc[GRAD ? NS::NACC : 1];
-#pragma unroll
-    for (int q = 0; q < (GRAD ? NS::NACC : 1); ++q) acc[q] = 0.0;
     double beta = 0.0, covv = 0.0;
+    double* const myNode = sNode + tid;
+    double* const myAcc = sAcc + tid;
+    double* const myDG = sDG + tid;
 
     if (active) {
         Kin Kc;
@@ -317,7 +363,6 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
             if (NS::NIN > 2) z = fma(sW[2 * W + q], covv, z);
             c[q] = z;
         }
-        const double nn0 = mlp_forward<NS>(sW, c, 0.0);   // network([0; beta]) — identical at every call
 
         const double abstol = A.abstol, reltol = A.reltol;
         const double dtmax = tend - t0;
@@ -326,8 +371,8 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
         const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
 
         double2 rec[GRAD ? REC_CAP : 1];
+        double acc[GRAD ? NS::NACC : 1];
         int stop_at = 0x7fffffff;   // replay limit (GRAD)
-        int N_steps = 0;
         // adjoint carry
         double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
         int kobs_top = nobs - 1;
@@ -348,53 +393,73 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
                 ++iobs;
                 next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
             }
-            double p1 = mlp_forward<NS>(sW, c, kn.dG(t0)) - nn0;   // production at t0 (dG = 0 -> 0)
+            // production at t0 is NN([0;beta]) - NN([0;beta]) = 0 exactly (dG(t0) = 0)
             double k10, k11;
-            kinetics(Kc, u0, u1, p1, k10, k11);
-            // ---- Hairer initial step (ode_determine_initdt) ----
-            double dt;
+            kinetics(Kc, u0, u1, 0.0, k10, k11);
+            // ---- Hairer initial step (ode_determine_initdt), part 1 ----
+            const double sk0 = fma(fabs(u0), reltol, abstol), sk1 = fma(fabs(u1), reltol, abstol);
+            const double isk0 = 1.0 / sk0, isk1 = 1.0 / sk1;
+            double dt0, d1;
             {
-                const double sk0 = fma(fabs(u0), reltol, abstol), sk1 = fma(fabs(u1), reltol, abstol);
-                const double isk0 = 1.0 / sk0, isk1 = 1.0 / sk1;
                 double x0 = u0 * isk0, x1 = u1 * isk1;
                 const double d0 = sqrt((x0 * x0 + x1 * x1) * 0.5);
                 x0 = k10 * isk0; x1 = k11 * isk1;
-                const double d1 = sqrt((x0 * x0 + x1 * x1) * 0.5);
-                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+                d1 = sqrt((x0 * x0 + x1 * x1) * 0.5);
+                dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
                 dt0 = fmin(dt0, dtmax);
-                const double pe = mlp_forward<NS>(sW, c, kn.dG(t0 + dt0)) - nn0;
-                double f0, f1;
-                kinetics(Kc, fma(dt0, k10, u0), fma(dt0, k11, u1), pe, f0, f1);
-                x0 = (f0 - k10) * isk0; x1 = (f1 - k11) * isk1;
-                const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
-                const double dm = fmax(d1, d2);
-                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0);
-                dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
             }
-            int ret = 0;
-            if (!(isfinite(dt) && isfinite(k10) && isfinite(k11))) ret = 3;
-            double qold = qoldinit;
-            int iter = 0;
-            while (ret == 0 && t < tend && na < stop_at) {
-                if (++iter > A.maxiters) { ret = 1; break; }
-                dt = fmin(dt, tend - t);                       // modify_dt_for_tstops!
-                if (!(dt > dtmin)) { ret = (dt != dt) ? 3 : 2; break; }
-                // ---- stages: production at the 5 new nodes, kinetics is linear ----
+            double dt = dt0, nn0 = 0.0, lnqold = -9.210340371976182;   // ln(qoldinit = 1e-4)
+            int ret = 0, iter = 0;
+            bool init = true;
+            for (;;) {
+                // ---- which nodes does this pass of the (single, shared) network-evaluation loop serve? ----
+                int nq;
+                const double* cn;
+                if (init) { nq = 2; cn = CN_INIT; }
+                else {
+                    if (!(ret == 0 && t < tend && na < stop_at)) break;
+                    if (++iter > A.maxiters) { ret = 1; break; }
+                    dt = fmin(dt, tend - t);                       // modify_dt_for_tstops!
+                    if (!(dt > dtmin)) { ret = (dt != dt) ? 3 : 2; break; }
+                    nq = 5; cn = CN_STEP;
+                }
+                {
+                    double tau[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], dt, t);
+                    kn.dG5(tau, myNode, B);                       // dG of the node times, staged in myNode
+                }
+                CUDE_UNROLL(CUDE_FWD_UNROLL)
+                for (int q = 0; q < 5; ++q)
+                    if (q < nq) myNode[q * B] = mlp_forward<NS>(sW, c, myNode[q * B]);
+                if (init) {
+                    // ---- Hairer, part 2: probe f(u0 + dt0 f0, t0 + dt0) ----
+                    init = false;
+                    nn0 = myNode[0];                              // network([0; beta]) — identical at every call
+                    const double pe = myNode[B] - nn0;
+                    double f0, f1;
+                    kinetics(Kc, fma(dt0, k10, u0), fma(dt0, k11, u1), pe, f0, f1);
+                    const double x0 = (f0 - k10) * isk0, x1 = (f1 - k11) * isk1;
+                    const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
+                    const double dm = fmax(d1, d2);
+                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0);
+                    dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
+                    if (!(isfinite(dt) && isfinite(k10) && isfinite(k11) && isfinite(f0) && isfinite(nn0))) ret = 3;
+                    continue;
+                }
+                const double p2 = myNode[0] - nn0, p3 = myNode[B] - nn0, p4 = myNode[2 * B] - nn0,
+                             p5 = myNode[3 * B] - nn0, p6 = myNode[4 * B] - nn0;   // p6: stages 6, 7 and the next k1
+                // ---- stages: the kinetics are linear, the production enters additively ----
                 double f0, f1, g0, g1;
-                const double p2 = mlp_forward<NS>(sW, c, kn.dG(fma(c2, dt, t))) - nn0;
                 g0 = fma(dt * a21, k10, u0); g1 = fma(dt * a21, k11, u1);
                 double k20, k21; kinetics(Kc, g0, g1, p2, k20, k21);
-                const double p3 = mlp_forward<NS>(sW, c, kn.dG(fma(c3, dt, t))) - nn0;
                 g0 = fma(dt, fma(a31, k10, a32 * k20), u0); g1 = fma(dt, fma(a31, k11, a32 * k21), u1);
                 double k30, k31; kinetics(Kc, g0, g1, p3, k30, k31);
-                const double p4 = mlp_forward<NS>(sW, c, kn.dG(fma(c4, dt, t))) - nn0;
                 g0 = fma(dt, fma(a41, k10, fma(a42, k20, a43 * k30)), u0); g1 = fma(dt, fma(a41, k11, fma(a42, k21, a43 * k31)), u1);
                 double k40, k41; kinetics(Kc, g0, g1, p4, k40, k41);
-                const double p5 = mlp_forward<NS>(sW, c, kn.dG(fma(c5, dt, t))) - nn0;
                 g0 = fma(dt, fma(a51, k10, fma(a52, k20, fma(a53, k30, a54 * k40))), u0);
                 g1 = fma(dt, fma(a51, k11, fma(a52, k21, fma(a53, k31, a54 * k41))), u1);
                 double k50, k51; kinetics(Kc, g0, g1, p5, k50, k51);
-                const double p6 = mlp_forward<NS>(sW, c, kn.dG(t + dt)) - nn0;   // shared by stages 6, 7 and the next k1
                 g0 = fma(dt, fma(a61, k10, fma(a62, k20, fma(a63, k30, fma(a64, k40, a65 * k50)))), u0);
                 g1 = fma(dt, fma(a61, k11, fma(a62, k21, fma(a63, k31, fma(a64, k41, a65 * k51)))), u1);
                 double k60, k61; kinetics(Kc, g0, g1, p6, k60, k61);
@@ -404,20 +469,17 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
                 // ---- error estimate ----
                 f0 = dt * fma(e1, k10, fma(e2, k20, fma(e3, k30, fma(e4, k40, fma(e5, k50, fma(e6, k60, e7 * k70))))));
                 f1 = dt * fma(e1, k11, fma(e2, k21, fma(e3, k31, fma(e4, k41, fma(e5, k51, fma(e6, k61, e7 * k71))))));
-                f0 = f0 / fma(fmax(fabs(u0), fabs(un0)), reltol, abstol);
-                f1 = f1 / fma(fmax(fabs(u1), fabs(un1)), reltol, abstol);
-                const double EEst = sqrt((f0 * f0 + f1 * f1) * 0.5);
-                if (!(EEst == EEst) || !isfinite(un0) || !isfinite(un1)) { ret = 3; break; }
-                CUDE_TRACE_STEP(t, dt, EEst)
-                // ---- PI controller ----
-                double q, q11 = 0.0;
-                if (EEst == 0.0) q = 1.0 / qmax;
-                else {
-                    q11 = m_pow(EEst, beta1);
-                    q = q11 / m_pow(qold, beta2);
-                    q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
-                }
-                if (EEst <= 1.0) {
+                f0 = f0 * m_rcp(fma(fmax(fabs(u0), fabs(un0)), reltol, abstol));   // denominators >= abstol > 0
+                f1 = f1 * m_rcp(fma(fmax(fabs(u1), fabs(un1)), reltol, abstol));
+                // EEst = sqrt(E2); accept iff EEst <= 1 iff E2 <= 1; the controller only needs ln EEst = ln(E2)/2
+                const double E2 = (f0 * f0 + f1 * f1) * 0.5;
+                if (!(E2 == E2) || !isfinite(un0) || !isfinite(un1)) { ret = 3; break; }
+                CUDE_TRACE_STEP(t, dt, sqrt(E2))
+                // ---- PI controller: q = EEst^beta1 / qold^beta2 / gamma, clamped to [1/qmax, 1/qmin];
+                //      E2 == 0 gives ln = -690 -> q saturates at 1/qmax like the reference's explicit branch ----
+                const double lnE = 0.5 * m_log_pos(E2);
+                if (E2 <= 1.0) {
+                    const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold)) * (1.0 / gamma)));
                     double tnew = t + dt;
                     if (fabs(tnew - tend) < snap) tnew = tend;
                     // saveat by dense output: observation times in (t, tnew]
@@ -426,7 +488,7 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
                         if (next_ot == tnew) y = un0;
                         else {
                             double bw[7];
-                            dense_weights((next_ot - t) / dt, bw);
+                            dense_weights((next_ot - t) * m_rcp(dt), bw);
                             const double sdo = fma(bw[0], k10, fma(bw[1], k20, fma(bw[2], k30, fma(bw[3], k40, fma(bw[4], k50, fma(bw[5], k60, bw[6] * k70))))));
                             y = fma(dt, sdo, u0);
                         }
@@ -438,114 +500,135 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
                     }
                     if (GRAD) rec[na % REC_CAP] = make_double2(t, dt);
                     ++na;
-                    qold = fmax(EEst, qoldinit);
-                    dt = fmin(dt / q, dtmax);
+                    lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
+                    dt = fmin(dt * m_rcp(q), dtmax);               // q in [1/qmax, 1/qmin]
                     t = tnew; u0 = un0; u1 = un1; k10 = k70; k11 = k71;   // FSAL
                 } else {
                     ++nr;
-                    dt = dt / fmin(1.0 / qmin, q11 / gamma);
+                    dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE) * (1.0 / gamma)));
                 }
             }
             if (first_pass) {
                 if (ret == 0 && iobs < nobs) ret = 3;   // observation beyond tend: not produced by saveat
-                nacc = na; nrej = nr; N_steps = na;
+                nacc = na; nrej = nr;
                 failed = (ret != 0);
                 sse = failed ? CUDART_INF : fsse;
                 stop_at = na;
-                first_pass = false;
             }
+            const bool was_first = first_pass;
+            first_pass = false;
             if (!GRAD || failed) break;
             if constexpr (GRAD) {
+            // accumulators: zero after the first pass, otherwise back from shared memory (parked for the replay)
+#pragma unroll
+            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? 0.0 : myAcc[k * B];
             // =================== adjoint over steps [lo, stop_at) held in the ring ===================
+            // The last chunk appends the virtual step n = -1: the NN([0;beta]) term, one node at dG = 0
+            // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
             const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
-            for (int n = stop_at - 1; n >= lo; --n) {
-                const double2 r2 = rec[n % REC_CAP];
-                const double tn = r2.x, h = r2.y;
-                double kb[7][2];
+            const int nlast = (lo == 0) ? -1 : lo;
+            for (int n = stop_at - 1; n >= nlast; --n) {
+                int nq;
+                const double* cn;
+                double tn, h;
+                if (n < 0) {
+                    nq = 1; cn = CN_INIT; tn = t0; h = 0.0;
+                    myNode[0] = -wsum;
+                } else {
+                    const double2 r2 = rec[n % REC_CAP];
+                    tn = r2.x; h = r2.y;
+                    nq = 5; cn = CN_STEP;
+                    double kb[7][2];
 #pragma unroll
-                for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
-                double ub0 = 0.0, ub1 = 0.0;
-                // observations in (tn, t_next]
-                while (kobs_top >= 0) {
-                    const double ts = obs_t[(size_t)kobs_top * N];
-                    if (!(ts > tn)) break;
-                    const double wr = 2.0 * sRes[kobs_top * B + tid];
-                    if (ts == t_next) lam0 += wr;
-                    else {
-                        double bw[7];
-                        dense_weights((ts - tn) / h, bw);
-                        ub0 += wr;
-                        const double wh = wr * h;
+                    for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
+                    double ub0 = 0.0, ub1 = 0.0;
+                    // observations in (tn, t_next]
+                    while (kobs_top >= 0) {
+                        const double ts = obs_t[(size_t)kobs_top * N];
+                        if (!(ts > tn)) break;
+                        const double wr = 2.0 * sRes[kobs_top * B + tid];
+                        if (ts == t_next) lam0 += wr;
+                        else {
+                            double bw[7];
+                            dense_weights((ts - tn) * m_rcp(h), bw);
+                            ub0 += wr;
+                            const double wh = wr * h;
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
+                            for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
+                        }
+                        --kobs_top;
                     }
-                    --kobs_top;
-                }
-                // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
-                const double pb7 = kb[6][0];
-                lam0 = fma(Kc.d00, kb[6][0], lam0);   // kb7[1] == 0
-                lam1 = fma(Kc.k1, kb[6][0], lam1);
-                // un = u + h sum b_j k_j
-                ub0 += lam0; ub1 += lam1;
-                {
-                    const double hl0 = h * lam0, hl1 = h * lam1;
-                    kb[0][0] = fma(b1, hl0, kb[0][0]); kb[0][1] = fma(b1, hl1, kb[0][1]);
-                    kb[1][0] = fma(b2, hl0, kb[1][0]); kb[1][1] = fma(b2, hl1, kb[1][1]);
-                    kb[2][0] = fma(b3, hl0, kb[2][0]); kb[2][1] = fma(b3, hl1, kb[2][1]);
-                    kb[3][0] = fma(b4, hl0, kb[3][0]); kb[3][1] = fma(b4, hl1, kb[3][1]);
-                    kb[4][0] = fma(b5, hl0, kb[4][0]); kb[4][1] = fma(b5, hl1, kb[4][1]);
-                    kb[5][0] = fma(b6, hl0, kb[5][0]); kb[5][1] = fma(b6, hl1, kb[5][1]);
-                }
-                // stage i: k_i = A g_i + b + e1 p_i, g_i = u + h sum_{j<i} a_ij k_j
-                // gb = A^T kb_i = [d00*kb0 + k2*kb1, k1*kb0 - k1*kb1]
-                double gb0, gb1, hg0, hg1;
+                    // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
+                    const double pb7 = kb[6][0];
+                    lam0 = fma(Kc.d00, kb[6][0], lam0);   // kb7[1] == 0
+                    lam1 = fma(Kc.k1, kb[6][0], lam1);
+                    // un = u + h sum b_j k_j
+                    ub0 += lam0; ub1 += lam1;
+                    {
+                        const double hl0 = h * lam0, hl1 = h * lam1;
+                        kb[0][0] = fma(b1, hl0, kb[0][0]); kb[0][1] = fma(b1, hl1, kb[0][1]);
+                        kb[1][0] = fma(b2, hl0, kb[1][0]); kb[1][1] = fma(b2, hl1, kb[1][1]);
+                        kb[2][0] = fma(b3, hl0, kb[2][0]); kb[2][1] = fma(b3, hl1, kb[2][1]);
+                        kb[3][0] = fma(b4, hl0, kb[3][0]); kb[3][1] = fma(b4, hl1, kb[3][1]);
+                        kb[4][0] = fma(b5, hl0, kb[4][0]); kb[4][1] = fma(b5, hl1, kb[4][1]);
+                        kb[5][0] = fma(b6, hl0, kb[5][0]); kb[5][1] = fma(b6, hl1, kb[5][1]);
+                    }
+                    // stage i: k_i = A g_i + b + e1 p_i, g_i = u + h sum_{j<i} a_ij k_j
+                    // gb = A^T kb_i = [d00*kb0 + k2*kb1, k1*kb0 - k1*kb1]
+                    double gb0, gb1, hg0, hg1;
 #define CUDE_STAGE_BACK(I)                                                    \
     gb0 = fma(Kc.d00, kb[I][0], Kc.k2 * kb[I][1]);                            \
     gb1 = Kc.k1 * (kb[I][0] - kb[I][1]);                                      \
     ub0 += gb0; ub1 += gb1; hg0 = h * gb0; hg1 = h * gb1;
 #define CUDE_PUSH(J, COEF) kb[J][0] = fma(COEF, hg0, kb[J][0]); kb[J][1] = fma(COEF, hg1, kb[J][1]);
-                const double pb6 = kb[5][0];
-                CUDE_STAGE_BACK(5) CUDE_PUSH(0, a61) CUDE_PUSH(1, a62) CUDE_PUSH(2, a63) CUDE_PUSH(3, a64) CUDE_PUSH(4, a65)
-                const double pb5 = kb[4][0];
-                CUDE_STAGE_BACK(4) CUDE_PUSH(0, a51) CUDE_PUSH(1, a52) CUDE_PUSH(2, a53) CUDE_PUSH(3, a54)
-                const double pb4 = kb[3][0];
-                CUDE_STAGE_BACK(3) CUDE_PUSH(0, a41) CUDE_PUSH(1, a42) CUDE_PUSH(2, a43)
-                const double pb3 = kb[2][0];
-                CUDE_STAGE_BACK(2) CUDE_PUSH(0, a31) CUDE_PUSH(1, a32)
-                const double pb2 = kb[1][0];
-                CUDE_STAGE_BACK(1) CUDE_PUSH(0, a21)
-                const double pb1 = kb[0][0];
-                CUDE_STAGE_BACK(0)
+                    const double pb6 = kb[5][0];
+                    CUDE_STAGE_BACK(5) CUDE_PUSH(0, a61) CUDE_PUSH(1, a62) CUDE_PUSH(2, a63) CUDE_PUSH(3, a64) CUDE_PUSH(4, a65)
+                    const double pb5 = kb[4][0];
+                    CUDE_STAGE_BACK(4) CUDE_PUSH(0, a51) CUDE_PUSH(1, a52) CUDE_PUSH(2, a53) CUDE_PUSH(3, a54)
+                    const double pb4 = kb[3][0];
+                    CUDE_STAGE_BACK(3) CUDE_PUSH(0, a41) CUDE_PUSH(1, a42) CUDE_PUSH(2, a43)
+                    const double pb3 = kb[2][0];
+                    CUDE_STAGE_BACK(2) CUDE_PUSH(0, a31) CUDE_PUSH(1, a32)
+                    const double pb2 = kb[1][0];
+                    CUDE_STAGE_BACK(1) CUDE_PUSH(0, a21)
+                    const double pb1 = kb[0][0];
+                    CUDE_STAGE_BACK(0)
 #undef CUDE_STAGE_BACK
 #undef CUDE_PUSH
-                // ---- network gradient at the 5 nodes of this step ----
-                const double w6 = pb6 + pb7 + wnode;   // node tn+h: stages 6, 7 and the next step's stage 1
-                mlp_backward<NS>(sW, c, kn.dG(tn + h), w6, acc);
-                mlp_backward<NS>(sW, c, kn.dG(fma(c5, h, tn)), pb5, acc);
-                mlp_backward<NS>(sW, c, kn.dG(fma(c4, h, tn)), pb4, acc);
-                mlp_backward<NS>(sW, c, kn.dG(fma(c3, h, tn)), pb3, acc);
-                mlp_backward<NS>(sW, c, kn.dG(fma(c2, h, tn)), pb2, acc);
-                wsum += w6 + pb5 + pb4 + pb3 + pb2;
-                wnode = pb1;
-                lam0 = ub0; lam1 = ub1;
-                t_next = tn;
+                    (void)hg0; (void)hg1;
+                    // node weights, in CN_STEP order; node tn+h serves stages 6, 7 and the next step's stage 1
+                    const double w6 = pb6 + pb7 + wnode;
+                    myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
+                    wsum += w6 + pb5 + pb4 + pb3 + pb2;
+                    wnode = pb1;
+                    lam0 = ub0; lam1 = ub1;
+                    t_next = tn;
+                }
+                // ---- network gradient at the nodes (single, shared forward+backward evaluation loop) ----
+                {
+                    double tau[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], h, tn);
+                    kn.dG5(tau, myDG, B);
+                }
+                CUDE_UNROLL(CUDE_BWD_UNROLL)
+                for (int q = 0; q < 5; ++q)
+                    if (q < nq) mlp_backward<NS>(sW, c, myDG[q * B], myNode[q * B], acc);
             }
             stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
+            // park the accumulators (for the replay's register budget, or for the block reduction)
+#pragma unroll
+            for (int k = 0; k < NS::NACC; ++k) myAcc[k * B] = acc[k];
             }  // if constexpr (GRAD)
         } while (stop_at > 0);
 
         if constexpr (GRAD) if (!failed) {
-            // node t0 carries weight wnode; NN([0;beta]) is subtracted at every node
-            mlp_backward<NS>(sW, c, kn.dG(t0), wnode, acc);
-            wsum += wnode;
-            mlp_backward<NS>(sW, c, 0.0, -wsum, acc);
             // d sse / d cond = (sum_q dz1_q * W1[q,1]) * beta      (beta = exp(cond))
             double db = 0.0;
 #pragma unroll
-            for (int q = 0; q < W; ++q) db = fma(acc[W + q], sW[W + q], db);
+            for (int q = 0; q < W; ++q) db = fma(myAcc[(W + q) * B], sW[W + q], db);
             gcond = db * beta;
         }
-        (void)N_steps;
     }
 
     // ---- outputs ----
@@ -557,19 +640,19 @@ __global__ void __launch_bounds__(128) cude_eval_kernel(const EvalArgs A) {
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     if (A.partials) {
         constexpr int nred = GRAD ? P + 1 : 1;
-#pragma unroll
-        for (int q = 0; q < nred; ++q) {   // fully unrolled: acc[] must only see compile-time indices
+#pragma unroll 1
+        for (int q = 0; q < nred; ++q) {
             double v = 0.0;
             if (active) {
                 if (q == 0) v = sse;
                 else if constexpr (GRAD) { if (!failed) {
                     // expand the compressed accumulators to the SimpleChains layout
                     const int p = q - 1;
-                    if (p < W) v = acc[p];                                   // W1[:,0]  (dG column)
-                    else if (p < 2 * W) v = acc[W + (p - W)] * beta;         // W1[:,1]  (beta column)
-                    else if (NS::NIN > 2 && p < 3 * W) v = acc[W + (p - 2 * W)] * covv;   // W1[:,2] (covariate)
-                    else if (p < NS::L1) v = acc[W + (p - NS::NIN * W)];     // b1
-                    else v = acc[2 * W + (p - NS::L1)];                      // hidden + output layers
+                    if (p < W) v = myAcc[p * B];                                   // W1[:,0]  (dG column)
+                    else if (p < 2 * W) v = myAcc[(W + (p - W)) * B] * beta;       // W1[:,1]  (beta column)
+                    else if (NS::NIN > 2 && p < 3 * W) v = myAcc[(W + (p - 2 * W)) * B] * covv;   // W1[:,2] (covariate)
+                    else if (p < NS::L1) v = myAcc[(W + (p - NS::NIN * W)) * B];   // b1
+                    else v = myAcc[(2 * W + (p - NS::L1)) * B];                    // hidden + output layers
                 } }
             }
 #pragma unroll

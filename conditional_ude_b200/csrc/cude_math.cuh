@@ -1,6 +1,18 @@
-// cude_math.cuh — FP64 elementary functions used by the kernels.
-// Kept behind m_* names so that hand-tuned versions can replace the CUDA library ones
-// without touching the integrator.
+// =====================================================================================
+// cude_math.cuh — branch-free FP64 elementary functions for the cUDE kernels.
+//
+// The MLP (8 tanh + softplus per evaluation) dominates the instruction stream, and CUDA's libm
+// versions (branches for special cases, ~4x the instructions, large code footprint) made the v1
+// kernel instruction-fetch bound (ncu: "no_instruction" stall 4.5 per issue, profiles/r01_v1_*).
+// These versions are straight-line code on the FP64 pipe:
+//   exp core   : Cody-Waite reduction (magic-number rounding) + degree-11 near-minimax polynomial
+//                (Chebyshev-node fit, max rel. error 1.6e-17 before rounding) + exponent-field add.
+//   reciprocal : MUFU.RCP64H seed + 2 Newton steps (4 DFMA).
+//   tanh       : 1 - 2/(exp(2x)+1) on x clamped to [-20,20] (tanh == +-1 beyond 19.06 in FP64);
+//                absolute error <= ~2e-16 (relative error grows like 1e-16/|x| near 0, irrelevant here).
+//   log core   : exponent split + 2*atanh((m-1)/(m+1)) with a degree-6 polynomial in q^2.
+// NaN inputs propagate (comparison-based clamps keep NaN; hardware NaNs are canonical, low word 0).
+// =====================================================================================
 #pragma once
 #ifndef CUDE_HOST_EMU
 #include <cuda_runtime.h>
@@ -8,14 +20,138 @@
 
 namespace cude {
 
+#ifdef CUDE_HOST_EMU
+// host stand-ins (tests/emu): same bit manipulations through memcpy, a float-accurate reciprocal seed
+static inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) { long long b = ((long long)hi << 32) | (unsigned int)lo; double x; memcpy(&x, &b, 8); return x; }
+static inline double rcp_seed(double d) { return (double)(float)(1.0 / d); }
+#else
+__device__ __forceinline__ double rcp_seed(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));   // MUFU.RCP64H: ~20 correct bits
+    return y;
+}
+#endif
+
+// 1/d for normal positive d (no special cases needed by the callers): seed y0 with relative error
+// e (|e| <~ 2^-20), then y0*(1 + e + e^2) leaves e^3 — one third-order step, 3 DFMA.
+__device__ __forceinline__ double m_rcp(double d) {
+    const double y = rcp_seed(d);
+    const double e = fma(-d, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// exp(x) for |x| <= ~700 (callers clamp); branch-free
+__device__ __forceinline__ double m_exp_core(double x) {
+    const double L2E = 1.4426950408889634, SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+    const double LN2_HI = 0.6931471803691238, LN2_LO = 1.9082149292705877e-10;
+    const double t = fma(x, L2E, SHIFT);
+    const int n = __double2loint(t);
+    const double nf = t - SHIFT;
+    double r = fma(nf, -LN2_HI, x);
+    r = fma(nf, -LN2_LO, r);
+#if !defined(CUDE_EXP_HORNER)
+    // even/odd split: two independent Horner chains of half the depth (one extra multiply)
+    const double r2 = r * r;
+    double pe = 2.763265472252779e-07, po = 2.5110049204818658e-08;
+    pe = fma(pe, r2, 2.4801485441561313e-05); po = fma(po, r2, 2.755724088722987e-06);
+    pe = fma(pe, r2, 0.0013888888952352863);  po = fma(po, r2, 0.00019841269890076403);
+    pe = fma(pe, r2, 0.04166666666648795);    po = fma(po, r2, 0.008333333333319589);
+    pe = fma(pe, r2, 0.5000000000000019);     po = fma(po, r2, 0.1666666666666668);
+    pe = fma(pe, r2, 1.0);                    po = fma(po, r2, 1.0);
+    double p = fma(po, r, pe);
+#else
+    double p = 2.5110049204818658e-08;
+    p = fma(p, r, 2.763265472252779e-07);
+    p = fma(p, r, 2.755724088722987e-06);
+    p = fma(p, r, 2.4801485441561313e-05);
+    p = fma(p, r, 0.00019841269890076403);
+    p = fma(p, r, 0.0013888888952352863);
+    p = fma(p, r, 0.008333333333319589);
+    p = fma(p, r, 0.04166666666648795);
+    p = fma(p, r, 0.1666666666666668);
+    p = fma(p, r, 0.5000000000000019);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+#endif
+    // p in [0.70, 1.42]; multiply by 2^n through the exponent field
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+__device__ __forceinline__ double m_clamp(double x, double lo, double hi) {
+    x = (x < lo) ? lo : x;     // comparisons keep NaN (fmin/fmax would swallow it)
+    return (x > hi) ? hi : x;
+}
+
+// |x| >= 20 saturates (integer compare on the high word keeps the clamp off the FP64 pipe); NaN propagates
+__device__ __forceinline__ double m_tanh(double x) {
+    const int hi = __double2hiint(x);
+    const int ahi = hi & 0x7fffffff;
+    const bool big = ahi >= 0x40340000;                       // |x| >= 20, Inf or NaN
+    const double xc = __hiloint2double(big ? ((hi & 0x80000000) | 0x40340000) : hi, big ? 0 : __double2loint(x));
+    const double e = m_exp_core(xc + xc);
+    const double r = fma(-2.0, m_rcp(e + 1.0), 1.0);
+    return (ahi > 0x7ff00000) ? x : r;                        // NaN in -> NaN out
+}
+
+// log(s) for normal positive s
+__device__ __forceinline__ double m_log_core(double s) {
+    int hi = __double2hiint(s);
+    const int lo = __double2loint(s);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;          // m in [1, 2)
+    if (hi >= 0x3ff6a09e) { hi -= 0x00100000; ++k; }   // m in [sqrt(2)/2, sqrt(2))   (predicated)
+    const double m = __hiloint2double(hi, lo);
+    const double q = (m - 1.0) * m_rcp(m + 1.0);
+    const double w = q * q;
+    double g = 0.07308903576708663;
+    g = fma(g, w, 0.07665805861027504);
+    g = fma(g, w, 0.09091446216268435);
+    g = fma(g, w, 0.11111105544689748);
+    g = fma(g, w, 0.14285714313126918);
+    g = fma(g, w, 0.19999999999949444);
+    g = fma(g, w, 0.3333333333333335);
+    const double LN2_HI = 0.6931471803691238, LN2_LO = 1.9082149292705877e-10;
+    const double kf = (double)k;
+    // log(s) = k ln2 + 2q + 2q*w*g
+    double res = fma(kf, LN2_LO, (q + q) * (w * g));
+    res += q + q;
+    return fma(kf, LN2_HI, res);
+}
+
+// softplus(x) = log(1 + exp(x)), the naive form of reference src/neural-network.jl:13-15, including its
+// overflow: exp(x) = Inf for x > 709.78 -> Inf.  For 36.8 < x the naive form equals x in FP64; for
+// x < -40 it equals 0 (1 + exp(x) rounds to 1), as here.
+__device__ __forceinline__ double m_softplus(double x) {
+    const double xc = m_clamp(x, -40.0, 36.8);
+    double sp = m_log_core(1.0 + m_exp_core(xc));
+    sp = (x > 36.8) ? x : sp;
+    sp = (x > 709.782712893384) ? CUDART_INF : sp;
+    return (x != x) ? x : sp;                      // the log core does not propagate NaN by itself
+}
+
+// d softplus / dx = 1/(1+exp(-x))
+__device__ __forceinline__ double m_sigmoid(double x) {
+    const double xc = m_clamp(-x, -40.0, 40.0);
+    return m_rcp(1.0 + m_exp_core(xc));
+}
+
+// natural log for the step controller: EEst^b1 / qold^b2 = exp(b1 ln EEst - b2 ln qold); the controller
+// clamps the result to [1/qmax, 1/qmin], so saturating the exponent at +-40 changes nothing.
+__device__ __forceinline__ double m_log_pos(double x) {
+    const double xs = m_clamp(x, 1e-300, 1e300);
+    return m_log_core(xs);
+}
+__device__ __forceinline__ double m_exp_sat(double x) { return m_exp_core(m_clamp(x, -40.0, 40.0)); }
+__device__ __forceinline__ double m_log10(double x) {
+    const double xs = (x < 1e-300) ? 1e-300 : x;
+    return m_log_core(xs) * 0.4342944819032518;
+}
+__device__ __forceinline__ double m_pow10(double x) { return m_exp_core(m_clamp(x * 2.302585092994046, -700.0, 700.0)); }
+
+// exp(cond): once per trajectory, full range semantics (Inf / 0 / NaN) from the CUDA library
 __device__ __forceinline__ double m_exp(double x) { return exp(x); }
-__device__ __forceinline__ double m_tanh(double x) { return tanh(x); }
-// softplus(x) = log(1 + exp(x)) — the naive form of reference src/neural-network.jl:13-15
-__device__ __forceinline__ double m_softplus(double x) { return log(1.0 + exp(x)); }
-// d softplus / dx
-__device__ __forceinline__ double m_sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
-__device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ double m_log10(double x) { return log10(x); }
-__device__ __forceinline__ double m_pow10(double x) { return pow(10.0, x); }
 
 }  // namespace cude

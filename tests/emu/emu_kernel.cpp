@@ -17,6 +17,8 @@ using std::isfinite;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__
+#define __constant__ static const
+#define __host__
 #define CUDART_INF INFINITY
 struct emu_dim3 { int x, y, z; };
 static emu_dim3 blockIdx, threadIdx, blockDim;

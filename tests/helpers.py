@@ -44,3 +44,11 @@ def random_starts(rng, chain, n_ind, n_starts, scale=1.0):
     neural = np.stack([chain.init_params(rng) * scale for _ in range(n_starts)])
     cond = rng.uniform(-2.0, 0.0, size=(n_starts, n_ind))
     return neural, cond
+
+
+def noise_ok(d, contract):
+    """Distribution test for an adaptive solve (see test_oracle.py::test_noise_floor): typical agreement at
+    round-off level, the contract for 99 % of the entries, and the rare accept/reject flips bounded by the
+    solver tolerance."""
+    d = np.asarray(d)
+    return bool(np.median(d) < 1e-8 and np.percentile(d, 99) < contract and d.max() < 2e-2)

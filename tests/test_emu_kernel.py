@@ -14,7 +14,7 @@ import pytest
 
 import conditional_ude_b200 as cu
 from oracle import oracle
-from helpers import train57, mixed_population, ohashi_models, random_starts
+from helpers import train57, mixed_population, ohashi_models, random_starts, noise_ok
 import emu_wrap
 
 DET = dict(abstol=1e3, reltol=1e3)
@@ -49,9 +49,10 @@ def test_default_tolerance_within_noise_floor(fx):
     pk = cu.pack_models(models, t, c)
     g = oracle.OraclePopulation(pk).eval(nn, betas, grad_mode=0)
     e = emu_wrap.emu_eval(pk, nn, betas)
-    d = np.abs(e["sse"] - g["sse"]) / g["sse"]
-    assert np.median(d) < 1e-8 and d.max() < 1e-5
-    assert relmax(e["g_cond"], g["g_cond"]) < 1e-4 and relmax(e["g_neural"], g["g_neural"]) < 1e-4
+    assert noise_ok(np.abs(e["sse"] - g["sse"]) / g["sse"], 1e-5)
+    # gradients relative to the scale of the individual terms (at the stored optimum the net d/dbeta is ~0)
+    assert noise_ok(np.abs(e["g_cond"] - g["g_cond"]) / np.abs(g["g_cond"]).max(), 1e-4)
+    assert noise_ok(np.abs(e["g_neural"] - g["g_neural"]) / np.abs(g["g_neural"]).max(axis=-1, keepdims=True), 1e-4)
     assert abs(e["sse"].mean() - 0.4281389) < 1e-6
 
 
