@@ -1,0 +1,174 @@
+# CUDEB200.jl — Julia host side of the B200 cUDE hot path (thin `ccall` shim over libcude_b200.so).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image, so this file is
+# reviewed against include/cude_b200.h only.  The tested host mirror is the Python package
+# conditional_ude_b200 (same names, same argument meaning).
+#
+# Drop-in usage inside the reference repository (after `include("src/parameter-estimation.jl")`):
+#
+#     include("CUDEB200.jl"); using .CUDEB200
+#     idx  = indices_train
+#     pop  = CUDEB200.Population(train_data.glucose[idx, :], train_data.timepoints, train_data.ages[idx],
+#                                train_data.types[idx] .== "T2DM", train_data.timepoints, train_data.cpeptide[idx, :])
+#     optf = CUDEB200.optimization_function(pop)          # replaces OptimizationFunction(loss, AutoForwardDiff())
+#     prob = OptimizationProblem(optf, θ0, nothing)       # θ0::ComponentArray(neural=…, conditional=…)
+#
+# and `CUDEB200.loss(θ, (pop, timepoints, cpeptide_data[, nn]))` evaluates the tuple shapes of
+# src/parameter-estimation.jl:56, :93, :126 on the GPU (the Population stands in for the model vector).
+module CUDEB200
+
+using ComponentArrays: ComponentArray
+using SciMLBase: OptimizationFunction
+
+const libcude = get(ENV, "CUDE_B200_LIB", "libcude_b200.so")
+
+struct CudeNet
+    n_in::Cint
+    depth::Cint
+    width::Cint
+end
+
+struct CudeOpts
+    abstol::Cdouble
+    reltol::Cdouble
+    maxiters::Cint
+    precision::Cint
+    block::Cint
+end
+CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=100_000) = CudeOpts(abstol, reltol, maxiters, 0, 0)
+
+check(rc::Cint, ctx=C_NULL) = rc == 0 ? nothing :
+    error("cude_b200 error $rc: " * unsafe_string(ccall((:cude_last_error, libcude), Cstring, (Ptr{Cvoid},), ctx)))
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:cude_ctx_create, libcude), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h))
+        ctx = new(h[])
+        finalizer(c -> ccall((:cude_ctx_destroy, libcude), Cint, (Ptr{Cvoid},), c.handle), ctx)
+        ctx
+    end
+end
+
+const default_context = Ref{Union{Nothing,Context}}(nothing)
+context() = (default_context[] === nothing && (default_context[] = Context(0)); default_context[])
+
+"""
+Device-resident image of a vector of `CPeptideConditionalUDEModel` (src/c-peptide-models.jl:170-194) and
+its data.  The constants are read back out of the reference's own model objects: `problem.u0`,
+`problem.tspan`; the kinetic parameters are recomputed with `van_cauter_parameters(age, t2dm)`, so the
+constructor additionally needs `ages` and `t2dm` (the reference's ODEProblem closure does not expose them).
+"""
+mutable struct Population
+    handle::Ptr{Cvoid}
+    ctx::Context
+    n::Int
+    net::CudeNet
+    nparams::Int
+end
+
+function Population(glucose::AbstractMatrix, glucose_timepoints::AbstractVector, ages::AbstractVector,
+                    t2dm::AbstractVector{Bool}, timepoints::AbstractVector, cpeptide::AbstractMatrix;
+                    net::CudeNet=CudeNet(2, 2, 4), covariate=nothing, ctx::Context=context())
+    n, K, M = size(glucose, 1), length(glucose_timepoints), length(timepoints)
+    # row-major [n x K] for the C side == column-major [K x n] here
+    knot_t = repeat(Float64.(glucose_timepoints), 1, n)
+    knot_g = permutedims(Float64.(glucose))
+    obs_t = repeat(Float64.(timepoints), 1, n)
+    obs_y = permutedims(Float64.(cpeptide))
+    kin = zeros(4, n)
+    for i in 1:n
+        k0 = Ref(0.0); k1 = Ref(0.0); k2 = Ref(0.0)
+        ccall((:cude_van_cauter_parameters, libcude), Cvoid, (Cdouble, Cint, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}),
+              ages[i], t2dm[i], k0, k1, k2)
+        kin[:, i] .= (k0[], k1[], k2[], cpeptide[i, 1])        # c0 = cpeptide_data[1], c-peptide-models.jl:174
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    cov = covariate === nothing ? C_NULL : Float64.(covariate)      # ccall roots the array for the call
+    check(ccall((:cude_population_create, libcude), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                ctx.handle, n, K, fill(Cint(K), n), knot_t, knot_g, M, fill(Cint(M), n), obs_t, obs_y, kin, cov, h), ctx.handle)
+    P = Int(ccall((:cude_net_nparams, libcude), Cint, (Ref{CudeNet},), net))
+    pop = Population(h[], ctx, n, net, P)
+    finalizer(x -> ccall((:cude_population_destroy, libcude), Cint, (Ptr{Cvoid},), x.handle), pop)
+    pop
+end
+
+"""
+    loss(pop, neural, cond; opts) -> Vector{Float64}
+
+Batched loss: `neural` is `P` (shared network: fixed-NN / profile case) or `P × S`; `cond` is `N × S`
+(column s = start s).  Returns the S population losses (mean over individuals, `Inf` on solver failure) —
+the batched form of src/parameter-estimation.jl:126-140, :362-366 and src/likelihood-profiles.jl:11-14.
+"""
+function loss(pop::Population, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}; opts=CudeOpts(),
+              sse::Union{Nothing,Matrix{Float64}}=nothing)
+    S = size(cond, 2)
+    out = Vector{Float64}(undef, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    check(ccall((:cude_loss, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, sse === nothing ? C_NULL : sse, out),
+          pop.ctx.handle)
+    out
+end
+
+"""
+    loss_grad(pop, neural, cond; opts, mean=true) -> (loss[S], g_neural[P×S], g_cond[N×S])
+
+Value and gradient — what `OptimizationFunction(loss, AutoForwardDiff())` (:231, :281, :299, :370) computes
+with 8 chunked dual-number re-solves, here one adjoint pass per trajectory.
+"""
+function loss_grad(pop::Population, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}; opts=CudeOpts(),
+                   mean::Bool=true, neural_grad::Bool=true)
+    S = size(cond, 2)
+    l = Vector{Float64}(undef, S)
+    gn = neural_grad ? Matrix{Float64}(undef, pop.nparams, S) : nothing
+    gc = Matrix{Float64}(undef, pop.n, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    check(ccall((:cude_loss_grad, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Cint,
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, mean ? 1 : 0,
+                C_NULL, l, gn === nothing ? C_NULL : gn, gc), pop.ctx.handle)
+    l, gn, gc
+end
+
+# --- the reference's own entry points, same tuple shapes (src/parameter-estimation.jl:56, :93, :126) ---------------
+# `p` carries a Population in place of the model (vector): (pop, timepoints, cpeptide_data[, nn]).
+loss(θ, (pop, _, _)::Tuple{Population,Any,Any}) =
+    loss(pop, collect(Float64, θ.neural), reshape(collect(Float64, θ.conditional), :, 1))[1]
+loss(β, (pop, _, _, nn)::Tuple{Population,Any,Any,AbstractVector}) =
+    loss(pop, collect(Float64, nn), fill(Float64(first(β)), pop.n, 1))[1]
+loss_sigma(θ, p::Tuple{Population,Any,Any,AbstractVector}) =
+    (n = length(p[2]); (n / 2) * log(θ.sigma^2) + loss(θ.ode, p) / (2 * θ.sigma^2))
+
+"""
+`OptimizationFunction` with the analytic gradient from the GPU — drop-in for
+`OptimizationFunction(loss, AutoForwardDiff())` in `train` (src/parameter-estimation.jl:370).
+"""
+function optimization_function(pop::Population; opts=CudeOpts())
+    f(θ, _) = loss(pop, collect(Float64, θ.neural), reshape(collect(Float64, θ.conditional), :, 1); opts)[1]
+    function g!(G, θ, _)
+        _, gn, gc = loss_grad(pop, collect(Float64, θ.neural), reshape(collect(Float64, θ.conditional), :, 1); opts)
+        G.neural .= vec(gn); G.conditional .= vec(gc)
+        nothing
+    end
+    OptimizationFunction(f; grad=g!)
+end
+
+"""
+    likelihood_profile(β, nn, pop_one, lower, upper, sigma; steps=1000)
+
+src/likelihood-profiles.jl:4-17 with the whole grid evaluated as one launch (`pop_one` holds one individual).
+"""
+function likelihood_profile(β, nn, pop::Population, lower_bound, upper_bound, sigma; steps=1000, opts=CudeOpts())
+    parameter_values = range(lower_bound, stop=upper_bound, length=steps)
+    cond = reshape(vcat(Float64(first(β)), collect(parameter_values)), 1, :)
+    sse = loss(pop, collect(Float64, nn), cond; opts)
+    sse[2:end] ./ (2 * sigma^2), sse[1] / (2 * sigma^2), parameter_values
+end
+
+end # module
