@@ -191,6 +191,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    from conditional_ude_b200.distributed import DevicePopulationShard
     pk = synthetic_population(n_loc, 1000 + rank)
     pop = cu.Population(packed=pk, ctx=ctx)
     P = pop.n_params
@@ -200,23 +201,22 @@ def run_ours(args):
     cond_p = torch.from_numpy(cond_h).pin_memory()
     gcond_p = torch.empty((S, n_loc), dtype=torch.float64).pin_memory()
     sums_p = torch.empty((S, P + 1), dtype=torch.float64).pin_memory()
-    d_neural = neural_p.to(dev)
-    d_cond = cond_p.to(dev)
-    d_sums = torch.zeros((S, P + 1), dtype=torch.float64, device=dev)
-    d_gcond = torch.empty((S, n_loc), dtype=torch.float64, device=dev)
+    shard = DevicePopulationShard(pop, N_total, S, dev)      # device tensors + kernel/reduce/all-reduce sequence
+    shard.neural.copy_(neural_p)
+    shard.cond.copy_(cond_p)
+    d_sums = shard.sums
     opts = cu.SolverOptions(block=args.block)
 
     def step_resident():
-        pop.eval_dev(S, d_neural.data_ptr(), P, d_cond.data_ptr(), 3, 1.0 / N_total, 0, d_sums.data_ptr(), d_gcond.data_ptr(), opts)
-        if world > 1:
-            dist.all_reduce(d_sums)           # {sum sse, sum d sse/d neural} over ranks: 64 x 38 doubles
+        # loss+gradient kernel -> block-partial reduction into `sums` -> NCCL all-reduce of `sums` (N > 1)
+        shard.step(opts)
 
     def step_e2e():
-        d_neural.copy_(neural_p, non_blocking=True)
-        d_cond.copy_(cond_p, non_blocking=True)
-        step_resident()
-        sums_p.copy_(d_sums, non_blocking=True)
-        gcond_p.copy_(d_gcond, non_blocking=True)
+        shard.neural.copy_(neural_p, non_blocking=True)
+        shard.cond.copy_(cond_p, non_blocking=True)
+        shard.step(opts)
+        sums_p.copy_(shard.sums, non_blocking=True)
+        gcond_p.copy_(shard.g_cond, non_blocking=True)
         stream.synchronize()
         return sums_p[:, 0].numpy() / N_total   # the step's result: loss per start
 
