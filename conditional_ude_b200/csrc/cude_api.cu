@@ -457,6 +457,22 @@ extern "C" int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const c
                      sse_out, loss_out, g_neural, g_cond);
 }
 
+// ---------------------------------------------------------------- elementary-function probe (tests)
+extern "C" int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y) {
+    if (!ctx || !x || !y || n < 1 || which < 0 || which > 5) return fail(ctx, CUDE_EINVAL, "cude_math_probe: bad argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->scratch, 2 * (size_t)n * sizeof(double));
+    if (rc) return rc;
+    double* dx = (double*)ctx->scratch.p;
+    double* dy = dx + n;
+    CU_TRY(ctx, cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cude_math_probe_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which, n, dx, dy);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CUDE_OK;
+}
+
 // ---------------------------------------------------------------- FP64 peak
 extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return CUDE_EINVAL;

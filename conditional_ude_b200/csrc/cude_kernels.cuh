@@ -176,11 +176,11 @@ __constant__ double CN_INIT[5] = {0.0, 1.0, 1.0, 1.0, 1.0};
 
 // forward: returns softplus(z_out) for input dG; c[] = first-layer pre-activation constant part
 template <class NS>
-__device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, const double (&c)[NS::W], double dG) {
+__device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W], double dG) {
     constexpr int W = NS::W;
     double a[W], b[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[j], dG, c[j]));
+    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[j], dG, c[j]), tab);
     int off = NS::L1;
 #pragma unroll
     for (int l = 1; l < NS::DEPTH; ++l) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
             double z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
-            b[j] = m_tanh(z);
+            b[j] = m_tanh(z, tab);
         }
 #pragma unroll
         for (int j = 0; j < W; ++j) a[j] = b[j];
@@ -198,7 +198,7 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
     double z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
-    return m_softplus(z);
+    return m_softplus(z, tab);
 }
 
 // forward + backward at one time node with scalar seed w: acc += w * d softplus(z_out)/d(params).
@@ -210,12 +210,12 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
 // forward replay and for the final block reduction.  Layout:
 // [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
 template <class NS>
-__device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, const double (&c)[NS::W], double dG, double w,
+__device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W], double dG, double w,
                                              double (&g)[NS::NACC]) {
     constexpr int W = NS::W, D = NS::DEPTH;
     double a[D][W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[j], dG, c[j]));
+    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[j], dG, c[j]), tab);
     int off = NS::L1;
 #pragma unroll
     for (int l = 1; l < D; ++l) {
@@ -224,14 +224,14 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
             double z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
-            a[l][j] = m_tanh(z);
+            a[l][j] = m_tanh(z, tab);
         }
         off += NS::LH;
     }
     double z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
-    const double dz = w * m_sigmoid(z);   // d softplus = sigmoid
+    const double dz = w * m_sigmoid(z, tab);   // d softplus = sigmoid
     double da[W];
     int aoff = 2 * W + (D - 1) * NS::LH;
 #pragma unroll
@@ -279,7 +279,7 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
 __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad) {
-    return (size_t)((P + 1) & ~1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
+    return (size_t)64 + (size_t)((P + 1) & ~1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
            (size_t)((B + 31) / 32) * (P + 1);
 }
 
@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
 
     // ---- shared memory carve-up ----
-    double* sW = smem;                               // [P] (padded to even)
+    double* sTab = smem;                             // [64] 2^(j/64) for the exp core
+    double* sW = sTab + 64;                          // [P] (padded to even)
     double* sKt = sW + ((P + 1) & ~1);               // [K][B]
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
         for (int p = tid; p < P; p += B) sW[p] = gW[p];
+        for (int p = tid; p < 64; p += B) sTab[p] = EXP_TAB64[p];
     }
     // ---- stage this thread's knots ----
     const int nk = A.pop.n_knots[i];
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 CUDE_UNROLL(CUDE_FWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) myNode[q * B] = mlp_forward<NS>(sW, c, myNode[q * B]);
+                    if (q < nq) myNode[q * B] = mlp_forward<NS>(sW, sTab, c, myNode[q * B]);
                 if (init) {
                     // ---- Hairer, part 2: probe f(u0 + dt0 f0, t0 + dt0) ----
                     init = false;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     const double x0 = (f0 - k10) * isk0, x1 = (f1 - k11) * isk1;
                     const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
                     const double dm = fmax(d1, d2);
-                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0);
+                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
                     dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
                     if (!(isfinite(dt) && isfinite(k10) && isfinite(k11) && isfinite(f0) && isfinite(nn0))) ret = 3;
                     continue;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 //      E2 == 0 gives ln = -690 -> q saturates at 1/qmax like the reference's explicit branch ----
                 const double lnE = 0.5 * m_log_pos(E2);
                 if (E2 <= 1.0) {
-                    const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold)) * (1.0 / gamma)));
+                    const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
                     double tnew = t + dt;
                     if (fabs(tnew - tend) < snap) tnew = tend;
                     // saveat by dense output: observation times in (t, tnew]
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     t = tnew; u0 = un0; u1 = un1; k10 = k70; k11 = k71;   // FSAL
                 } else {
                     ++nr;
-                    dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE) * (1.0 / gamma)));
+                    dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
                 }
             }
             if (first_pass) {
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 CUDE_UNROLL(CUDE_BWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) mlp_backward<NS>(sW, c, myDG[q * B], myNode[q * B], acc);
+                    if (q < nq) mlp_backward<NS>(sW, sTab, c, myDG[q * B], myNode[q * B], acc);
             }
             stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
             // park the accumulators (for the replay's register budget, or for the block reduction)
@@ -713,6 +715,26 @@ __global__ void cude_sum_sse(const double* __restrict__ sse, int n_ind, int n_st
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sums[(size_t)s * np1] = v;
+}
+
+// elementary-function probe (tests): 0 tanh, 1 softplus, 2 sigmoid, 3 exp (clamped to +-40), 4 log, 5 rcp
+__global__ void cude_math_probe_kernel(int which, int n, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double sTab[64];
+    for (int p = threadIdx.x; p < 64; p += blockDim.x) sTab[p] = EXP_TAB64[p];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r;
+    switch (which) {
+        case 0: r = m_tanh(v, sTab); break;
+        case 1: r = m_softplus(v, sTab); break;
+        case 2: r = m_sigmoid(v, sTab); break;
+        case 3: r = m_exp_sat(v, sTab); break;
+        case 4: r = m_log_pos(v); break;
+        default: r = m_rcp(v); break;
+    }
+    y[i] = r;
 }
 
 // FP64 FMA peak micro-benchmark: 8 independent DFMA chains per thread.

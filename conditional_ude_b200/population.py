@@ -62,6 +62,13 @@ class Context:
         """Launch on a caller-owned cudaStream_t (int address), e.g. torch.cuda.current_stream().cuda_stream."""
         _lib.check(self._lib.cude_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None), self._h)
 
+    def math_probe(self, which, x):
+        """Evaluate one of the kernels' elementary functions on the device (tests)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        _lib.check(self._lib.cude_math_probe(self._h, int(which), x.size, _dptr(x), _dptr(y)), self._h)
+        return y
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         _lib.check(self._lib.cude_measure_fp64_peak(self._h, C.byref(v)), self._h)

@@ -137,6 +137,10 @@ int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net
                   int want_grad, double cond_scale,
                   double* d_sse_out, double* d_sums_out, double* d_g_cond);
 
+/* Test hook: evaluates the kernels' own branch-free FP64 elementary functions on the device
+ * (which: 0 tanh, 1 softplus, 2 sigmoid, 3 exp clamped to +-40, 4 log of a positive normal, 5 reciprocal). */
+int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y);
+
 /* Measured FP64 FMA peak of the context's device (dependent-chain-free DFMA micro-benchmark),
  * the denominator of the roofline.  Returns TFLOP/s in *tflops. */
 int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops);

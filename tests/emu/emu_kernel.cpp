@@ -81,4 +81,17 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
 
 extern "C" void emu_set_trace(double* buf, int cap) { g_trace_buf = buf; g_trace_cap = cap; g_trace_n = 0; }
 extern "C" int emu_trace_count(void) { return g_trace_n; }
+// elementary functions of cude_math.cuh: 0 tanh, 1 softplus, 2 sigmoid, 3 exp (clamped to +-40), 4 log, 5 rcp
+extern "C" void emu_math(int which, int n, const double* x, double* y) {
+    for (int i = 0; i < n; ++i) {
+        switch (which) {
+            case 0: y[i] = m_tanh(x[i], EXP_TAB64); break;
+            case 1: y[i] = m_softplus(x[i], EXP_TAB64); break;
+            case 2: y[i] = m_sigmoid(x[i], EXP_TAB64); break;
+            case 3: y[i] = m_exp_sat(x[i], EXP_TAB64); break;
+            case 4: y[i] = m_log_pos(x[i]); break;
+            default: y[i] = m_rcp(x[i]); break;
+        }
+    }
+}
 extern "C" int emu_rec_cap(void) { return REC_CAP; }

@@ -52,3 +52,37 @@ def noise_ok(d, contract):
     solver tolerance."""
     d = np.asarray(d)
     return bool(np.median(d) < 1e-8 and np.percentile(d, 99) < contract and d.max() < 2e-2)
+
+
+def _math_cases():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-25, 25, 20000), rng.uniform(-1, 1, 20000), rng.uniform(-1e-3, 1e-3, 2000),
+                        [0.0, -0.0, 19.9, 20.0, 20.1, -20.0, 36.7, 36.9, 40.0, -40.0, 700.0, -700.0, 1e300, -1e300, np.inf, -np.inf]])
+    return x
+
+
+def check_math(fn):
+    """fn(which, x) -> y: accuracy of the kernels' elementary functions against numpy/mpmath-grade references."""
+    x = _math_cases()
+    t = fn(0, x)
+    assert np.abs(t - np.tanh(x)).max() < 4e-16                      # absolute (see cude_math.cuh)
+    assert fn(0, np.array([np.nan]))[0] != fn(0, np.array([np.nan]))[0] or np.isnan(fn(0, np.array([np.nan]))[0])
+    xs = x[np.isfinite(x)]
+    sp = fn(1, xs)
+    big = xs > 709.782712893384                                      # exp overflows in the reference's naive form
+    assert np.all(np.isinf(sp[big]))
+    xs, sp = xs[~big], sp[~big]
+    ref = np.where(xs > 36.8, xs, np.log1p(np.exp(np.minimum(xs, 36.8))))
+    assert np.all(np.abs(sp - ref) <= 8e-16 * np.maximum(1.0, np.abs(ref)))      # ~2 ulp
+    assert np.isinf(fn(1, np.array([710.0]))[0]) and fn(1, np.array([709.0]))[0] == 709.0      # naive-form overflow
+    assert np.isnan(fn(1, np.array([np.nan]))[0])
+    xs = x[np.isfinite(x)]
+    sg = fn(2, xs)
+    with np.errstate(over="ignore"):
+        assert np.abs(sg - 1.0 / (1.0 + np.exp(-xs))).max() < 4e-16
+    xe = np.random.default_rng(1).uniform(-40, 40, 20000)
+    assert np.abs(fn(3, xe) / np.exp(xe) - 1).max() < 6e-16
+    xl = np.exp(np.random.default_rng(2).uniform(-600, 600, 20000))
+    assert np.abs(fn(4, xl) - np.log(xl)).max() < 3e-13 and np.abs(fn(4, xl) / np.log(xl) - 1)[np.abs(np.log(xl)) > 1e-3].max() < 1e-15
+    xr = np.exp(np.random.default_rng(3).uniform(-30, 30, 20000))
+    assert np.abs(fn(5, xr) * xr - 1).max() < 5e-16

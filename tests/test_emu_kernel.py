@@ -14,7 +14,7 @@ import pytest
 
 import conditional_ude_b200 as cu
 from oracle import oracle
-from helpers import train57, mixed_population, ohashi_models, random_starts, noise_ok
+from helpers import train57, mixed_population, ohashi_models, random_starts, noise_ok, check_math
 import emu_wrap
 
 DET = dict(abstol=1e3, reltol=1e3)
@@ -104,3 +104,18 @@ def test_failures(fx):
     assert np.isinf(e["sse"][0, 5]) and e["g_cond"][0, 5] == 0 and np.all(e["g_neural"][0, 5] == 0) and e["n_fail"] == 1
     e = emu_wrap.emu_eval(pk, nn, betas, maxiters=5)
     assert np.isinf(e["sse"]).all() and e["n_fail"] == 57
+
+
+def test_elementary_functions_host_build():
+    """cude_math.cuh compiled for the host (the MUFU reciprocal seed is replaced by a float-accurate one)."""
+    L = C.CDLL(emu_wrap.build())
+    D = C.POINTER(C.c_double)
+    L.emu_math.argtypes = [C.c_int, C.c_int, D, D]
+
+    def fn(which, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        L.emu_math(which, x.size, x.ctypes.data_as(D), y.ctypes.data_as(D))
+        return y
+
+    check_math(fn)

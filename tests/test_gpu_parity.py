@@ -15,7 +15,7 @@ import pytest
 import conditional_ude_b200 as cu
 from conditional_ude_b200 import SolverOptions
 from oracle import oracle
-from helpers import train57, mixed_population, ohashi_models, random_starts, noise_ok as _noise_ok
+from helpers import train57, mixed_population, ohashi_models, random_starts, check_math, noise_ok as _noise_ok
 
 pytestmark = pytest.mark.gpu
 
@@ -227,3 +227,9 @@ def test_large_batch_properties(fx, ctx):
     lp, gnp, gcp = pop.loss_grad(neural[perm], cond[perm], mean=False)
     assert np.array_equal(lp, loss[perm]) and np.array_equal(gnp, gn[perm]) and np.array_equal(gcp, gc[perm])
     assert np.isfinite(loss).all()
+
+
+def test_elementary_functions_on_device(ctx):
+    """The kernels' branch-free FP64 tanh / softplus / sigmoid / exp / log / reciprocal (MUFU.RCP64H seed +
+    one third-order step) evaluated on the B200 against numpy."""
+    check_math(lambda which, x: ctx.math_probe(which, x))
