@@ -10,10 +10,14 @@ from .models import (Chain, chain, softplus, van_cauter_parameters, CPeptideCond
 from .population import Context, Population, SolverOptions, default_context
 from .losses import loss, loss_sigma, loss_and_gradient, ComponentVector
 from .profiles import likelihood_profile, likelihood_profile_population, find_confidence_intervals
+from .estimation import (initial_parameters, train, train_with_sigma, evaluate_model, stratified_split, argmedian,
+                         OptimizationSolution)
 
 __all__ = [
     "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel",
     "CPeptideConditionalCovariateUDEModel", "pack_models", "Context", "Population", "SolverOptions",
     "default_context", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",
     "likelihood_profile", "likelihood_profile_population", "find_confidence_intervals",
+    "initial_parameters", "train", "train_with_sigma", "evaluate_model", "stratified_split", "argmedian",
+    "OptimizationSolution",
 ]

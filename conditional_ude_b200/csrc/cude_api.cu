@@ -332,7 +332,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     if ((rc = ensure(ctx, ctx->counters, 3 * sizeof(unsigned long long)))) return rc;
     double* d_partials = nullptr;
     if (!flat && d_sums_out) {
-        if ((rc = ensure(ctx, ctx->partials, (size_t)nblocks * np1 * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, ctx->partials, (size_t)nblocks * (B / 32) * np1 * sizeof(double)))) return rc;
         d_partials = (double*)ctx->partials.p;
     }
     double* d_sse = d_sse_out;
@@ -377,7 +377,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
             const int wpb = 8;
             const long long nwarps = (long long)n_starts * np1;
             cude_reduce_partials<<<(unsigned)((nwarps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-                d_partials, nchunks, n_starts, np1, want_neural_grad ? np1 : 1, d_sums_out);
+                d_partials, nchunks * (B / 32), n_starts, np1, want_neural_grad ? np1 : 1, d_sums_out);
         }
         CU_TRY(ctx, cudaGetLastError());
         ++launches;

@@ -102,7 +102,7 @@ struct EvalArgs {
     int nchunks;                // tiles per start (tile mode)
     double cond_scale;          // g_cond = cond_scale * d sse / d cond
     double* sse_out;            // [N x S] or nullptr
-    double* partials;           // [n_blocks][P+1]: {sum sse, sum d sse/d neural} per block (GRAD or loss sums) or nullptr
+    double* partials;           // [n_blocks * warps_per_block][P+1]: {sum sse, sum d sse/d neural} per warp, or nullptr
     double* g_cond;             // [N x S] or nullptr
     unsigned long long* counters;  // {n_acc, n_rej, n_fail}
 };
@@ -638,10 +638,12 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         if (A.sse_out) A.sse_out[j] = sse;
         if (GRAD && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
     }
-    // ---- block reduction: {sse, d sse/d neural[0..P)} and the step counters ----
+    // ---- warp reduction: {sse, d sse/d neural[0..P)}; one partial row per WARP, no block barrier (warps of a
+    //      block finish at different times; a barrier here idled their slots: ncu v4 epilogue 45 % barrier) ----
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     if (A.partials) {
         constexpr int nred = GRAD ? P + 1 : 1;
+        double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
 #pragma unroll 1
         for (int q = 0; q < nred; ++q) {
             double v = 0.0;
@@ -659,13 +661,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sRed[wid * (P + 1) + q] = v;
-        }
-        __syncthreads();
-        for (int q = tid; q < nred; q += B) {
-            double v = 0.0;
-            for (int w2 = 0; w2 < nw; ++w2) v += sRed[w2 * (P + 1) + q];
-            A.partials[(size_t)blockIdx.x * (P + 1) + q] = v;
+            if (lane == 0) row[q] = v;
         }
     }
     if (A.counters) {

@@ -86,3 +86,28 @@ def check_math(fn):
     assert np.abs(fn(4, xl) - np.log(xl)).max() < 3e-13 and np.abs(fn(4, xl) / np.log(xl) - 1)[np.abs(np.log(xl)) > 1e-3].max() < 1e-15
     xr = np.exp(np.random.default_rng(3).uniform(-30, 30, 20000))
     assert np.abs(fn(5, xr) * xr - 1).max() < 5e-16
+
+
+class OraclePopulationAdapter:
+    """Test double with the Population interface (loss / loss_grad) computed by the CPU oracle — lets the
+    CPU-only tier exercise conditional_ude_b200.estimation end to end.  Tests only."""
+
+    def __init__(self, models, timepoints, cpeptide_data):
+        from oracle import oracle
+        pk = cu.pack_models(models, timepoints, cpeptide_data)
+        self.op = oracle.OraclePopulation(pk)
+        self.chain, self.n_ind, self.n_params = pk["chain"], pk["n_ind"], pk["chain"].n_params
+        self.calls = 0
+
+    def loss(self, neural, cond, opts=None, return_sse=False):
+        self.calls += 1
+        r = self.op.eval(neural, cond)
+        loss = r["sse"].mean(axis=1)
+        return (loss, r["sse"]) if return_sse else loss
+
+    def loss_grad(self, neural, cond, opts=None, neural_grad=True, mean=True, return_sse=False):
+        self.calls += 1
+        r = self.op.eval(neural, cond, grad_mode=0)
+        sc = 1.0 / self.n_ind if mean else 1.0
+        out = (r["sse"].sum(axis=1) * sc, r["g_neural"].sum(axis=1) * sc if neural_grad else None, r["g_cond"] * sc)
+        return out + (r["sse"],) if return_sse else out
