@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         // adjoint carry
         double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
         int kobs_top = nobs - 1;
+        double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;   // time of observation kobs_top
         bool first_pass = true;
 
         do {
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
             const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
             const int nlast = (lo == 0) ? -1 : lo;
+            double2 rnext = rec[(stop_at - 1) % REC_CAP];        // step records are fetched one step ahead
             for (int n = stop_at - 1; n >= nlast; --n) {
                 int nq;
                 const double* cn;
@@ -537,7 +539,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     nq = 1; cn = CN_INIT; tn = t0; h = 0.0;
                     myNode[0] = -wsum;
                 } else {
-                    const double2 r2 = rec[n % REC_CAP];
+                    const double2 r2 = rnext;
+                    if (n > lo) rnext = rec[(n - 1) % REC_CAP];
                     tn = r2.x; h = r2.y;
                     nq = 5; cn = CN_STEP;
                     double kb[7][2];
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     double ub0 = 0.0, ub1 = 0.0;
                     // observations in (tn, t_next]
                     while (kobs_top >= 0) {
-                        const double ts = obs_t[(size_t)kobs_top * N];
+                        const double ts = top_ot;                 // kept in a register: no global load per step
                         if (!(ts > tn)) break;
                         const double wr = 2.0 * sRes[kobs_top * B + tid];
                         if (ts == t_next) lam0 += wr;
@@ -559,6 +562,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                             for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
                         }
                         --kobs_top;
+                        top_ot = (kobs_top >= 0) ? obs_t[(size_t)kobs_top * N] : -CUDART_INF;
                     }
                     // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
                     const double pb7 = kb[6][0];

@@ -122,8 +122,40 @@ def main():
          63, 65, 66, 69, 71, 72, 73, 74, 79, 80, 81], dtype=np.int64)
     assert fx["train_split_idx"].size == 57
 
+    # ---- cross-check the fixed offsets above with the structural JLD2 reader (conditional_ude_b200/jld2.py) ----
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    from conditional_ude_b200 import jld2
+    c = jld2.load(os.path.join(REF, cu))
+    assert np.array_equal(np.stack(c["parameters"]), fx["cude_neural"]) and np.array_equal(np.stack(c["betas"]), fx["cude_betas"])
+    assert c["best_model_index"] == 14 and c["width"] == 4 and c["depth"] == 2
+    c = jld2.load(os.path.join(REF, cv))
+    assert np.array_equal(np.stack(c["parameters"]), fx["cov_neural"]) and np.array_equal(np.stack(c["betas"]), fx["cov_betas"])
+    assert c["best_model_index"] == 2
+
     np.savez_compressed(OUT, **fx)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(fx), "arrays")
+
+    # ---- suppression example (suppression/suppression.jl:76-91): data tensors + trained networks per lambda ----
+    sup = {}
+    for lam in ("0.0", "0.01", "1.0"):
+        d = jld2.load(os.path.join(REF, f"suppression/results/lambda={lam}.jld2"))
+        assert d["group_data"].shape == (3, 8, 37) and d["validation_data"].shape == (3, 8, 30)
+        assert len(d["neural_parameters"]) == 25 and d["neural_parameters"][0].shape == (67,)
+        key = lam.replace(".", "p")
+        sup[f"neural_{key}"] = np.stack(d["neural_parameters"])
+        sup[f"losses_{key}"] = d["losses"]
+        sup[f"losses_valid_{key}"] = d["losses_valid"]
+        sup[f"lambda_{key}"] = np.array(d["λ"])
+        if lam == "0.0":
+            sup["group_data"], sup["validation_data"] = d["group_data"], d["validation_data"]
+            sup["validation_data_nonoise"] = d["validation_data_nonoise"]
+            sup["gt_sup_param"], sup["gt_validation_param"] = d["gt_sup_param"], d["gt_validation_param"]
+        else:
+            assert np.array_equal(d["group_data"], sup["group_data"])       # same data for every lambda
+    sup["timepoints"] = np.linspace(0.0, 30.0, 8)                            # range(0, stop=30, length=8)
+    out2 = os.path.join(os.path.dirname(OUT), "suppression_fixtures.npz")
+    np.savez_compressed(out2, **sup)
+    print("wrote", out2, os.path.getsize(out2), "bytes;", len(sup), "arrays")
 
 
 if __name__ == "__main__":

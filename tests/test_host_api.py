@@ -117,3 +117,24 @@ def test_component_vector():
     assert th.neural[2] == 2.0 and th["conditional"] == [1.0]
     th.sigma = 0.5
     assert th["sigma"] == 0.5
+
+
+def test_jld2_reader_on_reference_artifacts(fx):
+    """The structural JLD2 reader (conditional_ude_b200/jld2.py) against the reference's own files; the files are
+    only present in the build container (skipped on the GPU box), the derived arrays are the golden fixtures."""
+    import os
+    from conditional_ude_b200 import jld2
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    c = jld2.load(os.path.join(ref, "source_data/cude_neural_parameters.jld2"))
+    assert c["best_model_index"] == 14 and (c["width"], c["depth"]) == (4, 2)
+    assert np.array_equal(np.stack(c["parameters"]), fx["cude_neural"])
+    assert np.array_equal(np.stack(c["betas"]), fx["cude_betas"])
+    d = jld2.load(os.path.join(ref, "suppression/results/lambda=0.01.jld2"))
+    assert d["group_data"].shape == (3, 8, 37) and d["λ"] == 0.01 and len(d["neural_parameters"]) == 25
+    assert np.all(d["group_data"][1:, 0, :] == 0)              # u0 = [x, 0, 0] (multiplicative noise keeps the zeros)
+    sup = dict(np.load(os.path.join(ROOT, "tests", "golden", "suppression_fixtures.npz")))
+    assert np.array_equal(sup["group_data"], d["group_data"]) and np.array_equal(sup["neural_0p01"], np.stack(d["neural_parameters"]))
+    with pytest.raises(ValueError):
+        jld2.JLD2File(os.path.join(ref, "data/ohashi.jld2"))["train"]      # NamedTuple: outside the subset
