@@ -56,7 +56,7 @@
 
 namespace {
 
-constexpr int MAXP = 64;   // max partials carried by a Dual
+constexpr int MAXP = 72;   // max partials carried by a Dual (suppression example: 67 weights + theta)
 constexpr int MAXW = 16;   // max MLP layer width
 constexpr int MAXOBS = 64;
 
@@ -372,6 +372,176 @@ static typename O::T solve_sse(const O& ops, const NetDesc& nd, const Indiv& I, 
     return sse;
 }
 
+
+// =====================================================================================
+// Suppression example (second variant of the same pattern), reference suppression/src/suppression_model.jl:
+//   ude_lsup!            :88-95   u_hat = network([u; exp.(theta_i)], neural)[1]
+//                                 du1 = -p1 u1;  du2 = p1 u1 - u_hat;  du3 = u_hat - p3 u3      (p_true = [0.4, 0.9, 0.3])
+//   neural_network_model :78-86   input_dims=4 -> `depth` tanh layers of `width` -> 1 softplus (suppression.jl:18: 5 x 3)
+//   suppression_loss     :117-130 solve(ensemble, Tsit5(), saveat=timepoints) per individual with u0 = data[:,1,i];
+//                                 sum(abs2, (sims - data) ./ scale) / N + lambda * sum(abs2, neural)
+// Here: the per-trajectory scaled SSE and its gradient; the mean over individuals and the ridge term are
+// assembled by the caller.  Explicit Tsit5 at OrdinaryDiffEq's default tolerances, all 3 states saved.
+// =====================================================================================
+struct SupIndiv {
+    double u0[3];
+    int nobs; const double* ot;      // shared time grid
+    const double* y;                 // [nobs][3] observations of this individual (state fastest)
+    double p1, p3;
+    double scale[3];
+    double t0, tend;
+};
+
+template <class O>
+struct SupRhs {
+    typedef typename O::T T;
+    const O& ops; const NetDesc& nd; const SupIndiv& I; const T* neural; T etheta; int* nrhs;
+    SupRhs(const O& o, const NetDesc& n, const SupIndiv& i, const T* p, const T& theta, int* cnt)
+        : ops(o), nd(n), I(i), neural(p), nrhs(cnt) { etheta = O::exp_(theta); }
+    void operator()(const T* u, double, T* du) const {
+        ++*nrhs;
+        T x[4] = { u[0], u[1], u[2], etheta };
+        T uhat = mlp_forward(ops, nd, neural, x);
+        du[0] = O::smul(-I.p1, u[0]);
+        du[1] = O::sub(O::smul(I.p1, u[0]), uhat);
+        du[2] = O::sub(uhat, O::smul(I.p3, u[2]));
+    }
+};
+
+template <class O>
+static double normD(const O& ops, const typename O::T* x, int D) {
+    double s = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < D; ++j) {
+        s += O::val(x[j]) * O::val(x[j]);
+        ++cnt;
+    }
+    (void)ops;
+    return std::sqrt(s / cnt);
+}
+
+// generic D-state adaptive Tsit5 + scaled SSE over all states (frozen-primal norm: values only)
+template <class O, int D, class F>
+static typename O::T solve_scaled_sse(const O& ops, const F& f, const double* u0v, double t0, double tend,
+                                      int nobs, const double* ot, const double* y, const double* scale,
+                                      const Opts& opt, Stats* st, double* yhat_out, int* nrhs) {
+    typedef typename O::T T;
+    int nacc = 0, nrej = 0;
+    const double dtmax = tend - t0;
+    const double dtmin = std::max(std::nextafter(std::fabs(t0), INFINITY) - std::fabs(t0),
+                                  std::nextafter(std::fabs(tend), INFINITY) - std::fabs(tend));
+    T u[D], k1[D], k2[D], k3[D], k4[D], k5[D], k6[D], k7[D], un[D], g[D];
+    for (int j = 0; j < D; ++j) u[j] = ops.cst(u0v[j]);
+    T sse = ops.cst(0.0);
+    int retcode = RET_SUCCESS, iobs = 0;
+    auto record = [&](const T* yv, int k) {
+        for (int j = 0; j < D; ++j) {
+            if (yhat_out) yhat_out[k * D + j] = O::val(yv[j]);
+            T r = O::smul(1.0 / scale[j], O::sadd(-y[k * D + j], yv[j]));
+            sse = O::add(sse, O::mul(r, r));
+        }
+    };
+    auto finish = [&](int rc) { st->nacc = nacc; st->nrej = nrej; st->nrhs = *nrhs; st->retcode = rc; };
+    auto nonfinite = [&](const T* x) { for (int j = 0; j < D; ++j) if (!std::isfinite(O::val(x[j]))) return true; return false; };
+    while (iobs < nobs && ot[iobs] <= t0) { record(u, iobs); ++iobs; }
+    f(u, t0, k1);
+    double dt;
+    {
+        double sk[D]; T tmp[D];
+        for (int j = 0; j < D; ++j) sk[j] = opt.abstol + std::fabs(O::val(u[j])) * opt.reltol;
+        for (int j = 0; j < D; ++j) tmp[j] = O::smul(1.0 / sk[j], u[j]);
+        double d0 = normD(ops, tmp, D);
+        for (int j = 0; j < D; ++j) tmp[j] = O::smul(1.0 / sk[j], k1[j]);
+        double d1 = normD(ops, tmp, D);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+        dt0 = std::min(dt0, dtmax);
+        T u1[D], f1[D];
+        for (int j = 0; j < D; ++j) u1[j] = O::add(u[j], O::smul(dt0, k1[j]));
+        f(u1, t0 + dt0, f1);
+        for (int j = 0; j < D; ++j) tmp[j] = O::smul(1.0 / sk[j], O::sub(f1[j], k1[j]));
+        double d2 = normD(ops, tmp, D) / dt0;
+        double dm = std::max(d1, d2);
+        double dt1 = (dm <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(dm)) / 5.0);
+        dt = std::max(dtmin, std::min(std::min(100.0 * dt0, dt1), dtmax));
+    }
+    if (!std::isfinite(dt) || nonfinite(k1)) { finish(RET_UNSTABLE); return ops.cst(INFINITY); }
+    double t = t0, qold = QOLDINIT;
+    int iter = 0;
+    const double* A[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    (void)A;
+    while (t < tend) {
+        if (++iter > opt.maxiters) { retcode = RET_MAXITERS; break; }
+        dt = std::min(dt, tend - t);
+        if (!(dt > dtmin)) { retcode = std::isnan(dt) ? RET_UNSTABLE : RET_DTMIN; break; }
+        for (int j = 0; j < D; ++j) g[j] = O::add(u[j], O::smul(dt * A21, k1[j]));
+        f(g, t + C2 * dt, k2);
+        for (int j = 0; j < D; ++j) g[j] = O::add(u[j], O::smul(dt, O::add(O::smul(A31, k1[j]), O::smul(A32, k2[j]))));
+        f(g, t + C3 * dt, k3);
+        for (int j = 0; j < D; ++j) g[j] = O::add(u[j], O::smul(dt, O::add(O::add(O::smul(A41, k1[j]), O::smul(A42, k2[j])), O::smul(A43, k3[j]))));
+        f(g, t + C4 * dt, k4);
+        for (int j = 0; j < D; ++j) g[j] = O::add(u[j], O::smul(dt, O::add(O::add(O::add(O::smul(A51, k1[j]), O::smul(A52, k2[j])), O::smul(A53, k3[j])), O::smul(A54, k4[j]))));
+        f(g, t + C5 * dt, k5);
+        for (int j = 0; j < D; ++j) g[j] = O::add(u[j], O::smul(dt, O::add(O::add(O::add(O::add(O::smul(A61, k1[j]), O::smul(A62, k2[j])), O::smul(A63, k3[j])), O::smul(A64, k4[j])), O::smul(A65, k5[j]))));
+        f(g, t + dt, k6);
+        for (int j = 0; j < D; ++j) un[j] = O::add(u[j], O::smul(dt, O::add(O::add(O::add(O::add(O::add(O::smul(A71, k1[j]), O::smul(A72, k2[j])), O::smul(A73, k3[j])), O::smul(A74, k4[j])), O::smul(A75, k5[j])), O::smul(A76, k6[j]))));
+        f(un, t + dt, k7);
+        T res[D];
+        for (int j = 0; j < D; ++j) {
+            T ut = O::smul(dt, O::add(O::add(O::add(O::add(O::add(O::add(O::smul(BT1, k1[j]), O::smul(BT2, k2[j])), O::smul(BT3, k3[j])), O::smul(BT4, k4[j])), O::smul(BT5, k5[j])), O::smul(BT6, k6[j])), O::smul(BT7, k7[j])));
+            T den = O::sadd(opt.abstol, O::smul(opt.reltol, O::max_(O::abs_(u[j]), O::abs_(un[j]))));
+            res[j] = O::div(ut, den);
+        }
+        double EEst = normD(ops, res, D);
+        if (std::isnan(EEst) || nonfinite(un)) { retcode = RET_UNSTABLE; break; }
+        if (g_trace && g_trace->n < g_trace->cap) {
+            double* r = g_trace->buf + 4 * g_trace->n++;
+            r[0] = t; r[1] = dt; r[2] = EEst; r[3] = (EEst <= 1.0) ? 1.0 : 0.0;
+        }
+        double q, q11 = 0.0;
+        if (EEst == 0.0) q = 1.0 / QMAX;
+        else {
+            q11 = std::pow(EEst, BETA1);
+            q = q11 / std::pow(qold, BETA2);
+            q = std::max(1.0 / QMAX, std::min(1.0 / QMIN, q / GAMMA));
+        }
+        if (EEst <= 1.0) {
+            ++nacc;
+            double tnew = t + dt;
+            const double m = std::fabs(tend);
+            if (std::fabs(tnew - tend) < 100.0 * (std::nextafter(m, INFINITY) - m)) tnew = tend;
+            while (iobs < nobs && ot[iobs] <= tnew) {
+                double ts = ot[iobs];
+                if (ts == tnew) record(un, iobs);
+                else {
+                    double th = (ts - t) / dt, th2 = th * th;
+                    double b1 = th * (R11 + th * (R12 + th * (R13 + th * R14)));
+                    double b2 = th2 * (R22 + th * (R23 + th * R24)), b3 = th2 * (R32 + th * (R33 + th * R34));
+                    double b4 = th2 * (R42 + th * (R43 + th * R44)), b5 = th2 * (R52 + th * (R53 + th * R54));
+                    double b6 = th2 * (R62 + th * (R63 + th * R64)), b7 = th2 * (R72 + th * (R73 + th * R74));
+                    T yv[D];
+                    for (int j = 0; j < D; ++j) {
+                        T sdo = O::add(O::add(O::add(O::add(O::add(O::add(O::smul(b1, k1[j]), O::smul(b2, k2[j])), O::smul(b3, k3[j])), O::smul(b4, k4[j])), O::smul(b5, k5[j])), O::smul(b6, k6[j])), O::smul(b7, k7[j]));
+                        yv[j] = O::add(u[j], O::smul(dt, sdo));
+                    }
+                    record(yv, iobs);
+                }
+                ++iobs;
+            }
+            qold = std::max(EEst, QOLDINIT);
+            dt = std::min(dt / q, dtmax);
+            t = tnew;
+            for (int j = 0; j < D; ++j) { u[j] = un[j]; k1[j] = k7[j]; }
+        } else {
+            ++nrej;
+            dt = dt / std::min(1.0 / QMIN, q11 / GAMMA);
+        }
+    }
+    if (retcode == RET_SUCCESS && iobs < nobs) retcode = RET_UNSTABLE;
+    finish(retcode);
+    if (retcode != RET_SUCCESS) return ops.cst(INFINITY);
+    return sse;
+}
+
 struct Pop {
     int n_ind, max_knots, max_obs;
     const int* n_knots; const double* knot_t; const double* knot_g;
@@ -553,6 +723,56 @@ int cude_oracle_trace(const cude_oracle_pop* cp, int n_in, int depth, int width,
     g_trace = nullptr;
     if (sse_out) *sse_out = v;
     return tr.n;
+}
+
+// ---- suppression example ----
+// data: Julia layout data[state + 3*(k + n_obs*i)] (3 x n_obs x n_ind), theta[i + n_ind*s], neural + s*neural_stride.
+// scale[3]: mean over individuals of the per-state maximum over time (suppression_model.jl:125); p_true = {p1, p2, p3}.
+// Outputs per trajectory j = i + n_ind*s: sse (scaled), g_neural_traj[j*P + p], g_theta[j], stats[j*4..], yhat[j*n_obs*3..].
+int cude_oracle_sup_eval(int n_ind, int n_obs, const double* obs_t, const double* data, const double* p_true,
+                         const double* scale, double t0, double tend, int depth, int width,
+                         int n_starts, const double* neural, long neural_stride, const double* theta,
+                         double abstol, double reltol, int maxiters, int with_grad, int n_threads,
+                         double* sse, double* yhat, int* stats, double* g_neural_traj, double* g_theta) {
+    NetDesc nd{4, depth, width};
+    const int P = net_nparams(nd);
+    if (P + 1 > MAXP || width > MAXW) return -1;
+    Opts opt{abstol, reltol, maxiters};
+    const long ntraj = (long)n_ind * n_starts;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long j = 0; j < ntraj; ++j) {
+        const int i = (int)(j % n_ind);
+        const long s = j / n_ind;
+        SupIndiv I;
+        I.nobs = n_obs; I.ot = obs_t; I.y = data + (size_t)i * n_obs * 3;
+        for (int q = 0; q < 3; ++q) { I.u0[q] = I.y[q]; I.scale[q] = scale[q]; }   // u0 = data[:,1,i], :99-104
+        I.p1 = p_true[0]; I.p3 = p_true[2]; I.t0 = t0; I.tend = tend;
+        const double* p = neural + s * neural_stride;
+        Stats st; int nrhs = 0;
+        double* yh = yhat ? yhat + j * n_obs * 3 : nullptr;
+        if (!with_grad) {
+            RealOps ops;
+            SupRhs<RealOps> f(ops, nd, I, p, theta[j], &nrhs);
+            double v = solve_scaled_sse<RealOps, 3>(ops, f, I.u0, t0, tend, n_obs, obs_t, I.y, I.scale, opt, &st, yh, &nrhs);
+            if (sse) sse[j] = v;
+        } else {
+            DualOps ops; ops.n = P + 1; ops.norm_partials = false;
+            std::vector<Dual> dp(P);
+            for (int a = 0; a < P; ++a) { dp[a] = dconst(p[a], P + 1); dp[a].d[a] = 1.0; }
+            Dual dth = dconst(theta[j], P + 1); dth.d[P] = 1.0;
+            SupRhs<DualOps> f(ops, nd, I, dp.data(), dth, &nrhs);
+            Dual v = solve_scaled_sse<DualOps, 3>(ops, f, I.u0, t0, tend, n_obs, obs_t, I.y, I.scale, opt, &st, yh, &nrhs);
+            if (sse) sse[j] = v.v;
+            const bool ok = std::isfinite(v.v);
+            if (g_neural_traj) for (int a = 0; a < P; ++a) g_neural_traj[j * P + a] = ok ? v.d[a] : 0.0;
+            if (g_theta) g_theta[j] = ok ? v.d[P] : 0.0;
+        }
+        if (stats) { stats[j * 4 + 0] = st.nacc; stats[j * 4 + 1] = st.nrej; stats[j * 4 + 2] = st.nrhs; stats[j * 4 + 3] = st.retcode; }
+    }
+    return 0;
 }
 
 int cude_oracle_max_threads(void) {

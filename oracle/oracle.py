@@ -47,6 +47,9 @@ def lib():
         L.cude_oracle_population_loss.argtypes = [C.POINTER(_Pop), C.c_int, C.c_int, C.c_int, C.c_int, _D, C.c_long, _D,
                                                   C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _D, _D, _D,
                                                   C.POINTER(C.c_long)]
+        L.cude_oracle_sup_eval.argtypes = [C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_int, C.c_int,
+                                           C.c_int, _D, C.c_long, _D, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                           _D, _D, _I, _D, _D]
         L.cude_oracle_trace.argtypes = [C.POINTER(_Pop), C.c_int, C.c_int, C.c_int, C.c_int, _D, C.c_double, C.c_double,
                                         C.c_double, C.c_int, _D, C.c_int, _D]
         _lib = L
@@ -142,3 +145,36 @@ def glucose(kt, kg, tau):
 
 def max_threads():
     return lib().cude_oracle_max_threads()
+
+
+def suppression_scale(data):
+    """scale = mean(maximum(individual_data, dims=2), dims=3)[:]  (suppression_model.jl:125); data is [3, n_obs, n_ind]."""
+    return np.asarray(data, dtype=np.float64).max(axis=1).mean(axis=1)
+
+
+def sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), depth=5, width=3, tspan=None, scale=None,
+             abstol=1e-6, reltol=1e-3, maxiters=100000, with_grad=False, n_threads=0, want_yhat=False):
+    """Suppression example, per-trajectory scaled SSE (+ gradient): data [3, n_obs, n_ind] (Julia layout),
+    neural [P] or [S, P], theta [S, n_ind].  Returns dict(sse[S,N], stats, g_neural[S,N,P], g_theta[S,N], yhat[S,N,n_obs,3])."""
+    data = np.asarray(data, dtype=np.float64)
+    _, n_obs, n_ind = data.shape
+    dj = np.ascontiguousarray(data.transpose(2, 1, 0))               # [i][k][state] == Julia column-major 3 x n_obs x n_ind
+    ot = np.ascontiguousarray(timepoints, dtype=np.float64)
+    sc = np.ascontiguousarray(suppression_scale(data) if scale is None else scale, dtype=np.float64)
+    pt = np.ascontiguousarray(p_true, dtype=np.float64)
+    t0, tend = (float(ot[0]), float(ot[-1])) if tspan is None else tspan
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1, n_ind))
+    S = theta.shape[0]
+    P = lib().cude_oracle_nparams(4, depth, width)
+    stride = 0 if neural.ndim == 1 else P
+    sse = np.empty((S, n_ind))
+    stats = np.empty((S, n_ind, 4), dtype=np.int32)
+    yhat = np.full((S, n_ind, n_obs, 3), np.nan) if want_yhat else None
+    gn = np.zeros((S, n_ind, P)) if with_grad else None
+    gt = np.zeros((S, n_ind)) if with_grad else None
+    rc = lib().cude_oracle_sup_eval(n_ind, n_obs, _dp(ot), _dp(dj), _dp(pt), _dp(sc), t0, tend, depth, width, S, _dp(neural),
+                                    stride, _dp(theta), abstol, reltol, maxiters, int(with_grad), n_threads, _dp(sse), _dp(yhat),
+                                    stats.ctypes.data_as(_I), _dp(gn), _dp(gt))
+    assert rc == 0
+    return dict(sse=sse, stats=stats, g_neural=gn, g_theta=gt, yhat=yhat)
