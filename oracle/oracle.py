@@ -50,6 +50,8 @@ def lib():
         L.cude_oracle_sup_eval.argtypes = [C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_int, C.c_int,
                                            C.c_int, _D, C.c_long, _D, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                            _D, _D, _I, _D, _D]
+        L.cude_oracle_eval_generic.argtypes = [C.POINTER(_Pop), C.c_int, C.c_int, C.c_int, C.c_int, _D, C.c_long, _D,
+                                               C.c_double, C.c_double, C.c_int, _D, _I]
         L.cude_oracle_trace.argtypes = [C.POINTER(_Pop), C.c_int, C.c_int, C.c_int, C.c_int, _D, C.c_double, C.c_double,
                                         C.c_double, C.c_int, _D, C.c_int, _D]
         _lib = L
@@ -100,6 +102,16 @@ class OraclePopulation:
                                     stats.ctypes.data_as(_I), _dp(gn), _dp(gc))
         assert rc == 0
         return dict(sse=sse, stats=stats, g_neural=gn, g_cond=gc, yhat=yhat)
+
+    def eval_generic(self, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000):
+        """The same loss through the generic D-state Tsit5 core (the one pinned by the suppression artifacts)."""
+        neural, stride, cond, S = self._prep(neural, cond)
+        sse = np.empty((S, self.n_ind))
+        stats = np.empty((S, self.n_ind, 4), dtype=np.int32)
+        rc = lib().cude_oracle_eval_generic(C.byref(self._c), self.n_in, self.depth, self.width, S, _dp(neural), stride,
+                                            _dp(cond), abstol, reltol, maxiters, _dp(sse), stats.ctypes.data_as(_I))
+        assert rc == 0
+        return dict(sse=sse, stats=stats)
 
     def trace(self, i, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, cap=100000):
         """Step trace of individual i: array of rows (t, dt, EEst, accepted) and the sse."""

@@ -80,3 +80,22 @@ def test_gradient_vs_finite_differences(sup):
         assert np.allclose(g["g_neural"][0, :, p], fd, rtol=1e-6, atol=1e-8)
     fd = fd4(lambda d: oracle.sup_eval(data, t, nn, th + d, scale=sc, **tol)["sse"][0])
     assert np.allclose(g["g_theta"][0], fd, rtol=1e-6, atol=1e-8)
+
+
+def test_cpeptide_solver_is_the_pinned_core(fx):
+    """The c-peptide oracle (solve_sse, specialised 2-state code) and the generic D-state core that the stored
+    suppression losses pin produce bit-identical losses and step counts on the c-peptide problem: the pin carries
+    over to the c-peptide path's integrator (Tsit5 tableau, error norm, PI controller, initial step, dense output)."""
+    import conditional_ude_b200 as cu
+    from helpers import mixed_population, random_starts
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    op = oracle.OraclePopulation(pk)
+    rng = np.random.default_rng(0)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 4)
+    a = op.eval(neural, cond)
+    b = op.eval_generic(neural, cond)
+    assert np.array_equal(a["sse"], b["sse"])
+    assert np.array_equal(a["stats"][..., :2], b["stats"][..., :2])
+    for tol in (dict(abstol=1e-10, reltol=1e-8), dict(abstol=1e3, reltol=1e3)):
+        assert np.array_equal(op.eval(neural, cond, **tol)["sse"], op.eval_generic(neural, cond, **tol)["sse"])
