@@ -13,7 +13,11 @@ from .profiles import likelihood_profile, likelihood_profile_population, find_co
 from .estimation import (initial_parameters, train, train_with_sigma, evaluate_model, stratified_split, argmedian,
                          OptimizationSolution)
 
+from .suppression import (SuppressionPopulation, neural_network_model, suppression_loss, fit_suppression_model,
+                          validate_suppression_model)
+
 __all__ = [
+    "SuppressionPopulation", "neural_network_model", "suppression_loss", "fit_suppression_model", "validate_suppression_model",
     "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel",
     "CPeptideConditionalCovariateUDEModel", "pack_models", "Context", "Population", "SolverOptions",
     "default_context", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",

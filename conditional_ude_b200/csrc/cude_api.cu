@@ -12,6 +12,7 @@
 
 #include "../../include/cude_b200.h"
 #include "cude_kernels.cuh"
+#include "cude_sup_kernel.cuh"
 
 using namespace cude;
 
@@ -455,6 +456,154 @@ extern "C" int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const c
                               double* sse_out, double* loss_out, double* g_neural, double* g_cond) {
     return eval_host(ctx, pop, net, opts, n_starts, neural, neural_stride, cond, 1, mean_over_individuals,
                      sse_out, loss_out, g_neural, g_cond);
+}
+
+// ---------------------------------------------------------------- suppression variant
+struct cude_sup_population {
+    cude_ctx* ctx = nullptr;
+    int n_ind = 0, n_obs = 0;
+    double* d_data = nullptr;    // [M][3][N]
+    double* d_obs_t = nullptr;   // [M]
+    double p1 = 0, p3 = 0, iscale[3] = {1, 1, 1}, t0 = 0, tend = 0;
+};
+
+extern "C" int cude_sup_population_create(cude_ctx* ctx, int n_ind, int n_obs, const double* obs_t, const double* data,
+                                          const double* p_true, const double* scale, double t0, double tend,
+                                          cude_sup_population** out) {
+    if (!ctx || !out || !obs_t || !data || !p_true || n_ind < 1 || n_obs < 1 || !(tend > t0))
+        return fail(ctx, CUDE_EINVAL, "cude_sup_population_create: bad argument");
+    *out = nullptr;
+    for (int k = 0; k < n_obs; ++k) {
+        if (!(obs_t[k] >= t0 && obs_t[k] <= tend) || (k > 0 && !(obs_t[k] > obs_t[k - 1])))
+            return fail(ctx, CUDE_EINVAL, "cude_sup_population_create: observation times must be increasing inside tspan");
+    }
+    const size_t N = n_ind, M = n_obs;
+    std::vector<double> h(M * 3 * N);
+    double sc[3] = {0, 0, 0};
+    for (size_t i = 0; i < N; ++i) {
+        double mx[3] = {-1e300, -1e300, -1e300};
+        for (size_t k = 0; k < M; ++k)
+            for (int j = 0; j < 3; ++j) {
+                const double v = data[j + 3 * (k + M * i)];
+                h[(k * 3 + j) * N + i] = v;
+                if (v > mx[j]) mx[j] = v;
+            }
+        for (int j = 0; j < 3; ++j) sc[j] += mx[j];
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cude_sup_population* pop = new (std::nothrow) cude_sup_population();
+    if (!pop) return fail(ctx, CUDE_ENOMEM, "out of host memory");
+    pop->ctx = ctx; pop->n_ind = n_ind; pop->n_obs = n_obs; pop->p1 = p_true[0]; pop->p3 = p_true[2]; pop->t0 = t0; pop->tend = tend;
+    for (int j = 0; j < 3; ++j) pop->iscale[j] = 1.0 / (scale ? scale[j] : sc[j] / (double)N);   // suppression_model.jl:125
+    if (cudaMalloc(&pop->d_data, h.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&pop->d_obs_t, M * sizeof(double)) != cudaSuccess) {
+        cude_sup_population_destroy(pop);
+        return fail(ctx, CUDE_ENOMEM, "cude_sup_population_create: cudaMalloc failed");
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(pop->d_data, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pop->d_obs_t, obs_t, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = pop;
+    return CUDE_OK;
+}
+
+extern "C" int cude_sup_population_destroy(cude_sup_population* pop) {
+    if (!pop) return CUDE_OK;
+    if (pop->ctx) cudaSetDevice(pop->ctx->device);
+    if (pop->d_data) cudaFree(pop->d_data);
+    if (pop->d_obs_t) cudaFree(pop->d_obs_t);
+    delete pop;
+    return CUDE_OK;
+}
+
+typedef void (*sup_kernel_t)(const SupArgs);
+
+extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth, int width, const cude_opts* opts_in,
+                                  int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
+                                  double* sse_out, double* loss_out, double* g_neural, double* g_theta) {
+    if (!ctx || !pop || !neural || !theta || n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: bad argument");
+    if (pop->ctx != ctx) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: population belongs to another context");
+    if (!(depth == 5 && width == 3)) return fail(ctx, CUDE_EUNSUPPORTED, "cude_sup_loss_grad: network shape not compiled in (available: depth 5, width 3)");
+    typedef SupNet<5, 3> SN;
+    cude_opts o;
+    if (opts_in) o = *opts_in; else cude_default_opts(&o);
+    if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: bad solver options");
+    const int P = SN::P, np1 = P + 1, N = pop->n_ind, M = pop->n_obs;
+    if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: neural_stride < n_params");
+    const bool grad = (g_neural != nullptr) || (g_theta != nullptr);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int B = o.block > 0 ? o.block : (N > 32 ? 64 : 32);
+    if (B < 32 || B > 128 || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: block must be 32, 64, 96 or 128");
+    const int nchunks = (N + B - 1) / B, nw = B / 32;
+    const long long nblocks = (long long)n_starts * nchunks;
+    const size_t ntraj = (size_t)N * n_starts;
+    const size_t n_neural = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
+    int rc;
+    if ((rc = ensure(ctx, ctx->counters, 3 * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(ctx, ctx->neural, n_neural * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->cond, ntraj * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->sums, (size_t)np1 * n_starts * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->partials, (size_t)nblocks * nw * np1 * sizeof(double)))) return rc;
+    if (sse_out && (rc = ensure(ctx, ctx->sse, ntraj * sizeof(double)))) return rc;
+    if (g_theta && (rc = ensure(ctx, ctx->gcond, ntraj * sizeof(double)))) return rc;
+    if (ctx->h_sums_cap < (size_t)np1 * n_starts) {
+        if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+        ctx->h_sums = nullptr; ctx->h_sums_cap = 0;
+        CU_TRY(ctx, cudaMallocHost(&ctx->h_sums, (size_t)np1 * n_starts * sizeof(double)));
+        ctx->h_sums_cap = (size_t)np1 * n_starts;
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->neural.p, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cond.p, theta, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SupArgs a{};
+    a.n_ind = N; a.n_obs = M; a.n_starts = n_starts; a.nchunks = nchunks;
+    a.obs_t = pop->d_obs_t; a.data = pop->d_data; a.p1 = pop->p1; a.p3 = pop->p3;
+    for (int j = 0; j < 3; ++j) a.iscale[j] = pop->iscale[j];
+    a.t0 = pop->t0; a.tend = pop->tend;
+    a.neural = (const double*)ctx->neural.p; a.neural_stride = neural_stride; a.theta = (const double*)ctx->cond.p;
+    a.abstol = o.abstol; a.reltol = o.reltol; a.maxiters = o.maxiters;
+    a.theta_scale = 1.0 / N;
+    a.sse_out = sse_out ? (double*)ctx->sse.p : nullptr;
+    a.partials = (double*)ctx->partials.p;
+    a.g_theta = g_theta ? (double*)ctx->gcond.p : nullptr;
+    a.counters = (unsigned long long*)ctx->counters.p;
+    sup_kernel_t kern = grad ? cude_sup_kernel<SN, true> : cude_sup_kernel<SN, false>;
+    const size_t smem = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, grad);
+    if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: too many observations for shared memory; lower opts.block");
+    if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
+    CU_TRY(ctx, cudaGetLastError());
+    {
+        const int wpb = 8;
+        const long long nwarps = (long long)n_starts * np1;
+        cude_reduce_partials<<<(unsigned)((nwarps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+            (const double*)ctx->partials.p, nchunks * nw, n_starts, np1, grad ? np1 : 1, (double*)ctx->sums.p);
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->stats = cude_stats{};
+    ctx->stats.n_traj = (unsigned long long)ntraj;
+    ctx->stats.launches = 2;
+    ctx->stats_pending = true;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, ctx->sse.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g_theta) CU_TRY(ctx, cudaMemcpyAsync(g_theta, ctx->gcond.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, CUDE_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(e));
+    }
+    for (int s = 0; s < n_starts; ++s) {
+        const double* row = ctx->h_sums + (size_t)s * np1;
+        const double* w = neural + (size_t)s * neural_stride;
+        const bool ok = std::isfinite(row[0]);
+        double ridge = 0.0;
+        for (int p = 0; p < P; ++p) ridge += w[p] * w[p];
+        if (loss_out) loss_out[s] = row[0] / N + lambda * ridge;                 // suppression_model.jl:126-128
+        if (g_neural) for (int p = 0; p < P; ++p) g_neural[(size_t)s * P + p] = ok ? row[1 + p] / N + 2.0 * lambda * w[p] : 0.0;
+        if (g_theta && !ok) for (int i = 0; i < N; ++i) g_theta[(size_t)s * N + i] = 0.0;
+    }
+    return CUDE_OK;
 }
 
 // ---------------------------------------------------------------- elementary-function probe (tests)

@@ -1,0 +1,496 @@
+// =====================================================================================
+// cude_sup_kernel.cuh — second kernel variant: the suppression example's state-dependent cUDE.
+//
+// Reference: suppression/src/suppression_model.jl
+//   ude_lsup! :88-95    u_hat = network([u1;u2;u3; exp(theta_i)], neural)[1]
+//                       du1 = -p1 u1;  du2 = p1 u1 - u_hat;  du3 = u_hat - p3 u3        (p_true = [0.4, 0.9, 0.3])
+//   suppression_loss :117-130   per individual: solve(prob, Tsit5(), saveat=timepoints), u0 = data[:,1,i];
+//                       sum(abs2, (sims - data) ./ scale)/N + lambda*sum(abs2, neural)
+// One thread = one trajectory (individual, start).  Unlike the c-peptide kernel the network sits inside the state
+// feedback, so the discrete adjoint is the genuinely nonlinear one: per accepted step the ring keeps (t, dt, u[3]);
+// the backward sweep replays the step's stages (keeping only the stage inputs g_i), then walks the stages in
+// reverse, re-evaluating the network (forward + backward) at each g_i with the scalar seed kb_i[3] - kb_i[2].
+// Stages, stage inputs and stage adjoints live in shared memory so that the stage loops stay rolled (one inlined
+// network site per phase); the 64 compressed gradient accumulators live in shared memory and are updated in
+// per-layer batches.
+// =====================================================================================
+#pragma once
+#include "cude_kernels.cuh"
+
+namespace cude {
+
+struct SupArgs {
+    int n_ind, n_obs, n_starts, nchunks;
+    const double* obs_t;        // [M] common time grid
+    const double* data;         // [M][3][N]: data[(k*3 + j)*N + i]
+    double p1, p3;
+    double iscale[3];           // 1/scale_j
+    double t0, tend;
+    const double* neural;       // start s: neural + s*neural_stride
+    long long neural_stride;
+    const double* theta;        // [N x S]
+    double abstol, reltol;
+    int maxiters;
+    double theta_scale;         // g_theta = theta_scale * d sse / d theta
+    double* sse_out;            // [N x S] or nullptr
+    double* partials;           // [blocks * warps][P+1]
+    double* g_theta;            // [N x S] or nullptr
+    unsigned long long* counters;
+};
+
+template <int DEPTH_, int WIDTH_>
+struct SupNet {
+    static constexpr int NIN = 4, DEPTH = DEPTH_, W = WIDTH_;
+    static constexpr int L1 = W * (NIN + 1);
+    static constexpr int LH = W * (W + 1);
+    static constexpr int OFF_OUT = L1 + (DEPTH - 1) * LH;
+    static constexpr int P = OFF_OUT + W + 1;
+    // compressed accumulators: dW1[:,0:3] (3W), sum dz1 (W), hidden layers, output layer
+    static constexpr int NACC = 4 * W + (DEPTH - 1) * LH + W + 1;
+};
+
+// Tsit5 coefficient rows for the rolled stage loops: AROW[i][j] = a_{i+2,j+1} (i = 0..4), AROW[5] = b (stage 7 / update)
+__constant__ double SUP_A[6][6] = {
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+__constant__ double SUP_E[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                                0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+
+// network forward at state (u0,u1,u2); c[] = first-layer constant part (theta column + bias)
+template <class SN>
+__device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, const double* __restrict__ tab,
+                                                 const double (&c)[SN::W], double u0, double u1, double u2) {
+    constexpr int W = SN::W;
+    double a[W], b[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab);
+    int off = SN::L1;
+#pragma unroll
+    for (int l = 1; l < SN::DEPTH; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            double z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
+            b[j] = m_tanh(z, tab);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) a[j] = b[j];
+        off += SN::LH;
+    }
+    double z = sW[off + W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
+    return m_softplus(z, tab);
+}
+
+// forward + backward with scalar seed s: returns d(u_hat)/d(u) * s in du[], accumulates parameter gradients
+// into acc (shared memory, [k][tid], stride as) in per-layer batches.
+template <class SN>
+__device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, const double* __restrict__ tab,
+                                                const double (&c)[SN::W], double u0, double u1, double u2, double s,
+                                                double* __restrict__ acc, int as, double (&du)[3]) {
+    constexpr int W = SN::W, D = SN::DEPTH;
+    double a[D][W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab);
+    int off = SN::L1;
+#pragma unroll
+    for (int l = 1; l < D; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            double z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
+            a[l][j] = m_tanh(z, tab);
+        }
+        off += SN::LH;
+    }
+    double z = sW[off + W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
+    const double dz = s * m_sigmoid(z, tab);
+    int aoff = 4 * W + (D - 1) * SN::LH;
+    double da[W];
+    {   // output layer batch
+        double g[W + 1];
+#pragma unroll
+        for (int i = 0; i <= W; ++i) g[i] = acc[(aoff + i) * as];
+#pragma unroll
+        for (int i = 0; i < W; ++i) { g[i] = fma(dz, a[D - 1][i], g[i]); da[i] = dz * sW[off + i]; }
+        g[W] += dz;
+#pragma unroll
+        for (int i = 0; i <= W; ++i) acc[(aoff + i) * as] = g[i];
+    }
+#pragma unroll
+    for (int l = D - 1; l >= 1; --l) {
+        off -= SN::LH;
+        aoff -= SN::LH;
+        double dzl[W], dprev[W], g[SN::LH];
+#pragma unroll
+        for (int k = 0; k < SN::LH; ++k) g[k] = acc[(aoff + k) * as];
+#pragma unroll
+        for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], 1.0);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                g[i * W + j] = fma(dzl[j], a[l - 1][i], g[i * W + j]);
+                sum = fma(sW[off + i * W + j], dzl[j], sum);
+            }
+            dprev[i] = sum;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) { g[W * W + j] += dzl[j]; da[j] = dprev[j]; }
+#pragma unroll
+        for (int k = 0; k < SN::LH; ++k) acc[(aoff + k) * as] = g[k];
+    }
+    {   // first layer batch: dW1[:,0:3] and sum dz1
+        double g[4 * W], dz1[W];
+#pragma unroll
+        for (int k = 0; k < 4 * W; ++k) g[k] = acc[k * as];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            dz1[j] = da[j] * fma(-a[0][j], a[0][j], 1.0);
+            g[j] = fma(dz1[j], u0, g[j]);
+            g[W + j] = fma(dz1[j], u1, g[W + j]);
+            g[2 * W + j] = fma(dz1[j], u2, g[2 * W + j]);
+            g[3 * W + j] += dz1[j];
+        }
+#pragma unroll
+        for (int k = 0; k < 4 * W; ++k) acc[k * as] = g[k];
+        du[0] = du[1] = du[2] = 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            du[0] = fma(sW[j], dz1[j], du[0]);
+            du[1] = fma(sW[W + j], dz1[j], du[1]);
+            du[2] = fma(sW[2 * W + j], dz1[j], du[2]);
+        }
+    }
+}
+
+__host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad) {
+    // exp table, weights, per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] + residuals M*3 + accumulators)
+    return (size_t)64 + (size_t)((P + 1) & ~1) + (size_t)(21 + (grad ? 42 + 3 * M + NACC : 0)) * B;
+}
+
+constexpr int SUP_REC_CAP = 64;   // ring of accepted-step records (t, dt, u[3]) per thread, local memory
+
+template <class SN, bool GRAD>
+__global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
+    using namespace tab;
+    constexpr int W = SN::W, P = SN::P;
+    extern __shared__ double smem[];
+    const int B = blockDim.x, tid = threadIdx.x;
+    const int N = A.n_ind, M = A.n_obs;
+    double* sTab = smem;
+    double* sW = sTab + 64;
+    double* sK = sW + ((P + 1) & ~1);                 // [7][3][B] stages
+    double* sG = sK + (size_t)21 * B;                 // [7][3][B] stage inputs (GRAD)
+    double* sKb = sG + (GRAD ? (size_t)21 * B : 0);   // [7][3][B] stage adjoints (GRAD)
+    double* sRes = sKb + (GRAD ? (size_t)21 * B : 0); // [M][3][B] weighted residuals (GRAD)
+    double* sAcc = sRes + (GRAD ? (size_t)3 * M * B : 0);   // [NACC][B]
+
+    const int s = blockIdx.x / A.nchunks;
+    const int ch = blockIdx.x - s * A.nchunks;
+    const int i = ch * B + tid;
+    const bool active = i < N;
+    const long long jt = (long long)s * N + (active ? i : 0);
+    {
+        const double* gW = A.neural + (long long)s * A.neural_stride;
+        for (int p = tid; p < P; p += B) sW[p] = gW[p];
+        for (int p = tid; p < 64; p += B) sTab[p] = EXP_TAB64[p];
+    }
+    double* const myK = sK + tid;
+    double* const myG = sG + tid;
+    double* const myKb = sKb + tid;
+    double* const myRes = sRes + tid;
+    double* const myAcc = sAcc + tid;
+    if (GRAD) {
+#pragma unroll 1
+        for (int q = 0; q < SN::NACC; ++q) myAcc[q * B] = 0.0;
+    }
+    __syncthreads();
+
+    double sse = 0.0, gtheta = 0.0, etheta = 0.0;
+    int nacc = 0, nrej = 0;
+    bool failed = false;
+
+    if (active) {
+        const double p1 = A.p1, p3 = A.p3, abstol = A.abstol, reltol = A.reltol;
+        const double t0 = A.t0, tend = A.tend;
+        const double* yd = A.data + i;               // y(k, j) = yd[(k*3 + j)*N]
+        etheta = m_exp(A.theta[jt]);
+        double c[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) c[q] = fma(sW[3 * W + q], etheta, sW[4 * W + q]);
+        const double dtmax = tend - t0;
+        const double at0 = fabs(t0), at1 = fabs(tend);
+        const double dtmin = fmax(nextafter(at0, CUDART_INF) - at0, nextafter(at1, CUDART_INF) - at1);
+        const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
+
+        // rhs: f(u) = [-p1 u0, p1 u0 - uhat, uhat - p3 u2]
+#define SUP_RHS(U0, U1, U2, F0, F1, F2)                                   \
+    {                                                                     \
+        const double uh__ = sup_nn_forward<SN>(sW, sTab, c, U0, U1, U2);  \
+        F0 = -p1 * (U0); F1 = fma(p1, (U0), -uh__); F2 = fma(-p3, (U2), uh__); \
+    }
+        struct Rec { double t, h, u0, u1, u2; };
+        Rec rec[GRAD ? SUP_REC_CAP : 1];
+
+        // ---------------- forward pass ----------------
+        double u0 = yd[0], u1 = yd[(size_t)N], u2 = yd[(size_t)2 * N];      // u0 = data[:,1,i]
+        double t = t0;
+        int iobs = 0, ret = 0;
+        while (iobs < M && A.obs_t[iobs] <= t0) {                            // save_start: residual at t0 is 0 by construction
+            const double r0 = (u0 - yd[(size_t)(iobs * 3) * N]) * A.iscale[0];
+            const double r1 = (u1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
+            const double r2 = (u2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
+            if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
+            sse += r0 * r0 + r1 * r1 + r2 * r2;
+            ++iobs;
+        }
+        double k10, k11, k12;
+        SUP_RHS(u0, u1, u2, k10, k11, k12)
+        double dt;
+        {   // Hairer initial step
+            const double isk0 = 1.0 / fma(fabs(u0), reltol, abstol), isk1 = 1.0 / fma(fabs(u1), reltol, abstol),
+                         isk2 = 1.0 / fma(fabs(u2), reltol, abstol);
+            double x0 = u0 * isk0, x1 = u1 * isk1, x2 = u2 * isk2;
+            const double d0 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0);
+            x0 = k10 * isk0; x1 = k11 * isk1; x2 = k12 * isk2;
+            const double d1 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0);
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            dt0 = fmin(dt0, dtmax);
+            double f0, f1, f2;
+            SUP_RHS(fma(dt0, k10, u0), fma(dt0, k11, u1), fma(dt0, k12, u2), f0, f1, f2)
+            x0 = (f0 - k10) * isk0; x1 = (f1 - k11) * isk1; x2 = (f2 - k12) * isk2;
+            const double d2 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0) / dt0;
+            const double dm = fmax(d1, d2);
+            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
+            dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
+            if (!(isfinite(dt) && isfinite(k10) && isfinite(k11) && isfinite(k12))) ret = 3;
+        }
+        myK[0] = k10; myK[B] = k11; myK[2 * B] = k12;
+        double lnqold = -9.210340371976182;
+        int iter = 0;
+        while (ret == 0 && t < tend) {
+            if (++iter > A.maxiters) { ret = 1; break; }
+            dt = fmin(dt, tend - t);
+            if (!(dt > dtmin)) { ret = (dt != dt) ? 3 : 2; break; }
+            // stages 2..7 (rolled): g = u + dt sum_j a_ij k_j ; k_i = f(g)
+            double g0 = u0, g1 = u1, g2 = u2;
+#pragma unroll 1
+            for (int st = 0; st < 6; ++st) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q <= st; ++q) {
+                    const double a = SUP_A[st][q];
+                    s0 = fma(a, myK[(q * 3) * B], s0); s1 = fma(a, myK[(q * 3 + 1) * B], s1); s2 = fma(a, myK[(q * 3 + 2) * B], s2);
+                }
+                g0 = fma(dt, s0, u0); g1 = fma(dt, s1, u1); g2 = fma(dt, s2, u2);
+                double f0, f1, f2;
+                SUP_RHS(g0, g1, g2, f0, f1, f2)
+                myK[((st + 1) * 3) * B] = f0; myK[((st + 1) * 3 + 1) * B] = f1; myK[((st + 1) * 3 + 2) * B] = f2;
+            }
+            const double un0 = g0, un1 = g1, un2 = g2;     // the last stage input (row b) is the new state
+            // error estimate
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                e0 = fma(SUP_E[q], myK[(q * 3) * B], e0); e1 = fma(SUP_E[q], myK[(q * 3 + 1) * B], e1); e2 = fma(SUP_E[q], myK[(q * 3 + 2) * B], e2);
+            }
+            e0 = dt * e0 * m_rcp(fma(fmax(fabs(u0), fabs(un0)), reltol, abstol));
+            e1 = dt * e1 * m_rcp(fma(fmax(fabs(u1), fabs(un1)), reltol, abstol));
+            e2 = dt * e2 * m_rcp(fma(fmax(fabs(u2), fabs(un2)), reltol, abstol));
+            const double E2 = (e0 * e0 + e1 * e1 + e2 * e2) / 3.0;
+            if (!(E2 == E2) || !isfinite(un0) || !isfinite(un1) || !isfinite(un2)) { ret = 3; break; }
+            CUDE_TRACE_STEP(t, dt, sqrt(E2))
+            const double lnE = 0.5 * m_log_pos(E2);
+            if (E2 <= 1.0) {
+                const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
+                double tnew = t + dt;
+                if (fabs(tnew - tend) < snap) tnew = tend;
+                while (iobs < M && A.obs_t[iobs] <= tnew) {
+                    const double ts = A.obs_t[iobs];
+                    double y0, y1, y2;
+                    if (ts == tnew) { y0 = un0; y1 = un1; y2 = un2; }
+                    else {
+                        double bw[7];
+                        dense_weights((ts - t) * m_rcp(dt), bw);
+                        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) { d0 = fma(bw[q], myK[(q * 3) * B], d0); d1 = fma(bw[q], myK[(q * 3 + 1) * B], d1); d2 = fma(bw[q], myK[(q * 3 + 2) * B], d2); }
+                        y0 = fma(dt, d0, u0); y1 = fma(dt, d1, u1); y2 = fma(dt, d2, u2);
+                    }
+                    const double r0 = (y0 - yd[(size_t)(iobs * 3) * N]) * A.iscale[0];
+                    const double r1 = (y1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
+                    const double r2 = (y2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
+                    if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
+                    sse += r0 * r0 + r1 * r1 + r2 * r2;
+                    ++iobs;
+                }
+                if (GRAD) {
+                    if (nacc < SUP_REC_CAP) { Rec r; r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2; rec[nacc] = r; }
+                }
+                ++nacc;
+                lnqold = fmax(lnE, -9.210340371976182);
+                dt = fmin(dt * m_rcp(q), dtmax);
+                t = tnew; u0 = un0; u1 = un1; u2 = un2;
+                myK[0] = myK[18 * B]; myK[B] = myK[19 * B]; myK[2 * B] = myK[20 * B];      // FSAL: k1 <- k7
+            } else {
+                ++nrej;
+                dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
+            }
+        }
+        if (ret == 0 && iobs < M) ret = 3;
+        if (GRAD && ret == 0 && nacc > SUP_REC_CAP) ret = 4;      // more accepted steps than the ring holds: not supported (Inf)
+        failed = (ret != 0);
+        if (failed) sse = CUDART_INF;
+
+        if constexpr (GRAD) if (!failed) {
+            // ---------------- discrete adjoint ----------------
+            double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0, t_next = tend;
+            int kobs = M - 1;
+            for (int n = nacc - 1; n >= 0; --n) {
+                const Rec r = rec[n];
+                const double tn = r.t, h = r.h;
+                // replay the stages of step n from u_n, keeping the stage inputs g_1..g_7
+                myG[0] = r.u0; myG[B] = r.u1; myG[2 * B] = r.u2;
+                {
+                    double f0, f1, f2;
+                    SUP_RHS(r.u0, r.u1, r.u2, f0, f1, f2)
+                    myK[0] = f0; myK[B] = f1; myK[2 * B] = f2;
+                }
+#pragma unroll 1
+                for (int st = 0; st < 6; ++st) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                    for (int q = 0; q <= st; ++q) {
+                        const double a = SUP_A[st][q];
+                        s0 = fma(a, myK[(q * 3) * B], s0); s1 = fma(a, myK[(q * 3 + 1) * B], s1); s2 = fma(a, myK[(q * 3 + 2) * B], s2);
+                    }
+                    const double g0 = fma(h, s0, r.u0), g1 = fma(h, s1, r.u1), g2 = fma(h, s2, r.u2);
+                    myG[((st + 1) * 3) * B] = g0; myG[((st + 1) * 3 + 1) * B] = g1; myG[((st + 1) * 3 + 2) * B] = g2;
+                    if (st < 5) {     // k7 itself is not needed by the adjoint (only its input g_7 = u_{n+1})
+                        double f0, f1, f2;
+                        SUP_RHS(g0, g1, g2, f0, f1, f2)
+                        myK[((st + 1) * 3) * B] = f0; myK[((st + 1) * 3 + 1) * B] = f1; myK[((st + 1) * 3 + 2) * B] = f2;
+                    }
+                }
+                // stage adjoints
+#pragma unroll 1
+                for (int q = 0; q < 21; ++q) myKb[q * B] = 0.0;
+                double ub0 = 0.0, ub1 = 0.0, ub2 = 0.0;
+                bool kb7 = false;
+                while (kobs >= 0) {
+                    const double ts = A.obs_t[kobs];
+                    if (!(ts > tn)) break;
+                    const double w0 = 2.0 * myRes[(kobs * 3) * B], w1 = 2.0 * myRes[(kobs * 3 + 1) * B], w2 = 2.0 * myRes[(kobs * 3 + 2) * B];
+                    if (ts == t_next) { lam0 += w0; lam1 += w1; lam2 += w2; }
+                    else {
+                        double bw[7];
+                        dense_weights((ts - tn) * m_rcp(h), bw);
+                        ub0 += w0; ub1 += w1; ub2 += w2;
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) {
+                            const double hb = h * bw[q];
+                            myKb[(q * 3) * B] = fma(w0, hb, myKb[(q * 3) * B]);
+                            myKb[(q * 3 + 1) * B] = fma(w1, hb, myKb[(q * 3 + 1) * B]);
+                            myKb[(q * 3 + 2) * B] = fma(w2, hb, myKb[(q * 3 + 2) * B]);
+                        }
+                        kb7 = true;
+                    }
+                    --kobs;
+                }
+                // stage 7 (k7 = f(u_{n+1}), dense output only), then u_{n+1} = u_n + h sum b_j k_j, then stages 6..1
+#pragma unroll 1
+                for (int st = 6; st >= 0; --st) {
+                    if (st == 6 && !kb7) {
+                        // no interior observation: k7 carries no adjoint
+                    } else {
+                        const double v0 = myKb[(st * 3) * B], v1 = myKb[(st * 3 + 1) * B], v2 = myKb[(st * 3 + 2) * B];
+                        double du[3];
+                        sup_nn_backward<SN>(sW, sTab, c, myG[(st * 3) * B], myG[(st * 3 + 1) * B], myG[(st * 3 + 2) * B], v2 - v1, myAcc, B, du);
+                        // gb = J^T v = [-p1 v0 + p1 v1, 0, -p3 v2] + grad_u(u_hat) (v2 - v1)
+                        const double gb0 = fma(p1, v1 - v0, du[0]), gb1 = du[1], gb2 = fma(-p3, v2, du[2]);
+                        if (st == 6) { lam0 += gb0; lam1 += gb1; lam2 += gb2; }
+                        else {
+                            ub0 += gb0; ub1 += gb1; ub2 += gb2;
+                            for (int q = 0; q < st; ++q) {          // g_{st+1} = u + h sum_{q<st} a_{st+1,q+1} k_{q+1}
+                                const double ha = h * SUP_A[st - 1][q];
+                                myKb[(q * 3) * B] = fma(ha, gb0, myKb[(q * 3) * B]);
+                                myKb[(q * 3 + 1) * B] = fma(ha, gb1, myKb[(q * 3 + 1) * B]);
+                                myKb[(q * 3 + 2) * B] = fma(ha, gb2, myKb[(q * 3 + 2) * B]);
+                            }
+                        }
+                    }
+                    if (st == 6) {
+                        // u_{n+1} = u_n + h sum_{j<=6} b_j k_j
+                        ub0 += lam0; ub1 += lam1; ub2 += lam2;
+                        for (int q = 0; q < 6; ++q) {
+                            const double hb = h * SUP_A[5][q];
+                            myKb[(q * 3) * B] = fma(hb, lam0, myKb[(q * 3) * B]);
+                            myKb[(q * 3 + 1) * B] = fma(hb, lam1, myKb[(q * 3 + 1) * B]);
+                            myKb[(q * 3 + 2) * B] = fma(hb, lam2, myKb[(q * 3 + 2) * B]);
+                        }
+                    }
+                }
+                lam0 = ub0; lam1 = ub1; lam2 = ub2;
+                t_next = tn;
+            }
+            // d sse / d theta = (sum_j dz1_j W1[j,3]) * exp(theta)
+            double db = 0.0;
+#pragma unroll
+            for (int q = 0; q < W; ++q) db = fma(myAcc[(3 * W + q) * B], sW[3 * W + q], db);
+            gtheta = db * etheta;
+        }
+#undef SUP_RHS
+    }
+
+    if (active) {
+        if (A.sse_out) A.sse_out[jt] = sse;
+        if (GRAD && A.g_theta) A.g_theta[jt] = failed ? 0.0 : gtheta * A.theta_scale;
+    }
+    const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
+    if (A.partials) {
+        constexpr int nred = GRAD ? P + 1 : 1;
+        double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
+#pragma unroll 1
+        for (int q = 0; q < nred; ++q) {
+            double v = 0.0;
+            if (active) {
+                if (q == 0) v = sse;
+                else if constexpr (GRAD) { if (!failed) {
+                    const int p = q - 1;      // expand to the SimpleChains layout: W1 is [W x 4] column-major, then b1
+                    if (p < 3 * W) v = myAcc[p * B];                                   // W1[:,0:3]
+                    else if (p < 4 * W) v = myAcc[(3 * W + (p - 3 * W)) * B] * etheta; // W1[:,3]  (exp(theta) column)
+                    else if (p < SN::L1) v = myAcc[(3 * W + (p - 4 * W)) * B];         // b1
+                    else v = myAcc[(4 * W + (p - SN::L1)) * B];                        // hidden + output layers
+                } }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) row[q] = v;
+        }
+    }
+    if (A.counters) {
+        unsigned int ca = active ? (unsigned)nacc : 0u, cr = active ? (unsigned)nrej : 0u, cf = (active && failed) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ca += __shfl_xor_sync(0xffffffffu, ca, o);
+            cr += __shfl_xor_sync(0xffffffffu, cr, o);
+            cf += __shfl_xor_sync(0xffffffffu, cf, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&A.counters[0], (unsigned long long)ca);
+            atomicAdd(&A.counters[1], (unsigned long long)cr);
+            if (cf) atomicAdd(&A.counters[2], (unsigned long long)cf);
+        }
+    }
+}
+
+}  // namespace cude

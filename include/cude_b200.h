@@ -137,6 +137,28 @@ int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net
                   int want_grad, double cond_scale,
                   double* d_sse_out, double* d_sums_out, double* d_g_cond);
 
+/* ---- second variant: the suppression example (suppression/src/suppression_model.jl).
+ * State-dependent cUDE: du1 = -p1 u1; du2 = p1 u1 - NN([u; exp(theta_i)]); du3 = NN(.) - p3 u3  (ude_lsup! :88-95),
+ * network input_dims 4 -> `depth` tanh layers of `width` -> 1 softplus (neural_network_model :78-86; suppression.jl:18
+ * builds depth 5, width 3 = 67 parameters), explicit Tsit5 at default tolerances, all three states observed.
+ *   data   : [3 x n_obs x n_ind] column-major as in Julia (state fastest); u0 of individual i = data[:,1,i] (:99-104)
+ *   obs_t  : [n_obs] common time grid (saveat); tspan = (t0, tend)
+ *   p_true : {p1, p2, p3} (p2 unused by the hybrid model); scale[3] or NULL = mean_i max_t data (:125)            */
+typedef struct cude_sup_population cude_sup_population;
+int cude_sup_population_create(cude_ctx* ctx, int n_ind, int n_obs, const double* obs_t, const double* data,
+                               const double* p_true, const double* scale, double t0, double tend,
+                               cude_sup_population** out);
+int cude_sup_population_destroy(cude_sup_population* pop);
+/* suppression_loss(p, (prob, data, timepoints, lambda)) :117-130 for n_starts parameter sets and its gradient:
+ *   loss_out[s] = sum_i sse_i / N + lambda * sum(neural_s .^ 2)   (Inf if a trajectory failed)
+ *   g_neural[P x n_starts] (may be NULL), g_theta[n_ind x n_starts] (may be NULL => loss only)
+ *   sse_out [n_ind x n_starts] (may be NULL): per-individual scaled SSE
+ * Limitation: the gradient pass keeps at most 64 accepted steps per trajectory (default tolerances take ~25);
+ * a longer trajectory is reported as failed (Inf).                                                              */
+int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth, int width, const cude_opts* opts,
+                       int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
+                       double* sse_out, double* loss_out, double* g_neural, double* g_theta);
+
 /* Test hook: evaluates the kernels' own branch-free FP64 elementary functions on the device
  * (which: 0 tanh, 1 softplus, 2 sigmoid, 3 exp clamped to +-40, 4 log of a positive normal, 5 reciprocal). */
 int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y);

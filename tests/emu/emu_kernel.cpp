@@ -32,6 +32,7 @@ namespace cude { double smem[1 << 16]; }   // the kernel's `extern __shared__ do
 static double* g_trace_buf = nullptr; static int g_trace_cap = 0, g_trace_n = 0;
 #define CUDE_TRACE_STEP(t, dt, eest) if (g_trace_buf && g_trace_n < g_trace_cap) { double* r_ = g_trace_buf + 4 * g_trace_n++; r_[0] = t; r_[1] = dt; r_[2] = eest; r_[3] = (eest <= 1.0) ? 1.0 : 0.0; }
 #include "../../conditional_ude_b200/csrc/cude_kernels.cuh"
+#include "../../conditional_ude_b200/csrc/cude_sup_kernel.cuh"
 
 using namespace cude;
 
@@ -81,6 +82,38 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
 
 extern "C" void emu_set_trace(double* buf, int cap) { g_trace_buf = buf; g_trace_cap = cap; g_trace_n = 0; }
 extern "C" int emu_trace_count(void) { return g_trace_n; }
+// suppression variant: data in Julia layout [3 x n_obs x n_ind]; one thread per block
+extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const double* data, const double* p_true, const double* scale,
+                            double t0, double tend, int n_starts, const double* neural, long long neural_stride, const double* theta,
+                            double abstol, double reltol, int maxiters, int grad,
+                            double* sse, double* g_neural_traj, double* g_theta, unsigned long long* counters) {
+    typedef SupNet<5, 3> SN;
+    const size_t N = n_ind, M = n_obs;
+    std::vector<double> h(M * 3 * N);
+    for (size_t i = 0; i < N; ++i)
+        for (size_t k = 0; k < M; ++k)
+            for (int j = 0; j < 3; ++j) h[(k * 3 + j) * N + i] = data[j + 3 * (k + M * i)];
+    SupArgs a{};
+    a.n_ind = n_ind; a.n_obs = n_obs; a.n_starts = n_starts; a.nchunks = n_ind;
+    a.obs_t = obs_t; a.data = h.data(); a.p1 = p_true[0]; a.p3 = p_true[2];
+    for (int j = 0; j < 3; ++j) a.iscale[j] = 1.0 / scale[j];
+    a.t0 = t0; a.tend = tend; a.neural = neural; a.neural_stride = neural_stride; a.theta = theta;
+    a.abstol = abstol; a.reltol = reltol; a.maxiters = maxiters; a.theta_scale = 1.0;
+    a.sse_out = sse; a.g_theta = g_theta; a.counters = counters;
+    const long long nblocks = (long long)n_ind * n_starts;
+    std::vector<double> partials((size_t)nblocks * (SN::P + 1), 0.0);
+    a.partials = partials.data();
+    blockDim.x = 1; threadIdx.x = 0;
+    for (long long b = 0; b < nblocks; ++b) {
+        blockIdx.x = (int)b;
+        if (grad) cude_sup_kernel<SN, true>(a); else cude_sup_kernel<SN, false>(a);
+    }
+    if (grad && g_neural_traj)
+        for (long long b = 0; b < nblocks; ++b)
+            for (int p = 0; p < SN::P; ++p) g_neural_traj[b * SN::P + p] = partials[b * (SN::P + 1) + 1 + p];
+    return 0;
+}
+
 // elementary functions of cude_math.cuh: 0 tanh, 1 softplus, 2 sigmoid, 3 exp (clamped to +-40), 4 log, 5 rcp
 extern "C" void emu_math(int which, int n, const double* x, double* y) {
     for (int i = 0; i < n; ++i) {

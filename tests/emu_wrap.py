@@ -13,7 +13,8 @@ _I = C.POINTER(C.c_int)
 
 def build():
     src = [os.path.join(_HERE, "emu_kernel.cpp")] + [
-        os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f) for f in ("cude_kernels.cuh", "cude_math.cuh")]
+        os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f)
+        for f in ("cude_kernels.cuh", "cude_math.cuh", "cude_sup_kernel.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in src):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-o", LIB, src[0]])
@@ -48,3 +49,27 @@ def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, gr
                     _dp(sse), _dp(gn), _dp(gc), cnt)
     assert rc == 0
     return dict(sse=sse, g_neural=gn, g_cond=gc, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
+
+
+def emu_sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), scale=None, abstol=1e-6, reltol=1e-3,
+                 maxiters=100000, grad=True):
+    """Suppression variant through the host-compiled kernel source; same conventions as oracle.sup_eval."""
+    L = C.CDLL(build())
+    L.emu_sup_eval.argtypes = [C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_int, _D, C.c_longlong, _D,
+                               C.c_double, C.c_double, C.c_int, C.c_int, _D, _D, _D, C.POINTER(C.c_ulonglong)]
+    data = np.asarray(data, dtype=np.float64)
+    _, n_obs, n_ind = data.shape
+    dj = np.ascontiguousarray(data.transpose(2, 1, 0))
+    ot = np.ascontiguousarray(timepoints, dtype=np.float64)
+    sc = np.ascontiguousarray(data.max(axis=1).mean(axis=1) if scale is None else scale, dtype=np.float64)
+    pt = np.ascontiguousarray(p_true, dtype=np.float64)
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1, n_ind))
+    S, P = theta.shape[0], 67
+    stride = 0 if neural.ndim == 1 else P
+    sse = np.empty((S, n_ind)); gn = np.zeros((S, n_ind, P)); gt = np.zeros((S, n_ind))
+    cnt = (C.c_ulonglong * 3)()
+    rc = L.emu_sup_eval(n_ind, n_obs, _dp(ot), _dp(dj), _dp(pt), _dp(sc), float(ot[0]), float(ot[-1]), S, _dp(neural), stride,
+                        _dp(theta), abstol, reltol, maxiters, int(grad), _dp(sse), _dp(gn), _dp(gt), cnt)
+    assert rc == 0
+    return dict(sse=sse, g_neural=gn, g_theta=gt, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])

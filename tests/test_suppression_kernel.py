@@ -1,0 +1,100 @@
+"""The suppression kernel variant (csrc/cude_sup_kernel.cuh): CPU tier through the host-compiled kernel source,
+GPU tier through the C ABI, both against the oracle (which the reference's stored losses pin)."""
+import numpy as np
+import pytest
+
+import conditional_ude_b200 as cu
+from oracle import oracle
+from helpers import noise_ok
+import emu_wrap
+
+
+@pytest.fixture(scope="module")
+def sup():
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return dict(np.load(os.path.join(here, "tests", "golden", "suppression_fixtures.npz")))
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def _starts(sup, n, seed=0):
+    rng = np.random.default_rng(seed)
+    nns = sup["neural_0p01"][:n] + 0.02 * rng.standard_normal((n, 67))
+    th = rng.uniform(-1, 1, (n, 37))
+    return nns, th
+
+
+def test_emulated_kernel_matches_oracle(sup):
+    data, t = sup["group_data"], sup["timepoints"]
+    nns, th = _starts(sup, 3)
+    g = oracle.sup_eval(data, t, nns, th, with_grad=True)
+    e = emu_wrap.emu_sup_eval(data, t, nns, th)
+    assert noise_ok(np.abs(e["sse"] - g["sse"]) / g["sse"], 1e-5)
+    assert noise_ok(np.abs(e["g_theta"] - g["g_theta"]) / np.abs(g["g_theta"]).max(), 1e-4)
+    assert noise_ok(np.abs(e["g_neural"] - g["g_neural"]) / np.abs(g["g_neural"]).max(axis=-1, keepdims=True), 1e-4)
+    assert e["n_acc"] == g["stats"][..., 0].sum() and e["n_fail"] == 0
+    e0 = emu_wrap.emu_sup_eval(data, t, nns, th, grad=False)
+    assert np.array_equal(e0["sse"], e["sse"])
+    # stored lambda = 1 networks: the reference's own stored losses through the kernel source
+    e1 = emu_wrap.emu_sup_eval(data, t, sup["neural_1p0"][:5], np.zeros((5, 37)), grad=False)
+    loss = e1["sse"].sum(axis=1) / 37 + (sup["neural_1p0"][:5] ** 2).sum(axis=1)
+    assert np.abs(loss / sup["losses_1p0"][:5] - 1).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_stored_reference_losses(sup):
+    """All 25 stored training and validation losses of suppression/results/lambda=1.0.jld2 on the B200."""
+    data, vdata, t, nns = sup["group_data"], sup["validation_data"], sup["timepoints"], sup["neural_1p0"]
+    pop = cu.SuppressionPopulation(data, t)
+    loss = pop.loss(nns, np.zeros((25, 37)), lam=1.0)
+    assert np.abs(loss / sup["losses_1p0"] - 1).max() < 1e-8
+    vpop = cu.SuppressionPopulation(vdata, t)
+    assert np.abs(vpop.loss(nns, np.zeros((25, 30)), lam=0.0) / sup["losses_valid_1p0"] - 1).max() < 1e-8
+    # reference-named entry point
+    p = cu.ComponentVector(neural=nns[0], theta=np.zeros(37))
+    assert abs(cu.suppression_loss(p, (None, data, t, 1.0)) / sup["losses_1p0"][0] - 1) < 1e-8
+    assert cu.neural_network_model(5, 3, input_dims=4).n_params == 67
+
+
+@pytest.mark.gpu
+def test_gpu_loss_and_gradient_match_oracle(sup):
+    data, t = sup["group_data"], sup["timepoints"]
+    nns, th = _starts(sup, 8, seed=1)
+    lam = 0.01
+    pop = cu.SuppressionPopulation(data, t)
+    g = oracle.sup_eval(data, t, nns, th, with_grad=True)
+    loss, gn, gt, sse = pop.loss_grad(nns, th, lam, return_sse=True)
+    assert noise_ok(np.abs(sse - g["sse"]) / g["sse"], 1e-5)
+    ref_loss = g["sse"].sum(axis=1) / 37 + lam * (nns ** 2).sum(axis=1)
+    ref_gn = g["g_neural"].sum(axis=1) / 37 + 2 * lam * nns
+    assert relmax(loss, ref_loss) < 1e-5 and relmax(gn, ref_gn) < 1e-4 and relmax(gt, g["g_theta"] / 37) < 1e-4
+    # shared network (stride 0) and loss-only path
+    l1 = pop.loss(nns[0], th, lam)
+    l2 = pop.loss(np.tile(nns[0], (8, 1)), th, lam)
+    assert np.array_equal(l1, l2) and l1[0] == loss[0]
+    a = pop.loss_grad(nns, th, lam)
+    assert all(np.array_equal(x, y) for x, y in zip(a, (loss, gn, gt)))       # run-to-run determinism
+    # failure: NaN parameter -> Inf loss, zero gradient
+    th2 = th.copy(); th2[3, 5] = np.nan
+    loss, gn, gt = pop.loss_grad(nns, th2, lam)
+    assert np.isinf(loss[3]) and np.all(gn[3] == 0) and np.all(gt[3] == 0) and np.isfinite(np.delete(loss, 3)).all()
+
+
+@pytest.mark.gpu
+def test_gpu_fit_and_validate(sup):
+    """fit_suppression_model / validate_suppression_model in miniature (reference: 10 000 initials, 2000 + 2000 iterations)."""
+    data, vdata, t = sup["group_data"], sup["validation_data"], sup["timepoints"]
+    rng = np.random.default_rng(0)
+    net = cu.neural_network_model(5, 3, input_dims=4)
+    p_init = [cu.ComponentVector(theta=rng.standard_normal(37), neural=net.init_params(rng)) for _ in range(64)]
+    pop = cu.SuppressionPopulation(data, t)
+    sols, traces = cu.fit_suppression_model(p_init, pop, data, t, 0.01, select_best_n=3, adam_iters=40, lbfgs_iters=40)
+    assert len(sols) == 3 and all(s.u.neural.shape == (67,) and s.u.theta.shape == (37,) for s in sols)
+    for s, tr in zip(sols, traces):
+        assert s.objective < tr[0]
+        assert abs(cu.suppression_loss(s.u, (pop, data, t, 0.01)) - s.objective) < 1e-9
+    th, obj = cu.validate_suppression_model([rng.random(30) for _ in range(16)], None, vdata, t, sols[0].u.neural, lbfgs_iters=30)
+    assert th.shape == (30,) and np.isfinite(obj)
