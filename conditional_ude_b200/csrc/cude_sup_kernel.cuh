@@ -179,7 +179,7 @@ __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B
     return (size_t)64 + (size_t)((P + 1) & ~1) + (size_t)(21 + (grad ? 42 + 3 * M + NACC : 0)) * B;
 }
 
-constexpr int SUP_REC_CAP = 64;   // ring of accepted-step records (t, dt, u[3]) per thread, local memory
+constexpr int SUP_REC_CAP = 512;  // accepted-step records (t, dt, u[3]) kept per thread in local memory (20 KB)
 
 template <class SN, bool GRAD>
 __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {

@@ -185,6 +185,9 @@ def lbfgs_batched(f, fg, x0, maxiters=1000, m=10, g_tol=1e-8, lb=None, ub=None, 
         moved = active & ~searching
         stuck = active & searching                  # line search failed: stop this problem (Optim: terminates)
         fnew, gnew = fg(np.where(moved[:, None], xt, x))
+        lost = moved & ~(np.isfinite(fnew) & np.all(np.isfinite(gnew), axis=1))   # value ok but gradient pass failed there
+        moved &= ~lost
+        stuck |= lost
         s_vec = np.where(moved[:, None], xt - x, 0.0)
         y_vec = np.where(moved[:, None], gnew - g, 0.0)
         ys = np.einsum("sd,sd->s", y_vec, s_vec)
