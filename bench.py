@@ -207,7 +207,7 @@ def run_ours(args):
     shard.neural.copy_(neural_p)
     shard.cond.copy_(cond_p)
     d_sums = shard.sums
-    opts = cu.SolverOptions(block=args.block)
+    opts = cu.SolverOptions(block=args.block, precision=args.precision)
 
     def step_resident():
         # loss+gradient kernel -> block-partial reduction into `sums` -> NCCL all-reduce of `sums` (N > 1)
@@ -280,7 +280,8 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.precision == 0 else "f32 network / f64 integrator (NOT the parity-gated mode)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "individuals": N_total, "starts": S, "trajectories_per_step": N_total * S,
                        "abstol": opts.abstol, "reltol": opts.reltol, "network": "chain(4,2,tanh): 37 parameters",
@@ -314,6 +315,7 @@ def main():
     ap.add_argument("--individuals", type=int, default=1_000_000)
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--precision", type=int, default=0, help="0 = FP64 (headline, parity-gated); 1 = FP32 network (looser bound)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-individuals", type=int, default=4000)
     ap.add_argument("--cpu-starts", type=int, default=64)

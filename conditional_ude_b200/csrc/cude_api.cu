@@ -280,12 +280,15 @@ extern "C" int cude_population_size(const cude_population* pop) { return pop ? p
 typedef void (*eval_kernel_t)(const EvalArgs);
 
 template <class NS>
-static eval_kernel_t pick(bool grad) { return grad ? cude_eval_kernel<NS, true> : cude_eval_kernel<NS, false>; }
+static eval_kernel_t pick(bool grad, bool mixed) {
+    if (mixed) return grad ? cude_eval_kernel<NS, true, true> : cude_eval_kernel<NS, false, true>;
+    return grad ? cude_eval_kernel<NS, true, false> : cude_eval_kernel<NS, false, false>;
+}
 
-static eval_kernel_t select_kernel(const cude_net* net, bool grad) {
+static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed) {
     if (net->depth == 2 && net->width == 4) {
-        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad);   // chain(4, 2, tanh), 02-conditional.jl:22
-        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad);   // covariate net, 07-covariate-inclusion.jl:32
+        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed);   // chain(4, 2, tanh), 02-conditional.jl:22
+        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed);   // covariate net, 07-covariate-inclusion.jl:32
     }
     return nullptr;
 }
@@ -308,12 +311,13 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     cude_opts o;
     if (opts_in) o = *opts_in; else cude_default_opts(&o);
     if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad solver options");
-    if (o.precision != 0) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: only precision 0 (FP64) is available");
+    if (o.precision != 0 && o.precision != 1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: precision must be 0 (FP64) or 1 (FP32 network, FP64 integrator)");
+    const bool mixed = o.precision == 1;
     const int P = cude_net_nparams(net);
     if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad network description");
     if (net->n_in == 3 && !pop->dev.cov) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: 3-input network needs a population with a covariate");
     const bool grad = want_grad != 0;
-    eval_kernel_t kern = select_kernel(net, grad);
+    eval_kernel_t kern = select_kernel(net, grad, mixed);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -359,7 +363,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
 
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
-    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, grad);
+    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, grad, mixed);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 

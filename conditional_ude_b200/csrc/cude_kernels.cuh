@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #endif
+#include <type_traits>
 #include "cude_math.cuh"
 
 #ifndef CUDE_TRACE_STEP   // host-emulation test hook; compiles to nothing in the CUDA build
@@ -175,10 +176,11 @@ __constant__ double CN_STEP[5] = {0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
 __constant__ double CN_INIT[5] = {0.0, 1.0, 1.0, 1.0, 1.0};
 
 // forward: returns softplus(z_out) for input dG; c[] = first-layer pre-activation constant part
-template <class NS>
-__device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W], double dG) {
+// R = double (parity-gated FP64 path) or float (precision = 1: FP32 network, FP64 integrator).
+template <class NS, class R>
+__device__ __forceinline__ R mlp_forward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG) {
     constexpr int W = NS::W;
-    double a[W], b[W];
+    R a[W], b[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[j], dG, c[j]), tab);
     int off = NS::L1;
@@ -186,7 +188,7 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
     for (int l = 1; l < NS::DEPTH; ++l) {
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            double z = sW[off + W * W + j];
+            R z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
             b[j] = m_tanh(z, tab);
@@ -195,7 +197,7 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
         for (int j = 0; j < W; ++j) a[j] = b[j];
         off += NS::LH;
     }
-    double z = sW[off + W];
+    R z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
     return m_softplus(z, tab);
@@ -209,11 +211,11 @@ __device__ __forceinline__ double mlp_forward(const double* __restrict__ sW, con
 // serialised on the LDS latency: ncu v2 short_scoreboard); they are parked in shared memory only around a
 // forward replay and for the final block reduction.  Layout:
 // [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
-template <class NS>
-__device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W], double dG, double w,
-                                             double (&g)[NS::NACC]) {
+template <class NS, class R>
+__device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG, R w,
+                                             R (&g)[NS::NACC]) {
     constexpr int W = NS::W, D = NS::DEPTH;
-    double a[D][W];
+    R a[D][W];
 #pragma unroll
     for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[j], dG, c[j]), tab);
     int off = NS::L1;
@@ -221,18 +223,18 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
     for (int l = 1; l < D; ++l) {
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            double z = sW[off + W * W + j];
+            R z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
             a[l][j] = m_tanh(z, tab);
         }
         off += NS::LH;
     }
-    double z = sW[off + W];
+    R z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
-    const double dz = w * m_sigmoid(z, tab);   // d softplus = sigmoid
-    double da[W];
+    const R dz = w * m_sigmoid(z, tab);   // d softplus = sigmoid
+    R da[W];
     int aoff = 2 * W + (D - 1) * NS::LH;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -244,12 +246,12 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
     for (int l = D - 1; l >= 1; --l) {
         off -= NS::LH;
         aoff -= NS::LH;
-        double dzl[W], dprev[W];
+        R dzl[W], dprev[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], 1.0);
+        for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], R(1));
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            double s = 0.0;
+            R s = R(0);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 g[aoff + i * W + j] = fma(dzl[j], a[l - 1][i], g[aoff + i * W + j]);
@@ -262,7 +264,7 @@ __device__ __forceinline__ void mlp_backward(const double* __restrict__ sW, cons
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const double dz1 = da[j] * fma(-a[0][j], a[0][j], 1.0);
+        const R dz1 = da[j] * fma(-a[0][j], a[0][j], R(1));
         g[j] = fma(dz1, dG, g[j]);
         g[W + j] += dz1;
     }
@@ -278,15 +280,16 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 }
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
-__host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad) {
-    return (size_t)64 + (size_t)((P + 1) & ~1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
+__host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false) {
+    return (size_t)64 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
            (size_t)((B + 31) / 32) * (P + 1);
 }
 
-template <class NS, bool GRAD>
+template <class NS, bool GRAD, bool MIXED = false>
 __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const EvalArgs A) {
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
+    typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the network evaluation
     extern __shared__ double smem[];
     const int B = blockDim.x, tid = threadIdx.x;
     const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
@@ -294,7 +297,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     // ---- shared memory carve-up ----
     double* sTab = smem;                             // [64] 2^(j/64) for the exp core
     double* sW = sTab + 64;                          // [P] (padded to even)
-    double* sKt = sW + ((P + 1) & ~1);               // [K][B]
+    R* sWr = MIXED ? reinterpret_cast<R*>(sW + ((P + 1) & ~1)) : reinterpret_cast<R*>(sW);   // network weights as R
+    double* sKt = sW + ((P + 1) & ~1) * (MIXED ? 2 : 1);   // [K][B]  (MIXED: a float copy of the weights sits in between)
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
     double* sNode = sSl + (size_t)K * B;             // [5][B] network outputs (forward) / node weights (adjoint)
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     // ---- stage the start's weights (block-uniform) ----
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
-        for (int p = tid; p < P; p += B) sW[p] = gW[p];
+        for (int p = tid; p < P; p += B) { sW[p] = gW[p]; if (MIXED) sWr[p] = (R)gW[p]; }
         for (int p = tid; p < 64; p += B) sTab[p] = EXP_TAB64[p];
     }
     // ---- stage this thread's knots ----
@@ -365,6 +369,9 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             if (NS::NIN > 2) z = fma(sW[2 * W + q], covv, z);
             c[q] = z;
         }
+        R cr[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) cr[q] = (R)c[q];
 
         const double abstol = A.abstol, reltol = A.reltol;
         const double dtmax = tend - t0;
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
 
         double2 rec[GRAD ? REC_CAP : 1];
-        double acc[GRAD ? NS::NACC : 1];
+        R acc[GRAD ? NS::NACC : 1];
         int stop_at = 0x7fffffff;   // replay limit (GRAD)
         // adjoint carry
         double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 CUDE_UNROLL(CUDE_FWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) myNode[q * B] = mlp_forward<NS>(sW, sTab, c, myNode[q * B]);
+                    if (q < nq) myNode[q * B] = (double)mlp_forward<NS, R>(sWr, sTab, cr, (R)myNode[q * B]);
                 if (init) {
                     // ---- Hairer, part 2: probe f(u0 + dt0 f0, t0 + dt0) ----
                     init = false;
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             if constexpr (GRAD) {
             // accumulators: zero after the first pass, otherwise back from shared memory (parked for the replay)
 #pragma unroll
-            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? 0.0 : myAcc[k * B];
+            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? R(0) : (R)myAcc[k * B];
             // =================== adjoint over steps [lo, stop_at) held in the ring ===================
             // The last chunk appends the virtual step n = -1: the NN([0;beta]) term, one node at dG = 0
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
@@ -619,12 +626,12 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 CUDE_UNROLL(CUDE_BWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) mlp_backward<NS>(sW, sTab, c, myDG[q * B], myNode[q * B], acc);
+                    if (q < nq) mlp_backward<NS, R>(sWr, sTab, cr, (R)myDG[q * B], (R)myNode[q * B], acc);
             }
             stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
             // park the accumulators (for the replay's register budget, or for the block reduction)
 #pragma unroll
-            for (int k = 0; k < NS::NACC; ++k) myAcc[k * B] = acc[k];
+            for (int k = 0; k < NS::NACC; ++k) myAcc[k * B] = (double)acc[k];
             }  // if constexpr (GRAD)
         } while (stop_at > 0);
 

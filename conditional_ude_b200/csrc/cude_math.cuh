@@ -162,6 +162,37 @@ __device__ __forceinline__ double m_log10(double x) {
 }
 __device__ __forceinline__ double m_pow10(double x, const double* __restrict__ tab) { return m_exp_core(m_clamp(x * 2.302585092994046, -700.0, 700.0), tab); }
 
+// ---------------------------------------------------------------- FP32 network math (precision = 1, "mixed")
+// Optional mode with a documented looser bound: the MLP is evaluated in FP32 on the FMA / MUFU pipes
+// (ex2.approx, rcp.approx, lg2.approx: ~1e-7 relative each), the integrator, adjoint and reductions stay FP64.
+#ifdef CUDE_HOST_EMU
+static inline float f_ex2(float x) { return exp2f(x); }
+static inline float f_rcp(float x) { return 1.0f / x; }
+static inline float f_lg2(float x) { return log2f(x); }
+#else
+__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+__device__ __forceinline__ float f_clamp(float x, float lo, float hi) {
+    x = (x < lo) ? lo : x;     // comparisons keep NaN
+    return (x > hi) ? hi : x;
+}
+__device__ __forceinline__ float m_tanh(float x, const double* __restrict__) {
+    const float e = f_ex2(f_clamp(x, -15.0f, 15.0f) * 2.8853900817779268f);     // exp(2x)
+    return fmaf(-2.0f, f_rcp(e + 1.0f), 1.0f);
+}
+__device__ __forceinline__ float m_softplus(float x, const double* __restrict__) {
+    const float e = f_ex2(f_clamp(x, -30.0f, 15.0f) * 1.4426950408889634f);
+    float sp = f_lg2(1.0f + e) * 0.6931471805599453f;
+    sp = (x > 15.0f) ? x : sp;
+    sp = (x > 709.782712893384f) ? (float)CUDART_INF : sp;      // the reference's naive form overflows there
+    return (x != x) ? x : sp;
+}
+__device__ __forceinline__ float m_sigmoid(float x, const double* __restrict__) {
+    return f_rcp(1.0f + f_ex2(f_clamp(-x, -30.0f, 30.0f) * 1.4426950408889634f));
+}
+
 // exp(cond): once per trajectory, full range semantics (Inf / 0 / NaN) from the CUDA library
 __device__ __forceinline__ double m_exp(double x) { return exp(x); }
 

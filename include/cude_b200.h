@@ -54,7 +54,8 @@ typedef struct {
     double abstol;
     double reltol;
     int maxiters;
-    int precision; /* 0 = FP64 (the only parity-gated mode) */
+    int precision; /* 0 = FP64 (the parity-gated mode); 1 = FP32 network evaluation (MUFU ex2/rcp/lg2) with the
+                    * integrator, adjoint and reductions in FP64: looser documented bound, see DESIGN.md */
     int block;     /* threads per block (individuals per tile); 0 = library default */
 } cude_opts;
 

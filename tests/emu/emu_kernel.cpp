@@ -41,7 +41,7 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
                         const double* kin, const double* cov,
                         int n_in, int n_starts, const double* neural, long long neural_stride, const double* cond,
                         double abstol, double reltol, int maxiters, int grad, int flat,
-                        double* sse, double* g_neural_traj, double* g_cond, unsigned long long* counters) {
+                        double* sse, double* g_neural_traj, double* g_cond, unsigned long long* counters, int mixed) {
     const size_t N = n_ind, K = max_knots, M = max_obs;
     std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N), cv(N, 0.0);
     for (size_t i = 0; i < N; ++i) {
@@ -71,7 +71,8 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
     blockDim.x = 1; threadIdx.x = 0;
     for (long long b = 0; b < nblocks; ++b) {
         blockIdx.x = (int)b;
-        if (n_in == 2) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false>(a); }
+        if (mixed) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false, true>(a); }
+        else if (n_in == 2) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false>(a); }
         else { if (grad) cude_eval_kernel<NetShape<3, 2, 4>, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false>(a); }
     }
     if (!flat && grad && g_neural_traj)

@@ -25,10 +25,10 @@ def _dp(a):
     return a.ctypes.data_as(_D) if a is not None else None
 
 
-def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, grad=True, flat=False):
+def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, grad=True, flat=False, mixed=False):
     L = C.CDLL(build())
     L.emu_eval.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.c_int, C.c_int, _D, C.c_longlong, _D,
-                           C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.POINTER(C.c_ulonglong)]
+                           C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.POINTER(C.c_ulonglong), C.c_int]
     ch = packed["chain"]
     N, P = int(packed["n_ind"]), ch.n_params
     a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
@@ -46,7 +46,7 @@ def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, gr
     rc = L.emu_eval(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
                     int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]), _dp(cov),
                     ch.input_dims, S, _dp(neural), stride, _dp(cond), abstol, reltol, maxiters, int(grad), int(flat),
-                    _dp(sse), _dp(gn), _dp(gc), cnt)
+                    _dp(sse), _dp(gn), _dp(gc), cnt, int(mixed))
     assert rc == 0
     return dict(sse=sse, g_neural=gn, g_cond=gc, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
 

@@ -119,3 +119,21 @@ def test_elementary_functions_host_build():
         return y
 
     check_math(fn)
+
+
+def test_mixed_precision_documented_bound(fx):
+    """precision = 1 (FP32 network, FP64 integrator).  FP32 noise in the right-hand side perturbs the step-size
+    control, so the loss agrees with the FP64 path only to the *solver's own tolerance* (reltol 1e-3): documented
+    bound = median 2e-3, 99 % within 5e-2 per trajectory, 2e-3 on a population loss, 1e-2 on population gradients."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    rng = np.random.default_rng(2)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 4)
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0)
+    m = emu_wrap.emu_eval(pk, neural, cond, mixed=True)
+    d = np.abs(m["sse"] - g["sse"]) / g["sse"]
+    assert np.median(d) < 2e-3 and np.percentile(d, 99) < 5e-2
+    assert np.abs(m["sse"].sum(axis=1) / g["sse"].sum(axis=1) - 1).max() < 2e-3
+    gp, mp = g["g_neural"].sum(axis=1), m["g_neural"].sum(axis=1)
+    assert (np.abs(mp - gp) / np.abs(gp).max(axis=1, keepdims=True)).max() < 1e-2
+    assert d.max() > 1e-9          # it really is a different arithmetic

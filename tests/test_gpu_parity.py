@@ -233,3 +233,25 @@ def test_elementary_functions_on_device(ctx):
     """The kernels' branch-free FP64 tanh / softplus / sigmoid / exp / log / reciprocal (MUFU.RCP64H seed +
     one third-order step) evaluated on the B200 against numpy."""
     check_math(lambda which, x: ctx.math_probe(which, x))
+
+
+def test_mixed_precision_option(fx, ctx):
+    """opts.precision = 1 on the device: same documented bound as the emulation test (the FP64 mode stays the
+    parity-gated default)."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(2)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 16)
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0)
+    loss, gn, gc, sse = pop.loss_grad(neural, cond, opts=SolverOptions(precision=1), mean=False, return_sse=True)
+    d = np.abs(sse - g["sse"]) / g["sse"]
+    assert np.median(d) < 2e-3 and np.percentile(d, 99) < 5e-2
+    assert relmax(loss, g["sse"].sum(axis=1)) < 2e-3
+    gp = g["g_neural"].sum(axis=1)
+    assert (np.abs(gn - gp) / np.abs(gp).max(axis=1, keepdims=True)).max() < 1e-2
+    l64 = pop.loss(neural, cond)
+    l32 = pop.loss(neural, cond, opts=SolverOptions(precision=1))
+    assert not np.array_equal(l64, l32) and relmax(l32, l64) < 2e-3
+    with pytest.raises(Exception):
+        pop.loss(neural, cond, opts=SolverOptions(precision=2))
