@@ -137,3 +137,31 @@ def test_mixed_precision_documented_bound(fx):
     gp, mp = g["g_neural"].sum(axis=1), m["g_neural"].sum(axis=1)
     assert (np.abs(mp - gp) / np.abs(gp).max(axis=1, keepdims=True)).max() < 1e-2
     assert d.max() > 1e-9          # it really is a different arithmetic
+
+
+def _ragged_obs_population(fx):
+    """Individuals with different observation grids: interior-only points, points not aligned with knots, a single
+    observation, observations only at the end points."""
+    models, t, c = ohashi_models(fx, "train")
+    grids = [np.array([0.0, 30.0, 60.0, 90.0, 120.0]), np.array([15.0, 47.5, 101.0]), np.array([120.0]),
+             np.array([0.0, 120.0]), np.array([1e-3, 29.999, 30.0, 30.001, 119.5])]
+    ms, ts, ys = [], [], []
+    rng = np.random.default_rng(9)
+    for i in range(20):
+        g = grids[i % len(grids)]
+        ms.append(models[i]); ts.append(g); ys.append(np.interp(g, t, c[i]) + 0.05 * rng.standard_normal(g.size))
+    return ms, ts, ys
+
+
+def test_ragged_observation_grids(fx):
+    ms, ts, ys = _ragged_obs_population(fx)
+    pk = cu.pack_models(ms, ts, ys)
+    assert pk["max_obs"] == 5 and set(pk["n_obs"]) == {1, 2, 3, 5}
+    rng = np.random.default_rng(1)
+    neural, cond = random_starts(rng, pk["chain"], len(ms), 3)
+    for tol in (DET, dict(abstol=1e-6, reltol=1e-3)):
+        g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **tol)
+        e = emu_wrap.emu_eval(pk, neural, cond, **tol)
+        bound = (1e-10, 1e-9) if tol is DET else (1e-5, 1e-3)
+        assert relmax(e["sse"], g["sse"]) < bound[0]
+        assert relmax(e["g_cond"], g["g_cond"]) < bound[1] and relmax(e["g_neural"], g["g_neural"]) < bound[1]

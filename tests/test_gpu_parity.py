@@ -255,3 +255,56 @@ def test_mixed_precision_option(fx, ctx):
     assert not np.array_equal(l64, l32) and relmax(l32, l64) < 2e-3
     with pytest.raises(Exception):
         pop.loss(neural, cond, opts=SolverOptions(precision=2))
+
+
+def test_ragged_observation_grids(fx, ctx):
+    """Per-individual observation grids (interior-only, a single point, end points only, points 1e-3 off a knot)."""
+    from test_emu_kernel import _ragged_obs_population
+    ms, ts, ys = _ragged_obs_population(fx)
+    pk = cu.pack_models(ms, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(1)
+    neural, cond = random_starts(rng, pk["chain"], len(ms), 3)
+    ref = oracle.OraclePopulation(pk)
+    g = ref.eval(neural, cond, grad_mode=0, **DET)
+    loss, gn, gc, sse = pop.loss_grad(neural, cond, opts=SolverOptions(**DET), mean=False, return_sse=True)
+    assert relmax(sse, g["sse"]) < 1e-10 and relmax(gc, g["g_cond"]) < 1e-9 and relmax(gn, g["g_neural"].sum(axis=1)) < 1e-9
+    g = ref.eval(neural, cond, grad_mode=0)
+    loss, gn, gc, sse = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    assert relmax(sse, g["sse"]) < 1e-5 and relmax(gc, g["g_cond"]) < 1e-3
+
+
+def test_abi_error_paths(fx, ctx):
+    """Argument validation of the C ABI: negative status + message, no exception across the boundary, no crash."""
+    import ctypes as C
+    from conditional_ude_b200 import _lib
+    models, t, c, nn, betas = train57(fx)
+    pk = cu.pack_models(models[:4], t, c[:4])
+    bad = dict(pk); bad["knot_t"] = pk["knot_t"].copy(); bad["knot_t"][1, 2] = bad["knot_t"][1, 1]        # not increasing
+    with pytest.raises(_lib.CudeError) as ei:
+        cu.Population(packed=bad, ctx=ctx)
+    assert ei.value.code == _lib.CUDE_EINVAL and "increasing" in str(ei.value)
+    bad = dict(pk); bad["obs_t"] = pk["obs_t"].copy(); bad["obs_t"][0, 4] = 500.0                          # outside tspan
+    with pytest.raises(_lib.CudeError) as ei:
+        cu.Population(packed=bad, ctx=ctx)
+    assert ei.value.code == _lib.CUDE_EINVAL and "outside" in str(ei.value)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    with pytest.raises(ValueError):
+        pop.loss(nn[:30], betas[None, :4])                                                                # wrong parameter count
+    with pytest.raises(_lib.CudeError) as ei:
+        pop.loss(nn, betas[None, :4], opts=SolverOptions(reltol=-1.0))
+    assert ei.value.code == _lib.CUDE_EINVAL
+    with pytest.raises(_lib.CudeError) as ei:
+        pop.loss(nn, betas[None, :4], opts=SolverOptions(block=48))
+    assert ei.value.code == _lib.CUDE_EINVAL
+    # a network shape that is not compiled in: explicit EUNSUPPORTED, not a silent fallback
+    lib = _lib.load()
+    net = _lib.cude_net(2, 3, 8)
+    o = SolverOptions().c()
+    out = np.empty(1)
+    w = np.zeros(lib.cude_net_nparams(C.byref(net)))
+    rc = lib.cude_loss(ctx.handle, pop.handle, C.byref(net), C.byref(o), 1, w.ctypes.data_as(_lib._D), 0,
+                       betas[:4].copy().ctypes.data_as(_lib._D), None, out.ctypes.data_as(_lib._D))
+    assert rc == _lib.CUDE_EUNSUPPORTED and b"not compiled" in lib.cude_last_error(ctx.handle)
+    # still usable afterwards
+    assert np.isfinite(pop.loss(nn, betas[None, :4])[0])
