@@ -258,6 +258,12 @@ def run_ours(args):
     n_acc, n_rej, n_fail, n_traj = [float(x) for x in cnt.tolist()]
     loss0 = (d_sums[:, 0] / N_total).cpu().numpy()
 
+    # secondary figure (not the headline): loss-only throughput of the same batch (screening / profile workloads)
+    def step_loss_only():
+        shard.step(opts, want_grad=False)
+    step_loss_only()
+    loss_only_value = N_total * S / (timed(step_loss_only, 2) / 2 * 1e-3)
+
     # end-to-end through host buffers (pinned): H2D of the step's inputs + D2H of its results every step
     for _ in range(2):
         step_e2e()
@@ -287,7 +293,8 @@ def run_ours(args):
                        "abstol": opts.abstol, "reltol": opts.reltol, "network": "chain(4,2,tanh): 37 parameters",
                        "sharding": f"individuals over {world} rank(s); all-reduce of {S}x{P + 1} f64",
                        "l2": "inputs larger than L2 (cond + g_cond = %.0f MB per rank)" % (2 * S * n_loc * 8 / 1e6),
-                       "n_fail": n_fail, "mean_loss_start0": float(loss0[0])},
+                       "n_fail": n_fail, "mean_loss_start0": float(loss0[0]),
+                       "loss_only_evals_per_s": loss_only_value},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e},
