@@ -274,6 +274,7 @@ def run_ours(args):
 
     # roofline of the dominant kernel (cude_eval_kernel<..., GRAD>): FP64 CUDA-core pipe
     peak = ctx.fp64_peak_tflops()
+    peak_rrr = ctx.fp64_peak_tflops(register_operands=True)
     fl, tr = alg_flops(n_traj / world, n_acc / world, n_rej / world, grad=True)   # per launch (one rank)
     kernel_s = float(kms.item()) * 1e-3
     achieved = (fl + tr) / kernel_s / 1e12
@@ -281,6 +282,11 @@ def run_ours(args):
                 "traffic": None, "kernel": "cude_eval_kernel<NetShape<2,2,4>,GRAD>", "kernel_ms": float(kms.item()),
                 "alg_flops_per_traj": fl / (n_traj / world), "alg_transcendentals_per_traj": tr / (n_traj / world),
                 "peak_source": "measured live: DFMA micro-benchmark (cude_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_register_operands": peak_rrr,
+                "note": "peak = DFMA chains whose other operands come from the uniform path (upper bound); "
+                        "peak_register_operands = DFMA with three register operands, the shape of real code. One FP64 "
+                        "tanh/exp/log costs 10-22 DFMA-class instructions but counts once in `achieved`; ncu "
+                        "(profiles/) shows the FP64 pipe 52 % active.",
                 "n_acc_per_traj": n_acc / n_traj, "n_rej_per_traj": n_rej / n_traj}
 
     if rank == 0:

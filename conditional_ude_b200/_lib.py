@@ -61,6 +61,7 @@ SYMBOLS = {
     "cude_eval_dev": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _P, C.c_longlong, _P,
                                 C.c_int, C.c_double, _P, _P, _P]),
     "cude_measure_fp64_peak": (C.c_int, [_P, _D]),
+    "cude_measure_fp64_peak_rrr": (C.c_int, [_P, _D]),
     "cude_math_probe": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "cude_sup_population_create": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.POINTER(_P)]),
     "cude_sup_population_destroy": (C.c_int, [_P]),

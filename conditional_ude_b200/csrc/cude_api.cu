@@ -652,3 +652,29 @@ extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
     *tflops = best;
     return CUDE_OK;
 }
+
+// diagnostic: DFMA rate with three register operands per instruction
+extern "C" int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    int rc = ensure(ctx, ctx->scratch, (size_t)threads * blocks * sizeof(double));
+    if (rc) return rc;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        cude_dfma_peak_rrr_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch.p, iters, 0.999999, 1e-9);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double tf = 2.0 * 64.0 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->stats_pending = false;
+    *tflops = best;
+    return CUDE_OK;
+}

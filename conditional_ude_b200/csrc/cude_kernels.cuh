@@ -757,4 +757,20 @@ __global__ void cude_dfma_peak_kernel(double* out, int iters, double a, double b
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// Same, but every DFMA takes three distinct *register* operands (the shape of real code: the chains above read
+// two of their operands from the uniform/constant path).  Diagnostic for the roofline discussion.
+__global__ void cude_dfma_peak_rrr_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    double y0 = a + 1e-9 * threadIdx.x, y1 = y0 + 1e-10, y2 = y0 + 2e-10, y3 = y0 + 3e-10;
+    double z0 = b + 1e-12 * threadIdx.x, z1 = z0 + 1e-13, z2 = z0 + 2e-13, z3 = z0 + 3e-13;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, y0, z0); x1 = fma(x1, y1, z1); x2 = fma(x2, y2, z2); x3 = fma(x3, y3, z3);
+            x4 = fma(x4, y0, z1); x5 = fma(x5, y1, z2); x6 = fma(x6, y2, z3); x7 = fma(x7, y3, z0);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace cude

@@ -69,9 +69,11 @@ class Context:
         _lib.check(self._lib.cude_math_probe(self._h, int(which), x.size, _dptr(x), _dptr(y)), self._h)
         return y
 
-    def fp64_peak_tflops(self):
+    def fp64_peak_tflops(self, register_operands=False):
+        """Measured DFMA peak; register_operands=True uses three distinct register operands per DFMA (diagnostic)."""
         v = C.c_double()
-        _lib.check(self._lib.cude_measure_fp64_peak(self._h, C.byref(v)), self._h)
+        fn = self._lib.cude_measure_fp64_peak_rrr if register_operands else self._lib.cude_measure_fp64_peak
+        _lib.check(fn(self._h, C.byref(v)), self._h)
         return v.value
 
 

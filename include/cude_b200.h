@@ -167,6 +167,8 @@ int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y)
 /* Measured FP64 FMA peak of the context's device (dependent-chain-free DFMA micro-benchmark),
  * the denominator of the roofline.  Returns TFLOP/s in *tflops. */
 int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops);
+/* Diagnostic: the same with three distinct register operands per DFMA (register-file-bandwidth bound shape). */
+int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }
