@@ -130,6 +130,14 @@ def cpu_baseline(n_ind, n_starts, threads, seed=7):
     return n_ind * n_starts / dt, dt, r
 
 
+def host_threads():
+    """Host cores this process may use (affinity mask), independent of OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation cannot run (Julia is absent from the image),
     so this arm times the oracle port of it on all host cores; each step is a bounded sample."""
@@ -137,7 +145,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()       # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     n_ind, n_starts = args.ref_individuals, args.ref_starts
     pk = synthetic_population(n_ind, 7)
     neural, cond = synthetic_starts(n_ind, n_starts, 11, 8)
@@ -308,8 +316,7 @@ def run_ours(args):
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle
-            threads = oracle.max_threads()
+            threads = host_threads()
             v, secs, _ = cpu_baseline(args.cpu_individuals, args.cpu_starts, threads)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{args.cpu_individuals} individuals x {args.cpu_starts} starts, {secs:.1f} s "
