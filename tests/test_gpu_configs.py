@@ -1,0 +1,105 @@
+"""GPU tier: BASELINE.json's configurations at their full sizes.  Each is checked (a) against the oracle on a random
+subsample of its trajectories and (b) through size-independent properties (determinism, path equivalence, sums)."""
+import numpy as np
+import pytest
+
+import conditional_ude_b200 as cu
+from conditional_ude_b200 import SolverOptions
+from oracle import oracle
+from helpers import train57, mixed_population, ohashi_models, noise_ok
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cu.Context(0)
+
+
+def _subsample_check(pk, neural, cond, sse, gcond, rng, n=1500, shared=False):
+    """Oracle on n random (start, individual) pairs of a big batch."""
+    S, N = cond.shape
+    ss, ii = rng.integers(0, S, n), rng.integers(0, N, n)
+    # evaluate pair k as a 1-start problem on a population of the picked individuals (one pair per 'individual')
+    sub = {k: (v[ii] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in pk.items()}
+    sub["n_ind"] = n
+    op = oracle.OraclePopulation(sub)
+    if shared:
+        r = op.eval(neural, cond[ss, ii][None], grad_mode=0 if gcond is not None else -1)
+        want, wantg = r["sse"][0], (r["g_cond"][0] if gcond is not None else None)
+    else:
+        # distinct networks: group by start
+        want, wantg = np.empty(n), np.empty(n)
+        for s in np.unique(ss):
+            m = ss == s
+            subs = {k: (v[ii[m]] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in pk.items()}
+            subs["n_ind"] = int(m.sum())
+            r = oracle.OraclePopulation(subs).eval(neural[s], cond[s, ii[m]][None], grad_mode=0 if gcond is not None else -1)
+            want[m] = r["sse"][0]
+            if gcond is not None:
+                wantg[m] = r["g_cond"][0]
+    got = sse[ss, ii]
+    assert noise_ok(np.abs(got - want) / want, 1e-5)
+    if gcond is not None:
+        assert noise_ok(np.abs(gcond[ss, ii] - wantg) / np.abs(wantg).max(), 1e-4)
+
+
+def test_config2_beta_only_137_individuals_x_1000_starts(fx, ctx):
+    """configs[1]: beta-only estimation, NN fixed, all Ohashi + Fujita individuals x 1000 starts (loss + d/dbeta)."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    nn = fx["cude_neural"][int(fx["cude_best_model_index"]) - 1]
+    rng = np.random.default_rng(0)
+    cond = rng.uniform(-4.0, 1.0, size=(1000, 137))                     # LBFGS bounds, parameter-estimation.jl:275-276
+    loss, gn, gc, sse = pop.loss_grad(nn, cond, neural_grad=False, mean=False, return_sse=True)
+    assert ctx.stats()["n_traj"] == 137000 and ctx.stats()["n_fail"] == 0 and np.isfinite(sse).all()
+    a = pop.loss_grad(nn, cond, neural_grad=False, mean=False, return_sse=True)
+    assert np.array_equal(a[3], sse) and np.array_equal(a[2], gc)                     # determinism
+    assert np.allclose(loss, sse.sum(axis=1), rtol=1e-13)
+    # flat (shared-network) path == tile path on a slice of the starts
+    l2, gn2, gc2 = pop.loss_grad(nn, cond[:16], neural_grad=True, mean=False)
+    assert np.array_equal(gc2, gc[:16]) and np.array_equal(l2, loss[:16])
+    _subsample_check(pk, nn, cond, sse, gc, rng, shared=True)
+
+
+def test_config3_screening_57_individuals_x_25000_guesses(fx, ctx):
+    """configs[2], screening stage of `train` (:360-366): 25 000 Glorot/LHS guesses x 57 individuals, loss only,
+    then the selected starts with gradients."""
+    models, t, c, nn, betas = train57(fx)
+    pk = cu.pack_models(models, t, c)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(1)
+    neural = np.stack(cu.initial_parameters(pop.chain, 25_000, rng=rng))
+    cond = cu.initial_parameters(57, -2.0, 0.0, 25_000, rng).T
+    loss, sse = pop.loss(neural, cond, return_sse=True)
+    assert ctx.stats()["n_traj"] == 57 * 25_000 and np.isfinite(loss).all()
+    assert np.allclose(loss, sse.mean(axis=1), rtol=1e-13)
+    best = np.argsort(loss, kind="stable")[:25]
+    lg, gn, gc, sse_g = pop.loss_grad(neural[best], cond[best], return_sse=True)
+    assert np.array_equal(sse_g, sse[best]) and np.array_equal(lg, loss[best])        # same forward pass in both kernels
+    _subsample_check(pk, neural, cond, sse, None, rng, n=800)
+
+
+def test_config4_profiles_117_individuals_x_1000_grid_points(fx, ctx):
+    """configs[3]: likelihood profiles over beta for all Ohashi individuals (02-conditional.jl:371-377), one launch."""
+    m1, t, c1 = ohashi_models(fx, "train")
+    m2, _, c2 = ohashi_models(fx, "test")
+    models, c = m1 + m2, np.vstack([c1, c2])
+    pk = cu.pack_models(models, t, c)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    nn = fx["cude_neural"][int(fx["cude_best_model_index"]) - 1]
+    fit = cu.train(pop, t, c, nn, initial_beta=-1.0, lbfgs_lower_bound=-6.0, lbfgs_upper_bound=1.0, lbfgs_iterations=60)
+    bhat = np.array([s.u[0] for s in fit])
+    nll, nll_min, grid = cu.likelihood_profile_population(bhat, nn, pop, bhat - 10.0, bhat + 10.0, 0.1, steps=1000)
+    assert nll.shape == (1000, 117) and grid.shape == (1000, 117) and np.isfinite(nll).all()
+    # the fitted beta is (close to) the profile minimum of its individual
+    assert np.mean(nll_min <= nll.min(axis=0) + 0.05 * np.maximum(1.0, nll.min(axis=0))) > 0.9
+    # single-individual entry point == column of the population profile
+    i = 11
+    n1, m1_, g1 = cu.likelihood_profile(bhat[i], nn, models[i], t, c[i], bhat[i] - 10.0, bhat[i] + 10.0, 0.1, steps=1000)
+    assert np.array_equal(g1, grid[:, i]) and np.array_equal(n1, nll[:, i]) and m1_ == nll_min[i]
+    lo, hi = cu.find_confidence_intervals(nll[:, i], nll_min[i], grid[:, i])
+    assert lo < bhat[i] < hi
+    rng = np.random.default_rng(2)
+    _subsample_check(pk, nn, np.vstack([bhat[None], grid]), np.vstack([nll_min[None], nll]) * (2 * 0.1 ** 2), None, rng, n=1000, shared=True)
