@@ -59,7 +59,7 @@ def test_config2_beta_only_137_individuals_x_1000_starts(fx, ctx):
     assert np.allclose(loss, sse.sum(axis=1), rtol=1e-13)
     # flat (shared-network) path == tile path on a slice of the starts
     l2, gn2, gc2 = pop.loss_grad(nn, cond[:16], neural_grad=True, mean=False)
-    assert np.array_equal(gc2, gc[:16]) and np.array_equal(l2, loss[:16])
+    assert np.array_equal(gc2, gc[:16]) and np.allclose(l2, loss[:16], rtol=1e-13)   # sums in a different (fixed) order
     _subsample_check(pk, nn, cond, sse, gc, rng, shared=True)
 
 
