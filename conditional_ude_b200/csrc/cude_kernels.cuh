@@ -21,8 +21,10 @@
 // Per block: the start's MLP weights are staged once in shared memory (block-uniform broadcast
 // reads), each thread's glucose knots are staged in shared memory ([k][tid], conflict-free), state,
 // stages, adjoint and the gradient accumulators live in registers.
-// Reduction: per-thread gradients -> warp shuffles -> one partial row per block ->
+// Reduction: per-thread gradients -> warp shuffles -> one partial row per warp ->
 // deterministic second-stage kernel (no atomics on the data path).
+// Measured tuning notes (B200, profiles/): unrolling the node loops (CUDE_FWD_UNROLL / CUDE_BWD_UNROLL > 1) and
+// keeping activations for the adjoint were both slower; 3 resident blocks per SM (168 registers) beat 2 and 4.
 // =====================================================================================
 #pragma once
 #ifndef CUDE_HOST_EMU   // tests/emu compiles this file with g++ behind a shim (CI without a GPU)
@@ -281,8 +283,8 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
 __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false) {
-    return (size_t)64 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0) +
-           (size_t)((B + 31) / 32) * (P + 1);
+    // exp table + weights (+ float copy) + per-thread rows: knots 3K, node values 5, GRAD: dG 5 + residuals M + parked accumulators
+    return (size_t)64 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0);
 }
 
 template <class NS, bool GRAD, bool MIXED = false>
@@ -305,7 +307,6 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD)
     double* sRes = sDG + (GRAD ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
     double* sAcc = sRes + (GRAD ? (size_t)M * B : 0);           // [NACC][B] gradient accumulators (GRAD)
-    double* sRed = sAcc + (GRAD ? (size_t)NS::NACC * B : 0);    // [nwarps][P+1]
 
     // ---- which trajectory ----
     long long j;
