@@ -211,7 +211,7 @@ def run_ours(args):
     cond_p = torch.from_numpy(cond_h).pin_memory()
     gcond_p = torch.empty((S, n_loc), dtype=torch.float64).pin_memory()
     sums_p = torch.empty((S, P + 1), dtype=torch.float64).pin_memory()
-    shard = DevicePopulationShard(pop, N_total, S, dev)      # device tensors + kernel/reduce/all-reduce sequence
+    shard = DevicePopulationShard(pop, N_total, S, dev, stream=stream)      # device tensors + kernel/reduce/all-reduce sequence
     shard.neural.copy_(neural_p)
     shard.cond.copy_(cond_p)
     d_sums = shard.sums

@@ -63,6 +63,8 @@ SYMBOLS = {
     "cude_measure_fp64_peak": (C.c_int, [_P, _D]),
     "cude_measure_fp64_peak_rrr": (C.c_int, [_P, _D]),
     "cude_math_probe": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "cude_adam_dev": (C.c_int, [_P, C.c_longlong, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                C.c_double, _P, C.c_longlong, C.c_longlong]),
     "cude_sup_population_create": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.POINTER(_P)]),
     "cude_sup_population_destroy": (C.c_int, [_P]),
     "cude_sup_loss_grad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, C.c_double,

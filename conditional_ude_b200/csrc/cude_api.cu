@@ -626,6 +626,23 @@ extern "C" int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x,
     return CUDE_OK;
 }
 
+// ---------------------------------------------------------------- device-resident Adam step
+extern "C" int cude_adam_dev(cude_ctx* ctx, long long n, double* d_x, const double* d_g, double* d_m, double* d_v,
+                             double lr, double beta1, double beta2, double eps, int t, double grad_scale,
+                             const double* d_row_flag, long long row_len, long long flag_stride) {
+    if (!ctx || !d_x || !d_g || !d_m || !d_v || n < 1 || t < 1) return fail(ctx, CUDE_EINVAL, "cude_adam_dev: bad argument");
+    if (d_row_flag && (row_len < 1 || flag_stride < 1)) return fail(ctx, CUDE_EINVAL, "cude_adam_dev: bad row description");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const double b1t = std::pow(beta1, t), b2t = std::pow(beta2, t);
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_adam_dev: too many elements");
+    cude_adam_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(n, d_x, d_g, d_m, d_v, lr, beta1, beta2, eps, b1t, b2t, grad_scale,
+                                                                     d_row_flag, row_len, flag_stride);
+    CU_TRY(ctx, cudaGetLastError());
+    return CUDE_OK;
+}
+
 // ---------------------------------------------------------------- FP64 peak
 extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return CUDE_EINVAL;

@@ -745,6 +745,27 @@ __global__ void cude_math_probe_kernel(int which, int n, const double* __restric
     y[i] = r;
 }
 
+// Adam update on device-resident parameters (Optimisers.Adam: m, v moments, bias correction through the running
+// powers b1t = beta1^t, b2t = beta2^t): x -= lr * (m/(1-b1t)) / (sqrt(v/(1-b2t)) + eps).  `scale` multiplies the raw
+// gradient (e.g. 1/N for sums of per-individual gradients).  With `rows` > 0 the gradient of row r is skipped when
+// ok[r] == 0 (a start whose loss is Inf keeps its parameters, like the host optimiser).
+__global__ void cude_adam_kernel(long long n, double* __restrict__ x, const double* __restrict__ g, double* __restrict__ m,
+                                 double* __restrict__ v, double lr, double beta1, double beta2, double eps, double b1t, double b2t,
+                                 double scale, const double* __restrict__ row_flag, long long row_len, long long flag_stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (row_flag) {
+        const double f = row_flag[(i / row_len) * flag_stride];
+        if (!(f - f == 0.0)) return;           // Inf / NaN loss: leave this start untouched
+    }
+    const double gi = g[i] * scale;
+    const double mi = fma(beta1, m[i], (1.0 - beta1) * gi);
+    const double vi = fma(beta2, v[i], (1.0 - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    x[i] -= lr * (mi / (1.0 - b1t)) / (sqrt(vi / (1.0 - b2t)) + eps);
+}
+
 // FP64 FMA peak micro-benchmark: 8 independent DFMA chains per thread.
 __global__ void cude_dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -57,25 +57,64 @@ class DevicePopulationShard:
     (loss+gradient kernel -> deterministic block-partial reduction into `sums` -> NCCL all-reduce of
     `sums` in place on the same stream)."""
 
-    def __init__(self, population, n_total, n_starts, device, group=None):
+    def __init__(self, population, n_total, n_starts, device, group=None, stream=None):
         import torch
         self.torch = torch
         self.pop, self.n_total, self.S, self.group = population, int(n_total), int(n_starts), group
         self.P = population.n_params
         self.n_loc = population.n_ind
+        # one explicit stream for the kernels, the torch ops on the shard's tensors and the NCCL ordering
+        cur = torch.cuda.current_stream(device)
+        self.stream = stream or (cur if cur.cuda_stream != 0 else torch.cuda.Stream(device=device))
+        population.ctx.set_stream(self.stream.cuda_stream)
         f64 = dict(dtype=torch.float64, device=device)
-        self.neural = torch.empty((self.S, self.P), **f64)
-        self.cond = torch.empty((self.S, self.n_loc), **f64)
-        self.sums = torch.zeros((self.S, self.P + 1), **f64)
-        self.g_cond = torch.empty((self.S, self.n_loc), **f64)
+        with torch.cuda.stream(self.stream):
+            self.neural = torch.empty((self.S, self.P), **f64)
+            self.cond = torch.empty((self.S, self.n_loc), **f64)
+            self.sums = torch.zeros((self.S, self.P + 1), **f64)
+            self.g_cond = torch.empty((self.S, self.n_loc), **f64)
 
     def step(self, opts=None, want_grad=True):
         """Asynchronous: after it returns the stream holds kernel + reduction + all-reduce."""
-        self.pop.eval_dev(self.S, self.neural.data_ptr(), self.P, self.cond.data_ptr(), 3 if want_grad else 0,
-                          1.0 / self.n_total, 0, self.sums.data_ptr(), self.g_cond.data_ptr() if want_grad else 0, opts)
-        allreduce_sums(self.sums, self.group)
+        with self.torch.cuda.stream(self.stream):
+            self.pop.eval_dev(self.S, self.neural.data_ptr(), self.P, self.cond.data_ptr(), 3 if want_grad else 0,
+                              1.0 / self.n_total, 0, self.sums.data_ptr(), self.g_cond.data_ptr() if want_grad else 0, opts)
+            allreduce_sums(self.sums, self.group)
         return self.sums
+
+    # ---- device-resident Adam (population-scale training: the N x S conditional parameters stay in HBM) ----
+    def adam_init(self):
+        t = self.torch
+        self._adam_t = 0
+        with t.cuda.stream(self.stream):
+            self._m_n, self._v_n = t.zeros_like(self.neural), t.zeros_like(self.neural)
+            self._m_c, self._v_c = t.zeros_like(self.cond), t.zeros_like(self.cond)
+
+    def adam_step(self, lr=1e-2, beta=(0.9, 0.999), eps=1e-8, opts=None):
+        """One training iteration of the population loss (parameter-estimation.jl:126-140 + Optimisers.Adam), all
+        starts in lock-step, no host synchronisation: loss+gradient kernel, partial reduction, all-reduce of the
+        [S x (P+1)] sums, Adam on the (replicated) network weights and on this rank's conditional parameters."""
+        from . import _lib
+        import ctypes as C
+        if not hasattr(self, "_adam_t"):
+            self.adam_init()
+        self.step(opts)                       # sums[:, 0] = sum sse, sums[:, 1:] = sum d sse/d neural (global after all-reduce)
+        self._adam_t += 1
+        lib, h = self.pop.ctx._lib, self.pop.ctx.handle
+        p = lambda x: C.c_void_p(x.data_ptr())
+        flag = C.c_void_p(self.sums.data_ptr())
+        # network weights: gradient rows live inside `sums` (stride P+1) -> contiguous copy, scaled by 1/N_total
+        with self.torch.cuda.stream(self.stream):
+            g_n = self.sums[:, 1:].contiguous()
+        _lib.check(lib.cude_adam_dev(h, g_n.numel(), p(self.neural), p(g_n), p(self._m_n), p(self._v_n), lr, beta[0], beta[1], eps,
+                                     self._adam_t, 1.0 / self.n_total, flag, self.P, self.P + 1), h)
+        # conditional parameters of this shard: g_cond already carries the 1/N_total factor
+        _lib.check(lib.cude_adam_dev(h, self.g_cond.numel(), p(self.cond), p(self.g_cond), p(self._m_c), p(self._v_c), lr, beta[0],
+                                     beta[1], eps, self._adam_t, 1.0, flag, self.n_loc, self.P + 1), h)
 
     def result(self):
         """(loss[S], g_neural[S,P]) on the host; synchronises."""
-        return finalize_sums(self.sums.cpu().numpy(), self.n_total)
+        with self.torch.cuda.stream(self.stream):
+            h = self.sums.cpu()
+        self.stream.synchronize()
+        return finalize_sums(h.numpy(), self.n_total)

@@ -160,6 +160,16 @@ int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth,
                        int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
                        double* sse_out, double* loss_out, double* g_neural, double* g_theta);
 
+/* Device-resident Adam step (Optimisers.Adam(eta, (beta1, beta2), eps), `_optimize` step 1,
+ * src/parameter-estimation.jl:170-183) for population-scale training, where the parameter vector (one beta per
+ * individual per start) never leaves HBM:  g <- grad_scale * d_g;  m, v moments;  x -= lr * mhat / (sqrt(vhat) + eps)
+ * with bias correction for iteration t >= 1.  Asynchronous on the context stream.  If d_row_flag is given, element i
+ * belongs to row i / row_len and is skipped when d_row_flag[row * flag_stride] is not finite (a start whose loss is
+ * Inf keeps its parameters). */
+int cude_adam_dev(cude_ctx* ctx, long long n, double* d_x, const double* d_g, double* d_m, double* d_v,
+                  double lr, double beta1, double beta2, double eps, int t, double grad_scale,
+                  const double* d_row_flag, long long row_len, long long flag_stride);
+
 /* Test hook: evaluates the kernels' own branch-free FP64 elementary functions on the device
  * (which: 0 tanh, 1 softplus, 2 sigmoid, 3 exp clamped to +-40, 4 log of a positive normal, 5 reciprocal). */
 int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y);

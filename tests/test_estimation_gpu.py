@@ -67,3 +67,41 @@ def test_multi_start_training_decreases_loss(fx):
     for s in sols:
         assert s.u.neural.shape == (37,) and s.u.conditional.shape == (57,)
         assert abs(cu.loss(s.u, (models, t, c)) - s.objective) < 1e-9
+
+
+def test_device_resident_adam_matches_host_adam(fx):
+    """Population-scale training keeps the [S x N] conditional parameters in HBM: DevicePopulationShard.adam_step
+    (loss+gradient kernel -> reduction -> Adam kernels, no host round trip) must follow the host adam_batched
+    trajectory on the same problem."""
+    import torch
+    from conditional_ude_b200.distributed import DevicePopulationShard
+    models, t, c, nn, betas = train57(fx)
+    ctx = cu.Context(0)
+    pop = cu.Population(models, t, c, ctx=ctx)
+    rng = np.random.default_rng(3)
+    S, P, N = 5, 37, 57
+    neural0 = nn[None] + 0.05 * rng.standard_normal((S, P))
+    cond0 = np.tile(betas, (S, 1)) + 0.2 * rng.standard_normal((S, N))
+    shard = DevicePopulationShard(pop, N, S, torch.device("cuda", 0))
+    with torch.cuda.stream(shard.stream):
+        shard.neural.copy_(torch.from_numpy(neural0))
+        shard.cond.copy_(torch.from_numpy(cond0))
+    iters = 25
+    for _ in range(iters):
+        shard.adam_step(lr=1e-2)
+    loss_dev, _ = shard.result()                                   # loss at iterate `iters - 1` (before the last update)
+    shard.stream.synchronize()
+    x_dev = np.concatenate([shard.neural.cpu().numpy(), shard.cond.cpu().numpy()], axis=1)
+
+    # host reference of the same recursion (no best-iterate bookkeeping): plain Adam on pop.loss_grad
+    x = np.concatenate([neural0, cond0], axis=1)
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    for it in range(1, iters + 1):
+        l, gn, gc = pop.loss_grad(x[:, :P], x[:, P:])
+        g = np.concatenate([gn, gc], axis=1)
+        m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+        x = x - 1e-2 * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    assert np.abs(x_dev - x).max() < 1e-6               # same trajectory up to the adaptive solve's noise floor
+    assert np.allclose(loss_dev, l, rtol=1e-6)
+    l0 = pop.loss(neural0, cond0)
+    assert np.all(loss_dev < l0)
