@@ -371,6 +371,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
     kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
     CU_TRY(ctx, cudaGetLastError());
     int launches = 1;
@@ -575,6 +576,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
     kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
     CU_TRY(ctx, cudaGetLastError());
     {
@@ -612,13 +614,14 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
 
 // ---------------------------------------------------------------- elementary-function probe (tests)
 extern "C" int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y) {
-    if (!ctx || !x || !y || n < 1 || which < 0 || which > 5) return fail(ctx, CUDE_EINVAL, "cude_math_probe: bad argument");
+    if (!ctx || !x || !y || n < 1 || which < 0 || which > 9) return fail(ctx, CUDE_EINVAL, "cude_math_probe: bad argument");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = ensure(ctx, ctx->scratch, 2 * (size_t)n * sizeof(double));
     if (rc) return rc;
     double* dx = (double*)ctx->scratch.p;
     double* dy = dx + n;
     CU_TRY(ctx, cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    (void)cudaGetLastError();
     cude_math_probe_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which, n, dx, dy);
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaMemcpyAsync(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -637,6 +640,7 @@ extern "C" int cude_adam_dev(cude_ctx* ctx, long long n, double* d_x, const doub
     const int threads = 256;
     const long long blocks = (n + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_adam_dev: too many elements");
+    (void)cudaGetLastError();
     cude_adam_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(n, d_x, d_g, d_m, d_v, lr, beta1, beta2, eps, b1t, b2t, grad_scale,
                                                                      d_row_flag, row_len, flag_stride);
     CU_TRY(ctx, cudaGetLastError());
@@ -655,6 +659,7 @@ extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        (void)cudaGetLastError();
         cude_dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch.p, iters, 0.999999, 1e-9);
         CU_TRY(ctx, cudaGetLastError());
         CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -682,6 +687,7 @@ extern "C" int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        (void)cudaGetLastError();
         cude_dfma_peak_rrr_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch.p, iters, 0.999999, 1e-9);
         CU_TRY(ctx, cudaGetLastError());
         CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -177,49 +177,92 @@ struct Knots {
 __constant__ double CN_STEP[5] = {0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
 __constant__ double CN_INIT[5] = {0.0, 1.0, 1.0, 1.0, 1.0};
 
-// forward: returns softplus(z_out) for input dG; c[] = first-layer pre-activation constant part
+// Output-unit pre-activation z_out for input dG; c[] = first-layer pre-activation constant part.  The softplus is
+// applied by the caller to the 5 nodes of a step at once (one dependent chain per node: batching them gives the
+// scheduler 5-way ILP; inside the rolled loop it was a serial tail with 5x the stall samples per instruction, ncu v6).
 // R = double (parity-gated FP64 path) or float (precision = 1: FP32 network, FP64 integrator).
-template <class NS, class R>
-__device__ __forceinline__ R mlp_forward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG) {
+template <class NS>
+__device__ __forceinline__ double mlp_zout(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W], double dG) {
     constexpr int W = NS::W;
-    R a[W], b[W];
+    int nanmax = 0;
+    double a[W], b[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[j], dG, c[j]), tab);
+    for (int j = 0; j < W; ++j) a[j] = t_tanh(fma(sW[j], dG, c[j]), tab, nanmax);
     int off = NS::L1;
 #pragma unroll
     for (int l = 1; l < NS::DEPTH; ++l) {
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            R z = sW[off + W * W + j];
+            double z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
+            b[j] = t_tanh(z, tab, nanmax);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) a[j] = b[j];
+        off += NS::LH;
+    }
+    double z = sW[off + W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
+    return t_nan_inject(z, nanmax);
+}
+template <class NS>
+__device__ __forceinline__ float mlp_zout(const float* __restrict__ sW, const double* __restrict__ tab, const float (&c)[NS::W], float dG) {
+    constexpr int W = NS::W;
+    float a[W], b[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[j] = m_tanh(fmaf(sW[j], dG, c[j]), tab);
+    int off = NS::L1;
+#pragma unroll
+    for (int l = 1; l < NS::DEPTH; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            float z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fmaf(sW[off + i * W + j], a[i], z);
             b[j] = m_tanh(z, tab);
         }
 #pragma unroll
         for (int j = 0; j < W; ++j) a[j] = b[j];
         off += NS::LH;
     }
-    R z = sW[off + W];
+    float z = sW[off + W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
-    return m_softplus(z, tab);
+    for (int i = 0; i < W; ++i) z = fmaf(sW[off + i], a[i], z);
+    return z;
+}
+// softplus of z_out and d = 1 + exp(z_out) (kept per accepted step for the adjoint: d softplus = 1 - 1/d)
+__device__ __forceinline__ void softplus_d(double z, bool /*mixed*/, const double* __restrict__ tab, double& sp, double& d) { t_softplus_d(z, tab, sp, d); }
+__device__ __forceinline__ void softplus_d_mixed(double z, const double* __restrict__ tab, double& sp, double& d) {
+    const float x = (float)z;
+    sp = (double)m_softplus(x, tab);
+    d = 1.0 + (double)f_ex2(f_clamp(x, -30.0f, 30.0f) * 1.4426950408889634f);
 }
 
-// forward + backward at one time node with scalar seed w: acc += w * d softplus(z_out)/d(params).
-// The activations are recomputed: keeping them from the forward pass (9 doubles per node, ~7 KB per
-// trajectory in local memory) was measured slower on B200 (1.05e8 vs 1.30e8 evals/s) — the footprint of
-// all resident threads exceeds L2 and the kernel has too few warps to hide the HBM latency.
+// Adjoint at one time node: acc += dz * d z_out/d(params), dz = (node weight) * (1 - 1/d).  The hidden activations are
+// recomputed (8 tanh): keeping them from the forward pass (9 doubles per node, ~7 KB per trajectory in local memory)
+// was measured slower on B200 (1.05e8 vs 1.30e8 evals/s) — the footprint of all resident threads exceeds L2 and the
+// kernel has too few warps to hide the HBM latency; only d (5 doubles per step, 45 MB over all resident threads) is kept.
 // The accumulators g[] stay in registers during the adjoint sweep (updating them in shared memory
 // serialised on the LDS latency: ncu v2 short_scoreboard); they are parked in shared memory only around a
 // forward replay and for the final block reduction.  Layout:
 // [0,W) dW1[:,0]; [W,2W) sum dz1; then per hidden layer LH; then W+1 output.
+template <class R>
+struct TanhEval;
+template <>
+struct TanhEval<double> { static __device__ __forceinline__ double f(double x, const double* tab, int& nm) { return t_tanh(x, tab, nm); } };
+template <>
+struct TanhEval<float> { static __device__ __forceinline__ float f(float x, const double* tab, int&) { return m_tanh(x, tab); } };
+
 template <class NS, class R>
-__device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG, R w,
+__device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG, R dz,
                                              R (&g)[NS::NACC]) {
     constexpr int W = NS::W, D = NS::DEPTH;
+    int nanmax = 0;   // the forward pass succeeded on the same inputs: nothing to re-inject here
     R a[D][W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[j], dG, c[j]), tab);
+    for (int j = 0; j < W; ++j) a[0][j] = TanhEval<R>::f(fma(sW[j], dG, c[j]), tab, nanmax);
     int off = NS::L1;
 #pragma unroll
     for (int l = 1; l < D; ++l) {
@@ -228,14 +271,10 @@ __device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const dou
             R z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
-            a[l][j] = m_tanh(z, tab);
+            a[l][j] = TanhEval<R>::f(z, tab, nanmax);
         }
         off += NS::LH;
     }
-    R z = sW[off + W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
-    const R dz = w * m_sigmoid(z, tab);   // d softplus = sigmoid
     R da[W];
     int aoff = 2 * W + (D - 1) * NS::LH;
 #pragma unroll
@@ -283,8 +322,8 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
 __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false) {
-    // exp table + weights (+ float copy) + per-thread rows: knots 3K, node values 5, GRAD: dG 5 + residuals M + parked accumulators
-    return (size_t)64 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0);
+    // exp table (256) + weights (+ float copy) + per-thread rows: knots 3K, node values 5, GRAD: dG 5 + residuals M + parked accumulators
+    return (size_t)256 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0);
 }
 
 template <class NS, bool GRAD, bool MIXED = false>
@@ -297,8 +336,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
 
     // ---- shared memory carve-up ----
-    double* sTab = smem;                             // [64] 2^(j/64) for the exp core
-    double* sW = sTab + 64;                          // [P] (padded to even)
+    double* sTab = smem;                             // [256] 2^(j/256) for the exp core
+    double* sW = sTab + 256;                         // [P] (padded to even)
     R* sWr = MIXED ? reinterpret_cast<R*>(sW + ((P + 1) & ~1)) : reinterpret_cast<R*>(sW);   // network weights as R
     double* sKt = sW + ((P + 1) & ~1) * (MIXED ? 2 : 1);   // [K][B]  (MIXED: a float copy of the weights sits in between)
     double* sKg = sKt + (size_t)K * B;               // [K][B]
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
         for (int p = tid; p < P; p += B) { sW[p] = gW[p]; if (MIXED) sWr[p] = (R)gW[p]; }
-        for (int p = tid; p < 64; p += B) sTab[p] = EXP_TAB64[p];
+        for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     }
     // ---- stage this thread's knots ----
     const int nk = A.pop.n_knots[i];
@@ -380,7 +419,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         const double dtmin = fmax(nextafter(at0, CUDART_INF) - at0, nextafter(at1, CUDART_INF) - at1);
         const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
 
-        double2 rec[GRAD ? REC_CAP : 1];
+        double rec[GRAD ? REC_CAP * 7 : 1];   // accepted-step records {t, dt, d[5] = 1 + exp(z_out) at the step's nodes}
+        double d_nn0 = 1.0;                   // d at the node t0, dG = 0: the NN([0;beta]) term
         R acc[GRAD ? NS::NACC : 1];
         int stop_at = 0x7fffffff;   // replay limit (GRAD)
         // adjoint carry
@@ -442,24 +482,32 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 CUDE_UNROLL(CUDE_FWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) myNode[q * B] = (double)mlp_forward<NS, R>(sWr, sTab, cr, (R)myNode[q * B]);
+                    if (q < nq) myNode[q * B] = (double)mlp_zout<NS>(sWr, sTab, cr, (R)myNode[q * B]);
+                // softplus of the 5 nodes together (init: entries >= nq hold dG values — evaluated and ignored)
+                double sp[5], dd[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    if (MIXED) softplus_d_mixed(myNode[q * B], sTab, sp[q], dd[q]);
+                    else t_softplus_d(myNode[q * B], sTab, sp[q], dd[q]);
+                }
                 if (init) {
                     // ---- Hairer, part 2: probe f(u0 + dt0 f0, t0 + dt0) ----
                     init = false;
-                    nn0 = myNode[0];                              // network([0; beta]) — identical at every call
-                    const double pe = myNode[B] - nn0;
+                    nn0 = sp[0];                                  // network([0; beta]) — identical at every call
+                    d_nn0 = dd[0];
+                    const double pe = sp[1] - nn0;
                     double f0, f1;
                     kinetics(Kc, fma(dt0, k10, u0), fma(dt0, k11, u1), pe, f0, f1);
                     const double x0 = (f0 - k10) * isk0, x1 = (f1 - k11) * isk1;
                     const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
                     const double dm = fmax(d1, d2);
-                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
+                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : t_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
                     dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
                     if (!(isfinite(dt) && isfinite(k10) && isfinite(k11) && isfinite(f0) && isfinite(nn0))) ret = 3;
                     continue;
                 }
-                const double p2 = myNode[0] - nn0, p3 = myNode[B] - nn0, p4 = myNode[2 * B] - nn0,
-                             p5 = myNode[3 * B] - nn0, p6 = myNode[4 * B] - nn0;   // p6: stages 6, 7 and the next k1
+                const double p2 = sp[0] - nn0, p3 = sp[1] - nn0, p4 = sp[2] - nn0,
+                             p5 = sp[3] - nn0, p6 = sp[4] - nn0;   // p6: stages 6, 7 and the next k1
                 // ---- stages: the kinetics are linear, the production enters additively ----
                 double f0, f1, g0, g1;
                 g0 = fma(dt * a21, k10, u0); g1 = fma(dt * a21, k11, u1);
@@ -490,7 +538,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 //      E2 == 0 gives ln = -690 -> q saturates at 1/qmax like the reference's explicit branch ----
                 const double lnE = 0.5 * m_log_pos(E2);
                 if (E2 <= 1.0) {
-                    const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
+                    const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, t_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
                     double tnew = t + dt;
                     if (fabs(tnew - tend) < snap) tnew = tend;
                     // saveat by dense output: observation times in (t, tnew]
@@ -509,14 +557,19 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                         ++iobs;
                         next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
                     }
-                    if (GRAD) rec[na % REC_CAP] = make_double2(t, dt);
+                    if (GRAD) {
+                        double* const r7 = rec + (na % REC_CAP) * 7;
+                        r7[0] = t; r7[1] = dt;
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) r7[2 + q] = dd[q];
+                    }
                     ++na;
                     lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
                     dt = fmin(dt * m_rcp(q), dtmax);               // q in [1/qmax, 1/qmin]
                     t = tnew; u0 = un0; u1 = un1; k10 = k70; k11 = k71;   // FSAL
                 } else {
                     ++nr;
-                    dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
+                    dt = dt * m_rcp(fmin(1.0 / qmin, t_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
                 }
             }
             if (first_pass) {
@@ -538,18 +591,23 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
             const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
             const int nlast = (lo == 0) ? -1 : lo;
-            double2 rnext = rec[(stop_at - 1) % REC_CAP];        // step records are fetched one step ahead
+            double rn_t = rec[((stop_at - 1) % REC_CAP) * 7], rn_h = rec[((stop_at - 1) % REC_CAP) * 7 + 1];   // (t, dt) fetched one step ahead
             for (int n = stop_at - 1; n >= nlast; --n) {
                 int nq;
                 const double* cn;
                 double tn, h;
                 if (n < 0) {
                     nq = 1; cn = CN_INIT; tn = t0; h = 0.0;
-                    myNode[0] = -wsum;
+                    myNode[0] = -wsum * fma(-1.0, m_rcp(d_nn0), 1.0);
                 } else {
-                    const double2 r2 = rnext;
-                    if (n > lo) rnext = rec[(n - 1) % REC_CAP];
-                    tn = r2.x; h = r2.y;
+                    tn = rn_t; h = rn_h;
+                    double dd[5];                                  // needed after the stage recursion: the loads overlap it
+                    {
+                        const double* const r7 = rec + (n % REC_CAP) * 7;
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) dd[q] = r7[2 + q];
+                    }
+                    if (n > lo) { rn_t = rec[((n - 1) % REC_CAP) * 7]; rn_h = rec[((n - 1) % REC_CAP) * 7 + 1]; }
                     nq = 5; cn = CN_STEP;
                     double kb[7][2];
 #pragma unroll
@@ -612,7 +670,10 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     (void)hg0; (void)hg1;
                     // node weights, in CN_STEP order; node tn+h serves stages 6, 7 and the next step's stage 1
                     const double w6 = pb6 + pb7 + wnode;
-                    myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
+                    // dz = node weight * d softplus(z_out) = w * (1 - 1/d)
+                    myNode[0] = pb2 * fma(-1.0, m_rcp(dd[0]), 1.0); myNode[B] = pb3 * fma(-1.0, m_rcp(dd[1]), 1.0);
+                    myNode[2 * B] = pb4 * fma(-1.0, m_rcp(dd[2]), 1.0); myNode[3 * B] = pb5 * fma(-1.0, m_rcp(dd[3]), 1.0);
+                    myNode[4 * B] = w6 * fma(-1.0, m_rcp(dd[4]), 1.0);
                     wsum += w6 + pb5 + pb4 + pb3 + pb2;
                     wnode = pb1;
                     lam0 = ub0; lam1 = ub1;
@@ -725,24 +786,33 @@ __global__ void cude_sum_sse(const double* __restrict__ sse, int n_ind, int n_st
     if (lane == 0) sums[(size_t)s * np1] = v;
 }
 
-// elementary-function probe (tests): 0 tanh, 1 softplus, 2 sigmoid, 3 exp (clamped to +-40), 4 log, 5 rcp
+// elementary-function probe (tests).  c-peptide kernel (256-entry table): 0 tanh, 1 softplus, 2 d softplus = 1 - 1/d,
+// 3 exp (clamped to +-40), 4 log, 5 rcp; suppression kernel (64-entry table): 6 tanh, 7 softplus, 8 sigmoid, 9 exp
+__device__ __forceinline__ double cude_math_probe_eval(int which, double v, const double* t256, const double* t64) {
+    double r, d;
+    int nm = 0;
+    switch (which) {
+        case 0: r = t_tanh(v, t256, nm); r = t_nan_inject(r, nm); break;
+        case 1: t_softplus_d(v, t256, r, d); break;
+        case 2: t_softplus_d(v, t256, r, d); r = fma(-1.0, m_rcp(d), 1.0); break;
+        case 3: r = t_exp_sat(v, t256); break;
+        case 4: r = m_log_pos(v); break;
+        case 5: r = m_rcp(v); break;
+        case 6: r = m_tanh(v, t64); break;
+        case 7: r = m_softplus(v, t64); break;
+        case 8: r = m_sigmoid(v, t64); break;
+        default: r = m_exp_sat(v, t64); break;
+    }
+    return r;
+}
 __global__ void cude_math_probe_kernel(int which, int n, const double* __restrict__ x, double* __restrict__ y) {
-    __shared__ double sTab[64];
-    for (int p = threadIdx.x; p < 64; p += blockDim.x) sTab[p] = EXP_TAB64[p];
+    __shared__ double sTab[256 + 64];
+    for (int p = threadIdx.x; p < 256; p += blockDim.x) sTab[p] = EXP_TAB256[p];
+    for (int p = threadIdx.x; p < 64; p += blockDim.x) sTab[256 + p] = EXP_TAB64[p];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double v = x[i];
-    double r;
-    switch (which) {
-        case 0: r = m_tanh(v, sTab); break;
-        case 1: r = m_softplus(v, sTab); break;
-        case 2: r = m_sigmoid(v, sTab); break;
-        case 3: r = m_exp_sat(v, sTab); break;
-        case 4: r = m_log_pos(v); break;
-        default: r = m_rcp(v); break;
-    }
-    y[i] = r;
+    y[i] = cude_math_probe_eval(which, x[i], sTab, sTab + 256);
 }
 
 // Adam update on device-resident parameters (Optimisers.Adam: m, v moments, bias correction through the running

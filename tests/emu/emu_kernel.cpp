@@ -115,17 +115,8 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
     return 0;
 }
 
-// elementary functions of cude_math.cuh: 0 tanh, 1 softplus, 2 sigmoid, 3 exp (clamped to +-40), 4 log, 5 rcp
+// elementary functions of cude_math.cuh (ids as in cude_math_probe_eval)
 extern "C" void emu_math(int which, int n, const double* x, double* y) {
-    for (int i = 0; i < n; ++i) {
-        switch (which) {
-            case 0: y[i] = m_tanh(x[i], EXP_TAB64); break;
-            case 1: y[i] = m_softplus(x[i], EXP_TAB64); break;
-            case 2: y[i] = m_sigmoid(x[i], EXP_TAB64); break;
-            case 3: y[i] = m_exp_sat(x[i], EXP_TAB64); break;
-            case 4: y[i] = m_log_pos(x[i]); break;
-            default: y[i] = m_rcp(x[i]); break;
-        }
-    }
+    for (int i = 0; i < n; ++i) y[i] = cude_math_probe_eval(which, x[i], EXP_TAB256, EXP_TAB64);
 }
 extern "C" int emu_rec_cap(void) { return REC_CAP; }
