@@ -34,6 +34,9 @@ struct cude_ctx {
     double* h_sums = nullptr;   // pinned
     size_t h_sums_cap = 0;
     unsigned long long* h_counters = nullptr;  // pinned [3]
+    const void* carve_kern = nullptr;   // last kernel configuration whose shared-memory carve-out was set
+    size_t carve_smem = 0;
+    int carve_block = 0;
 };
 
 struct cude_population {
@@ -366,6 +369,18 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, grad, mixed);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((const void*)kern != ctx->carve_kern || smem != ctx->carve_smem || B != ctx->carve_block) {
+        // Shared-memory carve-out = what the resident blocks need and no more: the rest of the 256 KB stays L1, which
+        // serves the per-thread step ring and the register spills of the gradient kernel.
+        int nb = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kern, B, smem));
+        if (nb < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: kernel does not fit on an SM with this block size");
+        const size_t need = (size_t)nb * (smem + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        ctx->carve_kern = (const void*)kern; ctx->carve_smem = smem; ctx->carve_block = B;
+    }
 
     CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))

@@ -322,8 +322,13 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
 __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false) {
-    // exp table (256) + weights (+ float copy) + per-thread rows: knots 3K, node values 5, GRAD: dG 5 + residuals M + parked accumulators
-    return (size_t)256 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + (size_t)3 * K * B + (size_t)5 * B + (grad ? (size_t)(5 + M + NACC) * B : 0);
+    // exp table (256) + weights (+ float copy) + per-thread rows: knots 3K, observations 2M, node values 5, GRAD: dG 5 + residuals M.
+    // Kept small on purpose: what shared memory does not take stays L1, which serves the per-thread step ring and the
+    // register spills (ncu v8: with 65 KB per block the L1 hit rate was 12 % and every spill reload went to L2).
+    // GRAD: at least NACC rows — the accumulators are parked in the (then dead) rows for the final warp reduction.
+    size_t rows = (size_t)(3 * K + 2 * M) + 5 + (grad ? (size_t)(5 + M) : 0);
+    if (grad && rows < (size_t)NACC) rows = (size_t)NACC;
+    return (size_t)256 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + rows * B;
 }
 
 template <class NS, bool GRAD, bool MIXED = false>
@@ -342,10 +347,11 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     double* sKt = sW + ((P + 1) & ~1) * (MIXED ? 2 : 1);   // [K][B]  (MIXED: a float copy of the weights sits in between)
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
-    double* sNode = sSl + (size_t)K * B;             // [5][B] network outputs (forward) / node weights (adjoint)
+    double* sOt = sSl + (size_t)K * B;               // [M][B] observation times
+    double* sOy = sOt + (size_t)M * B;               // [M][B] observed c-peptide
+    double* sNode = sOy + (size_t)M * B;             // [5][B] network outputs (forward) / node weights (adjoint)
     double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD)
     double* sRes = sDG + (GRAD ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
-    double* sAcc = sRes + (GRAD ? (size_t)M * B : 0);           // [NACC][B] gradient accumulators (GRAD)
 
     // ---- which trajectory ----
     long long j;
@@ -377,6 +383,11 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         sKg[k * B + tid] = A.pop.knot_g[(size_t)k * N + i];
         if (k < nk - 1) sSl[k * B + tid] = A.pop.slope[(size_t)k * N + i];
     }
+    const int nobs = A.pop.n_obs[i];
+    for (int k = 0; k < nobs; ++k) {
+        sOt[k * B + tid] = A.pop.obs_t[(size_t)k * N + i];
+        sOy[k * B + tid] = A.pop.obs_y[(size_t)k * N + i];
+    }
     __syncthreads();
 
     double sse = 0.0, gcond = 0.0;
@@ -384,7 +395,11 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     bool failed = false;
     double beta = 0.0, covv = 0.0;
     double* const myNode = sNode + tid;
-    double* const myAcc = sAcc + tid;
+    // gradient accumulators (compressed layout, see mlp_backward): registers for the whole adjoint sweep and the
+    // warp reduction at the end; zero for inactive / failed lanes
+    // After the solve the thread's knot / observation / node rows are dead: its gradient accumulators are parked there
+    // ([k][tid], >= NACC rows by eval_smem_doubles) for the rolled warp reduction at the end.
+    double* const myAcc = sKt + tid;
     double* const myDG = sDG + tid;
 
     if (active) {
@@ -395,9 +410,8 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
         kn.t = sKt + tid; kn.g = sKg + tid; kn.sl = sSl + tid; kn.nk = nk; kn.stride = B;
         kn.g0 = kn.g[0];
         const double t0 = kn.t[0], tend = kn.t[(nk - 1) * B];
-        const int nobs = A.pop.n_obs[i];
-        const double* obs_t = A.pop.obs_t + i;
-        const double* obs_y = A.pop.obs_y + i;
+        const double* const obs_t = sOt + tid;
+        const double* const obs_y = sOy + tid;
 
         // conditional_production: beta = exp(cond); first-layer constant part
         beta = m_exp(A.cond[j]);
@@ -421,12 +435,14 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
 
         double rec[GRAD ? REC_CAP * 7 : 1];   // accepted-step records {t, dt, d[5] = 1 + exp(z_out) at the step's nodes}
         double d_nn0 = 1.0;                   // d at the node t0, dG = 0: the NN([0;beta]) term
-        R acc[GRAD ? NS::NACC : 1];
+        R acc[GRAD ? NS::NACC : 1];           // gradient accumulators (compressed layout, see mlp_backward): registers during the adjoint sweep
+        volatile double park[GRAD ? NS::NACC : 1];   // ... local memory across a forward replay (solves longer than REC_CAP
+                                                     // steps: rare); volatile keeps it out of the register allocation
         int stop_at = 0x7fffffff;   // replay limit (GRAD)
         // adjoint carry
         double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
         int kobs_top = nobs - 1;
-        double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;   // time of observation kobs_top
+        double top_ot = (nobs > 0) ? obs_t[(nobs - 1) * B] : -CUDART_INF;   // time of observation kobs_top
         bool first_pass = true;
 
         do {
@@ -438,11 +454,11 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             double next_ot = (nobs > 0) ? obs_t[0] : CUDART_INF;
             // save_start: observations at (or before) t0 see u0
             while (iobs < nobs && next_ot <= t0) {
-                const double r = u0 - obs_y[(size_t)iobs * N];
+                const double r = u0 - obs_y[iobs * B];
                 if (GRAD) sRes[iobs * B + tid] = r;
                 fsse = fma(r, r, fsse);
                 ++iobs;
-                next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
+                next_ot = (iobs < nobs) ? obs_t[iobs * B] : CUDART_INF;
             }
             // production at t0 is NN([0;beta]) - NN([0;beta]) = 0 exactly (dG(t0) = 0)
             double k10, k11;
@@ -551,11 +567,11 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                             const double sdo = fma(bw[0], k10, fma(bw[1], k20, fma(bw[2], k30, fma(bw[3], k40, fma(bw[4], k50, fma(bw[5], k60, bw[6] * k70))))));
                             y = fma(dt, sdo, u0);
                         }
-                        const double r = y - obs_y[(size_t)iobs * N];
+                        const double r = y - obs_y[iobs * B];
                         if (GRAD) sRes[iobs * B + tid] = r;
                         fsse = fma(r, r, fsse);
                         ++iobs;
-                        next_ot = (iobs < nobs) ? obs_t[(size_t)iobs * N] : CUDART_INF;
+                        next_ot = (iobs < nobs) ? obs_t[iobs * B] : CUDART_INF;
                     }
                     if (GRAD) {
                         double* const r7 = rec + (na % REC_CAP) * 7;
@@ -583,9 +599,9 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
             first_pass = false;
             if (!GRAD || failed) break;
             if constexpr (GRAD) {
-            // accumulators: zero after the first pass, otherwise back from shared memory (parked for the replay)
+            // accumulators: zero after the first pass, otherwise back from local memory (parked for the replay)
 #pragma unroll
-            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? R(0) : (R)myAcc[k * B];
+            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? R(0) : (R)park[k];
             // =================== adjoint over steps [lo, stop_at) held in the ring ===================
             // The last chunk appends the virtual step n = -1: the NN([0;beta]) term, one node at dG = 0
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                             for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
                         }
                         --kobs_top;
-                        top_ot = (kobs_top >= 0) ? obs_t[(size_t)kobs_top * N] : -CUDART_INF;
+                        top_ot = (kobs_top >= 0) ? obs_t[kobs_top * B] : -CUDART_INF;
                     }
                     // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
                     const double pb7 = kb[6][0];
@@ -691,9 +707,13 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                     if (q < nq) mlp_backward<NS, R>(sWr, sTab, cr, (R)myDG[q * B], (R)myNode[q * B], acc);
             }
             stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
-            // park the accumulators (for the replay's register budget, or for the block reduction)
+            if (stop_at > 0) {   // park the accumulators for the replay's register budget
 #pragma unroll
-            for (int k = 0; k < NS::NACC; ++k) myAcc[k * B] = (double)acc[k];
+                for (int k = 0; k < NS::NACC; ++k) park[k] = (double)acc[k];
+            } else {             // done: hand them to the warp reduction through the thread's (now dead) shared rows
+#pragma unroll
+                for (int k = 0; k < NS::NACC; ++k) myAcc[k * B] = (double)acc[k];
+            }
             }  // if constexpr (GRAD)
         } while (stop_at > 0);
 
