@@ -122,6 +122,9 @@ struct NetShape {
     static constexpr int NACC = 2 * W + (DEPTH - 1) * LH + W + 1;
 };
 
+#ifndef CUDE_MAX_THREADS
+#define CUDE_MAX_THREADS 128  // largest block the kernel is launched with (opts.block <= this)
+#endif
 #ifndef CUDE_MIN_BLOCKS
 #define CUDE_MIN_BLOCKS 3   // resident 128-thread blocks per SM the register allocation is tuned for
 #endif
@@ -328,11 +331,12 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
     // GRAD: at least NACC rows — the accumulators are parked in the (then dead) rows for the final warp reduction.
     size_t rows = (size_t)(3 * K + 2 * M) + 5 + (grad ? (size_t)(5 + M) : 0);
     if (grad && rows < (size_t)NACC) rows = (size_t)NACC;
+    if (grad && rows < (size_t)P + 1) rows = (size_t)P + 1;   // expanded rows {sse, d/d neural[0..P)} for the warp reduction
     return (size_t)256 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + rows * B;
 }
 
 template <class NS, bool GRAD, bool MIXED = false>
-__global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const EvalArgs A) {
+__global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_kernel(const EvalArgs A) {
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
     typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the network evaluation
@@ -524,26 +528,39 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
                 }
                 const double p2 = sp[0] - nn0, p3 = sp[1] - nn0, p4 = sp[2] - nn0,
                              p5 = sp[3] - nn0, p6 = sp[4] - nn0;   // p6: stages 6, 7 and the next k1
-                // ---- stages: the kinetics are linear, the production enters additively ----
+                // ---- stages: the kinetics are linear, the production enters additively.  "Push" form: as soon as a stage
+                //      derivative k_j exists it is added to the partial sums of every later stage, so the dependent chain per
+                //      stage is sum-update -> g -> kinetics (5 DFMA) instead of a j-term sum (ncu v9: this region ran at
+                //      6.6 cycles per instruction on fixed-latency waits) ----
                 double f0, f1, g0, g1;
+                double s30 = a31 * k10, s31 = a31 * k11, s40 = a41 * k10, s41 = a41 * k11, s50 = a51 * k10, s51 = a51 * k11,
+                       s60 = a61 * k10, s61 = a61 * k11, sb0 = b1 * k10, sb1 = b1 * k11, se0 = e1 * k10, se1 = e1 * k11;
                 g0 = fma(dt * a21, k10, u0); g1 = fma(dt * a21, k11, u1);
                 double k20, k21; kinetics(Kc, g0, g1, p2, k20, k21);
-                g0 = fma(dt, fma(a31, k10, a32 * k20), u0); g1 = fma(dt, fma(a31, k11, a32 * k21), u1);
+                s30 = fma(a32, k20, s30); s31 = fma(a32, k21, s31); s40 = fma(a42, k20, s40); s41 = fma(a42, k21, s41);
+                s50 = fma(a52, k20, s50); s51 = fma(a52, k21, s51); s60 = fma(a62, k20, s60); s61 = fma(a62, k21, s61);
+                sb0 = fma(b2, k20, sb0); sb1 = fma(b2, k21, sb1); se0 = fma(e2, k20, se0); se1 = fma(e2, k21, se1);
+                g0 = fma(dt, s30, u0); g1 = fma(dt, s31, u1);
                 double k30, k31; kinetics(Kc, g0, g1, p3, k30, k31);
-                g0 = fma(dt, fma(a41, k10, fma(a42, k20, a43 * k30)), u0); g1 = fma(dt, fma(a41, k11, fma(a42, k21, a43 * k31)), u1);
+                s40 = fma(a43, k30, s40); s41 = fma(a43, k31, s41); s50 = fma(a53, k30, s50); s51 = fma(a53, k31, s51);
+                s60 = fma(a63, k30, s60); s61 = fma(a63, k31, s61);
+                sb0 = fma(b3, k30, sb0); sb1 = fma(b3, k31, sb1); se0 = fma(e3, k30, se0); se1 = fma(e3, k31, se1);
+                g0 = fma(dt, s40, u0); g1 = fma(dt, s41, u1);
                 double k40, k41; kinetics(Kc, g0, g1, p4, k40, k41);
-                g0 = fma(dt, fma(a51, k10, fma(a52, k20, fma(a53, k30, a54 * k40))), u0);
-                g1 = fma(dt, fma(a51, k11, fma(a52, k21, fma(a53, k31, a54 * k41))), u1);
+                s50 = fma(a54, k40, s50); s51 = fma(a54, k41, s51); s60 = fma(a64, k40, s60); s61 = fma(a64, k41, s61);
+                sb0 = fma(b4, k40, sb0); sb1 = fma(b4, k41, sb1); se0 = fma(e4, k40, se0); se1 = fma(e4, k41, se1);
+                g0 = fma(dt, s50, u0); g1 = fma(dt, s51, u1);
                 double k50, k51; kinetics(Kc, g0, g1, p5, k50, k51);
-                g0 = fma(dt, fma(a61, k10, fma(a62, k20, fma(a63, k30, fma(a64, k40, a65 * k50)))), u0);
-                g1 = fma(dt, fma(a61, k11, fma(a62, k21, fma(a63, k31, fma(a64, k41, a65 * k51)))), u1);
+                s60 = fma(a65, k50, s60); s61 = fma(a65, k51, s61);
+                sb0 = fma(b5, k50, sb0); sb1 = fma(b5, k51, sb1); se0 = fma(e5, k50, se0); se1 = fma(e5, k51, se1);
+                g0 = fma(dt, s60, u0); g1 = fma(dt, s61, u1);
                 double k60, k61; kinetics(Kc, g0, g1, p6, k60, k61);
-                const double un0 = fma(dt, fma(b1, k10, fma(b2, k20, fma(b3, k30, fma(b4, k40, fma(b5, k50, b6 * k60))))), u0);
-                const double un1 = fma(dt, fma(b1, k11, fma(b2, k21, fma(b3, k31, fma(b4, k41, fma(b5, k51, b6 * k61))))), u1);
+                sb0 = fma(b6, k60, sb0); sb1 = fma(b6, k61, sb1); se0 = fma(e6, k60, se0); se1 = fma(e6, k61, se1);
+                const double un0 = fma(dt, sb0, u0), un1 = fma(dt, sb1, u1);
                 double k70, k71; kinetics(Kc, un0, un1, p6, k70, k71);
                 // ---- error estimate ----
-                f0 = dt * fma(e1, k10, fma(e2, k20, fma(e3, k30, fma(e4, k40, fma(e5, k50, fma(e6, k60, e7 * k70))))));
-                f1 = dt * fma(e1, k11, fma(e2, k21, fma(e3, k31, fma(e4, k41, fma(e5, k51, fma(e6, k61, e7 * k71))))));
+                f0 = dt * fma(e7, k70, se0);
+                f1 = dt * fma(e7, k71, se1);
                 f0 = f0 * m_rcp(fma(fmax(fabs(u0), fabs(un0)), reltol, abstol));   // denominators >= abstol > 0
                 f1 = f1 * m_rcp(fma(fmax(fabs(u1), fabs(un1)), reltol, abstol));
                 // EEst = sqrt(E2); accept iff EEst <= 1 iff E2 <= 1; the controller only needs ln EEst = ln(E2)/2
@@ -723,7 +740,27 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
 #pragma unroll
             for (int q = 0; q < W; ++q) db = fma(myAcc[(W + q) * B], sW[W + q], db);
             gcond = db * beta;
+            // expand the compressed accumulators in place to the SimpleChains layout, rows 1..P (row 0: sse).
+            // Descending p: row 1+p is written after every compressed row it could alias has been read
+            // (compressed row of p is <= p, see the index map below).
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                double v;
+                if (p < W) v = myAcc[p * B];                                              // W1[:,0]  (dG column)
+                else if (p < 2 * W) v = myAcc[(W + (p - W)) * B] * beta;                  // W1[:,1]  (beta column)
+                else if (NS::NIN > 2 && p < 3 * W) v = myAcc[(W + (p - 2 * W)) * B] * covv;   // W1[:,2] (covariate)
+                else if (p < NS::L1) v = myAcc[(W + (p - NS::NIN * W)) * B];              // b1
+                else v = myAcc[(2 * W + (p - NS::L1)) * B];                               // hidden + output layers
+                myAcc[(1 + p) * B] = v;
+            }
         }
+    }
+    if constexpr (GRAD) {
+        if (!active || failed) {
+#pragma unroll 1
+            for (int p = 0; p < P; ++p) myAcc[(1 + p) * B] = 0.0;
+        }
+        myAcc[0] = active ? sse : 0.0;
     }
 
     // ---- outputs ----
@@ -735,26 +772,33 @@ __global__ void __launch_bounds__(128, CUDE_MIN_BLOCKS) cude_eval_kernel(const E
     //      block finish at different times; a barrier here idled their slots: ncu v4 epilogue 45 % barrier) ----
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     if (A.partials) {
-        constexpr int nred = GRAD ? P + 1 : 1;
         double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
+        if constexpr (GRAD) {
+            // rows [q][tid] of this warp's 32 columns -> lane l sums row l (and row 32 + l): 32 shared loads and adds
+            // per lane instead of 5 shuffle stages per row (the shuffle version was 4 % of the kernel, ncu v9).
+            // Column order (j + lane) & 31: lanes l and l + 16 share a bank, which 64-bit accesses tolerate.
+            __syncwarp();
+            const int wbase = tid & ~31;
+            const int nl = (B - wbase < 32) ? B - wbase : 32;      // 32 unless the host emulation runs one thread
 #pragma unroll 1
-        for (int q = 0; q < nred; ++q) {
-            double v = 0.0;
-            if (active) {
-                if (q == 0) v = sse;
-                else if constexpr (GRAD) { if (!failed) {
-                    // expand the compressed accumulators to the SimpleChains layout
-                    const int p = q - 1;
-                    if (p < W) v = myAcc[p * B];                                   // W1[:,0]  (dG column)
-                    else if (p < 2 * W) v = myAcc[(W + (p - W)) * B] * beta;       // W1[:,1]  (beta column)
-                    else if (NS::NIN > 2 && p < 3 * W) v = myAcc[(W + (p - 2 * W)) * B] * covv;   // W1[:,2] (covariate)
-                    else if (p < NS::L1) v = myAcc[(W + (p - NS::NIN * W)) * B];   // b1
-                    else v = myAcc[(2 * W + (p - NS::L1)) * B];                    // hidden + output layers
-                } }
+            for (int q = lane; q < P + 1; q += nl) {
+                const double* const src = smem + (myAcc - tid - smem) + (size_t)q * B + wbase;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const int j0 = (jj + lane) & 31, j1 = (jj + 1 + lane) & 31, j2 = (jj + 2 + lane) & 31, j3 = (jj + 3 + lane) & 31;
+                    s0 += (j0 < nl) ? src[j0] : 0.0;
+                    s1 += (j1 < nl) ? src[j1] : 0.0;
+                    s2 += (j2 < nl) ? src[j2] : 0.0;
+                    s3 += (j3 < nl) ? src[j3] : 0.0;
+                }
+                row[q] = (s0 + s1) + (s2 + s3);
             }
+        } else {
+            double v = active ? sse : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) row[q] = v;
+            if (lane == 0) row[0] = v;
         }
     }
     if (A.counters) {

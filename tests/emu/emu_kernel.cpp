@@ -25,6 +25,7 @@ static emu_dim3 blockIdx, threadIdx, blockDim;
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }   // lanes 1..31 are empty
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 namespace cude { double smem[1 << 16]; }   // the kernel's `extern __shared__ double smem[]`

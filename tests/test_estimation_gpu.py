@@ -101,10 +101,13 @@ def test_device_resident_adam_matches_host_adam(fx):
         g = np.concatenate([gn, gc], axis=1)
         m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
         x = x - 1e-2 * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
-    # same trajectory up to the adaptive solve's noise floor (a rare accept/reject flip moves one
-    # trajectory's gradient by ~5e-5 of its scale, and Adam's g/sqrt(v) normalisation amplifies that early on);
-    # total parameter movement here is ~0.2, so 5e-5 still pins the recursion (moments, bias correction, scale)
-    assert np.abs(x_dev - x).max() < 5e-5
-    assert np.allclose(loss_dev, l, rtol=1e-5)
+    # Same recursion, not bitwise the same numbers: the two paths sum the population gradient in different orders
+    # (1e-16), and an adaptive solve amplifies that — typically to 1e-9, but a rare accept/reject flip moves one
+    # trajectory's gradient by ~5e-5 of its scale and Adam's g/sqrt(v) normalisation carries it
+    # into the parameters.  Total parameter movement here is ~0.2: the median pins the recursion (moments, bias
+    # correction, scale), the maximum bounds the flips.
+    d = np.abs(x_dev - x)
+    assert np.median(d) < 1e-7 and d.max() < 1e-3
+    assert np.allclose(loss_dev, l, rtol=1e-4)
     l0 = pop.loss(neural0, cond0)
     assert np.all(loss_dev < l0)

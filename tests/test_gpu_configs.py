@@ -77,7 +77,8 @@ def test_config3_screening_57_individuals_x_25000_guesses(fx, ctx):
     assert np.allclose(loss, sse.mean(axis=1), rtol=1e-13)
     best = np.argsort(loss, kind="stable")[:25]
     lg, gn, gc, sse_g = pop.loss_grad(neural[best], cond[best], return_sse=True)
-    assert np.array_equal(sse_g, sse[best]) and np.array_equal(lg, loss[best])        # same forward pass in both kernels
+    assert np.array_equal(sse_g, sse[best])                                           # same forward pass in both kernels
+    assert np.allclose(lg, loss[best], rtol=1e-13, atol=0.0)                          # (their warp reductions sum in different orders)
     _subsample_check(pk, neural, cond, sse, None, rng, n=800)
 
 
