@@ -43,22 +43,27 @@ namespace cude {
 // ---------------------------------------------------------------- Tsit5 tableau
 // Published coefficients of Tsitouras' 5(4) pair as used by OrdinaryDiffEq.Tsit5.
 namespace tab {
-constexpr double c2 = 0.161, c3 = 0.327, c4 = 0.9, c5 = 0.9800255409045097;
-constexpr double a21 = 0.161;
-constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
-constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
-constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
-constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383;
-constexpr double b1 = 0.09646076681806523, b2 = 0.01, b3 = 0.4798896504144996, b4 = 1.379008574103742, b5 = -3.290069515436081, b6 = 2.324710524099774;
-constexpr double e1 = -0.00178001105222577714, e2 = -0.0008164344596567469, e3 = 0.007880878010261995, e4 = -0.1447110071732629,
+#ifdef CUDE_TAB_CONSTMEM   // coefficients as loads from constant memory (LDCU) instead of 64-bit immediates (2 UMOV each)
+#define CUDE_TABCONST __constant__
+#else
+#define CUDE_TABCONST constexpr
+#endif
+CUDE_TABCONST double c2 = 0.161, c3 = 0.327, c4 = 0.9, c5 = 0.9800255409045097;
+CUDE_TABCONST double a21 = 0.161;
+CUDE_TABCONST double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+CUDE_TABCONST double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+CUDE_TABCONST double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
+CUDE_TABCONST double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383;
+CUDE_TABCONST double b1 = 0.09646076681806523, b2 = 0.01, b3 = 0.4798896504144996, b4 = 1.379008574103742, b5 = -3.290069515436081, b6 = 2.324710524099774;
+CUDE_TABCONST double e1 = -0.00178001105222577714, e2 = -0.0008164344596567469, e3 = 0.007880878010261995, e4 = -0.1447110071732629,
                  e5 = 0.5823571654525552, e6 = -0.45808210592918697, e7 = 0.015151515151515152;
-constexpr double r11 = 1.0, r12 = -2.763706197274826, r13 = 2.9132554618219126, r14 = -1.0530884977290216;
-constexpr double r22 = 0.13169999999999998, r23 = -0.2234, r24 = 0.1017;
-constexpr double r32 = 3.9302962368947516, r33 = -5.941033872131505, r34 = 2.490627285651253;
-constexpr double r42 = -12.411077166933676, r43 = 30.33818863028232, r44 = -16.548102889244902;
-constexpr double r52 = 37.50931341651104, r53 = -88.1789048947664, r54 = 47.37952196281928;
-constexpr double r62 = -27.896526289197286, r63 = 65.09189467479366, r64 = -34.87065786149661;
-constexpr double r72 = 1.5, r73 = -4.0, r74 = 2.5;
+CUDE_TABCONST double r11 = 1.0, r12 = -2.763706197274826, r13 = 2.9132554618219126, r14 = -1.0530884977290216;
+CUDE_TABCONST double r22 = 0.13169999999999998, r23 = -0.2234, r24 = 0.1017;
+CUDE_TABCONST double r32 = 3.9302962368947516, r33 = -5.941033872131505, r34 = 2.490627285651253;
+CUDE_TABCONST double r42 = -12.411077166933676, r43 = 30.33818863028232, r44 = -16.548102889244902;
+CUDE_TABCONST double r52 = 37.50931341651104, r53 = -88.1789048947664, r54 = 47.37952196281928;
+CUDE_TABCONST double r62 = -27.896526289197286, r63 = 65.09189467479366, r64 = -34.87065786149661;
+CUDE_TABCONST double r72 = 1.5, r73 = -4.0, r74 = 2.5;
 // PI controller defaults of OrdinaryDiffEq for Tsit5
 constexpr double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0, qoldinit = 1e-4;
 }  // namespace tab
@@ -156,12 +161,17 @@ struct Knots {
         const double v = fma(sl[idx * stride], tau - t[idx * stride], g[idx * stride]);
         return v - g0;
     }
-    // the 5 node times of a step at once: one pass over the knots, 5 independent select chains, then
-    // 15 independent shared-memory loads (a per-node search serialised on the LDS latency, ncu v4)
-    __device__ __forceinline__ void dG5(const double (&tau)[5], double* out, int ostride) const {
-        int idx[5] = {0, 0, 0, 0, 0};
-        for (int k = 1; k < nk - 1; ++k) {
+    // The 5 node times of a step at once (tau increasing): 5 independent select chains, then 15 independent
+    // shared-memory loads (a per-node search serialised on the LDS latency, ncu v4).  `base` is an interval index the
+    // caller carries along the trajectory with t[base] <= tau[0] (or 0): only the knots in (t[base], tau[4]] are
+    // examined — usually none or one instead of all (ncu v9: the full scan was ~160 of the ~1400 instructions a
+    // step spends outside the network).  idx_last = interval of tau[4], the next step's base.
+    __device__ __forceinline__ void dG5(const double (&tau)[5], double* out, int ostride, int base, int& idx_last) const {
+        int idx[5] = {base, base, base, base, base};
+        const double tmax = tau[4];
+        for (int k = base + 1; k < nk - 1; ++k) {
             const double tk = t[k * stride];
+            if (!(tk <= tmax)) break;
 #pragma unroll
             for (int q = 0; q < 5; ++q) idx[q] = (tk <= tau[q]) ? k : idx[q];
         }
@@ -170,6 +180,7 @@ struct Knots {
             const double v = fma(sl[idx[q] * stride], tau[q] - t[idx[q] * stride], g[idx[q] * stride]);
             out[q * ostride] = v - g0;
         }
+        idx_last = idx[4];
     }
 };
 
@@ -456,6 +467,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
             int iobs = 0, na = 0, nr = 0;
             double fsse = 0.0;
             double next_ot = (nobs > 0) ? obs_t[0] : CUDART_INF;
+            int kbase = 0, klast = 0;      // glucose interval of the step's start time / of its end node
             // save_start: observations at (or before) t0 see u0
             while (iobs < nobs && next_ot <= t0) {
                 const double r = u0 - obs_y[iobs * B];
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
                     double tau[5];
 #pragma unroll
                     for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], dt, t);
-                    kn.dG5(tau, myNode, B);                       // dG of the node times, staged in myNode
+                    kn.dG5(tau, myNode, B, kbase, klast);         // dG of the node times, staged in myNode
                 }
                 CUDE_UNROLL(CUDE_FWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
@@ -600,6 +612,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
                     lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
                     dt = fmin(dt * m_rcp(q), dtmax);               // q in [1/qmax, 1/qmin]
                     t = tnew; u0 = un0; u1 = un1; k10 = k70; k11 = k71;   // FSAL
+                    kbase = klast;
                 } else {
                     ++nr;
                     dt = dt * m_rcp(fmin(1.0 / qmin, t_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
@@ -624,6 +637,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
             const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
             const int nlast = (lo == 0) ? -1 : lo;
+            int kb = nk - 2 > 0 ? nk - 2 : 0, kdummy;   // glucose interval of the step's start time (times decrease)
             double rn_t = rec[((stop_at - 1) % REC_CAP) * 7], rn_h = rec[((stop_at - 1) % REC_CAP) * 7 + 1];   // (t, dt) fetched one step ahead
             for (int n = stop_at - 1; n >= nlast; --n) {
                 int nq;
@@ -717,7 +731,8 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
                     double tau[5];
 #pragma unroll
                     for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], h, tn);
-                    kn.dG5(tau, myDG, B);
+                    while (kb > 0 && kn.t[kb * B] > tn) --kb;
+                    kn.dG5(tau, myDG, B, kb, kdummy);
                 }
                 CUDE_UNROLL(CUDE_BWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
