@@ -221,14 +221,20 @@ def run_ours(args):
         # loss+gradient kernel -> block-partial reduction into `sums` -> NCCL all-reduce of `sums` (N > 1)
         shard.step(opts)
 
+    sums_dev = torch.empty((S, P + 1), dtype=torch.float64, device=dev)
+    neural_np, cond_np, gcond_np, sums_np = neural_p.numpy(), cond_p.numpy(), gcond_p.numpy(), sums_p.numpy()
+
     def step_e2e():
-        shard.neural.copy_(neural_p, non_blocking=True)
-        shard.cond.copy_(cond_p, non_blocking=True)
-        shard.step(opts)
-        sums_p.copy_(shard.sums, non_blocking=True)
-        gcond_p.copy_(shard.g_cond, non_blocking=True)
-        stream.synchronize()
-        return sums_p[:, 0].numpy() / N_total   # the step's result: loss per start
+        # the C-ABI host-buffer call (cude_loss_grad_sums): page-locked host arrays in, page-locked host arrays out; inside,
+        # the H2D of the step's conditional parameters and the D2H of their gradients are pipelined against the kernels
+        # in chunks of starts.  N > 1: the [S x (P+1)] shard sums take one more round trip through the NCCL all-reduce.
+        pop.loss_grad_sums(neural_np, cond_np, 1.0 / N_total, opts, out_sums=sums_np, out_g_cond=gcond_np)
+        if world > 1:
+            sums_dev.copy_(sums_p, non_blocking=True)
+            dist.all_reduce(sums_dev)
+            sums_p.copy_(sums_dev, non_blocking=True)
+            stream.synchronize()
+        return sums_np[:, 0] / N_total   # the step's result: loss per start
 
     def barrier():
         if world > 1:

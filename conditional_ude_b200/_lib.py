@@ -58,6 +58,8 @@ SYMBOLS = {
     "cude_loss": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, _D, _D]),
     "cude_loss_grad": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
                                  C.c_int, _D, _D, _D, _D]),
+    "cude_loss_grad_sums": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
+                                      C.c_double, _D, _D]),
     "cude_eval_dev": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _P, C.c_longlong, _P,
                                 C.c_int, C.c_double, _P, _P, _P]),
     "cude_measure_fp64_peak": (C.c_int, [_P, _D]),

@@ -22,6 +22,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+#define CUDE_MAX_CHUNKS 16
 struct cude_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // stream in use
@@ -34,6 +35,10 @@ struct cude_ctx {
     double* h_sums = nullptr;   // pinned
     size_t h_sums_cap = 0;
     unsigned long long* h_counters = nullptr;  // pinned [3]
+    // host-buffer calls on large batches run as a pipeline of chunks of starts: H2D on s_in, kernels on `stream`, D2H on s_out
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[CUDE_MAX_CHUNKS] = {}, ev_comp[CUDE_MAX_CHUNKS] = {};
+    int chunk_mode = 0;                 // 0: single call; 1: first chunk of a pipelined call; 2: later chunk (counters/timer accumulate)
     const void* carve_kern = nullptr;   // last kernel configuration whose shared-memory carve-out was set
     size_t carve_smem = 0;
     int carve_block = 0;
@@ -145,6 +150,12 @@ extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < CUDE_MAX_CHUNKS; ++k) {
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return CUDE_OK;
@@ -382,10 +393,10 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
         ctx->carve_kern = (const void*)kern; ctx->carve_smem = smem; ctx->carve_block = B;
     }
 
-    CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
-    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
     kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
     CU_TRY(ctx, cudaGetLastError());
@@ -404,18 +415,32 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
         ++launches;
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->stats = cude_stats{};
-    ctx->stats.n_traj = (unsigned long long)ntraj;
-    ctx->stats.launches = launches;
+    if (ctx->chunk_mode != 2) ctx->stats = cude_stats{};
+    ctx->stats.n_traj += (unsigned long long)ntraj;
+    ctx->stats.launches += launches;
     ctx->stats_pending = true;
     return CUDE_OK;
 }
 
 // ---------------------------------------------------------------- host-buffer entry points
+// Chunks of starts for a host-buffer call: one chunk below ~4 M trajectories, otherwise up to CUDE_MAX_CHUNKS chunks of
+// whole starts, so that the H2D of chunk k+1 and the D2H of chunk k-1 overlap the kernels of chunk k.
+static int host_chunks(int n_starts, size_t ntraj) {
+    const size_t per = (size_t)4 << 20;
+    size_t n = ntraj / per;
+    if (n < 2) return 1;
+    if (n > CUDE_MAX_CHUNKS) n = CUDE_MAX_CHUNKS;
+    if (n > (size_t)n_starts) n = (size_t)n_starts;
+    return (int)n;
+}
+
+// raw_sums != NULL: raw_sums[(P+1) x S] = {sum_i sse, sum_i d sse/d neural} unscaled and g_cond scaled by cond_scale
+// (the sharded-population form); otherwise loss_out / g_neural / g_cond as documented for cude_loss / cude_loss_grad.
 static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
                      int n_starts, const double* neural, long long neural_stride, const double* cond,
                      int want_grad, int mean_over_individuals,
-                     double* sse_out, double* loss_out, double* g_neural, double* g_cond) {
+                     double* sse_out, double* loss_out, double* g_neural, double* g_cond,
+                     double* raw_sums = nullptr, double cond_scale = 1.0) {
     if (!ctx || !pop || !net || !neural || !cond) return fail(ctx, CUDE_EINVAL, "cude_loss: NULL argument");
     if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_loss: n_starts < 1");
     const int P = cude_net_nparams(net);
@@ -437,22 +462,76 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         CU_TRY(ctx, cudaMallocHost(&ctx->h_sums, (size_t)np1 * n_starts * sizeof(double)));
         ctx->h_sums_cap = (size_t)np1 * n_starts;
     }
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->neural.p, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->cond.p, cond, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     int wg = 0;
-    if (want_grad) wg = (g_neural ? 2 : 0) | 1;
-    const double scale = mean_over_individuals ? 1.0 / N : 1.0;
-    rc = cude_eval_dev(ctx, pop, net, opts, n_starts, (const double*)ctx->neural.p, neural_stride, (const double*)ctx->cond.p,
-                       wg, scale, sse_out ? (double*)ctx->sse.p : nullptr, (double*)ctx->sums.p,
-                       g_cond ? (double*)ctx->gcond.p : nullptr);
-    if (rc) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, ctx->sse.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond, ctx->gcond.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_grad) wg = ((g_neural || raw_sums) ? 2 : 0) | 1;
+    const double scale = raw_sums ? 1.0 : (mean_over_individuals ? 1.0 / N : 1.0);
+    const double cscale = raw_sums ? cond_scale : scale;
+    double* const d_neural = (double*)ctx->neural.p;
+    double* const d_cond = (double*)ctx->cond.p;
+    double* const d_sums = (double*)ctx->sums.p;
+    double* const d_sse = sse_out ? (double*)ctx->sse.p : nullptr;
+    double* const d_gc = g_cond ? (double*)ctx->gcond.p : nullptr;
+    const int nch = host_chunks(n_starts, ntraj);
+    CU_TRY(ctx, cudaMemcpyAsync(d_neural, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nch == 1) {
+        CU_TRY(ctx, cudaMemcpyAsync(d_cond, cond, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = cude_eval_dev(ctx, pop, net, opts, n_starts, d_neural, neural_stride, d_cond, wg, cscale, d_sse, d_sums, d_gc);
+        if (rc) return rc;
+        if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, d_sse, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond, d_gc, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        if (!ctx->s_in) {
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+            for (int k = 0; k < CUDE_MAX_CHUNKS; ++k) {
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+            }
+        }
+        // software pipeline in launch order H2D(k+1), kernels(k+1), D2H(k): with pageable host memory the copies block
+        // the host, but never before the next chunk's kernels are queued behind the running ones
+        auto lo = [&](int k) { return (int)((long long)n_starts * k / nch); };
+        auto h2d = [&](int k) -> int {
+            const size_t o = (size_t)lo(k) * N, n = (size_t)(lo(k + 1) - lo(k)) * N;
+            CU_TRY(ctx, cudaMemcpyAsync(d_cond + o, cond + o, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_in));
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_in[k], ctx->s_in));
+            return CUDE_OK;
+        };
+        auto run = [&](int k) -> int {
+            const int s0 = lo(k), ns = lo(k + 1) - s0;
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
+            ctx->chunk_mode = k == 0 ? 1 : 2;
+            const int r = cude_eval_dev(ctx, pop, net, opts, ns, d_neural + (size_t)s0 * neural_stride, neural_stride,
+                                        d_cond + (size_t)s0 * N, wg, cscale, d_sse ? d_sse + (size_t)s0 * N : nullptr,
+                                        d_sums + (size_t)s0 * np1, d_gc ? d_gc + (size_t)s0 * N : nullptr);
+            ctx->chunk_mode = 0;
+            if (r) return r;
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_comp[k], ctx->stream));
+            return CUDE_OK;
+        };
+        auto d2h = [&](int k) -> int {
+            const size_t o = (size_t)lo(k) * N, n = (size_t)(lo(k + 1) - lo(k)) * N;
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[k], 0));
+            if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out + o, d_sse + o, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+            if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond + o, d_gc + o, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+            return CUDE_OK;
+        };
+        if ((rc = h2d(0)) || (rc = run(0))) return rc;
+        for (int k = 0; k < nch; ++k) {
+            if (k + 1 < nch && ((rc = h2d(k + 1)) || (rc = run(k + 1)))) return rc;
+            if ((rc = d2h(k))) return rc;
+        }
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, d_sums, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nch > 1) CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
     {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(ctx, CUDE_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(e));
+    }
+    if (raw_sums) {
+        memcpy(raw_sums, ctx->h_sums, (size_t)np1 * n_starts * sizeof(double));
+        return CUDE_OK;
     }
     for (int s = 0; s < n_starts; ++s) {
         const double* row = ctx->h_sums + (size_t)s * np1;
@@ -476,6 +555,14 @@ extern "C" int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const c
                               double* sse_out, double* loss_out, double* g_neural, double* g_cond) {
     return eval_host(ctx, pop, net, opts, n_starts, neural, neural_stride, cond, 1, mean_over_individuals,
                      sse_out, loss_out, g_neural, g_cond);
+}
+
+extern "C" int cude_loss_grad_sums(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                                   int n_starts, const double* neural, long long neural_stride, const double* cond,
+                                   double cond_scale, double* sums_out, double* g_cond) {
+    if (!sums_out) return fail(ctx, CUDE_EINVAL, "cude_loss_grad_sums: sums_out is NULL");
+    return eval_host(ctx, pop, net, opts, n_starts, neural, neural_stride, cond, 1, 0, nullptr, nullptr, nullptr, g_cond,
+                     sums_out, cond_scale);
 }
 
 // ---------------------------------------------------------------- suppression variant

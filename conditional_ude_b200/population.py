@@ -159,6 +159,20 @@ class Population:
                    self.ctx.handle)
         return (loss, gn, gc, sse) if return_sse else (loss, gn, gc)
 
+    def loss_grad_sums(self, neural, cond, cond_scale=1.0, opts=None, out_sums=None, out_g_cond=None):
+        """Sharded-population form with host buffers (cude_loss_grad_sums): returns (sums[S x (P+1)], g_cond[S x N]) with
+        sums[s] = {sum_i sse_i, sum_i d sse_i/d neural} of this shard, unscaled, and g_cond = cond_scale * d sse_i/d cond.
+        `out_*` let the caller supply (page-locked) result buffers; large batches are pipelined inside the call."""
+        neural, stride, cond, S = self._prep(neural, cond)
+        o = (opts or SolverOptions()).c()
+        sums = out_sums if out_sums is not None else np.empty((S, self.n_params + 1))
+        gc = out_g_cond if out_g_cond is not None else np.empty((S, self.n_ind))
+        assert sums.flags.c_contiguous and sums.shape == (S, self.n_params + 1) and sums.dtype == np.float64
+        assert gc.flags.c_contiguous and gc.shape == (S, self.n_ind) and gc.dtype == np.float64
+        _lib.check(self._lib.cude_loss_grad_sums(self.ctx.handle, self._h, C.byref(self.net), C.byref(o), S, _dptr(neural), stride,
+                                                 _dptr(cond), float(cond_scale), _dptr(sums), _dptr(gc)), self.ctx.handle)
+        return sums, gc
+
     def eval_dev(self, n_starts, d_neural, neural_stride, d_cond, want_grad, cond_scale, d_sse, d_sums, d_g_cond, opts=None):
         """Asynchronous device-pointer call (ints are raw device addresses)."""
         o = (opts or SolverOptions()).c()

@@ -127,6 +127,17 @@ int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const cude_net* ne
                    int mean_over_individuals,
                    double* sse_out, double* loss_out, double* g_neural, double* g_cond);
 
+/* ---- sharded-population form of cude_loss_grad with host buffers (one rank's shard of the individuals,
+ * parameter-estimation.jl:126-140 split over ranks): sums_out[(P+1) x n_starts] receives for every start the *unscaled*
+ * { sum_i sse_i, sum_i d sse_i / d neural[0..P) } of this shard (sum the shards' sums, divide by the global N; a start
+ * whose sums_out[0] is not finite failed), g_cond[n_ind x n_starts] receives d sse_i / d cond scaled by cond_scale
+ * (pass 1/N_global).  Like cude_loss / cude_loss_grad, a call of more than ~8 M trajectories runs as a pipeline of
+ * chunks of starts: the host->device copy of chunk k+1 and the device->host copy of chunk k-1 overlap the kernels
+ * of chunk k (fully asynchronous when the host buffers are page-locked). */
+int cude_loss_grad_sums(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                        int n_starts, const double* neural, long long neural_stride, const double* cond,
+                        double cond_scale, double* sums_out, double* g_cond);
+
 /* ---- device-resident variants (asynchronous on the context stream; all pointers are device
  * pointers on the context's device).  Used by multi-GPU population training: each rank holds a
  * shard of the individuals, `sums_out` [(P+1) x n_starts] receives for every start
