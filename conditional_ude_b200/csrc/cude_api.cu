@@ -716,7 +716,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
 
 // ---------------------------------------------------------------- elementary-function probe (tests)
 extern "C" int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y) {
-    if (!ctx || !x || !y || n < 1 || which < 0 || which > 9) return fail(ctx, CUDE_EINVAL, "cude_math_probe: bad argument");
+    if (!ctx || !x || !y || n < 1 || which < 0 || which > 6) return fail(ctx, CUDE_EINVAL, "cude_math_probe: bad argument");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = ensure(ctx, ctx->scratch, 2 * (size_t)n * sizeof(double));
     if (rc) return rc;

@@ -865,33 +865,29 @@ __global__ void cude_sum_sse(const double* __restrict__ sse, int n_ind, int n_st
     if (lane == 0) sums[(size_t)s * np1] = v;
 }
 
-// elementary-function probe (tests).  c-peptide kernel (256-entry table): 0 tanh, 1 softplus, 2 d softplus = 1 - 1/d,
-// 3 exp (clamped to +-40), 4 log, 5 rcp; suppression kernel (64-entry table): 6 tanh, 7 softplus, 8 sigmoid, 9 exp
-__device__ __forceinline__ double cude_math_probe_eval(int which, double v, const double* t256, const double* t64) {
+// elementary-function probe (tests): 0 tanh, 1 softplus, 2 d softplus from d (1 - 1/d, the c-peptide adjoint),
+// 3 exp (clamped to +-40), 4 log, 5 rcp, 6 sigmoid (the suppression adjoint)
+__device__ __forceinline__ double cude_math_probe_eval(int which, double v, const double* tab) {
     double r, d;
     int nm = 0;
     switch (which) {
-        case 0: r = t_tanh(v, t256, nm); r = t_nan_inject(r, nm); break;
-        case 1: t_softplus_d(v, t256, r, d); break;
-        case 2: t_softplus_d(v, t256, r, d); r = fma(-1.0, m_rcp(d), 1.0); break;
-        case 3: r = t_exp_sat(v, t256); break;
+        case 0: r = t_tanh(v, tab, nm); r = t_nan_inject(r, nm); break;
+        case 1: t_softplus_d(v, tab, r, d); break;
+        case 2: t_softplus_d(v, tab, r, d); r = fma(-1.0, m_rcp(d), 1.0); break;
+        case 3: r = t_exp_sat(v, tab); break;
         case 4: r = m_log_pos(v); break;
         case 5: r = m_rcp(v); break;
-        case 6: r = m_tanh(v, t64); break;
-        case 7: r = m_softplus(v, t64); break;
-        case 8: r = m_sigmoid(v, t64); break;
-        default: r = m_exp_sat(v, t64); break;
+        default: r = t_sigmoid(v, tab); break;
     }
     return r;
 }
 __global__ void cude_math_probe_kernel(int which, int n, const double* __restrict__ x, double* __restrict__ y) {
-    __shared__ double sTab[256 + 64];
+    __shared__ double sTab[256];
     for (int p = threadIdx.x; p < 256; p += blockDim.x) sTab[p] = EXP_TAB256[p];
-    for (int p = threadIdx.x; p < 64; p += blockDim.x) sTab[256 + p] = EXP_TAB64[p];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    y[i] = cude_math_probe_eval(which, x[i], sTab, sTab + 256);
+    y[i] = cude_math_probe_eval(which, x[i], sTab);
 }
 
 // Adam update on device-resident parameters (Optimisers.Adam: m, v moments, bias correction through the running

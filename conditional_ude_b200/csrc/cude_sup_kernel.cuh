@@ -65,9 +65,10 @@ template <class SN>
 __device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, const double* __restrict__ tab,
                                                  const double (&c)[SN::W], double u0, double u1, double u2) {
     constexpr int W = SN::W;
+    int nanmax = 0;
     double a[W], b[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[j] = m_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab);
+    for (int j = 0; j < W; ++j) a[j] = t_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab, nanmax);
     int off = SN::L1;
 #pragma unroll
     for (int l = 1; l < SN::DEPTH; ++l) {
@@ -76,7 +77,7 @@ __device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, 
             double z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[i], z);
-            b[j] = m_tanh(z, tab);
+            b[j] = t_tanh(z, tab, nanmax);
         }
 #pragma unroll
         for (int j = 0; j < W; ++j) a[j] = b[j];
@@ -85,7 +86,9 @@ __device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, 
     double z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
-    return m_softplus(z, tab);
+    double sp, d;
+    t_softplus_d(t_nan_inject(z, nanmax), tab, sp, d);
+    return sp;
 }
 
 // forward + backward with scalar seed s: returns d(u_hat)/d(u) * s in du[], accumulates parameter gradients
@@ -95,9 +98,10 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
                                                 const double (&c)[SN::W], double u0, double u1, double u2, double s,
                                                 double* __restrict__ acc, int as, double (&du)[3]) {
     constexpr int W = SN::W, D = SN::DEPTH;
+    int nanmax = 0;   // the forward pass succeeded on the same inputs
     double a[D][W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[0][j] = m_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab);
+    for (int j = 0; j < W; ++j) a[0][j] = t_tanh(fma(sW[2 * W + j], u2, fma(sW[W + j], u1, fma(sW[j], u0, c[j]))), tab, nanmax);
     int off = SN::L1;
 #pragma unroll
     for (int l = 1; l < D; ++l) {
@@ -106,14 +110,14 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
             double z = sW[off + W * W + j];
 #pragma unroll
             for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
-            a[l][j] = m_tanh(z, tab);
+            a[l][j] = t_tanh(z, tab, nanmax);
         }
         off += SN::LH;
     }
     double z = sW[off + W];
 #pragma unroll
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
-    const double dz = s * m_sigmoid(z, tab);
+    const double dz = s * t_sigmoid(z, tab);
     int aoff = 4 * W + (D - 1) * SN::LH;
     double da[W];
     {   // output layer batch
@@ -176,7 +180,7 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
 
 __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad) {
     // exp table, weights, per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] + residuals M*3 + accumulators)
-    return (size_t)64 + (size_t)((P + 1) & ~1) + (size_t)(21 + (grad ? 42 + 3 * M + NACC : 0)) * B;
+    return (size_t)256 + (size_t)((P + 1) & ~1) + (size_t)(21 + (grad ? 42 + 3 * M + NACC : 0)) * B;
 }
 
 constexpr int SUP_REC_CAP = 512;  // accepted-step records (t, dt, u[3]) kept per thread in local memory (20 KB)
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
     const int B = blockDim.x, tid = threadIdx.x;
     const int N = A.n_ind, M = A.n_obs;
     double* sTab = smem;
-    double* sW = sTab + 64;
+    double* sW = sTab + 256;
     double* sK = sW + ((P + 1) & ~1);                 // [7][3][B] stages
     double* sG = sK + (size_t)21 * B;                 // [7][3][B] stage inputs (GRAD)
     double* sKb = sG + (GRAD ? (size_t)21 * B : 0);   // [7][3][B] stage adjoints (GRAD)
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
     {
         const double* gW = A.neural + (long long)s * A.neural_stride;
         for (int p = tid; p < P; p += B) sW[p] = gW[p];
-        for (int p = tid; p < 64; p += B) sTab[p] = EXP_TAB64[p];
+        for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     }
     double* const myK = sK + tid;
     double* const myG = sG + tid;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
             x0 = (f0 - k10) * isk0; x1 = (f1 - k11) * isk1; x2 = (f2 - k12) * isk2;
             const double d2 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0) / dt0;
             const double dm = fmax(d1, d2);
-            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : m_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
+            const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : t_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
             dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
             if (!(isfinite(dt) && isfinite(k10) && isfinite(k11) && isfinite(k12))) ret = 3;
         }
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
             CUDE_TRACE_STEP(t, dt, sqrt(E2))
             const double lnE = 0.5 * m_log_pos(E2);
             if (E2 <= 1.0) {
-                const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, m_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
+                const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, t_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
                 double tnew = t + dt;
                 if (fabs(tnew - tend) < snap) tnew = tend;
                 while (iobs < M && A.obs_t[iobs] <= tnew) {
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                 myK[0] = myK[18 * B]; myK[B] = myK[19 * B]; myK[2 * B] = myK[20 * B];      // FSAL: k1 <- k7
             } else {
                 ++nrej;
-                dt = dt * m_rcp(fmin(1.0 / qmin, m_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
+                dt = dt * m_rcp(fmin(1.0 / qmin, t_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
             }
         }
         if (ret == 0 && iobs < M) ret = 3;

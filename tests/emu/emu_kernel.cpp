@@ -118,6 +118,6 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
 
 // elementary functions of cude_math.cuh (ids as in cude_math_probe_eval)
 extern "C" void emu_math(int which, int n, const double* x, double* y) {
-    for (int i = 0; i < n; ++i) y[i] = cude_math_probe_eval(which, x[i], EXP_TAB256, EXP_TAB64);
+    for (int i = 0; i < n; ++i) y[i] = cude_math_probe_eval(which, x[i], EXP_TAB256);
 }
 extern "C" int emu_rec_cap(void) { return REC_CAP; }

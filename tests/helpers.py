@@ -62,28 +62,28 @@ def _math_cases():
 
 
 def check_math(fn):
-    """fn(which, x) -> y: accuracy of the kernels' elementary functions against numpy/mpmath-grade references.
-    ids 0-3: c-peptide kernel (256-entry table), 6-9: suppression kernel (64-entry table); 4 log, 5 rcp shared."""
+    """fn(which, x) -> y: accuracy of the kernels' elementary functions against numpy/mpmath-grade references
+    (ids: cude_math_probe_eval in cude_kernels.cuh)."""
     x = _math_cases()
-    for tanh_id, sp_id, sg_id, exp_id in ((0, 1, 2, 3), (6, 7, 8, 9)):
-        t = fn(tanh_id, x)
-        assert np.abs(t - np.tanh(x)).max() < 4e-16                      # absolute (see cude_math.cuh)
-        assert np.isnan(fn(tanh_id, np.array([np.nan]))[0])
-        xs = x[np.isfinite(x)]
-        sp = fn(sp_id, xs)
-        big = xs > 709.782712893384                                      # exp overflows in the reference's naive form
-        assert np.all(np.isinf(sp[big]))
-        xs, sp = xs[~big], sp[~big]
-        ref = np.where(xs > 36.8, xs, np.log1p(np.exp(np.minimum(xs, 36.8))))
-        assert np.all(np.abs(sp - ref) <= 8e-16 * np.maximum(1.0, np.abs(ref)))      # ~2 ulp
-        assert np.isinf(fn(sp_id, np.array([710.0]))[0]) and fn(sp_id, np.array([709.0]))[0] == 709.0      # naive-form overflow
-        assert np.isnan(fn(sp_id, np.array([np.nan]))[0])
-        xs = x[np.isfinite(x)]
-        sg = fn(sg_id, xs)
-        with np.errstate(over="ignore"):
-            assert np.abs(sg - 1.0 / (1.0 + np.exp(-xs))).max() < 4e-16
-        xe = np.random.default_rng(1).uniform(-40, 40, 20000)
-        assert np.abs(fn(exp_id, xe) / np.exp(xe) - 1).max() < (6e-16 if exp_id == 9 else 5e-15)   # one-constant reduction: |x| 1.1e-16
+    t = fn(0, x)
+    assert np.abs(t - np.tanh(x)).max() < 4e-16                      # absolute (see cude_math.cuh)
+    assert np.isnan(fn(0, np.array([np.nan]))[0])
+    xs = x[np.isfinite(x)]
+    sp = fn(1, xs)
+    big = xs > 709.782712893384                                      # exp overflows in the reference's naive form
+    assert np.all(np.isinf(sp[big]))
+    xs, sp = xs[~big], sp[~big]
+    ref = np.where(xs > 36.8, xs, np.log1p(np.exp(np.minimum(xs, 36.8))))
+    assert np.all(np.abs(sp - ref) <= 8e-16 * np.maximum(1.0, np.abs(ref)))      # ~2 ulp
+    assert np.isinf(fn(1, np.array([710.0]))[0]) and fn(1, np.array([709.0]))[0] == 709.0      # naive-form overflow
+    assert np.isnan(fn(1, np.array([np.nan]))[0])
+    xs = x[np.isfinite(x)]
+    with np.errstate(over="ignore"):
+        sig = 1.0 / (1.0 + np.exp(-xs))
+    assert np.abs(fn(2, xs) - sig).max() < 4e-16                     # 1 - 1/d from the softplus' d (c-peptide adjoint)
+    assert np.abs(fn(6, xs) - sig).max() < 4e-16                     # sigmoid (suppression adjoint)
+    xe = np.random.default_rng(1).uniform(-40, 40, 20000)
+    assert np.abs(fn(3, xe) / np.exp(xe) - 1).max() < 5e-15          # one-constant reduction: |x| 1.1e-16 relative
     xl = np.exp(np.random.default_rng(2).uniform(-600, 600, 20000))
     assert np.abs(fn(4, xl) - np.log(xl)).max() < 3e-13 and np.abs(fn(4, xl) / np.log(xl) - 1)[np.abs(np.log(xl)) > 1e-3].max() < 1e-15
     xr = np.exp(np.random.default_rng(3).uniform(-30, 30, 20000))
