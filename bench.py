@@ -158,7 +158,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = n_ind * n_starts / dt
     sample = f"{n_ind} individuals x {n_starts} starts per step (same generator as the GPU workload)"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -327,12 +327,30 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{args.cpu_individuals} individuals x {args.cpu_starts} starts, {secs:.1f} s "
                                              "(oracle: C++ port of the reference algorithm, forward-mode gradient)"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else written to fd 1 while the bench runs
+    (NCCL's version banner, library chatter) was redirected to stderr by main()."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for native libraries (NCCL prints its banner on stdout)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
