@@ -423,10 +423,11 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
 }
 
 // ---------------------------------------------------------------- host-buffer entry points
-// Chunks of starts for a host-buffer call: one chunk below ~4 M trajectories, otherwise up to CUDE_MAX_CHUNKS chunks of
-// whole starts, so that the H2D of chunk k+1 and the D2H of chunk k-1 overlap the kernels of chunk k.
+// Chunks of starts for a host-buffer call: one chunk below ~2 M trajectories, otherwise up to CUDE_MAX_CHUNKS chunks of
+// whole starts (>= ~1 M trajectories = ~5 ms of kernel each), so that the H2D of chunk k+1 and the D2H of chunk k-1
+// overlap the kernels of chunk k and only the first copy in and the last copy out are exposed.
 static int host_chunks(int n_starts, size_t ntraj) {
-    const size_t per = (size_t)4 << 20;
+    const size_t per = (size_t)1 << 20;
     size_t n = ntraj / per;
     if (n < 2) return 1;
     if (n > CUDE_MAX_CHUNKS) n = CUDE_MAX_CHUNKS;

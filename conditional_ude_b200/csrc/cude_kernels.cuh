@@ -141,10 +141,19 @@ struct NetShape {
 #endif
 #define CUDE_PRAGMA(x) _Pragma(#x)
 #define CUDE_UNROLL(n) CUDE_PRAGMA(unroll n)
+#ifndef CUDE_STASH_D
+// 0 (default): an accepted-step record is (t, dt); the adjoint recomputes z_out and its sigmoid from the activations
+//    it recomputes anyway.  1: the record also keeps d = 1 + exp(z_out) of the step's 5 nodes (7 doubles), which takes
+//    the sigmoid off the adjoint's dependent chain: +0.9 % throughput on B200, but the records (1.2 KB per trajectory
+//    in local memory) no longer stay in L2 and every one is written back: 76 GB of DRAM traffic per 64 M-trajectory
+//    launch instead of 3.6 GB (ncu, profiles/r01_v12_traffic.txt).  Not worth it.
+#define CUDE_STASH_D 0
+#endif
 #ifndef CUDE_REC_CAP
 #define CUDE_REC_CAP 48
 #endif
-constexpr int REC_CAP = CUDE_REC_CAP;  // ring of accepted-step records kept per thread (local memory)
+constexpr int REC_CAP = CUDE_REC_CAP;
+constexpr int REC_W = CUDE_STASH_D ? 7 : 2;   // doubles per record  // ring of accepted-step records kept per thread (local memory)
 
 // per-thread view of the staged glucose knots in shared memory, layout [k][tid]
 struct Knots {
@@ -254,10 +263,10 @@ __device__ __forceinline__ void softplus_d_mixed(double z, const double* __restr
     d = 1.0 + (double)f_ex2(f_clamp(x, -30.0f, 30.0f) * 1.4426950408889634f);
 }
 
-// Adjoint at one time node: acc += dz * d z_out/d(params), dz = (node weight) * (1 - 1/d).  The hidden activations are
-// recomputed (8 tanh): keeping them from the forward pass (9 doubles per node, ~7 KB per trajectory in local memory)
+// Adjoint at one time node: acc += dz * d z_out/d(params), dz = (node weight) * sigmoid(z_out).  The hidden activations
+// are recomputed (8 tanh): keeping them from the forward pass (9 doubles per node, ~7 KB per trajectory in local memory)
 // was measured slower on B200 (1.05e8 vs 1.30e8 evals/s) — the footprint of all resident threads exceeds L2 and the
-// kernel has too few warps to hide the HBM latency; only d (5 doubles per step, 45 MB over all resident threads) is kept.
+// kernel has too few warps to hide the HBM latency (see also CUDE_STASH_D).
 // The accumulators g[] stay in registers during the adjoint sweep (updating them in shared memory
 // serialised on the LDS latency: ncu v2 short_scoreboard); they are parked in shared memory only around a
 // forward replay and for the final block reduction.  Layout:
@@ -268,6 +277,13 @@ template <>
 struct TanhEval<double> { static __device__ __forceinline__ double f(double x, const double* tab, int& nm) { return t_tanh(x, tab, nm); } };
 template <>
 struct TanhEval<float> { static __device__ __forceinline__ float f(float x, const double* tab, int&) { return m_tanh(x, tab); } };
+
+template <class R>
+struct SigmoidEval;
+template <>
+struct SigmoidEval<double> { static __device__ __forceinline__ double f(double x, const double* tab) { return t_sigmoid(x, tab); } };
+template <>
+struct SigmoidEval<float> { static __device__ __forceinline__ float f(float x, const double* tab) { return m_sigmoid(x, tab); } };
 
 template <class NS, class R>
 __device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const double* __restrict__ tab, const R (&c)[NS::W], R dG, R dz,
@@ -288,6 +304,12 @@ __device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const dou
             a[l][j] = TanhEval<R>::f(z, tab, nanmax);
         }
         off += NS::LH;
+    }
+    if (!CUDE_STASH_D) {   // dz arrives as the bare node weight: times d softplus(z_out) = sigmoid(z_out)
+        R z = sW[off + W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
+        dz *= SigmoidEval<R>::f(z, tab);
     }
     R da[W];
     int aoff = 2 * W + (D - 1) * NS::LH;
@@ -369,7 +391,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
     double* sRes = sDG + (GRAD ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
 
     // ---- which trajectory ----
-    long long j;
+    long long j, prow = blockIdx.x;   // prow: this block's row group in `partials`, [start][chunk] order
     int i, s;
     bool active;
     if (A.flat) {
@@ -378,8 +400,12 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
         i = active ? (int)(j % N) : 0;
         s = active ? (int)(j / N) : 0;
     } else {
-        s = blockIdx.x / A.nchunks;
-        const int c = blockIdx.x - s * A.nchunks;
+        // chunk-major block order: the blocks resident at any time cover a few chunks of individuals x all starts, so the
+        // population data of a chunk is read from HBM once and served from L2 to the other starts (start-major order
+        // re-read the whole population per start: 15 GB per launch at 1 M individuals x 64 starts, ncu v11)
+        const int c = blockIdx.x / A.n_starts;
+        s = blockIdx.x - c * A.n_starts;
+        prow = (long long)s * A.nchunks + c;
         i = c * B + tid;
         active = i < N;
         j = (long long)s * N + i;
@@ -448,7 +474,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
         const double dtmin = fmax(nextafter(at0, CUDART_INF) - at0, nextafter(at1, CUDART_INF) - at1);
         const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
 
-        double rec[GRAD ? REC_CAP * 7 : 1];   // accepted-step records {t, dt, d[5] = 1 + exp(z_out) at the step's nodes}
+        double rec[GRAD ? REC_CAP * REC_W : 1];   // accepted-step records {t, dt} (+ d[5] = 1 + exp(z_out) of the step's nodes with CUDE_STASH_D)
         double d_nn0 = 1.0;                   // d at the node t0, dG = 0: the NN([0;beta]) term
         R acc[GRAD ? NS::NACC : 1];           // gradient accumulators (compressed layout, see mlp_backward): registers during the adjoint sweep
         volatile double park[GRAD ? NS::NACC : 1];   // ... local memory across a forward replay (solves longer than REC_CAP
@@ -603,10 +629,10 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
                         next_ot = (iobs < nobs) ? obs_t[iobs * B] : CUDART_INF;
                     }
                     if (GRAD) {
-                        double* const r7 = rec + (na % REC_CAP) * 7;
+                        double* const r7 = rec + (na % REC_CAP) * REC_W;
                         r7[0] = t; r7[1] = dt;
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) r7[2 + q] = dd[q];
+                        for (int q = 0; q < (CUDE_STASH_D ? 5 : 0); ++q) r7[2 + q] = dd[q];
                     }
                     ++na;
                     lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
@@ -638,23 +664,23 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
             const int lo = (stop_at > REC_CAP) ? stop_at - REC_CAP : 0;
             const int nlast = (lo == 0) ? -1 : lo;
             int kb = nk - 2 > 0 ? nk - 2 : 0, kdummy;   // glucose interval of the step's start time (times decrease)
-            double rn_t = rec[((stop_at - 1) % REC_CAP) * 7], rn_h = rec[((stop_at - 1) % REC_CAP) * 7 + 1];   // (t, dt) fetched one step ahead
+            double rn_t = rec[((stop_at - 1) % REC_CAP) * REC_W], rn_h = rec[((stop_at - 1) % REC_CAP) * REC_W + 1];   // (t, dt) fetched one step ahead
             for (int n = stop_at - 1; n >= nlast; --n) {
                 int nq;
                 const double* cn;
                 double tn, h;
                 if (n < 0) {
                     nq = 1; cn = CN_INIT; tn = t0; h = 0.0;
-                    myNode[0] = -wsum * fma(-1.0, m_rcp(d_nn0), 1.0);
+                    myNode[0] = CUDE_STASH_D ? -wsum * fma(-1.0, m_rcp(d_nn0), 1.0) : -wsum;
                 } else {
                     tn = rn_t; h = rn_h;
                     double dd[5];                                  // needed after the stage recursion: the loads overlap it
                     {
-                        const double* const r7 = rec + (n % REC_CAP) * 7;
+                        const double* const r7 = rec + (n % REC_CAP) * REC_W;
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) dd[q] = r7[2 + q];
+                        for (int q = 0; q < 5; ++q) dd[q] = CUDE_STASH_D ? r7[2 + q] : 0.0;
                     }
-                    if (n > lo) { rn_t = rec[((n - 1) % REC_CAP) * 7]; rn_h = rec[((n - 1) % REC_CAP) * 7 + 1]; }
+                    if (n > lo) { rn_t = rec[((n - 1) % REC_CAP) * REC_W]; rn_h = rec[((n - 1) % REC_CAP) * REC_W + 1]; }
                     nq = 5; cn = CN_STEP;
                     double kb[7][2];
 #pragma unroll
@@ -718,9 +744,13 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
                     // node weights, in CN_STEP order; node tn+h serves stages 6, 7 and the next step's stage 1
                     const double w6 = pb6 + pb7 + wnode;
                     // dz = node weight * d softplus(z_out) = w * (1 - 1/d)
-                    myNode[0] = pb2 * fma(-1.0, m_rcp(dd[0]), 1.0); myNode[B] = pb3 * fma(-1.0, m_rcp(dd[1]), 1.0);
-                    myNode[2 * B] = pb4 * fma(-1.0, m_rcp(dd[2]), 1.0); myNode[3 * B] = pb5 * fma(-1.0, m_rcp(dd[3]), 1.0);
-                    myNode[4 * B] = w6 * fma(-1.0, m_rcp(dd[4]), 1.0);
+                    if (CUDE_STASH_D) {
+                        myNode[0] = pb2 * fma(-1.0, m_rcp(dd[0]), 1.0); myNode[B] = pb3 * fma(-1.0, m_rcp(dd[1]), 1.0);
+                        myNode[2 * B] = pb4 * fma(-1.0, m_rcp(dd[2]), 1.0); myNode[3 * B] = pb5 * fma(-1.0, m_rcp(dd[3]), 1.0);
+                        myNode[4 * B] = w6 * fma(-1.0, m_rcp(dd[4]), 1.0);
+                    } else {
+                        myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
+                    }
                     wsum += w6 + pb5 + pb4 + pb3 + pb2;
                     wnode = pb1;
                     lam0 = ub0; lam1 = ub1;
@@ -787,7 +817,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
     //      block finish at different times; a barrier here idled their slots: ncu v4 epilogue 45 % barrier) ----
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     if (A.partials) {
-        double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
+        double* const row = A.partials + ((size_t)prow * nw + wid) * (P + 1);
         if constexpr (GRAD) {
             // rows [q][tid] of this warp's 32 columns -> lane l sums row l (and row 32 + l): 32 shared loads and adds
             // per lane instead of 5 shuffle stages per row (the shuffle version was 4 % of the kernel, ncu v9).

@@ -131,7 +131,7 @@ int cude_loss_grad(cude_ctx* ctx, const cude_population* pop, const cude_net* ne
  * parameter-estimation.jl:126-140 split over ranks): sums_out[(P+1) x n_starts] receives for every start the *unscaled*
  * { sum_i sse_i, sum_i d sse_i / d neural[0..P) } of this shard (sum the shards' sums, divide by the global N; a start
  * whose sums_out[0] is not finite failed), g_cond[n_ind x n_starts] receives d sse_i / d cond scaled by cond_scale
- * (pass 1/N_global).  Like cude_loss / cude_loss_grad, a call of more than ~8 M trajectories runs as a pipeline of
+ * (pass 1/N_global).  Like cude_loss / cude_loss_grad, a call of more than ~2 M trajectories runs as a pipeline of
  * chunks of starts: the host->device copy of chunk k+1 and the device->host copy of chunk k-1 overlap the kernels
  * of chunk k (fully asynchronous when the host buffers are page-locked). */
 int cude_loss_grad_sums(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,

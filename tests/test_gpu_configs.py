@@ -107,18 +107,18 @@ def test_config4_profiles_117_individuals_x_1000_grid_points(fx, ctx):
 
 
 def test_pipelined_host_call_equals_single_chunk_calls(ctx):
-    """Host-buffer calls above ~8 M trajectories run as a pipeline of chunks of starts (H2D / kernels / D2H on three
+    """Host-buffer calls above ~2 M trajectories run as a pipeline of chunks of starts (H2D / kernels / D2H on three
     streams, cude_api.cu eval_host).  The result must be bitwise the one of separate small calls, start by start."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
-    n, S = 70_000, 128                                   # 8.96 M trajectories -> 2 chunks of 64 starts
+    n, S = 70_000, 128                                   # 8.96 M trajectories -> 8 chunks of 16 starts
     pk = bench.synthetic_population(n, 5)
     neural, cond = bench.synthetic_starts(n, S, 11, 6)
     pop = cu.Population(packed=pk, ctx=ctx)
     sums, gc = pop.loss_grad_sums(neural, cond, cond_scale=0.5)
     assert ctx.stats()["n_traj"] == n * S
-    for s0 in (0, 63, 64, 127):                          # both sides of the chunk boundary
+    for s0 in (0, 15, 16, 63, 64, 127):                  # both sides of chunk boundaries
         l1, gn1, gc1 = pop.loss_grad(neural[s0:s0 + 1], cond[s0:s0 + 1], mean=False)
         assert np.array_equal(sums[s0, 0], l1[0]) and np.array_equal(sums[s0, 1:], gn1[0])
         assert np.array_equal(gc[s0], 0.5 * gc1[0])
