@@ -136,6 +136,24 @@ function loss_grad(pop::Population, neural::AbstractVecOrMat{Float64}, cond::Abs
     l, gn, gc
 end
 
+"""
+Sharded-population form (one rank's block of the individuals, `:126-140` split over ranks): unscaled per-start sums
+`sums[P+1, S] = {Σ_i sse_i, Σ_i ∂sse_i/∂neural}` of this shard and `g_cond = cond_scale · ∂sse_i/∂cond` (pass
+`1/N_global`); all-reduce `sums` over the ranks and divide by `N_global`.  A start whose `sums[1, s]` is not finite failed.
+"""
+function loss_grad_sums(pop::Population, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}, cond_scale::Float64;
+                        opts=CudeOpts())
+    S = size(cond, 2)
+    sums = Matrix{Float64}(undef, pop.nparams + 1, S)
+    gc = Matrix{Float64}(undef, pop.n, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    check(ccall((:cude_loss_grad_sums, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Cdouble,
+                 Ptr{Cdouble}, Ptr{Cdouble}),
+                pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, cond_scale, sums, gc), pop.ctx.handle)
+    sums, gc
+end
+
 # --- the reference's own entry points, same tuple shapes (src/parameter-estimation.jl:56, :93, :126) ---------------
 # `p` carries a Population in place of the model (vector): (pop, timepoints, cpeptide_data[, nn]).
 loss(θ, (pop, _, _)::Tuple{Population,Any,Any}) =
