@@ -27,7 +27,7 @@ class cude_net(C.Structure):
 
 class cude_opts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiters", C.c_int),
-                ("precision", C.c_int), ("block", C.c_int)]
+                ("precision", C.c_int), ("block", C.c_int), ("balance", C.c_int)]
 
 
 class cude_stats(C.Structure):
@@ -90,7 +90,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.cude_abi_version() != 1:
+    if lib.cude_abi_version() != 2:
         raise ImportError("libcude_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -11,6 +11,7 @@
 #include <new>
 
 #include "../../include/cude_b200.h"
+#include <cub/device/device_radix_sort.cuh>
 #include "cude_kernels.cuh"
 #include "cude_sup_kernel.cuh"
 
@@ -38,6 +39,8 @@ struct cude_ctx {
     // host-buffer calls on large batches run as a pipeline of chunks of starts: H2D on s_in, kernels on `stream`, D2H on s_out
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[CUDE_MAX_CHUNKS] = {}, ev_comp[CUDE_MAX_CHUNKS] = {};
+    const unsigned int* bal_order = nullptr;   // lane-balancing pointers of the call in flight (set by balance_prepare)
+    unsigned int* bal_keys_out = nullptr;
     int chunk_mode = 0;                 // 0: single call; 1: first chunk of a pipelined call; 2: later chunk (counters/timer accumulate)
     const void* carve_kern = nullptr;   // last kernel configuration whose shared-memory carve-out was set
     size_t carve_smem = 0;
@@ -51,6 +54,14 @@ struct cude_population {
     int* n_obs = nullptr;
     double* block = nullptr;   // one allocation holding all double arrays
     PopDev dev{};
+    // lane balancing state (opts.balance): keys[0] = sorted order in use, keys[1] = raw keys the kernel writes
+    mutable unsigned int* bal_keys[2] = {nullptr, nullptr};
+    mutable size_t bal_cap = 0;          // entries per buffer
+    mutable int bal_starts = 0;          // n_starts the state belongs to
+    mutable bool bal_valid = false;      // keys[0] holds a sorted order
+    mutable long long bal_calls = 0;     // balanced calls since (re)allocation
+    mutable void* bal_temp = nullptr;
+    mutable size_t bal_temp_bytes = 0;
 };
 
 static thread_local std::string g_err;
@@ -90,6 +101,7 @@ extern "C" void cude_default_opts(cude_opts* o) {
     o->maxiters = 100000;
     o->precision = 0;
     o->block = 0;
+    o->balance = 0;
 }
 
 extern "C" int cude_net_nparams(const cude_net* net) {
@@ -284,6 +296,8 @@ extern "C" int cude_population_destroy(cude_population* pop) {
     if (pop->block) cudaFree(pop->block);
     if (pop->n_knots) cudaFree(pop->n_knots);
     if (pop->n_obs) cudaFree(pop->n_obs);
+    for (int k = 0; k < 2; ++k) if (pop->bal_keys[k]) cudaFree(pop->bal_keys[k]);
+    if (pop->bal_temp) cudaFree(pop->bal_temp);
     delete pop;
     return CUDE_OK;
 }
@@ -313,6 +327,51 @@ static int choose_block(const cude_opts* o, int n_ind, bool flat) {
     if (n_ind > 64) return 128;
     if (n_ind > 32) return 64;
     return 32;
+}
+
+// ---- lane balancing (cude_opts.balance): per start, the individuals sorted by the step counts of an earlier call.
+// The kernel writes keys (steps << 24 | individual) in natural order on refresh calls; a stable radix sort over the top
+// 8 bits of each start's segment yields the order the following calls run in.
+static const int BAL_REFRESH = 8;            // refresh the grouping every this many balanced calls
+static bool balance_applies(const cude_opts& o, const cude_population* pop, bool grad, bool flat, int n_starts) {
+    return o.balance == 1 && grad && !flat && pop->n_ind >= 4096 && pop->n_ind < (1 << 24) && n_starts <= 65536;
+}
+// sets ctx->bal_order / ctx->bal_keys_out for a call over n_starts starts (pointers to start 0)
+static int balance_prepare(cude_ctx* ctx, const cude_population* pop, int n_starts) {
+    const size_t need = (size_t)pop->n_ind * n_starts;
+    if (pop->bal_starts != n_starts || pop->bal_cap < need) {
+        for (int k = 0; k < 2; ++k) { if (pop->bal_keys[k]) cudaFree(pop->bal_keys[k]); pop->bal_keys[k] = nullptr; }
+        pop->bal_cap = 0; pop->bal_valid = false; pop->bal_calls = 0; pop->bal_starts = n_starts;
+        for (int k = 0; k < 2; ++k) CU_TRY(ctx, cudaMalloc(&pop->bal_keys[k], need * sizeof(unsigned int)));
+        pop->bal_cap = need;
+    }
+    ctx->bal_order = pop->bal_valid ? pop->bal_keys[0] : nullptr;
+    ctx->bal_keys_out = (pop->bal_calls % BAL_REFRESH == 0) ? pop->bal_keys[1] : nullptr;
+    return CUDE_OK;
+}
+// after the kernels of the call: on refresh calls sort every start's keys into the order buffer (same stream)
+static int balance_finish(cude_ctx* ctx, const cude_population* pop, int n_starts, int* launches) {
+    const bool refresh = ctx->bal_keys_out != nullptr;
+    ctx->bal_order = nullptr; ctx->bal_keys_out = nullptr;
+    ++pop->bal_calls;
+    if (!refresh) return CUDE_OK;
+    const int N = pop->n_ind;
+    size_t bytes = 0;
+    CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, bytes, pop->bal_keys[1], pop->bal_keys[0], N, 24, 32, ctx->stream));
+    if (bytes > pop->bal_temp_bytes) {
+        if (pop->bal_temp) cudaFree(pop->bal_temp);
+        pop->bal_temp = nullptr; pop->bal_temp_bytes = 0;
+        CU_TRY(ctx, cudaMalloc(&pop->bal_temp, bytes));
+        pop->bal_temp_bytes = bytes;
+    }
+    for (int s = 0; s < n_starts; ++s) {
+        size_t b = pop->bal_temp_bytes;
+        CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(pop->bal_temp, b, pop->bal_keys[1] + (size_t)s * N, pop->bal_keys[0] + (size_t)s * N,
+                                                   N, 24, 32, ctx->stream));
+    }
+    if (launches) *launches += n_starts;
+    pop->bal_valid = true;
+    return CUDE_OK;
 }
 
 extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
@@ -348,6 +407,9 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     if (nblocks > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many blocks; split the call");
 
     int rc;
+    const bool bal = balance_applies(o, pop, grad, flat, n_starts);
+    const bool bal_own = bal && ctx->chunk_mode == 0;    // a pipelined host call prepares / finishes around its chunks
+    if (bal_own && (rc = balance_prepare(ctx, pop, n_starts))) return rc;
     if ((rc = ensure(ctx, ctx->counters, 3 * sizeof(unsigned long long)))) return rc;
     double* d_partials = nullptr;
     if (!flat && d_sums_out) {
@@ -374,6 +436,8 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     a.partials = d_partials;
     a.g_cond = grad ? d_g_cond : nullptr;
     a.counters = (unsigned long long*)ctx->counters.p;
+    a.order = bal ? ctx->bal_order : nullptr;
+    a.keys_out = bal ? ctx->bal_keys_out : nullptr;
 
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
@@ -414,6 +478,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
     }
+    if (bal_own && (rc = balance_finish(ctx, pop, n_starts, &launches))) return rc;
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     if (ctx->chunk_mode != 2) ctx->stats = cude_stats{};
     ctx->stats.n_traj += (unsigned long long)ntraj;
@@ -491,6 +556,12 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         }
         // software pipeline in launch order H2D(k+1), kernels(k+1), D2H(k): with pageable host memory the copies block
         // the host, but never before the next chunk's kernels are queued behind the running ones
+        cude_opts o;
+        if (opts) o = *opts; else cude_default_opts(&o);
+        const bool bal = balance_applies(o, pop, want_grad != 0, neural_stride == 0 && !(wg & 2), n_starts);
+        if (bal && (rc = balance_prepare(ctx, pop, n_starts))) return rc;
+        const unsigned int* const ord0 = bal ? ctx->bal_order : nullptr;
+        unsigned int* const keys0 = bal ? ctx->bal_keys_out : nullptr;
         auto lo = [&](int k) { return (int)((long long)n_starts * k / nch); };
         auto h2d = [&](int k) -> int {
             const size_t o = (size_t)lo(k) * N, n = (size_t)(lo(k + 1) - lo(k)) * N;
@@ -502,6 +573,8 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
             const int s0 = lo(k), ns = lo(k + 1) - s0;
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
             ctx->chunk_mode = k == 0 ? 1 : 2;
+            ctx->bal_order = ord0 ? ord0 + (size_t)s0 * N : nullptr;
+            ctx->bal_keys_out = keys0 ? keys0 + (size_t)s0 * N : nullptr;
             const int r = cude_eval_dev(ctx, pop, net, opts, ns, d_neural + (size_t)s0 * neural_stride, neural_stride,
                                         d_cond + (size_t)s0 * N, wg, cscale, d_sse ? d_sse + (size_t)s0 * N : nullptr,
                                         d_sums + (size_t)s0 * np1, d_gc ? d_gc + (size_t)s0 * N : nullptr);
@@ -521,6 +594,10 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         for (int k = 0; k < nch; ++k) {
             if (k + 1 < nch && ((rc = h2d(k + 1)) || (rc = run(k + 1)))) return rc;
             if ((rc = d2h(k))) return rc;
+        }
+        if (bal) {
+            ctx->bal_order = ord0; ctx->bal_keys_out = keys0;
+            if ((rc = balance_finish(ctx, pop, n_starts, nullptr))) return rc;
         }
     }
     CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, d_sums, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -113,6 +113,11 @@ struct EvalArgs {
     double* partials;           // [n_blocks * warps_per_block][P+1]: {sum sse, sum d sse/d neural} per warp, or nullptr
     double* g_cond;             // [N x S] or nullptr
     unsigned long long* counters;  // {n_acc, n_rej, n_fail}
+    // lane balancing (tile mode, opts.balance): position pos of start s runs individual order[s*N + pos] & 0xffffff —
+    // the start's individuals sorted by the step count of a previous call, so that the 32 lanes of a warp (and the 4
+    // warps of a block) finish together; keys_out[s*N + i] = (min(steps, 255) << 24) | i feeds the next sort.
+    const unsigned int* order;     // [N x S] or nullptr (natural order)
+    unsigned int* keys_out;        // [N x S] or nullptr
 };
 
 // ---------------------------------------------------------------- network shape
@@ -132,6 +137,9 @@ struct NetShape {
 #endif
 #ifndef CUDE_MIN_BLOCKS
 #define CUDE_MIN_BLOCKS 3   // resident 128-thread blocks per SM the register allocation is tuned for
+#endif
+#ifndef CUDE_MIN_BLOCKS_LOSS
+#define CUDE_MIN_BLOCKS_LOSS 3   // same for the loss-only instantiation
 #endif
 #ifndef CUDE_FWD_UNROLL
 #define CUDE_FWD_UNROLL 1   // unroll factor of the forward network-evaluation loop over a step's 5 nodes
@@ -369,7 +377,7 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 }
 
 template <class NS, bool GRAD, bool MIXED = false>
-__global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_kernel(const EvalArgs A) {
+__global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUDE_MIN_BLOCKS_LOSS) cude_eval_kernel(const EvalArgs A) {
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
     typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the network evaluation
@@ -408,8 +416,9 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
         prow = (long long)s * A.nchunks + c;
         i = c * B + tid;
         active = i < N;
-        j = (long long)s * N + i;
         if (!active) i = 0;
+        else if (A.order) i = (int)(A.order[(size_t)s * N + i] & 0xffffffu);
+        j = (long long)s * N + i;
     }
     // ---- stage the start's weights (block-uniform) ----
     {
@@ -810,6 +819,10 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, CUDE_MIN_BLOCKS) cude_eval_k
 
     // ---- outputs ----
     if (active) {
+        if (A.keys_out) {
+            const int ns = nacc + nrej;
+            A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
+        }
         if (A.sse_out) A.sse_out[j] = sse;
         if (GRAD && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
     }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CUDE_B200_ABI_VERSION 1
+#define CUDE_B200_ABI_VERSION 2
 
 enum {
     CUDE_OK = 0,
@@ -57,6 +57,12 @@ typedef struct {
     int precision; /* 0 = FP64 (the parity-gated mode); 1 = FP32 network evaluation (MUFU ex2/rcp/lg2) with the
                     * integrator, adjoint and reductions in FP64: looser documented bound, see DESIGN.md */
     int block;     /* threads per block (individuals per tile); 0 = library default */
+    int balance;   /* 0 (default) = lanes in natural order: the per-start sums are bitwise run-to-run deterministic.
+                    * 1 = iterative workloads (training): for loss+gradient calls on >= 4096 individuals with
+                    * per-start networks, the individuals of each start are regrouped by the step counts their
+                    * trajectories took in an earlier call on this population (refreshed every 8 calls), so that the
+                    * 32 lanes of a warp finish together (~12 % fewer warp-steps).  Per-trajectory results (sse,
+                    * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping. */
 } cude_opts;
 
 typedef struct {

@@ -126,3 +126,41 @@ def test_pipelined_host_call_equals_single_chunk_calls(ctx):
     loss, sse = pop.loss(neural, cond, return_sse=True)
     assert np.allclose(loss * n, sums[:, 0], rtol=1e-13)
     assert np.array_equal(sse[5], pop.loss(neural[5:6], cond[5:6], return_sse=True)[1][0])
+    # shared network (flat indexing: beta-only fits, profiles), pipelined: 70 000 x 64 = 4.5 M trajectories
+    l2, sse2 = pop.loss(neural[0], cond[:64], return_sse=True)
+    l1, sse1 = pop.loss(neural[0], cond[17:18], return_sse=True)
+    assert np.array_equal(sse2[17], sse1[0]) and l2[17] == l1[0]
+    lg, gn, gc2 = pop.loss_grad(neural[0], cond[:64], neural_grad=False, mean=False)
+    _, _, gc1 = pop.loss_grad(neural[0], cond[40:41], neural_grad=False, mean=False)
+    assert np.array_equal(gc2[40], gc1[0]) and np.allclose(lg, l2 * n, rtol=1e-13)
+
+
+def test_lane_balancing_changes_the_grouping_not_the_results(ctx):
+    """opts.balance = 1 (cude_b200.h): after the first call each start's individuals run grouped by their previous step
+    counts.  Per-trajectory outputs must be bitwise those of the natural order; per-start sums agree to summation
+    order; a changed parameter set on the same population still gives exact per-trajectory results."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n, S = 20_000, 6
+    pk = bench.synthetic_population(n, 9)
+    neural, cond = bench.synthetic_starts(n, S, 11, 10)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    ref = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    ob = cu.SolverOptions(balance=1)
+    acc0 = None
+    for it in range(3):                                   # call 0: natural order + sort; calls 1, 2: grouped
+        l, gn, gc, sse = pop.loss_grad(neural, cond, opts=ob, mean=False, return_sse=True)
+        assert np.array_equal(sse, ref[3]) and np.array_equal(gc, ref[2])
+        assert np.allclose(l, ref[0], rtol=1e-12) and np.allclose(gn, ref[1], rtol=1e-9, atol=1e-9 * np.abs(ref[1]).max())
+        st = ctx.stats()
+        acc0 = acc0 or st["n_acc"]
+        assert st["n_acc"] == acc0 and st["n_fail"] == 0
+    # other parameters on the same population (the grouping is now a prediction, not exact)
+    neural2, cond2 = bench.synthetic_starts(n, S, 12, 13)
+    r2 = pop.loss_grad(neural2, cond2, mean=False, return_sse=True)
+    b2 = pop.loss_grad(neural2, cond2, opts=ob, mean=False, return_sse=True)
+    assert np.array_equal(b2[3], r2[3]) and np.array_equal(b2[2], r2[2]) and np.allclose(b2[0], r2[0], rtol=1e-12)
+    # a different number of starts resets the state
+    b3 = pop.loss_grad(neural2[:2], cond2[:2], opts=ob, mean=False, return_sse=True)
+    assert np.array_equal(b3[3], r2[3][:2])

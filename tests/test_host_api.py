@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.cude_abi_version() == 1
+    assert lib.cude_abi_version() == 2
     o = _lib.cude_opts()
     lib.cude_default_opts(C.byref(o))
     assert (o.abstol, o.reltol, o.maxiters) == (1e-6, 1e-3, 100000)     # OrdinaryDiffEq defaults
