@@ -400,7 +400,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     const bool want_neural_grad = grad && (want_grad & 2);
     const bool flat = (neural_stride == 0) && !want_neural_grad;
     const int B = choose_block(&o, N, flat);
-    if (B < 32 || B > 128 || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: block must be 32, 64, 96 or 128");
+    if (B < 32 || B > CUDE_MAX_THREADS || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: block must be a multiple of 32, at most 128");
     const long long ntraj = (long long)N * n_starts;
     const int nchunks = (N + B - 1) / B;
     const long long nblocks = flat ? (ntraj + B - 1) / B : (long long)n_starts * nchunks;
