@@ -267,24 +267,62 @@ def train_with_sigma(models, timepoints, cpeptide_data, neural_network_parameter
 
 
 # ----------------------------------------------------------------------------- multi-start cUDE training
+class _Comm:
+    """Start-sharding helper for the communication-free configurations (multi-start screening / training, profiles):
+    every rank works on a contiguous slice of the starts and the (tiny) per-start results are all-gathered.
+    distributed=False (or an uninitialised torch.distributed) is the single-process case."""
+
+    def __init__(self, distributed=False, group=None):
+        self.rank, self.world, self.group, self.dist = 0, 1, group, None
+        if distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist, self.rank, self.world = dist, dist.get_rank(group), dist.get_world_size(group)
+
+    def bounds(self, n, rank=None):
+        r = self.rank if rank is None else rank
+        return r * n // self.world, (r + 1) * n // self.world
+
+    def allgather_rows(self, local, n_total):
+        """local = rows [lo:hi) of an [n_total x ...] float64 array -> the full array on every rank."""
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        if self.world == 1:
+            return local
+        import torch
+        full = np.zeros((n_total,) + local.shape[1:], dtype=np.float64)
+        lo, hi = self.bounds(n_total)
+        full[lo:hi] = local
+        t = torch.from_numpy(full)
+        if self.dist.get_backend(self.group) == "nccl":          # NCCL reduces device tensors only
+            t = t.cuda()
+        self.dist.all_reduce(t, group=self.group)                # disjoint slices: the sum is the concatenation
+        return t.cpu().numpy()
+
+
 def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=25_000, selected_initials=25,
           lhs_lower_bound=-2.0, lhs_upper_bound=0.0, n_conditional_parameters=1, number_of_iterations_adam=1000,
-          number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None, **kw):
+          number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None, distributed=False, group=None, **kw):
     """The two cUDE `train` methods of the reference, dispatched like Julia on the 4th argument:
       train(models, t, Y, rng::Generator; ...)  full training (:340-386)
-      train(models, t, Y, nn::vector; initial_beta, lbfgs_lower_bound, ...)  beta-only (:272-288)."""
+      train(models, t, Y, nn::vector; initial_beta, lbfgs_lower_bound, ...)  beta-only (:272-288).
+    distributed=True (one process per GPU under torch.distributed; BASELINE config "starts sharded over 8 x B200"):
+    every rank draws the same initial guesses from an identically seeded `rng`, screens its slice of them, the losses
+    are all-gathered, the globally best `selected_initials` starts are split over the ranks and optimised there, and
+    every rank returns all solutions in selection order.  No communication on the data path."""
     if not isinstance(rng_or_nn, np.random.Generator):
         return train_conditional(models, timepoints, cpeptide_data, rng_or_nn, opts=opts, **kw)
     if n_conditional_parameters != 1:
         raise NotImplementedError("one conditional parameter per individual")
     rng = rng_or_nn
+    comm = _Comm(distributed, group)
     pop = _as_population(models, timepoints, cpeptide_data)
     n, P = pop.n_ind, pop.n_params
     # sample initial parameters (:350-357)
     neural0 = np.stack(initial_parameters(pop.chain, initial_guesses, rng=rng))
     cond0 = initial_parameters(n, lhs_lower_bound, lhs_upper_bound, initial_guesses, rng).T        # [guesses x n]
-    # preselect (:360-366): ONE loss-only launch over all guesses
-    losses_initial = pop.loss(neural0, cond0, opts)
+    # preselect (:360-366): ONE loss-only launch over this rank's guesses
+    lo, hi = comm.bounds(initial_guesses)
+    losses_initial = comm.allgather_rows(pop.loss(neural0[lo:hi], cond0[lo:hi], opts) if hi > lo else np.empty(0), initial_guesses)
     pick = np.argsort(losses_initial, kind="stable")[:selected_initials]                            # partialsortperm
     x0 = np.concatenate([neural0[pick], cond0[pick]], axis=1)
 
@@ -295,16 +333,26 @@ def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=25_000, 
         l, gn, gc = pop.loss_grad(x[:, :P], x[:, P:], opts)
         return l, np.concatenate([gn, gc], axis=1)
 
-    # training step 1 (Adam) and 2 (LBFGS), :170-183 — all selected starts in lock-step
-    x1, _ = adam_batched(fg, x0, lr=learning_rate_adam, maxiters=number_of_iterations_adam)
-    x2, fx, iters, conv = lbfgs_batched(f, fg, x1, maxiters=number_of_iterations_lbfgs)
+    # training step 1 (Adam) and 2 (LBFGS), :170-183 — this rank's selected starts in lock-step
+    k = x0.shape[0]
+    lo, hi = comm.bounds(k)
+    res = np.full((hi - lo, P + n + 3), np.nan)
+    if hi > lo:
+        x1, _ = adam_batched(fg, x0[lo:hi], lr=learning_rate_adam, maxiters=number_of_iterations_adam)
+        x2, fx, iters, conv = lbfgs_batched(f, fg, x1, maxiters=number_of_iterations_lbfgs)
+        res = np.concatenate([x2, fx[:, None], np.asarray(iters, dtype=np.float64)[:, None],
+                              np.asarray(conv, dtype=np.float64)[:, None]], axis=1)
+    # Inf objectives travel as a flag (the gather is a sum over ranks)
+    bad = ~np.isfinite(res[:, P + n])
+    res = np.where(np.isfinite(res), res, 0.0)
+    res = comm.allgather_rows(np.concatenate([res, bad[:, None].astype(np.float64)], axis=1), k)
     sols = []
-    for s in range(x2.shape[0]):
-        if not np.isfinite(fx[s]):
+    for s_ in range(k):
+        if res[s_, -1] != 0.0:
             print("Optimization failed... Skipping")                                                # :378-380
             continue
-        sols.append(OptimizationSolution(ComponentVector(neural=x2[s, :P].copy(), conditional=x2[s, P:].copy()),
-                                         fx[s], iters[s], conv[s]))
+        sols.append(OptimizationSolution(ComponentVector(neural=res[s_, :P].copy(), conditional=res[s_, P:P + n].copy()),
+                                         res[s_, P + n], int(res[s_, P + n + 1]), bool(res[s_, P + n + 2])))
     return sols
 
 

@@ -26,18 +26,25 @@ def likelihood_profile(beta, neural_network_parameters, model, timepoints, cpept
 
 
 def likelihood_profile_population(betas, neural_network_parameters, population, lower_bounds, upper_bounds, sigmas,
-                                  steps=1000, opts=None):
+                                  steps=1000, opts=None, distributed=False, group=None):
     """All individuals' profiles in one launch: grid[s, i] = lower_i + s (upper_i - lower_i)/(steps-1).
-    Returns (nll[steps x N], nll_minimum[N], parameter_values[steps x N])."""
-    if not isinstance(population, Population):
+    Returns (nll[steps x N], nll_minimum[N], parameter_values[steps x N]).
+    distributed=True: the grid points are split over the torch.distributed ranks (no communication on the data path;
+    the sse rows are all-gathered) and every rank returns the full profile."""
+    from .estimation import _Comm
+    if not (isinstance(population, Population) or (hasattr(population, "loss") and hasattr(population, "n_ind"))):
         raise TypeError("population must be a Population")
+    comm = _Comm(distributed, group)
     n = population.n_ind
     lb = np.broadcast_to(np.asarray(lower_bounds, dtype=np.float64), (n,))
     ub = np.broadcast_to(np.asarray(upper_bounds, dtype=np.float64), (n,))
     sig = np.broadcast_to(np.asarray(sigmas, dtype=np.float64), (n,))
     grid = np.linspace(lb, ub, steps)                       # [steps x N]
     cond = np.vstack([np.asarray(betas, dtype=np.float64).reshape(1, n), grid])
-    _, sse = population.loss(np.asarray(neural_network_parameters, dtype=np.float64), cond, opts, return_sse=True)
+    lo, hi = comm.bounds(steps + 1)
+    nn = np.asarray(neural_network_parameters, dtype=np.float64)
+    sse = population.loss(nn, cond[lo:hi], opts, return_sse=True)[1] if hi > lo else np.empty((0, n))
+    sse = comm.allgather_rows(sse, steps + 1)
     scale = 1.0 / (2.0 * sig ** 2)
     return sse[1:] * scale, sse[0] * scale, grid
 

@@ -100,15 +100,18 @@ class OraclePopulationAdapter:
         self.op = oracle.OraclePopulation(pk)
         self.chain, self.n_ind, self.n_params = pk["chain"], pk["n_ind"], pk["chain"].n_params
         self.calls = 0
+        self.traj = 0            # trajectories evaluated (start-sharding tests)
 
     def loss(self, neural, cond, opts=None, return_sse=False):
         self.calls += 1
+        self.traj += int(np.asarray(cond).size)
         r = self.op.eval(neural, cond)
         loss = r["sse"].mean(axis=1)
         return (loss, r["sse"]) if return_sse else loss
 
     def loss_grad(self, neural, cond, opts=None, neural_grad=True, mean=True, return_sse=False):
         self.calls += 1
+        self.traj += int(np.asarray(cond).size)
         r = self.op.eval(neural, cond, grad_mode=0)
         sc = 1.0 / self.n_ind if mean else 1.0
         out = (r["sse"].sum(axis=1) * sc, r["g_neural"].sum(axis=1) * sc if neural_grad else None, r["g_cond"] * sc)

@@ -70,3 +70,47 @@ def test_two_rank_population_step_equals_single_rank(tmp_path, fx):
     gc = np.concatenate([r[0]["gc"], r[1]["gc"]], axis=1)
     assert np.allclose(gc, ref["g_cond"], rtol=1e-13, atol=0)
     assert np.array_equal(r[0]["loss"], r[1]["loss"]) and np.array_equal(r[0]["g"], r[1]["g"])
+
+
+def _worker_starts(rank, world, port, out_dir):
+    """Start-sharded configurations (multi-start training, profiles): no communication on the data path."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import conditional_ude_b200 as cu
+    from helpers import train57, OraclePopulationAdapter
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz")))
+    models, t, c, nn, betas = train57(fx)
+    pop = OraclePopulationAdapter(models[:6], t, c[:6])
+    sols = cu.train(pop, t, c[:6], np.random.default_rng(5), initial_guesses=21, selected_initials=3,
+                    number_of_iterations_adam=4, number_of_iterations_lbfgs=3, distributed=True)
+    nll, nmin, grid = cu.likelihood_profile_population(betas[:6], nn, pop, betas[:6] - 1.0, betas[:6] + 1.0, 0.1, steps=9,
+                                                       distributed=True)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), obj=[s.objective for s in sols], neural=[s.u.neural for s in sols],
+             cond=[s.u.conditional for s in sols], nll=nll, nmin=nmin, grid=grid, traj=pop.traj)
+    dist.destroy_process_group()
+
+
+def test_two_rank_start_sharded_train_and_profiles_equal_single_rank(tmp_path, fx):
+    world = 2
+    mp.spawn(_worker_starts, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conditional_ude_b200 as cu
+    from helpers import train57, OraclePopulationAdapter
+    models, t, c, nn, betas = train57(fx)
+    pop = OraclePopulationAdapter(models[:6], t, c[:6])
+    ref = cu.train(pop, t, c[:6], np.random.default_rng(5), initial_guesses=21, selected_initials=3,
+                   number_of_iterations_adam=4, number_of_iterations_lbfgs=3)
+    rnll, rmin, rgrid = cu.likelihood_profile_population(betas[:6], nn, pop, betas[:6] - 1.0, betas[:6] + 1.0, 0.1, steps=9)
+    r = [np.load(tmp_path / f"s{k}.npz") for k in range(world)]
+    assert len(ref) == 3
+    for k in range(world):
+        # every start is optimised independently of the others in its batch, so the split changes nothing
+        assert np.array_equal(r[k]["obj"], [s.objective for s in ref])
+        assert np.array_equal(r[k]["neural"], [s.u.neural for s in ref]) and np.array_equal(r[k]["cond"], [s.u.conditional for s in ref])
+        assert np.array_equal(r[k]["nll"], rnll) and np.array_equal(r[k]["nmin"], rmin) and np.array_equal(r[k]["grid"], rgrid)
+    # the work really was split: each rank evaluated about half of the trajectories
+    assert max(int(r[0]["traj"]), int(r[1]["traj"])) < 0.75 * pop.traj
