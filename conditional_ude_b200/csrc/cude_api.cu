@@ -24,6 +24,9 @@ struct DevBuf {
 };
 
 #define CUDE_MAX_CHUNKS 16
+#ifndef CUDE_BETA_FORWARD_SENSITIVITY
+#define CUDE_BETA_FORWARD_SENSITIVITY 1   // 0: beta-only gradients through the adjoint kernel (comparison builds)
+#endif
 struct cude_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // stream in use
@@ -307,16 +310,18 @@ extern "C" int cude_population_size(const cude_population* pop) { return pop ? p
 // ---------------------------------------------------------------- launch
 typedef void (*eval_kernel_t)(const EvalArgs);
 
+// grad: discrete adjoint (all gradients); bsens: d/d cond only by forward sensitivity (FP64 only)
 template <class NS>
-static eval_kernel_t pick(bool grad, bool mixed) {
+static eval_kernel_t pick(bool grad, bool mixed, bool bsens) {
+    if (bsens) return cude_eval_kernel<NS, false, false, true>;
     if (mixed) return grad ? cude_eval_kernel<NS, true, true> : cude_eval_kernel<NS, false, true>;
     return grad ? cude_eval_kernel<NS, true, false> : cude_eval_kernel<NS, false, false>;
 }
 
-static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed) {
+static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed, bool bsens = false) {
     if (net->depth == 2 && net->width == 4) {
-        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed);   // chain(4, 2, tanh), 02-conditional.jl:22
-        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed);   // covariate net, 07-covariate-inclusion.jl:32
+        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed, bsens);   // chain(4, 2, tanh), 02-conditional.jl:22
+        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed, bsens);   // covariate net, 07-covariate-inclusion.jl:32
     }
     return nullptr;
 }
@@ -390,7 +395,11 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad network description");
     if (net->n_in == 3 && !pop->dev.cov) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: 3-input network needs a population with a covariate");
     const bool grad = want_grad != 0;
-    eval_kernel_t kern = select_kernel(net, grad, mixed);
+    // beta-only gradient (want_grad == 1: d/d cond, no network gradient): one forward-sensitivity column inside the
+    // loss kernel instead of the adjoint sweep (src/parameter-estimation.jl:272-307, evaluate_model :406-433)
+    const bool bsens = want_grad == 1 && !mixed && CUDE_BETA_FORWARD_SENSITIVITY;
+    const bool adj = grad && !bsens;
+    eval_kernel_t kern = select_kernel(net, adj, mixed, bsens);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -441,7 +450,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
 
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
-    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, grad, mixed);
+    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, adj, mixed, bsens);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if ((const void*)kern != ctx->carve_kern || smem != ctx->carve_smem || B != ctx->carve_block) {

@@ -238,6 +238,55 @@ __device__ __forceinline__ double mlp_zout(const double* __restrict__ sW, const 
     for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[i], z);
     return t_nan_inject(z, nanmax);
 }
+// z_out and dzb = sum_q (d z_out / d z1_q) * W1[q, beta column]: the derivative of z_out w.r.t. the second network
+// input (beta), from the activations in hand — the beta-only fits (reference src/parameter-estimation.jl:272-307) need
+// d loss / d cond only, which one forward-sensitivity column delivers without an adjoint sweep.
+template <class NS>
+__device__ __forceinline__ double mlp_zout_dbeta(const double* __restrict__ sW, const double* __restrict__ tab, const double (&c)[NS::W],
+                                                 double dG, double& dzb) {
+    constexpr int W = NS::W, D = NS::DEPTH;
+    int nanmax = 0;
+    double a[D][W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[0][j] = t_tanh(fma(sW[j], dG, c[j]), tab, nanmax);
+    int off = NS::L1;
+#pragma unroll
+    for (int l = 1; l < D; ++l) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            double z = sW[off + W * W + j];
+#pragma unroll
+            for (int i = 0; i < W; ++i) z = fma(sW[off + i * W + j], a[l - 1][i], z);
+            a[l][j] = t_tanh(z, tab, nanmax);
+        }
+        off += NS::LH;
+    }
+    double z = sW[off + W];
+    double da[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) { z = fma(sW[off + i], a[D - 1][i], z); da[i] = sW[off + i]; }
+#pragma unroll
+    for (int l = D - 1; l >= 1; --l) {
+        off -= NS::LH;
+        double dzl[W], dprev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], 1.0);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) sacc = fma(sW[off + i * W + j], dzl[j], sacc);
+            dprev[i] = sacc;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) da[j] = dprev[j];
+    }
+    double g = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) g = fma(da[j] * fma(-a[0][j], a[0][j], 1.0), sW[W + j], g);
+    dzb = g;
+    return t_nan_inject(z, nanmax);
+}
 template <class NS>
 __device__ __forceinline__ float mlp_zout(const float* __restrict__ sW, const double* __restrict__ tab, const float (&c)[NS::W], float dG) {
     constexpr int W = NS::W;
@@ -365,19 +414,22 @@ __device__ __forceinline__ void kinetics(const Kin& K, double u0, double u1, dou
 }
 
 // dynamic shared memory (doubles) needed by cude_eval_kernel
-__host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false) {
+__host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int M, int B, bool grad, bool mixed = false, bool bsens = false) {
     // exp table (256) + weights (+ float copy) + per-thread rows: knots 3K, observations 2M, node values 5, GRAD: dG 5 + residuals M.
     // Kept small on purpose: what shared memory does not take stays L1, which serves the per-thread step ring and the
     // register spills (ncu v8: with 65 KB per block the L1 hit rate was 12 % and every spill reload went to L2).
     // GRAD: at least NACC rows — the accumulators are parked in the (then dead) rows for the final warp reduction.
-    size_t rows = (size_t)(3 * K + 2 * M) + 5 + (grad ? (size_t)(5 + M) : 0);
+    size_t rows = (size_t)(3 * K + 2 * M) + 5 + (grad ? (size_t)(5 + M) : 0) + (bsens ? 5 : 0);
     if (grad && rows < (size_t)NACC) rows = (size_t)NACC;
     if (grad && rows < (size_t)P + 1) rows = (size_t)P + 1;   // expanded rows {sse, d/d neural[0..P)} for the warp reduction
     return (size_t)256 + (size_t)((P + 1) & ~1) * (mixed ? 2 : 1) + rows * B;
 }
 
-template <class NS, bool GRAD, bool MIXED = false>
+// BSENS (only with GRAD = false, MIXED = false): loss + d sse / d cond by one forward-sensitivity column carried through
+// the same steps (frozen step sequence => the same derivative the adjoint produces), no step ring, no backward sweep.
+template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false>
 __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUDE_MIN_BLOCKS_LOSS) cude_eval_kernel(const EvalArgs A) {
+    static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
     typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the network evaluation
@@ -395,8 +447,8 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
     double* sOt = sSl + (size_t)K * B;               // [M][B] observation times
     double* sOy = sOt + (size_t)M * B;               // [M][B] observed c-peptide
     double* sNode = sOy + (size_t)M * B;             // [5][B] network outputs (forward) / node weights (adjoint)
-    double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD)
-    double* sRes = sDG + (GRAD ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
+    double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD) / d z_out/d beta at the nodes (BSENS)
+    double* sRes = sDG + ((GRAD || BSENS) ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
 
     // ---- which trajectory ----
     long long j, prow = blockIdx.x;   // prow: this block's row group in `partials`, [start][chunk] order
@@ -503,6 +555,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
             double fsse = 0.0;
             double next_ot = (nobs > 0) ? obs_t[0] : CUDART_INF;
             int kbase = 0, klast = 0;      // glucose interval of the step's start time / of its end node
+            double s0 = 0.0, s1 = 0.0, js10 = 0.0, js11 = 0.0, dnn0 = 0.0, gsens = 0.0;   // BSENS: d u/d cond, its FSAL stage, d NN0/d beta
             // save_start: observations at (or before) t0 see u0
             while (iobs < nobs && next_ot <= t0) {
                 const double r = u0 - obs_y[iobs * B];
@@ -520,9 +573,9 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
             double dt0, d1;
             {
                 double x0 = u0 * isk0, x1 = u1 * isk1;
-                const double d0 = sqrt((x0 * x0 + x1 * x1) * 0.5);
+                const double d0 = sqrt(m_sumsq(x0, x1) * 0.5);
                 x0 = k10 * isk0; x1 = k11 * isk1;
-                d1 = sqrt((x0 * x0 + x1 * x1) * 0.5);
+                d1 = sqrt(m_sumsq(x0, x1) * 0.5);
                 dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
                 dt0 = fmin(dt0, dtmax);
             }
@@ -547,9 +600,15 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                     for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], dt, t);
                     kn.dG5(tau, myNode, B, kbase, klast);         // dG of the node times, staged in myNode
                 }
-                CUDE_UNROLL(CUDE_FWD_UNROLL)
-                for (int q = 0; q < 5; ++q)
-                    if (q < nq) myNode[q * B] = (double)mlp_zout<NS>(sWr, sTab, cr, (R)myNode[q * B]);
+                if constexpr (BSENS) {
+#pragma unroll 1
+                    for (int q = 0; q < 5; ++q)
+                        if (q < nq) { double dzb; myNode[q * B] = mlp_zout_dbeta<NS>(sW, sTab, c, myNode[q * B], dzb); myDG[q * B] = dzb; }
+                } else {
+                    CUDE_UNROLL(CUDE_FWD_UNROLL)
+                    for (int q = 0; q < 5; ++q)
+                        if (q < nq) myNode[q * B] = (double)mlp_zout<NS>(sWr, sTab, cr, (R)myNode[q * B]);
+                }
                 // softplus of the 5 nodes together (init: entries >= nq hold dG values — evaluated and ignored)
                 double sp[5], dd[5];
 #pragma unroll
@@ -562,11 +621,12 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                     init = false;
                     nn0 = sp[0];                                  // network([0; beta]) — identical at every call
                     d_nn0 = dd[0];
+                    if (BSENS) dnn0 = fma(-1.0, m_rcp(dd[0]), 1.0) * myDG[0];   // d network([0; beta]) / d beta
                     const double pe = sp[1] - nn0;
                     double f0, f1;
                     kinetics(Kc, fma(dt0, k10, u0), fma(dt0, k11, u1), pe, f0, f1);
                     const double x0 = (f0 - k10) * isk0, x1 = (f1 - k11) * isk1;
-                    const double d2 = sqrt((x0 * x0 + x1 * x1) * 0.5) / dt0;
+                    const double d2 = sqrt(m_sumsq(x0, x1) * 0.5) / dt0;
                     const double dm = fmax(d1, d2);
                     const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : t_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
                     dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
@@ -608,10 +668,36 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                 // ---- error estimate ----
                 f0 = dt * fma(e7, k70, se0);
                 f1 = dt * fma(e7, k71, se1);
+                // ---- BSENS: the same stages for s = d u / d cond: s' = A s + e1 d prod/d cond, d prod/d cond =
+                //      beta (sigmoid(z_out) dzb - d NN([0;beta])/d beta) at the step's nodes ----
+                double sn0 = 0.0, sn1 = 0.0, j20 = 0.0, j30 = 0.0, j40 = 0.0, j50 = 0.0, j60 = 0.0, j70 = 0.0, j71 = 0.0;
+                if constexpr (BSENS) {
+                    double dq[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) dq[q] = beta * fma(fma(-1.0, m_rcp(dd[q]), 1.0), myDG[q * B], -dnn0);
+                    double j21, j31, j41, j51, j61, h0, h1;
+#define CUDE_SKIN(G0, G1, DP, F0, F1) F0 = fma(Kc.d00, G0, fma(Kc.k1, G1, DP)); F1 = fma(-Kc.k1, G1, Kc.k2 * (G0));
+                    h0 = fma(dt * a21, js10, s0); h1 = fma(dt * a21, js11, s1);
+                    CUDE_SKIN(h0, h1, dq[0], j20, j21)
+                    h0 = fma(dt, fma(a31, js10, a32 * j20), s0); h1 = fma(dt, fma(a31, js11, a32 * j21), s1);
+                    CUDE_SKIN(h0, h1, dq[1], j30, j31)
+                    h0 = fma(dt, fma(a41, js10, fma(a42, j20, a43 * j30)), s0); h1 = fma(dt, fma(a41, js11, fma(a42, j21, a43 * j31)), s1);
+                    CUDE_SKIN(h0, h1, dq[2], j40, j41)
+                    h0 = fma(dt, fma(a51, js10, fma(a52, j20, fma(a53, j30, a54 * j40))), s0);
+                    h1 = fma(dt, fma(a51, js11, fma(a52, j21, fma(a53, j31, a54 * j41))), s1);
+                    CUDE_SKIN(h0, h1, dq[3], j50, j51)
+                    h0 = fma(dt, fma(a61, js10, fma(a62, j20, fma(a63, j30, fma(a64, j40, a65 * j50)))), s0);
+                    h1 = fma(dt, fma(a61, js11, fma(a62, j21, fma(a63, j31, fma(a64, j41, a65 * j51)))), s1);
+                    CUDE_SKIN(h0, h1, dq[4], j60, j61)
+                    sn0 = fma(dt, fma(b1, js10, fma(b2, j20, fma(b3, j30, fma(b4, j40, fma(b5, j50, b6 * j60))))), s0);
+                    sn1 = fma(dt, fma(b1, js11, fma(b2, j21, fma(b3, j31, fma(b4, j41, fma(b5, j51, b6 * j61))))), s1);
+                    CUDE_SKIN(sn0, sn1, dq[4], j70, j71)
+#undef CUDE_SKIN
+                }
                 f0 = f0 * m_rcp(fma(fmax(fabs(u0), fabs(un0)), reltol, abstol));   // denominators >= abstol > 0
                 f1 = f1 * m_rcp(fma(fmax(fabs(u1), fabs(un1)), reltol, abstol));
                 // EEst = sqrt(E2); accept iff EEst <= 1 iff E2 <= 1; the controller only needs ln EEst = ln(E2)/2
-                const double E2 = (f0 * f0 + f1 * f1) * 0.5;
+                const double E2 = m_sumsq(f0, f1) * 0.5;
                 if (!(E2 == E2) || !isfinite(un0) || !isfinite(un1)) { ret = 3; break; }
                 CUDE_TRACE_STEP(t, dt, sqrt(E2))
                 // ---- PI controller: q = EEst^beta1 / qold^beta2 / gamma, clamped to [1/qmax, 1/qmin];
@@ -633,10 +719,21 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                         }
                         const double r = y - obs_y[iobs * B];
                         if (GRAD) sRes[iobs * B + tid] = r;
+                        if constexpr (BSENS) {
+                            double dy;
+                            if (next_ot == tnew) dy = sn0;
+                            else {
+                                double bw[7];
+                                dense_weights((next_ot - t) * m_rcp(dt), bw);
+                                dy = fma(dt, fma(bw[0], js10, fma(bw[1], j20, fma(bw[2], j30, fma(bw[3], j40, fma(bw[4], j50, fma(bw[5], j60, bw[6] * j70)))))), s0);
+                            }
+                            gsens = fma(2.0 * r, dy, gsens);
+                        }
                         fsse = fma(r, r, fsse);
                         ++iobs;
                         next_ot = (iobs < nobs) ? obs_t[iobs * B] : CUDART_INF;
                     }
+                    if (BSENS) { s0 = sn0; s1 = sn1; js10 = j70; js11 = j71; }
                     if (GRAD) {
                         double* const r7 = rec + (na % REC_CAP) * REC_W;
                         r7[0] = t; r7[1] = dt;
@@ -658,6 +755,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                 nacc = na; nrej = nr;
                 failed = (ret != 0);
                 sse = failed ? CUDART_INF : fsse;
+                if (BSENS) gcond = failed ? 0.0 : gsens;
                 stop_at = na;
             }
             const bool was_first = first_pass;
@@ -824,7 +922,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
             A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
         }
         if (A.sse_out) A.sse_out[j] = sse;
-        if (GRAD && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
+        if ((GRAD || BSENS) && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
     }
     // ---- warp reduction: {sse, d sse/d neural[0..P)}; one partial row per WARP, no block barrier (warps of a
     //      block finish at different times; a barrier here idled their slots: ncu v4 epilogue 45 % barrier) ----

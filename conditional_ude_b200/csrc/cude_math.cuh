@@ -36,6 +36,19 @@ __device__ __forceinline__ double rcp_seed(double d) {
 }
 #endif
 
+// a*a + b*b (+ c*c) with every product and sum rounded: nvcc is free to contract `a*a + b*b` into fma(a,a,b*b) or
+// fma(b,b,a*a) and decides per instantiation, which made the forward passes of the kernel variants differ in the last
+// bit of the error norm (and, through the adaptive steps, by ~1e-12 in the loss).  This form is also the oracle's.
+#ifdef CUDE_HOST_EMU
+static inline double m_sumsq(double a, double b) { return a * a + b * b; }
+static inline double m_sumsq(double a, double b, double c) { return a * a + b * b + c * c; }
+#else
+__device__ __forceinline__ double m_sumsq(double a, double b) { return __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)); }
+__device__ __forceinline__ double m_sumsq(double a, double b, double c) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c));
+}
+#endif
+
 // 1/d for normal positive d (no special cases needed by the callers): seed y0 with relative error
 // e (|e| <~ 2^-20), then y0*(1 + e + e^2) leaves e^3 — one third-order step, 3 DFMA.
 __device__ __forceinline__ double m_rcp(double d) {

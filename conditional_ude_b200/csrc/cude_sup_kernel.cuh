@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
             const double r1 = (u1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
             const double r2 = (u2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
             if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
-            sse += r0 * r0 + r1 * r1 + r2 * r2;
+            sse += m_sumsq(r0, r1, r2);
             ++iobs;
         }
         double k10, k11, k12;
@@ -266,15 +266,15 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
             const double isk0 = 1.0 / fma(fabs(u0), reltol, abstol), isk1 = 1.0 / fma(fabs(u1), reltol, abstol),
                          isk2 = 1.0 / fma(fabs(u2), reltol, abstol);
             double x0 = u0 * isk0, x1 = u1 * isk1, x2 = u2 * isk2;
-            const double d0 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0);
+            const double d0 = sqrt(m_sumsq(x0, x1, x2) / 3.0);
             x0 = k10 * isk0; x1 = k11 * isk1; x2 = k12 * isk2;
-            const double d1 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0);
+            const double d1 = sqrt(m_sumsq(x0, x1, x2) / 3.0);
             double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
             dt0 = fmin(dt0, dtmax);
             double f0, f1, f2;
             SUP_RHS(fma(dt0, k10, u0), fma(dt0, k11, u1), fma(dt0, k12, u2), f0, f1, f2)
             x0 = (f0 - k10) * isk0; x1 = (f1 - k11) * isk1; x2 = (f2 - k12) * isk2;
-            const double d2 = sqrt((x0 * x0 + x1 * x1 + x2 * x2) / 3.0) / dt0;
+            const double d2 = sqrt(m_sumsq(x0, x1, x2) / 3.0) / dt0;
             const double dm = fmax(d1, d2);
             const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : t_pow10(-(2.0 + m_log10(dm)) / 5.0, sTab);
             dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
             e0 = dt * e0 * m_rcp(fma(fmax(fabs(u0), fabs(un0)), reltol, abstol));
             e1 = dt * e1 * m_rcp(fma(fmax(fabs(u1), fabs(un1)), reltol, abstol));
             e2 = dt * e2 * m_rcp(fma(fmax(fabs(u2), fabs(un2)), reltol, abstol));
-            const double E2 = (e0 * e0 + e1 * e1 + e2 * e2) / 3.0;
+            const double E2 = m_sumsq(e0, e1, e2) / 3.0;
             if (!(E2 == E2) || !isfinite(un0) || !isfinite(un1) || !isfinite(un2)) { ret = 3; break; }
             CUDE_TRACE_STEP(t, dt, sqrt(E2))
             const double lnE = 0.5 * m_log_pos(E2);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                     const double r1 = (y1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
                     const double r2 = (y2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
                     if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
-                    sse += r0 * r0 + r1 * r1 + r2 * r2;
+                    sse += m_sumsq(r0, r1, r2);
                     ++iobs;
                 }
                 if (GRAD) {

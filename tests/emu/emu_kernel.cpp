@@ -72,11 +72,14 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
     blockDim.x = 1; threadIdx.x = 0;
     for (long long b = 0; b < nblocks; ++b) {
         blockIdx.x = (int)b;
-        if (mixed) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false, true>(a); }
+        if (grad == 2) {   // d/d cond by forward sensitivity (BSENS)
+            if (n_in == 2) cude_eval_kernel<NetShape<2, 2, 4>, false, false, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false, false, true>(a);
+        }
+        else if (mixed) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false, true>(a); }
         else if (n_in == 2) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false>(a); }
         else { if (grad) cude_eval_kernel<NetShape<3, 2, 4>, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false>(a); }
     }
-    if (!flat && grad && g_neural_traj)
+    if (!flat && grad == 1 && g_neural_traj)
         for (long long b = 0; b < nblocks; ++b)   // block b = s*N + i = trajectory index
             for (int p = 0; p < P; ++p) g_neural_traj[b * P + p] = partials[b * (P + 1) + 1 + p];
     return 0;

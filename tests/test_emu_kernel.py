@@ -165,3 +165,31 @@ def test_ragged_observation_grids(fx):
         bound = (1e-10, 1e-9) if tol is DET else (1e-5, 1e-3)
         assert relmax(e["sse"], g["sse"]) < bound[0]
         assert relmax(e["g_cond"], g["g_cond"]) < bound[1] and relmax(e["g_neural"], g["g_neural"]) < bound[1]
+
+
+def test_beta_forward_sensitivity_equals_the_adjoint(fx):
+    """grad=2: the beta-only gradient kernel (one forward-sensitivity column carried through the same steps, BSENS in
+    cude_kernels.cuh) must give the adjoint's d sse/d cond — both are the exact derivative of the same discrete solve —
+    with the loss kernel's forward pass, at default tolerance (adaptive steps, rejections) and for the covariate net."""
+    models, ts, ys = mixed_population(fx)                     # Ohashi (5 knots) + Fujita (14 knots, t0 = -10)
+    pk = cu.pack_models(models, ts, ys)
+    rng = np.random.default_rng(4)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 2)
+    for kw in (DET, {}):
+        a = emu_wrap.emu_eval(pk, neural, cond, grad=1, **kw)
+        b = emu_wrap.emu_eval(pk, neural, cond, grad=2, **kw)
+        assert np.array_equal(a["sse"], b["sse"]) and a["n_acc"] == b["n_acc"] and a["n_rej"] == b["n_rej"]
+        assert relmax(b["g_cond"], a["g_cond"]) < 1e-10
+        bf = emu_wrap.emu_eval(pk, neural[0], cond, grad=2, flat=True, **kw)
+        assert np.array_equal(bf["g_cond"][0], b["g_cond"][0])
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    assert relmax(emu_wrap.emu_eval(pk, neural, cond, grad=2, **DET)["g_cond"], g["g_cond"]) < 1e-9
+    cm, t, c = ohashi_models(fx, "train", covariate=True)
+    idx = fx["train_split_idx"][:12]
+    pkc = cu.pack_models([cm[i] for i in idx], t, c[idx])
+    nn, betas = fx["cov_neural"][1], fx["cov_betas"][1][:12]
+    assert relmax(emu_wrap.emu_eval(pkc, nn, betas, grad=2)["g_cond"], emu_wrap.emu_eval(pkc, nn, betas, grad=1)["g_cond"]) < 1e-10
+    # failed trajectory: Inf loss, zero gradient
+    bad = cond.copy(); bad[0, 3] = np.nan
+    e = emu_wrap.emu_eval(pk, neural, bad, grad=2)
+    assert np.isinf(e["sse"][0, 3]) and e["g_cond"][0, 3] == 0 and e["n_fail"] == 1

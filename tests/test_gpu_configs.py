@@ -59,7 +59,9 @@ def test_config2_beta_only_137_individuals_x_1000_starts(fx, ctx):
     assert np.allclose(loss, sse.sum(axis=1), rtol=1e-13)
     # flat (shared-network) path == tile path on a slice of the starts
     l2, gn2, gc2 = pop.loss_grad(nn, cond[:16], neural_grad=True, mean=False)
-    assert np.array_equal(gc2, gc[:16]) and np.allclose(l2, loss[:16], rtol=1e-13)   # sums in a different (fixed) order
+    # (beta-only calls run the forward-sensitivity kernel, calls with the network gradient the adjoint: the same
+    #  derivative of the same discrete solve computed two ways; sums in a different, fixed order)
+    assert np.abs(gc2 - gc[:16]).max() < 1e-9 * np.abs(gc[:16]).max() and np.allclose(l2, loss[:16], rtol=1e-13)
     _subsample_check(pk, nn, cond, sse, gc, rng, shared=True)
 
 
