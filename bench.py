@@ -311,7 +311,19 @@ def run_ours(args):
             traffic = json.load(f)["dram_bytes_per_trajectory"] * (n_traj / world)
     except Exception:
         pass
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+    # HBM view of the same launch (for completeness: the path is not HBM-bound): algorithmic bytes / kernel time against the
+    # measured copy bandwidth of MEASURED_PEAKS.json (MEASURED_PEAKS.json is git-ignored and may be absent on the box)
+    hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    alg_bytes = 29.0 * (n_traj / world)          # cond 8 + g_cond 8 + partial rows 9.5 + population data 3.4
+    hbm = {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9, "peak_gbs": hbm_peak,
+           "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+           "measured_dram_gbs": (traffic / kernel_s / 1e9) if traffic else None}
+    roofline = {"bound": "fp64", "hbm": hbm, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "cude_eval_kernel<NetShape<2,2,4>,GRAD>", "kernel_ms": float(kms.item()),
                 "alg_flops_per_traj": fl / (n_traj / world), "alg_transcendentals_per_traj": tr / (n_traj / world),
                 "peak_source": "measured live: DFMA micro-benchmark (cude_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
