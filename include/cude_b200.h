@@ -62,7 +62,8 @@ typedef struct {
                     * per-start networks, the individuals of each start are regrouped by the step counts their
                     * trajectories took in an earlier call on this population (refreshed every 8 calls), so that the
                     * 32 lanes of a warp finish together (~12 % fewer warp-steps).  Per-trajectory results (sse,
-                    * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping. */
+                    * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping.
+                    * Costs 8 bytes of device memory per trajectory on the population (two key buffers). */
 } cude_opts;
 
 typedef struct {
