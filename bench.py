@@ -340,7 +340,8 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if args.precision == 0 else "f32 network / f64 integrator (NOT the parity-gated mode)",
+            "dtype": {0: "f64", 1: "f32 network / f64 integrator (NOT the parity-gated mode)",
+                      2: "f64 forward pass, f32 network in the adjoint sweep (NOT the parity-gated mode)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "individuals": N_total, "starts": S, "trajectories_per_step": N_total * S,
                        "abstol": opts.abstol, "reltol": opts.reltol, "network": "chain(4,2,tanh): 37 parameters",
@@ -400,7 +401,7 @@ def main():
     ap.add_argument("--individuals", type=int, default=1_000_000)
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--block", type=int, default=0)
-    ap.add_argument("--precision", type=int, default=0, help="0 = FP64 (headline, parity-gated); 1 = FP32 network (looser bound)")
+    ap.add_argument("--precision", type=int, default=0, help="0 = FP64 (headline, parity-gated); 1 = FP32 network (looser bound); 2 = FP64 forward, FP32 adjoint network")
     ap.add_argument("--balance", type=int, default=0, help="cude_opts.balance for the headline: 0 = natural lane order (default), 1 = regroup lanes by earlier step counts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-individuals", type=int, default=4000)

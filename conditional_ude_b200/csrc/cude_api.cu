@@ -312,16 +312,17 @@ typedef void (*eval_kernel_t)(const EvalArgs);
 
 // grad: discrete adjoint (all gradients); bsens: d/d cond only by forward sensitivity (FP64 only)
 template <class NS>
-static eval_kernel_t pick(bool grad, bool mixed, bool bsens) {
+static eval_kernel_t pick(bool grad, bool mixed, bool bsens, bool fbwd) {
     if (bsens) return cude_eval_kernel<NS, false, false, true>;
+    if (fbwd && grad) return cude_eval_kernel<NS, true, false, false, true>;
     if (mixed) return grad ? cude_eval_kernel<NS, true, true> : cude_eval_kernel<NS, false, true>;
     return grad ? cude_eval_kernel<NS, true, false> : cude_eval_kernel<NS, false, false>;
 }
 
-static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed, bool bsens = false) {
+static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed, bool bsens = false, bool fbwd = false) {
     if (net->depth == 2 && net->width == 4) {
-        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed, bsens);   // chain(4, 2, tanh), 02-conditional.jl:22
-        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed, bsens);   // covariate net, 07-covariate-inclusion.jl:32
+        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed, bsens, fbwd);   // chain(4, 2, tanh), 02-conditional.jl:22
+        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed, bsens, fbwd);   // covariate net, 07-covariate-inclusion.jl:32
     }
     return nullptr;
 }
@@ -389,8 +390,9 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     cude_opts o;
     if (opts_in) o = *opts_in; else cude_default_opts(&o);
     if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad solver options");
-    if (o.precision != 0 && o.precision != 1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: precision must be 0 (FP64) or 1 (FP32 network, FP64 integrator)");
+    if (o.precision < 0 || o.precision > 2) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: precision must be 0 (FP64), 1 (FP32 network, FP64 integrator) or 2 (FP64 forward pass, FP32 network in the adjoint)");
     const bool mixed = o.precision == 1;
+    const bool fbwd = o.precision == 2;
     const int P = cude_net_nparams(net);
     if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad network description");
     if (net->n_in == 3 && !pop->dev.cov) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: 3-input network needs a population with a covariate");
@@ -399,7 +401,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     // loss kernel instead of the adjoint sweep (src/parameter-estimation.jl:272-307, evaluate_model :406-433)
     const bool bsens = want_grad == 1 && !mixed && CUDE_BETA_FORWARD_SENSITIVITY;
     const bool adj = grad && !bsens;
-    eval_kernel_t kern = select_kernel(net, adj, mixed, bsens);
+    eval_kernel_t kern = select_kernel(net, adj, mixed, bsens, fbwd && adj);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -450,7 +452,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
 
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
-    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, adj, mixed, bsens);
+    const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, adj, mixed || (fbwd && adj), bsens);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if ((const void*)kern != ctx->carve_kern || smem != ctx->carve_smem || B != ctx->carve_block) {

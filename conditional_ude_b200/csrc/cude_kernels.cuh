@@ -427,12 +427,17 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 
 // BSENS (only with GRAD = false, MIXED = false): loss + d sse / d cond by one forward-sensitivity column carried through
 // the same steps (frozen step sequence => the same derivative the adjoint produces), no step ring, no backward sweep.
-template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false>
+// FBWD (with GRAD): the forward pass — loss, step sequence — stays FP64 bit for bit, only the adjoint's network
+// evaluations and gradient accumulators are FP32 (opts.precision = 2): gradients to ~1e-6 instead of ~1e-13.
+template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false>
 __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUDE_MIN_BLOCKS_LOSS) cude_eval_kernel(const EvalArgs A) {
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
+    static_assert(!FBWD || (GRAD && !MIXED), "FBWD is a variant of the FP64 gradient kernel");
     using namespace tab;
     constexpr int W = NS::W, P = NS::P;
-    typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the network evaluation
+    typedef typename std::conditional<MIXED, float, double>::type R;     // scalar type of the forward network evaluation
+    typedef typename std::conditional<MIXED || FBWD, float, double>::type RB;   // ... of the adjoint's network evaluation
+    constexpr bool F32COPY = MIXED || FBWD;                              // a float copy of the weights sits behind the doubles
     extern __shared__ double smem[];
     const int B = blockDim.x, tid = threadIdx.x;
     const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
@@ -441,7 +446,8 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
     double* sTab = smem;                             // [256] 2^(j/256) for the exp core
     double* sW = sTab + 256;                         // [P] (padded to even)
     R* sWr = MIXED ? reinterpret_cast<R*>(sW + ((P + 1) & ~1)) : reinterpret_cast<R*>(sW);   // network weights as R
-    double* sKt = sW + ((P + 1) & ~1) * (MIXED ? 2 : 1);   // [K][B]  (MIXED: a float copy of the weights sits in between)
+    RB* sWb = F32COPY ? reinterpret_cast<RB*>(sW + ((P + 1) & ~1)) : reinterpret_cast<RB*>(sW);   // ... as RB
+    double* sKt = sW + ((P + 1) & ~1) * (F32COPY ? 2 : 1);   // [K][B]  (a float copy of the weights may sit in between)
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
     double* sOt = sSl + (size_t)K * B;               // [M][B] observation times
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
     // ---- stage the start's weights (block-uniform) ----
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
-        for (int p = tid; p < P; p += B) { sW[p] = gW[p]; if (MIXED) sWr[p] = (R)gW[p]; }
+        for (int p = tid; p < P; p += B) { sW[p] = gW[p]; if (F32COPY) sWb[p] = (RB)gW[p]; }
         for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     }
     // ---- stage this thread's knots ----
@@ -526,8 +532,9 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
             c[q] = z;
         }
         R cr[W];
+        RB cb[W];
 #pragma unroll
-        for (int q = 0; q < W; ++q) cr[q] = (R)c[q];
+        for (int q = 0; q < W; ++q) { cr[q] = (R)c[q]; cb[q] = (RB)c[q]; }
 
         const double abstol = A.abstol, reltol = A.reltol;
         const double dtmax = tend - t0;
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
 
         double rec[GRAD ? REC_CAP * REC_W : 1];   // accepted-step records {t, dt} (+ d[5] = 1 + exp(z_out) of the step's nodes with CUDE_STASH_D)
         double d_nn0 = 1.0;                   // d at the node t0, dG = 0: the NN([0;beta]) term
-        R acc[GRAD ? NS::NACC : 1];           // gradient accumulators (compressed layout, see mlp_backward): registers during the adjoint sweep
+        RB acc[GRAD ? NS::NACC : 1];          // gradient accumulators (compressed layout, see mlp_backward): registers during the adjoint sweep
         volatile double park[GRAD ? NS::NACC : 1];   // ... local memory across a forward replay (solves longer than REC_CAP
                                                      // steps: rare); volatile keeps it out of the register allocation
         int stop_at = 0x7fffffff;   // replay limit (GRAD)
@@ -764,7 +771,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
             if constexpr (GRAD) {
             // accumulators: zero after the first pass, otherwise back from local memory (parked for the replay)
 #pragma unroll
-            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? R(0) : (R)park[k];
+            for (int k = 0; k < NS::NACC; ++k) acc[k] = was_first ? RB(0) : (RB)park[k];
             // =================== adjoint over steps [lo, stop_at) held in the ring ===================
             // The last chunk appends the virtual step n = -1: the NN([0;beta]) term, one node at dG = 0
             // with weight -sum(w) (the node t0 itself has dG = 0 and cancels exactly).
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
                 }
                 CUDE_UNROLL(CUDE_BWD_UNROLL)
                 for (int q = 0; q < 5; ++q)
-                    if (q < nq) mlp_backward<NS, R>(sWr, sTab, cr, (R)myDG[q * B], (R)myNode[q * B], acc);
+                    if (q < nq) mlp_backward<NS, RB>(sWb, sTab, cb, (RB)myDG[q * B], (RB)myNode[q * B], acc);
             }
             stop_at = lo;   // steps below lo still to do: replay the forward pass up to lo
             if (stop_at > 0) {   // park the accumulators for the replay's register budget

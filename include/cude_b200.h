@@ -55,7 +55,9 @@ typedef struct {
     double reltol;
     int maxiters;
     int precision; /* 0 = FP64 (the parity-gated mode); 1 = FP32 network evaluation (MUFU ex2/rcp/lg2) with the
-                    * integrator, adjoint and reductions in FP64: looser documented bound, see DESIGN.md */
+                    * integrator, adjoint and reductions in FP64: looser documented bound, see DESIGN.md;
+                    * 2 = forward pass (loss, step sequence) in FP64 bit for bit, FP32 network and accumulators only in
+                    * the adjoint sweep: loss as in mode 0, gradients to ~1e-6 relative */
     int block;     /* threads per block (individuals per tile); 0 = library default */
     int balance;   /* 0 (default) = lanes in natural order: the per-start sums are bitwise run-to-run deterministic.
                     * 1 = iterative workloads (training): for loss+gradient calls on >= 4096 individuals with

@@ -36,7 +36,7 @@ struct CudeOpts
     block::Cint
     balance::Cint     # 1: regroup each start's individuals by earlier step counts (iterative workloads)
 end
-CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=100_000, balance=0) = CudeOpts(abstol, reltol, maxiters, 0, 0, balance)
+CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=100_000, precision=0, balance=0) = CudeOpts(abstol, reltol, maxiters, precision, 0, balance)
 
 check(rc::Cint, ctx=C_NULL) = rc == 0 ? nothing :
     error("cude_b200 error $rc: " * unsafe_string(ccall((:cude_last_error, libcude), Cstring, (Ptr{Cvoid},), ctx)))

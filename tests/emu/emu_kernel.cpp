@@ -75,6 +75,7 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
         if (grad == 2) {   // d/d cond by forward sensitivity (BSENS)
             if (n_in == 2) cude_eval_kernel<NetShape<2, 2, 4>, false, false, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false, false, true>(a);
         }
+        else if (mixed == 2 && grad) cude_eval_kernel<NetShape<2, 2, 4>, true, false, false, true>(a);   // FP32 adjoint network
         else if (mixed) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false, true>(a); }
         else if (n_in == 2) { if (grad) cude_eval_kernel<NetShape<2, 2, 4>, true>(a); else cude_eval_kernel<NetShape<2, 2, 4>, false>(a); }
         else { if (grad) cude_eval_kernel<NetShape<3, 2, 4>, true>(a); else cude_eval_kernel<NetShape<3, 2, 4>, false>(a); }

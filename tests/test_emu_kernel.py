@@ -193,3 +193,19 @@ def test_beta_forward_sensitivity_equals_the_adjoint(fx):
     bad = cond.copy(); bad[0, 3] = np.nan
     e = emu_wrap.emu_eval(pk, neural, bad, grad=2)
     assert np.isinf(e["sse"][0, 3]) and e["g_cond"][0, 3] == 0 and e["n_fail"] == 1
+
+
+def test_fp32_adjoint_network_mode(fx):
+    """precision = 2 (mixed=2 here): the forward pass stays FP64 bit for bit — same loss, same steps — and only the
+    adjoint's network evaluations and accumulators are FP32: gradients to ~1e-6 of their scale."""
+    models, t, c, nn, betas = train57(fx)
+    pk = cu.pack_models(models, t, c)
+    rng = np.random.default_rng(6)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 3)
+    a = emu_wrap.emu_eval(pk, neural, cond)
+    b = emu_wrap.emu_eval(pk, neural, cond, mixed=2)
+    assert np.array_equal(a["sse"], b["sse"]) and a["n_acc"] == b["n_acc"] and a["n_rej"] == b["n_rej"]
+    assert relmax(b["g_cond"], a["g_cond"]) < 1e-5
+    gn_a, gn_b = a["g_neural"].sum(axis=1), b["g_neural"].sum(axis=1)        # population gradient per start
+    assert np.abs(gn_b - gn_a).max() < 1e-5 * np.abs(gn_a).max()
+    assert np.abs(b["g_neural"] - a["g_neural"]).max() < 2e-5 * np.abs(a["g_neural"]).max()

@@ -257,7 +257,14 @@ def test_mixed_precision_option(fx, ctx):
     l32 = pop.loss(neural, cond, opts=SolverOptions(precision=1))
     assert not np.array_equal(l64, l32) and relmax(l32, l64) < 2e-3
     with pytest.raises(Exception):
-        pop.loss(neural, cond, opts=SolverOptions(precision=2))
+        pop.loss(neural, cond, opts=SolverOptions(precision=3))
+    # precision = 2: FP64 forward pass bit for bit (loss, steps), FP32 network only in the adjoint sweep
+    l0, gn0, gc0, sse0 = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    n0 = ctx.stats()["n_acc"]
+    l2, gn2, gc2, sse2 = pop.loss_grad(neural, cond, opts=SolverOptions(precision=2), mean=False, return_sse=True)
+    assert np.array_equal(sse2, sse0) and ctx.stats()["n_acc"] == n0
+    assert relmax(gc2, gc0) < 1e-5 and (np.abs(gn2 - gn0) / np.abs(gn0).max(axis=1, keepdims=True)).max() < 1e-5
+    assert np.array_equal(pop.loss(neural, cond, opts=SolverOptions(precision=2)), l64)      # loss-only: plain FP64
 
 
 def test_ragged_observation_grids(fx, ctx):
