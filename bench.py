@@ -289,6 +289,15 @@ def run_ours(args):
         step_balanced()                       # call 0 writes the keys and sorts, from call 1 on the lanes are grouped
     balanced_value = N_total * S / (timed(step_balanced, 3) / 3 * 1e-3)
 
+    # secondary figure: opts.precision = 2 (forward pass FP64 bit for bit, FP32 network only in the adjoint sweep)
+    fp32adj_value = None
+    if args.precision == 0:
+        opts_p2 = cu.SolverOptions(block=args.block, precision=2)
+        def step_p2():
+            shard.step(opts_p2)
+        step_p2()
+        fp32adj_value = N_total * S / (timed(step_p2, 3) / 3 * 1e-3)
+
     # end-to-end through host buffers (pinned): H2D of the step's inputs + D2H of its results every step
     for _ in range(2):
         step_e2e()
@@ -349,6 +358,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (cond + g_cond = %.0f MB per rank)" % (2 * S * n_loc * 8 / 1e6),
                        "lane_balance": "on (cude_opts.balance = 1)" if args.balance else "off (natural order)",
                        "lane_balanced_evals_per_s": balanced_value,
+                       "fp32_adjoint_evals_per_s": fp32adj_value,
+                       "fp32_adjoint_note": "secondary: cude_opts.precision = 2 — loss and step sequence bitwise those of the FP64 "
+                                            "headline, FP32 network only in the adjoint sweep (gradients to 1e-5 of their scale)",
                        "lane_balanced_note": "secondary: individuals of each start grouped by the step counts of an earlier "
                                              "call; exact prediction here because the bench repeats its inputs (under Adam "
                                              "training the measured gain is +3 %, profiles/r01_adam_balance.json)",
