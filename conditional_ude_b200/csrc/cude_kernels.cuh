@@ -18,13 +18,16 @@
 //
 // Data layout in HBM (struct-of-arrays, individual index fastest => coalesced per warp):
 //   knot_t/knot_g/slope [K][N], obs_t/obs_y [M][N], k0,k1,k2,c0,cov [N], cond/sse/g_cond [N x S].
-// Per block: the start's MLP weights are staged once in shared memory (block-uniform broadcast
-// reads), each thread's glucose knots are staged in shared memory ([k][tid], conflict-free), state,
-// stages, adjoint and the gradient accumulators live in registers.
-// Reduction: per-thread gradients -> warp shuffles -> one partial row per warp ->
+// Per block (one start x 128 individuals, blocks ordered chunk-major): the start's MLP weights and the 256-entry exp
+// table are staged once in shared memory, each thread's glucose knots and observations are staged in shared memory
+// ([k][tid], conflict-free), state, stages, adjoint and the gradient accumulators live in registers.
+// Instantiations: loss only; loss + adjoint gradient (GRAD); loss + d/d cond by forward sensitivity (BSENS, beta-only
+// fits); FP32 network throughout (MIXED) or only in the adjoint sweep (FBWD) as optional precisions.
+// Reduction: per-thread gradient rows in shared memory -> per warp, lane l sums row l -> one partial row per warp ->
 // deterministic second-stage kernel (no atomics on the data path).
-// Measured tuning notes (B200, profiles/): unrolling the node loops (CUDE_FWD_UNROLL / CUDE_BWD_UNROLL > 1) and
-// keeping activations for the adjoint were both slower; 3 resident blocks per SM (168 registers) beat 2 and 4.
+// Measured tuning notes (B200, profiles/README.md): unrolling the node loops (CUDE_FWD_UNROLL / CUDE_BWD_UNROLL > 1),
+// keeping activations for the adjoint, 2 / 4 resident blocks per SM, 32- / 64- / 192- / 384-thread blocks and
+// warp-persistent scheduling were all measured slower than 3 blocks of 128 threads at 168 registers.
 // =====================================================================================
 #pragma once
 #ifndef CUDE_HOST_EMU   // tests/emu compiles this file with g++ behind a shim (CI without a GPU)
