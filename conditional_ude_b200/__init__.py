@@ -15,6 +15,8 @@ from .estimation import (initial_parameters, train, train_with_sigma, evaluate_m
 
 from .suppression import (SuppressionPopulation, neural_network_model, suppression_loss, fit_suppression_model,
                           validate_suppression_model)
+from .saem import (SAEM, mcmc_step, individual_log_likelihood, total_nll, map_objective, compute_individual_maps,
+                   update_population_parameters)
 
 __all__ = [
     "SuppressionPopulation", "neural_network_model", "suppression_loss", "fit_suppression_model", "validate_suppression_model",
@@ -24,4 +26,6 @@ __all__ = [
     "likelihood_profile", "likelihood_profile_population", "find_confidence_intervals",
     "initial_parameters", "train", "train_with_sigma", "evaluate_model", "stratified_split", "argmedian",
     "OptimizationSolution",
+    "SAEM", "mcmc_step", "individual_log_likelihood", "total_nll", "map_objective", "compute_individual_maps",
+    "update_population_parameters",
 ]

@@ -102,6 +102,8 @@ class Population:
         arrs = {k: np.ascontiguousarray(pk[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
         nk = np.ascontiguousarray(pk["n_knots"], dtype=np.int32)
         no = np.ascontiguousarray(pk["n_obs"], dtype=np.int32)
+        self.n_obs = no.copy()                       # observations per individual (sigma-likelihoods, SAEM)
+        self.t_first = arrs["knot_t"][:, 0].copy()   # first glucose time point of every individual
         cov = None if pk.get("cov") is None else np.ascontiguousarray(pk["cov"], dtype=np.float64)
         h = C.c_void_p()
         _lib.check(self._lib.cude_population_create(

@@ -99,6 +99,8 @@ class OraclePopulationAdapter:
         pk = cu.pack_models(models, timepoints, cpeptide_data)
         self.op = oracle.OraclePopulation(pk)
         self.chain, self.n_ind, self.n_params = pk["chain"], pk["n_ind"], pk["chain"].n_params
+        self.n_obs = np.asarray(pk["n_obs"]).copy()
+        self.t_first = np.asarray(pk["knot_t"], dtype=np.float64)[:, 0].copy()
         self.calls = 0
         self.traj = 0            # trajectories evaluated (start-sharding tests)
 
