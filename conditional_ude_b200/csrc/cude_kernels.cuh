@@ -26,7 +26,7 @@
 // Reduction: per-thread gradient rows in shared memory -> per warp, lane l sums row l -> one partial row per warp ->
 // deterministic second-stage kernel (no atomics on the data path).
 // Measured tuning notes (B200, profiles/README.md): unrolling the node loops (CUDE_FWD_UNROLL / CUDE_BWD_UNROLL > 1),
-// keeping activations for the adjoint, 2 / 4 resident blocks per SM, 32- / 64- / 192- / 384-thread blocks and
+// keeping activations for the adjoint, 2 / 4 resident blocks per SM, 32- / 64- / 96- / 192- / 384-thread blocks and
 // warp-persistent scheduling were all measured slower than 3 blocks of 128 threads at 168 registers.
 // =====================================================================================
 #pragma once
