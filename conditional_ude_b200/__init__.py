@@ -15,6 +15,7 @@ from .estimation import (initial_parameters, train, train_with_sigma, evaluate_m
 
 from .suppression import (SuppressionPopulation, neural_network_model, suppression_loss, fit_suppression_model,
                           validate_suppression_model)
+from .dataprep import prepare_ohashi, prepare_fujita, split_like_reference
 from .saem import (SAEM, mcmc_step, individual_log_likelihood, total_nll, map_objective, compute_individual_maps,
                    update_population_parameters)
 
@@ -28,4 +29,5 @@ __all__ = [
     "OptimizationSolution",
     "SAEM", "mcmc_step", "individual_log_likelihood", "total_nll", "map_objective", "compute_individual_maps",
     "update_population_parameters",
+    "prepare_ohashi", "prepare_fujita", "split_like_reference",
 ]
