@@ -24,6 +24,9 @@ struct DevBuf {
 };
 
 #define CUDE_MAX_CHUNKS 16
+#ifndef CUDE_SUP_PACK_DEFAULT
+#define CUDE_SUP_PACK_DEFAULT 0            // 1: small suppression populations run several starts per 128-thread block by default
+#endif
 #ifndef CUDE_BETA_FORWARD_SENSITIVITY
 #define CUDE_BETA_FORWARD_SENSITIVITY 1   // 0: beta-only gradients through the adjoint kernel (comparison builds)
 #endif
@@ -727,10 +730,13 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: neural_stride < n_params");
     const bool grad = (g_neural != nullptr) || (g_theta != nullptr);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const int B = o.block > 0 ? o.block : (N > 32 ? 64 : 32);
+    // small populations (the reference's 37 / 30 / 60 individuals): blocks of 128 threads run floor(128 / N) whole
+    // starts side by side (87 - 94 % of the lanes busy instead of 58 % with one start per 64-thread block)
+    const int B = o.block > 0 ? o.block : (CUDE_SUP_PACK_DEFAULT && N <= 128 ? 128 : (N > 32 ? 64 : 32));
     if (B < 32 || B > 128 || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: block must be 32, 64, 96 or 128");
-    const int nchunks = (N + B - 1) / B, nw = B / 32;
-    const long long nblocks = (long long)n_starts * nchunks;
+    const int spb = ((CUDE_SUP_PACK_DEFAULT || o.block > 0) && N <= B) ? B / N : 0;
+    const int nchunks = spb > 0 ? 1 : (N + B - 1) / B, nw = spb > 0 ? 1 : B / 32;
+    const long long nblocks = spb > 0 ? ((long long)n_starts + spb - 1) / spb : (long long)n_starts * nchunks;
     const size_t ntraj = (size_t)N * n_starts;
     const size_t n_neural = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
     int rc;
@@ -738,7 +744,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     if ((rc = ensure(ctx, ctx->neural, n_neural * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->cond, ntraj * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->sums, (size_t)np1 * n_starts * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->partials, (size_t)nblocks * nw * np1 * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->partials, (spb > 0 ? (size_t)n_starts : (size_t)nblocks * nw) * np1 * sizeof(double)))) return rc;
     if (sse_out && (rc = ensure(ctx, ctx->sse, ntraj * sizeof(double)))) return rc;
     if (g_theta && (rc = ensure(ctx, ctx->gcond, ntraj * sizeof(double)))) return rc;
     if (ctx->h_sums_cap < (size_t)np1 * n_starts) {
@@ -750,7 +756,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     CU_TRY(ctx, cudaMemcpyAsync(ctx->neural.p, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cond.p, theta, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SupArgs a{};
-    a.n_ind = N; a.n_obs = M; a.n_starts = n_starts; a.nchunks = nchunks;
+    a.n_ind = N; a.n_obs = M; a.n_starts = n_starts; a.nchunks = nchunks; a.spb = spb;
     a.obs_t = pop->d_obs_t; a.data = pop->d_data; a.p1 = pop->p1; a.p3 = pop->p3;
     for (int j = 0; j < 3; ++j) a.iscale[j] = pop->iscale[j];
     a.t0 = pop->t0; a.tend = pop->tend;
@@ -762,7 +768,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     a.g_theta = g_theta ? (double*)ctx->gcond.p : nullptr;
     a.counters = (unsigned long long*)ctx->counters.p;
     sup_kernel_t kern = grad ? cude_sup_kernel<SN, true> : cude_sup_kernel<SN, false>;
-    const size_t smem = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, grad);
+    const size_t smem = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, grad, spb);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: too many observations for shared memory; lower opts.block");
     if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));

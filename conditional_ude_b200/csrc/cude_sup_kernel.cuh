@@ -21,6 +21,8 @@ namespace cude {
 
 struct SupArgs {
     int n_ind, n_obs, n_starts, nchunks;
+    int spb;                    // > 0: small population (n_ind <= block): every block runs `spb` whole starts side by side
+                                // (thread = start_in_block * n_ind + individual) and writes one partial row per start
     const double* obs_t;        // [M] common time grid
     const double* data;         // [M][3][N]: data[(k*3 + j)*N + i]
     double p1, p3;
@@ -178,9 +180,12 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
     }
 }
 
-__host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad) {
-    // exp table, weights, per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] + residuals M*3 + accumulators)
-    return (size_t)256 + (size_t)((P + 1) & ~1) + (size_t)(21 + (grad ? 42 + 3 * M + NACC : 0)) * B;
+__host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad, int spb = 0) {
+    // exp table, weights (one copy per start of the block), per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] +
+    // residuals M*3 + accumulators); the packed reduction re-uses the rows as [P+1][B]
+    size_t rows = (size_t)21 + (grad ? (size_t)(42 + 3 * M + NACC) : 0);
+    if (spb > 0 && grad && rows < (size_t)P + 1) rows = (size_t)P + 1;
+    return (size_t)256 + (size_t)(spb > 0 ? spb : 1) * ((P + 1) & ~1) + rows * B;
 }
 
 constexpr int SUP_REC_CAP = 512;  // accepted-step records (t, dt, u[3]) kept per thread in local memory (20 KB)
@@ -192,24 +197,39 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
     extern __shared__ double smem[];
     const int B = blockDim.x, tid = threadIdx.x;
     const int N = A.n_ind, M = A.n_obs;
+    constexpr int PP = (P + 1) & ~1;
+    const int spb = A.spb;
     double* sTab = smem;
-    double* sW = sTab + 256;
-    double* sK = sW + ((P + 1) & ~1);                 // [7][3][B] stages
+    double* sWall = sTab + 256;                       // [max(spb,1)][PP] weights of the block's start(s)
+    double* sK = sWall + (size_t)(spb > 0 ? spb : 1) * PP;   // [7][3][B] stages
     double* sG = sK + (size_t)21 * B;                 // [7][3][B] stage inputs (GRAD)
     double* sKb = sG + (GRAD ? (size_t)21 * B : 0);   // [7][3][B] stage adjoints (GRAD)
     double* sRes = sKb + (GRAD ? (size_t)21 * B : 0); // [M][3][B] weighted residuals (GRAD)
     double* sAcc = sRes + (GRAD ? (size_t)3 * M * B : 0);   // [NACC][B]
 
-    const int s = blockIdx.x / A.nchunks;
-    const int ch = blockIdx.x - s * A.nchunks;
-    const int i = ch * B + tid;
-    const bool active = i < N;
-    const long long jt = (long long)s * N + (active ? i : 0);
-    {
+    int s, i, sloc = 0;
+    bool active;
+    if (spb > 0) {                                    // packed: whole starts side by side in the block
+        sloc = tid / N;
+        i = tid - sloc * N;
+        s = blockIdx.x * spb + sloc;
+        active = sloc < spb && s < A.n_starts;
+        if (!active) { sloc = 0; s = blockIdx.x * spb; i = 0; }
+        for (int p = tid; p < spb * P; p += B) {
+            const int sl = p / P, pp = p - sl * P, ss = blockIdx.x * spb + sl;
+            if (ss < A.n_starts) sWall[sl * PP + pp] = A.neural[(long long)ss * A.neural_stride + pp];
+        }
+    } else {
+        s = blockIdx.x / A.nchunks;
+        const int ch = blockIdx.x - s * A.nchunks;
+        i = ch * B + tid;
+        active = i < N;
         const double* gW = A.neural + (long long)s * A.neural_stride;
-        for (int p = tid; p < P; p += B) sW[p] = gW[p];
-        for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
+        for (int p = tid; p < P; p += B) sWall[p] = gW[p];
     }
+    const double* const sW = sWall + (size_t)sloc * PP;
+    const long long jt = (long long)s * N + (active ? i : 0);
+    for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     double* const myK = sK + tid;
     double* const myG = sG + tid;
     double* const myKb = sKb + tid;
@@ -460,8 +480,42 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
         if (GRAD && A.g_theta) A.g_theta[jt] = failed ? 0.0 : gtheta * A.theta_scale;
     }
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
-    if (A.partials) {
-        constexpr int nred = GRAD ? P + 1 : 1;
+    constexpr int nred = GRAD ? P + 1 : 1;
+    if (A.partials && spb > 0) {
+        // packed blocks: a warp may hold lanes of two starts, so the rows go through shared memory: every thread writes
+        // its expanded values to [q][tid] (its own column of the — now dead — stage rows), then thread (start, q) sums
+        // the start's n_ind columns in index order (deterministic) into the start's single partial row
+        double vals_first = active ? sse : 0.0;
+        double* const myRow = sK + tid;
+        if constexpr (GRAD) {
+            double ex[P];
+#pragma unroll 1
+            for (int p = 0; p < P; ++p) {
+                double v = 0.0;
+                if (active && !failed) {
+                    if (p < 3 * W) v = myAcc[p * B];
+                    else if (p < 4 * W) v = myAcc[(3 * W + (p - 3 * W)) * B] * etheta;
+                    else if (p < SN::L1) v = myAcc[(3 * W + (p - 4 * W)) * B];
+                    else v = myAcc[(4 * W + (p - SN::L1)) * B];
+                }
+                ex[p] = v;
+            }
+            // (the expanded values are collected first: rows 1..P overlap the stage-input / adjoint rows, not the accumulators,
+            //  but keeping read and write phases apart makes that irrelevant)
+#pragma unroll 1
+            for (int p = 0; p < P; ++p) myRow[(1 + p) * B] = ex[p];
+        }
+        myRow[0] = vals_first;
+        __syncthreads();
+        for (int idx = tid; idx < spb * nred; idx += B) {
+            const int sl = idx / nred, q = idx - sl * nred, ss = blockIdx.x * spb + sl;
+            if (ss >= A.n_starts) continue;
+            const double* src = sK + (size_t)q * B + sl * N;
+            double v = 0.0;
+            for (int k = 0; k < N; ++k) v += src[k];
+            A.partials[(size_t)ss * (P + 1) + q] = v;
+        }
+    } else if (A.partials) {
         double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
 #pragma unroll 1
         for (int q = 0; q < nred; ++q) {
