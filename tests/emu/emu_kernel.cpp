@@ -101,6 +101,7 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
             for (int j = 0; j < 3; ++j) h[(k * 3 + j) * N + i] = data[j + 3 * (k + M * i)];
     SupArgs a{};
     a.n_ind = n_ind; a.n_obs = n_obs; a.n_starts = n_starts; a.nchunks = n_ind;
+    a.spb = (n_ind == 1) ? 1 : 0;      // one individual: exercise the packed (starts-per-block) code path, one start per "block"
     a.obs_t = obs_t; a.data = h.data(); a.p1 = p_true[0]; a.p3 = p_true[2];
     for (int j = 0; j < 3; ++j) a.iscale[j] = 1.0 / scale[j];
     a.t0 = t0; a.tend = tend; a.neural = neural; a.neural_stride = neural_stride; a.theta = theta;

@@ -44,6 +44,19 @@ def test_emulated_kernel_matches_oracle(sup):
     assert np.abs(loss / sup["losses_1p0"][:5] - 1).max() < 1e-8
 
 
+def test_emulated_packed_block_path(sup):
+    """Small populations run several whole starts per block and reduce through shared memory (SupArgs.spb); with one
+    individual the one-thread emulation takes that path: it must agree with the unpacked path's oracle result."""
+    data, t = sup["group_data"][:, :, 3:4], sup["timepoints"]
+    nns, th = _starts(sup, 4)
+    th = th[:, 3:4]
+    g = oracle.sup_eval(data, t, nns, th, with_grad=True, scale=np.ones(3))
+    e = emu_wrap.emu_sup_eval(data, t, nns, th, scale=np.ones(3))
+    assert noise_ok(np.abs(e["sse"] - g["sse"]) / g["sse"], 1e-5)
+    assert noise_ok(np.abs(e["g_theta"] - g["g_theta"]) / np.abs(g["g_theta"]).max(), 1e-4)
+    assert noise_ok(np.abs(e["g_neural"] - g["g_neural"]) / np.abs(g["g_neural"]).max(axis=-1, keepdims=True), 1e-4)
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_stored_reference_losses(sup):
     """All 25 stored training and validation losses of suppression/results/lambda=1.0.jld2 on the B200."""
