@@ -25,7 +25,7 @@ struct DevBuf {
 
 #define CUDE_MAX_CHUNKS 16
 #ifndef CUDE_SUP_PACK_DEFAULT
-#define CUDE_SUP_PACK_DEFAULT 0            // 1: small suppression populations run several starts per 128-thread block by default
+#define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
 #ifndef CUDE_BETA_FORWARD_SENSITIVITY
 #define CUDE_BETA_FORWARD_SENSITIVITY 1   // 0: beta-only gradients through the adjoint kernel (comparison builds)
