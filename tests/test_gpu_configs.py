@@ -128,6 +128,13 @@ def test_pipelined_host_call_equals_single_chunk_calls(ctx):
     loss, sse = pop.loss(neural, cond, return_sse=True)
     assert np.allclose(loss * n, sums[:, 0], rtol=1e-13)
     assert np.array_equal(sse[5], pop.loss(neural[5:6], cond[5:6], return_sse=True)[1][0])
+    # all options together on the pipelined path: lane balancing (second call runs grouped) + FP32 adjoint network
+    ob = cu.SolverOptions(balance=1, precision=2)
+    for _ in range(2):
+        sums2, gc2 = pop.loss_grad_sums(neural, cond, cond_scale=0.5, opts=ob)
+        assert np.allclose(sums2[:, 0], sums[:, 0], rtol=1e-12)                   # FP64 forward pass, other summation order
+        assert np.abs(sums2[:, 1:] - sums[:, 1:]).max() < 1e-5 * np.abs(sums[:, 1:]).max()
+        assert np.abs(gc2 - gc).max() < 1e-5 * np.abs(gc).max()
     # shared network (flat indexing: beta-only fits, profiles), pipelined: 70 000 x 64 = 4.5 M trajectories
     l2, sse2 = pop.loss(neural[0], cond[:64], return_sse=True)
     l1, sse1 = pop.loss(neural[0], cond[17:18], return_sse=True)
