@@ -152,7 +152,8 @@ int cude_loss_grad_sums(cude_ctx* ctx, const cude_population* pop, const cude_ne
  * shard of the individuals, `sums_out` [(P+1) x n_starts] receives for every start
  * { sum_i sse_i, sum_i d sse_i / d neural[0..P) } so that it can be all-reduced in place (NCCL)
  * and divided by the global N; g_cond receives d sse_i / d cond scaled by cond_scale
- * (pass 1/N_global).  want_grad = 0 computes only the sse sums (rows 1..P are zeroed). */
+ * (pass 1/N_global).  want_grad: 0 = only the sse sums (rows 1..P are zeroed); bit 0 = d/d cond; bit 1 = d/d neural
+ * (3 = both: the adjoint kernel; 1 = beta-only: the cheaper forward-sensitivity kernel). */
 int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
                   int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
                   int want_grad, double cond_scale,
