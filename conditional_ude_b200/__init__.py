@@ -5,7 +5,7 @@ Host side mirrors the reference's constructors and loss entry points; all numeri
 hand-written sm_100a CUDA kernels of csrc/ through the C ABI in include/cude_b200.h.
 There is no CPU fallback.
 """
-from .models import (Chain, chain, softplus, van_cauter_parameters, CPeptideConditionalUDEModel,
+from .models import (Chain, chain, softplus, van_cauter_parameters, CPeptideConditionalUDEModel, CPeptideUDEModel,
                      CPeptideConditionalCovariateUDEModel, pack_models)
 from .population import Context, Population, SolverOptions, default_context
 from .losses import loss, loss_sigma, loss_and_gradient, ComponentVector
@@ -21,7 +21,7 @@ from .saem import (SAEM, mcmc_step, individual_log_likelihood, total_nll, map_ob
 
 __all__ = [
     "SuppressionPopulation", "neural_network_model", "suppression_loss", "fit_suppression_model", "validate_suppression_model",
-    "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel",
+    "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel", "CPeptideUDEModel",
     "CPeptideConditionalCovariateUDEModel", "pack_models", "Context", "Population", "SolverOptions",
     "default_context", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",
     "likelihood_profile", "likelihood_profile_population", "find_confidence_intervals",

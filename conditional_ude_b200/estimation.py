@@ -299,16 +299,26 @@ class _Comm:
         return t.cpu().numpy()
 
 
-def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=25_000, selected_initials=25,
+def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=None, selected_initials=None,
           lhs_lower_bound=-2.0, lhs_upper_bound=0.0, n_conditional_parameters=1, number_of_iterations_adam=1000,
           number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None, distributed=False, group=None, **kw):
-    """The two cUDE `train` methods of the reference, dispatched like Julia on the 4th argument:
-      train(models, t, Y, rng::Generator; ...)  full training (:340-386)
+    """The `train` methods of the reference, dispatched like Julia on the first and 4th argument:
+      train(model::CPeptideUDEModel, t, y, rng; ...)  non-conditional UDE on one individual (:211-247; 10 000 / 10)
+      train(models, t, Y, rng::Generator; ...)  full cUDE training (:340-386; 25 000 guesses / 25 selected)
       train(models, t, Y, nn::vector; initial_beta, lbfgs_lower_bound, ...)  beta-only (:272-288).
     distributed=True (one process per GPU under torch.distributed; BASELINE config "starts sharded over 8 x B200"):
     every rank draws the same initial guesses from an identically seeded `rng`, screens its slice of them, the losses
     are all-gathered, the globally best `selected_initials` starts are split over the ranks and optimised there, and
     every rank returns all solutions in selection order.  No communication on the data path."""
+    from .models import CPeptideUDEModel
+    if isinstance(models, CPeptideUDEModel):           # train(model::CPeptideUDEModel, t, y, rng; ...) :211-247, its own defaults
+        return train_ude(models, timepoints, cpeptide_data, rng_or_nn,
+                         initial_guesses=10_000 if initial_guesses is None else initial_guesses,
+                         selected_initials=10 if selected_initials is None else selected_initials,
+                         number_of_iterations_adam=number_of_iterations_adam,
+                         number_of_iterations_lbfgs=number_of_iterations_lbfgs, learning_rate_adam=learning_rate_adam, opts=opts)
+    initial_guesses = 25_000 if initial_guesses is None else initial_guesses
+    selected_initials = 25 if selected_initials is None else selected_initials
     if not isinstance(rng_or_nn, np.random.Generator):
         return train_conditional(models, timepoints, cpeptide_data, rng_or_nn, opts=opts, **kw)
     if n_conditional_parameters != 1:
@@ -353,6 +363,39 @@ def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=25_000, 
             continue
         sols.append(OptimizationSolution(ComponentVector(neural=res[s_, :P].copy(), conditional=res[s_, P:P + n].copy()),
                                          res[s_, P + n], int(res[s_, P + n + 1]), bool(res[s_, P + n + 2])))
+    return sols
+
+
+def train_ude(model, timepoints, cpeptide_data, rng, initial_guesses=10_000, selected_initials=10,
+              number_of_iterations_adam=1000, number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None,
+              population=None):
+    """train(model::CPeptideUDEModel, timepoints, cpeptide_data, rng; ...) — src/parameter-estimation.jl:211-247: the
+    non-conditional UDE on one (mean) individual.  All initial guesses are screened in one launch (a population of one
+    individual x `initial_guesses` networks), the best `selected_initials` are trained in lock-step (Adam, then L-BFGS).
+    Solutions carry the plain 1-input network vector in `.u` (the reference's `optsol.u`)."""
+    from .models import embed_ude_parameters, extract_ude_gradient
+    pop = population if population is not None else _as_population(
+        [model], timepoints, np.asarray(cpeptide_data, dtype=np.float64).reshape(1, -1))   # `population`: test double
+    w = model.ude_chain.width
+    p0 = np.stack(initial_parameters(model.ude_chain, initial_guesses, rng=rng))
+
+    def f(x):
+        return pop.loss(embed_ude_parameters(x, w), np.zeros((x.shape[0], 1)), opts)
+
+    def fg(x):
+        l, gn, _ = pop.loss_grad(embed_ude_parameters(x, w), np.zeros((x.shape[0], 1)), opts)
+        return l, extract_ude_gradient(gn, w)
+
+    losses_initial = f(p0)
+    pick = np.argsort(losses_initial, kind="stable")[:selected_initials]
+    x1, _ = adam_batched(fg, p0[pick], lr=learning_rate_adam, maxiters=number_of_iterations_adam)
+    x2, fx, iters, conv = lbfgs_batched(f, fg, x1, maxiters=number_of_iterations_lbfgs)
+    sols = []
+    for s_ in range(x2.shape[0]):
+        if not np.isfinite(fx[s_]):
+            print("Optimization failed... Skipping")                                                # :239-241
+            continue
+        sols.append(OptimizationSolution(x2[s_].copy(), fx[s_], iters[s_], conv[s_]))
     return sols
 
 

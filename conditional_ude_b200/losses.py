@@ -14,7 +14,7 @@ import math
 
 import numpy as np
 
-from .models import CPeptideConditionalUDEModel
+from .models import CPeptideConditionalUDEModel, CPeptideUDEModel, embed_ude_parameters, extract_ude_gradient
 from .population import cached_population, SolverOptions
 
 
@@ -64,6 +64,8 @@ def loss(theta, p, opts=None):
     if len(p) != 3:
         raise TypeError("loss(theta, (model, timepoints, cpeptide_data[, neural_network_parameters]))")
     first, timepoints, cpeptide_data = p
+    if isinstance(first, CPeptideUDEModel):             # non-conditional UDE: theta is the plain 1-input network vector
+        return _single(first, timepoints, cpeptide_data, embed_ude_parameters(theta, first.ude_chain.width), 0.0, opts)
     if isinstance(first, CPeptideConditionalUDEModel):  # single individual (:56-68)
         return _single(first, timepoints, cpeptide_data, np.asarray(_get(theta, "neural"), dtype=np.float64),
                        _scalar(_get(theta, "conditional")), opts)
@@ -82,6 +84,10 @@ def loss_and_gradient(theta, p, opts=None):
         l, _, gb = _single(model, timepoints, cpeptide_data, np.asarray(nn, dtype=np.float64), _scalar(theta), opts, grad=True)
         return l, gb
     first, timepoints, cpeptide_data = p
+    if isinstance(first, CPeptideUDEModel):
+        w = first.ude_chain.width
+        l, gn, _ = _single(first, timepoints, cpeptide_data, embed_ude_parameters(theta, w), 0.0, opts, grad=True)
+        return l, extract_ude_gradient(gn, w)
     if isinstance(first, CPeptideConditionalUDEModel):
         l, gn, gb = _single(first, timepoints, cpeptide_data, np.asarray(_get(theta, "neural"), dtype=np.float64),
                             _scalar(_get(theta, "conditional")), opts, grad=True)

@@ -197,3 +197,32 @@ def pack_models(models, timepoints, cpeptide_data):
         out["kin"][i] = (m.k0, m.k1, m.k2, m.c0)
     out["chain"] = ch
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Non-conditional UDE (src/c-peptide-models.jl:144-168, src/types.jl:11-14): production = NN([dG]) - NN([0]) with a
+# 1-input network, e.g. chain(4, 2, tanh; input_dims=1) (c-peptide/01-non-conditional.jl:21-23).  The device kernels take
+# the conditional form NN([dG; beta]); a 1-input network is *exactly* the 2-input network whose beta column is zero
+# (fma(0, beta, b) = b), so the UDE model runs through the same kernels by embedding its parameter vector.
+def embed_ude_parameters(p, width):
+    """[W1[:,0], b1, rest] of a 1-input chain -> [W1[:,0], 0 (beta column), b1, rest] of the 2-input chain."""
+    p = np.asarray(p, dtype=np.float64)
+    return np.concatenate([p[..., :width], np.zeros(p.shape[:-1] + (width,)), p[..., width:]], axis=-1)
+
+
+def extract_ude_gradient(g, width):
+    """Inverse of `embed_ude_parameters` for gradients: drop the beta column."""
+    g = np.asarray(g, dtype=np.float64)
+    return np.concatenate([g[..., :width], g[..., 2 * width:]], axis=-1)
+
+
+class CPeptideUDEModel(CPeptideConditionalUDEModel):
+    """CPeptideUDEModel(glucose_data, glucose_timepoints, age, network, cpeptide_data, t2dm) with a 1-input network
+    (src/c-peptide-models.jl:144-168).  `chain` is the user's 1-input chain; `device_chain` the embedded 2-input one."""
+
+    def __init__(self, glucose_data, glucose_timepoints, age, network, cpeptide_data, t2dm):
+        if not isinstance(network, Chain) or network.input_dims != 1:
+            raise ValueError("CPeptideUDEModel needs a network with input_dims=1")
+        super().__init__(glucose_data, glucose_timepoints, age, Chain(2, network.width, network.depth), cpeptide_data, t2dm)
+        self.device_chain = self.chain
+        self.ude_chain = network
