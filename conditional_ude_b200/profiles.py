@@ -11,10 +11,23 @@ from .population import Population, cached_population
 CHISQ1_095 = 3.841458820694124  # quantile(Chisq(1), 0.95)
 
 
-def likelihood_profile(beta, neural_network_parameters, model, timepoints, cpeptide_data, lower_bound, upper_bound, sigma,
-                       steps=1000, opts=None):
+def likelihood_profile(beta, neural_network_parameters, model, timepoints, cpeptide_data, lower_bound, upper_bound=None,
+                       sigma=None, steps=1000, opts=None):
     """Returns (nll_values[steps], nll_minimum, parameter_values[steps]) like the reference: the loss at
-    `beta` and on range(lower_bound, upper_bound, length=steps), each scaled by 1/(2 sigma^2)."""
+    `beta` and on range(lower_bound, upper_bound, length=steps), each scaled by 1/(2 sigma^2).
+    The reference's second method (:19-32), likelihood_profile(beta, loss_function, args, lb, ub, sigma; steps), is
+    dispatched on a callable second argument; with this package's `loss` and a fixed-network 4-tuple as `args` the grid
+    still runs as one GPU batch, any other callable is evaluated point by point."""
+    if callable(neural_network_parameters):
+        loss_function, args = neural_network_parameters, model
+        lower_bound, upper_bound, sigma = timepoints, cpeptide_data, lower_bound      # positional shift of that method
+        from .losses import loss as _loss
+        if loss_function is _loss and len(args) == 4:
+            return likelihood_profile(beta, args[3], args[0], args[1], args[2], lower_bound, upper_bound, sigma, steps=steps, opts=opts)
+        parameter_values = np.linspace(lower_bound, upper_bound, steps)
+        scale = 1.0 / (2.0 * sigma ** 2)
+        return (np.array([scale * loss_function(b, args) for b in parameter_values]), scale * loss_function(beta, args),
+                parameter_values)
     pop = cached_population([model], np.asarray(timepoints, dtype=np.float64),
                             np.asarray(cpeptide_data, dtype=np.float64).reshape(1, -1))
     parameter_values = np.linspace(lower_bound, upper_bound, steps)

@@ -112,6 +112,12 @@ def test_find_confidence_intervals():
     assert lo == -np.inf and hi == np.inf
 
 
+def test_likelihood_profile_generic_method():
+    """likelihood_profile(beta, loss_function, args, lb, ub, sigma; steps) — src/likelihood-profiles.jl:19-32."""
+    nll, nmin, grid = cu.likelihood_profile(0.3, lambda b, a: (b - a) ** 2, 1.0, -1.0, 2.0, 0.5, steps=4)
+    assert np.allclose(grid, [-1, 0, 1, 2]) and np.allclose(nll, 2 * (grid - 1) ** 2) and np.isclose(nmin, 2 * 0.49)
+
+
 def test_component_vector():
     th = cu.ComponentVector(neural=np.arange(3.0), conditional=[1.0])
     assert th.neural[2] == 2.0 and th["conditional"] == [1.0]
