@@ -132,6 +132,14 @@ def main():
     assert np.array_equal(np.stack(c["parameters"]), fx["cov_neural"]) and np.array_equal(np.stack(c["betas"]), fx["cov_betas"])
     assert c["best_model_index"] == 2
 
+    # ---- second stored cUDE training run (c-peptide/02-conditional.jl with sigma, `cude_neural_parameters_sigma.jld2`):
+    #      25 x 37 weights, 25 x 57 betas, best_model_index = 2 — read with the structural reader ----
+    sg = jld2.load(os.path.join(REF, "source_data/cude_neural_parameters_sigma.jld2"))
+    fx["cude_sigma_neural"] = np.stack(sg["parameters"])
+    fx["cude_sigma_betas"] = np.stack(sg["betas"])
+    fx["cude_sigma_best_model_index"] = np.array(int(sg["best_model_index"]))
+    assert fx["cude_sigma_neural"].shape == (25, 37) and fx["cude_sigma_betas"].shape == (25, 57) and sg["width"] == 4
+
     np.savez_compressed(OUT, **fx)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(fx), "arrays")
 

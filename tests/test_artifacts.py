@@ -67,3 +67,25 @@ def test_covariate_artifact(fx):
     off = op.eval(fx["cov_neural"][best], fx["cov_betas"][best] + 0.5, grad_mode=0)
     assert np.abs(g["g_cond"]).mean() < 0.2 * np.abs(off["g_cond"]).mean()
     assert g["sse"].mean() < 1.0
+
+
+def test_all_fifty_stored_optima_are_stationary(fx):
+    """Both stored training runs (`cude_neural_parameters.jld2`, `cude_neural_parameters_sigma.jld2`): 2 x 25 networks,
+    each with its own 57 fitted betas.  Every one of the 50 (network, betas) pairs the reference's optimiser stopped at
+    must be a near-stationary point of the restated loss: |d loss_i/d beta_i| small (>= 30x smaller than half a unit
+    away), and the per-individual network gradients cancelling in the population mean.  A wrong kinetic constant,
+    interpolant, input order or weight layout would break all fifty at once."""
+    models, t, c, nn, betas = train57(fx)
+    op = oracle.OraclePopulation(cu.pack_models(models, t, c))
+    for name in ("cude", "cude_sigma"):
+        W, B = fx[name + "_neural"], fx[name + "_betas"]
+        r = op.eval(W, B, grad_mode=0)                                   # 25 starts x 57 individuals
+        off = op.eval(W, B + 0.5, grad_mode=0)
+        db, dboff = np.abs(r["g_cond"]).mean(axis=1), np.abs(off["g_cond"]).mean(axis=1)
+        assert db.max() < 0.5 and np.median(db) < 0.08 and (dboff / db).min() > 25
+        pop_grad = np.linalg.norm(r["g_neural"].sum(axis=1) / 57, axis=1)
+        largest_term = np.abs(r["g_neural"]).max(axis=(1, 2))
+        assert (pop_grad / largest_term).max() < 0.12
+        loss = r["sse"].mean(axis=1)
+        assert 0.25 < loss.min() and loss.max() < 0.5                    # the runs' objectives: 0.28 - 0.45
+    assert int(fx["cude_sigma_best_model_index"]) == 2
