@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <mutex>
 
 #include "../../include/cude_b200.h"
 #include <cub/device/device_radix_sort.cuh>
@@ -24,6 +25,9 @@ struct DevBuf {
 };
 
 #define CUDE_MAX_CHUNKS 16
+#ifndef CUDE_WEIGHTS_IN_CONSTANT_MEMORY
+#define CUDE_WEIGHTS_IN_CONSTANT_MEMORY 0   // 1: weights as uniform operands from constant memory when they fit (experimental)
+#endif
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
@@ -71,6 +75,11 @@ struct cude_population {
 };
 
 static thread_local std::string g_err;
+
+// last user of the per-device constant weight array (CW_CONST): uploads are ordered behind its kernel
+struct WConstUse { cudaEvent_t ev = nullptr; cudaStream_t stream = nullptr; bool used = false; };
+static std::mutex g_wconst_mutex;
+static WConstUse g_wconst_use[16];
 
 static int fail(cude_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -315,17 +324,21 @@ typedef void (*eval_kernel_t)(const EvalArgs);
 
 // grad: discrete adjoint (all gradients); bsens: d/d cond only by forward sensitivity (FP64 only)
 template <class NS>
-static eval_kernel_t pick(bool grad, bool mixed, bool bsens, bool fbwd) {
+static eval_kernel_t pick(bool grad, bool mixed, bool bsens, bool fbwd, bool wc) {
+    if (wc) {       // FP64 network with the weights in constant memory
+        if (bsens) return cude_eval_kernel<NS, false, false, true, false, true>;
+        return grad ? cude_eval_kernel<NS, true, false, false, false, true> : cude_eval_kernel<NS, false, false, false, false, true>;
+    }
     if (bsens) return cude_eval_kernel<NS, false, false, true>;
     if (fbwd && grad) return cude_eval_kernel<NS, true, false, false, true>;
     if (mixed) return grad ? cude_eval_kernel<NS, true, true> : cude_eval_kernel<NS, false, true>;
     return grad ? cude_eval_kernel<NS, true, false> : cude_eval_kernel<NS, false, false>;
 }
 
-static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed, bool bsens = false, bool fbwd = false) {
+static eval_kernel_t select_kernel(const cude_net* net, bool grad, bool mixed, bool bsens = false, bool fbwd = false, bool wc = false) {
     if (net->depth == 2 && net->width == 4) {
-        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed, bsens, fbwd);   // chain(4, 2, tanh), 02-conditional.jl:22
-        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed, bsens, fbwd);   // covariate net, 07-covariate-inclusion.jl:32
+        if (net->n_in == 2) return pick<NetShape<2, 2, 4>>(grad, mixed, bsens, fbwd, wc);   // chain(4, 2, tanh), 02-conditional.jl:22
+        if (net->n_in == 3) return pick<NetShape<3, 2, 4>>(grad, mixed, bsens, fbwd, wc);   // covariate net, 07-covariate-inclusion.jl:32
     }
     return nullptr;
 }
@@ -404,7 +417,10 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     // loss kernel instead of the adjoint sweep (src/parameter-estimation.jl:272-307, evaluate_model :406-433)
     const bool bsens = want_grad == 1 && !mixed && CUDE_BETA_FORWARD_SENSITIVITY;
     const bool adj = grad && !bsens;
-    eval_kernel_t kern = select_kernel(net, adj, mixed, bsens, fbwd && adj);
+    // weights as uniform operands from constant memory when the call's weights fit (see CW_CONST in cude_kernels.cuh)
+    const size_t n_w = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
+    const bool wc = CUDE_WEIGHTS_IN_CONSTANT_MEMORY && !mixed && !(fbwd && adj) && n_w <= CUDE_WCONST_DOUBLES;
+    eval_kernel_t kern = select_kernel(net, adj, mixed, bsens, fbwd && adj, wc);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -476,8 +492,21 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
-    kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
-    CU_TRY(ctx, cudaGetLastError());
+    if (wc) {
+        // the constant array is one per device and process: order this upload + launch after the last launch that read it
+        std::lock_guard<std::mutex> lk(g_wconst_mutex);
+        WConstUse& u = g_wconst_use[ctx->device % 16];
+        if (!u.ev) CU_TRY(ctx, cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+        if (u.used && u.stream != ctx->stream) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, u.ev, 0));
+        CU_TRY(ctx, cudaMemcpyToSymbolAsync(CW_CONST, d_neural, n_w * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaEventRecord(u.ev, ctx->stream));
+        u.used = true; u.stream = ctx->stream;
+    } else {
+        kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
+        CU_TRY(ctx, cudaGetLastError());
+    }
     int launches = 1;
     if (d_sums_out) {
         if (flat) {

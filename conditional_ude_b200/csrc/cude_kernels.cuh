@@ -407,6 +407,21 @@ __device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const dou
     }
 }
 
+// ---------------------------------------------------------------- weights in constant memory (WC instantiations)
+// Every lane of a block uses the same network, so its weights can be *uniform* operands: from constant memory they are
+// loaded into uniform registers (LDCU c[3][UR + off]) and enter the DFMAs as UR operands — no shared-memory load, no
+// vector-register operand.  (A DFMA with three vector-register operands issues at 74 % of the rate of one with a
+// uniform operand on B200, cude_measure_fp64_peak_rrr.)  cude_eval_dev copies the call's weights device-to-device
+// into this array on the stream before the launch; calls with more weights than fit use the shared-memory path.
+#ifndef CUDE_WCONST_DOUBLES
+#define CUDE_WCONST_DOUBLES 5120            // 40 KB of the 64 KB constant space: 138 starts of the 37-parameter network
+#endif
+#ifdef CUDE_HOST_EMU
+static double CW_CONST[CUDE_WCONST_DOUBLES];
+#else
+__constant__ double CW_CONST[CUDE_WCONST_DOUBLES];
+#endif
+
 // ---------------------------------------------------------------- the kernel
 struct Kin { double k0, k1, k2, c0, d00, kc; };  // d00 = -(k0+k2), kc = k0*c0
 
@@ -432,8 +447,9 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 // the same steps (frozen step sequence => the same derivative the adjoint produces), no step ring, no backward sweep.
 // FBWD (with GRAD): the forward pass — loss, step sequence — stays FP64 bit for bit, only the adjoint's network
 // evaluations and gradient accumulators are FP32 (opts.precision = 2): gradients to ~1e-6 instead of ~1e-13.
-template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false>
+template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false>
 __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUDE_MIN_BLOCKS_LOSS) cude_eval_kernel(const EvalArgs A) {
+    static_assert(!WC || (!MIXED && !FBWD), "WC (weights in constant memory) is an FP64-network variant");
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
     static_assert(!FBWD || (GRAD && !MIXED), "FBWD is a variant of the FP64 gradient kernel");
     using namespace tab;
@@ -447,10 +463,8 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
 
     // ---- shared memory carve-up ----
     double* sTab = smem;                             // [256] 2^(j/256) for the exp core
-    double* sW = sTab + 256;                         // [P] (padded to even)
-    R* sWr = MIXED ? reinterpret_cast<R*>(sW + ((P + 1) & ~1)) : reinterpret_cast<R*>(sW);   // network weights as R
-    RB* sWb = F32COPY ? reinterpret_cast<RB*>(sW + ((P + 1) & ~1)) : reinterpret_cast<RB*>(sW);   // ... as RB
-    double* sKt = sW + ((P + 1) & ~1) * (F32COPY ? 2 : 1);   // [K][B]  (a float copy of the weights may sit in between)
+    double* sWs = sTab + 256;                        // [P] (padded to even) — the start's weights in shared memory (unused with WC)
+    double* sKt = sWs + ((P + 1) & ~1) * (F32COPY ? 2 : 1);   // [K][B]  (a float copy of the weights may sit in between)
     double* sKg = sKt + (size_t)K * B;               // [K][B]
     double* sSl = sKg + (size_t)K * B;               // [K][B] (last row unused)
     double* sOt = sSl + (size_t)K * B;               // [M][B] observation times
@@ -481,10 +495,20 @@ __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUD
         else if (A.order) i = (int)(A.order[(size_t)s * N + i] & 0xffffffu);
         j = (long long)s * N + i;
     }
-    // ---- stage the start's weights (block-uniform) ----
+    // ---- the start's weights: staged in shared memory (block-uniform), or read from constant memory (WC) ----
+    // (offset from block-uniform values only, so that the compiler keeps it — and the weight loads — on the uniform path)
+    const long long wofs = A.flat ? 0 : (long long)(blockIdx.x % (unsigned)A.n_starts) * A.neural_stride;
+    double wuni[WC ? P : 1];         // WC: the weights as block-uniform values, loaded here in convergent code
+    if constexpr (WC) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[wofs + p];
+    }
+    const double* const sW = WC ? wuni : sWs;
+    R* const sWr = MIXED ? reinterpret_cast<R*>(sWs + ((P + 1) & ~1)) : reinterpret_cast<R*>(const_cast<double*>(sW));   // network weights as R
+    RB* const sWb = F32COPY ? reinterpret_cast<RB*>(sWs + ((P + 1) & ~1)) : reinterpret_cast<RB*>(const_cast<double*>(sW));   // ... as RB
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
-        for (int p = tid; p < P; p += B) { sW[p] = gW[p]; if (F32COPY) sWb[p] = (RB)gW[p]; }
+        if (!WC) for (int p = tid; p < P; p += B) { sWs[p] = gW[p]; if (F32COPY) sWb[p] = (RB)gW[p]; }
         for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     }
     // ---- stage this thread's knots ----
