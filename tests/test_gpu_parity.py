@@ -318,3 +318,35 @@ def test_abi_error_paths(fx, ctx):
     assert rc == _lib.CUDE_EUNSUPPORTED and b"not compiled" in lib.cude_last_error(ctx.handle)
     # still usable afterwards
     assert np.isfinite(pop.loss(nn, betas[None, :4])[0])
+
+
+def test_two_contexts_interleaved_gradient_calls(fx):
+    """The FP64 adjoint kernel reads its weights from one per-device constant array (cude_kernels.cuh CW_CONST) that the
+    library refills before every launch, ordered behind the previous launch that read it — also across contexts and
+    streams.  Two contexts evaluating different networks back to back (asynchronously, through the device API) must each
+    get their own result."""
+    import torch
+    from conditional_ude_b200.distributed import DevicePopulationShard
+    models, t, c, nn, betas = train57(fx)
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda", 0)
+    shards, want = [], []
+    for k in range(2):
+        ctx_k = cu.Context(0)
+        pop = cu.Population(models, t, c, ctx=ctx_k)
+        S = 3 + k
+        neural = nn[None] + 0.05 * (k + 1) * rng.standard_normal((S, 37))
+        cond = np.tile(betas, (S, 1)) + 0.1 * rng.standard_normal((S, 57))
+        want.append(pop.loss_grad(neural, cond, mean=True))                 # synchronous reference, one context at a time
+        sh = DevicePopulationShard(pop, 57, S, dev, stream=torch.cuda.Stream(device=dev))
+        with torch.cuda.stream(sh.stream):
+            sh.neural.copy_(torch.from_numpy(neural)); sh.cond.copy_(torch.from_numpy(cond))
+        shards.append(sh)
+    torch.cuda.synchronize()
+    for _ in range(5):                                                       # interleaved asynchronous launches on two streams
+        for sh in shards:
+            sh.step(cu.SolverOptions())
+    for sh, (l, gn, gc) in zip(shards, want):
+        loss, g = sh.result()
+        assert np.allclose(loss, l, rtol=1e-13) and np.allclose(g, gn, rtol=1e-11, atol=1e-13)
+        assert np.array_equal(sh.g_cond.cpu().numpy(), gc)
