@@ -29,7 +29,10 @@ struct DevBuf {
 #define CUDE_WEIGHTS_IN_CONSTANT_MEMORY 1   // weights of the FP64 adjoint kernel as uniform operands from constant memory when they fit (0: shared memory)
 #endif
 #ifndef CUDE_WC_LOSS
-#define CUDE_WC_LOSS 0                        // experiment: constant-memory weights in the loss-only kernel too
+#define CUDE_WC_LOSS 1                        // constant-memory weights in the loss-only kernel too (4 blocks per SM there)
+#endif
+#ifndef CUDE_WC_BSENS
+#define CUDE_WC_BSENS 1                       // ... and in the beta-sensitivity kernel (3.4e8 vs 3.1e8 evals/s)
 #endif
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
@@ -332,6 +335,9 @@ static eval_kernel_t pick(bool grad, bool mixed, bool bsens, bool fbwd, bool wc)
 #if CUDE_WC_LOSS
     if (wc && !bsens) return cude_eval_kernel<NS, false, false, false, false, true>;
 #endif
+#if CUDE_WC_BSENS
+    if (wc && bsens) return cude_eval_kernel<NS, false, false, true, false, true>;
+#endif
     if (bsens) return cude_eval_kernel<NS, false, false, true>;
     if (fbwd && grad) return cude_eval_kernel<NS, true, false, false, true>;
     if (mixed) return grad ? cude_eval_kernel<NS, true, true> : cude_eval_kernel<NS, false, true>;
@@ -424,7 +430,8 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     const size_t n_w = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
     // Only the FP64 adjoint kernel: there ptxas keeps the hoisted weights in uniform registers (+2.7 %); in the loss-only
     // instantiation it put them into 74 vector registers and the kernel lost 8 % (profiles/README.md).
-    const bool wc = CUDE_WEIGHTS_IN_CONSTANT_MEMORY && (adj || (CUDE_WC_LOSS && !grad)) && !mixed && !fbwd && n_w <= CUDE_WCONST_DOUBLES;
+    const bool wc = CUDE_WEIGHTS_IN_CONSTANT_MEMORY && (adj || (CUDE_WC_LOSS && !grad) || (CUDE_WC_BSENS && bsens)) && !mixed && !fbwd &&
+                    n_w <= CUDE_WCONST_DOUBLES;
     eval_kernel_t kern = select_kernel(net, adj, mixed, bsens, fbwd && adj, wc);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");
     if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: neural_stride < n_params");

@@ -144,6 +144,9 @@ struct NetShape {
 #ifndef CUDE_MIN_BLOCKS_LOSS
 #define CUDE_MIN_BLOCKS_LOSS 3   // same for the loss-only instantiation
 #endif
+#ifndef CUDE_MIN_BLOCKS_LOSS_WC
+#define CUDE_MIN_BLOCKS_LOSS_WC 4   // loss-only with the weights in constant memory: 128 registers keep them in uniform registers (5.1e8 vs 4.6e8 evals/s)
+#endif
 #ifndef CUDE_FWD_UNROLL
 #define CUDE_FWD_UNROLL 1   // unroll factor of the forward network-evaluation loop over a step's 5 nodes
 #endif
@@ -448,7 +451,8 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 // FBWD (with GRAD): the forward pass — loss, step sequence — stays FP64 bit for bit, only the adjoint's network
 // evaluations and gradient accumulators are FP32 (opts.precision = 2): gradients to ~1e-6 instead of ~1e-13.
 template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false>
-__global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : CUDE_MIN_BLOCKS_LOSS) cude_eval_kernel(const EvalArgs A) {
+__global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : ((WC && !BSENS) ? CUDE_MIN_BLOCKS_LOSS_WC : CUDE_MIN_BLOCKS_LOSS))
+cude_eval_kernel(const EvalArgs A) {
     static_assert(!WC || (!MIXED && !FBWD), "WC (weights in constant memory) is an FP64-network variant");
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
     static_assert(!FBWD || (GRAD && !MIXED), "FBWD is a variant of the FP64 gradient kernel");
