@@ -331,6 +331,7 @@ typedef void (*eval_kernel_t)(const EvalArgs);
 // grad: discrete adjoint (all gradients); bsens: d/d cond only by forward sensitivity (FP64 only)
 template <class NS>
 static eval_kernel_t pick(bool grad, bool mixed, bool bsens, bool fbwd, bool wc) {
+    if (wc && grad && fbwd) return cude_eval_kernel<NS, true, false, false, true, true>;   // FP32 adjoint network, FP64 forward weights in constant memory
     if (wc && grad) return cude_eval_kernel<NS, true, false, false, false, true>;   // FP64 adjoint kernel, weights in constant memory
 #if CUDE_WC_LOSS
     if (wc && !bsens) return cude_eval_kernel<NS, false, false, false, false, true>;
@@ -430,7 +431,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     const size_t n_w = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
     // Only the FP64 adjoint kernel: there ptxas keeps the hoisted weights in uniform registers (+2.7 %); in the loss-only
     // instantiation it put them into 74 vector registers and the kernel lost 8 % (profiles/README.md).
-    const bool wc = CUDE_WEIGHTS_IN_CONSTANT_MEMORY && (adj || (CUDE_WC_LOSS && !grad) || (CUDE_WC_BSENS && bsens)) && !mixed && !fbwd &&
+    const bool wc = CUDE_WEIGHTS_IN_CONSTANT_MEMORY && (adj || (CUDE_WC_LOSS && !grad) || (CUDE_WC_BSENS && bsens)) && !mixed &&
                     n_w <= CUDE_WCONST_DOUBLES;
     eval_kernel_t kern = select_kernel(net, adj, mixed, bsens, fbwd && adj, wc);
     if (!kern) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in (available: n_in 2|3, depth 2, width 4)");

@@ -453,7 +453,7 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false>
 __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : ((WC && !BSENS) ? CUDE_MIN_BLOCKS_LOSS_WC : CUDE_MIN_BLOCKS_LOSS))
 cude_eval_kernel(const EvalArgs A) {
-    static_assert(!WC || (!MIXED && !FBWD), "WC (weights in constant memory) is an FP64-network variant");
+    static_assert(!WC || !MIXED, "WC (weights in constant memory) needs an FP64 forward network");
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
     static_assert(!FBWD || (GRAD && !MIXED), "FBWD is a variant of the FP64 gradient kernel");
     using namespace tab;
@@ -512,7 +512,7 @@ cude_eval_kernel(const EvalArgs A) {
     RB* const sWb = F32COPY ? reinterpret_cast<RB*>(sWs + ((P + 1) & ~1)) : reinterpret_cast<RB*>(const_cast<double*>(sW));   // ... as RB
     {
         const double* gW = A.neural + (A.flat ? 0 : (long long)s * A.neural_stride);
-        if (!WC) for (int p = tid; p < P; p += B) { sWs[p] = gW[p]; if (F32COPY) sWb[p] = (RB)gW[p]; }
+        if (!WC || F32COPY) for (int p = tid; p < P; p += B) { if (!WC) sWs[p] = gW[p]; if (F32COPY) sWb[p] = (RB)gW[p]; }
         for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     }
     // ---- stage this thread's knots ----
