@@ -340,10 +340,10 @@ def run_ours(args):
     kernel_s = float(kms.item()) * 1e-3
     achieved = (fl + tr) / kernel_s / 1e12
     # DRAM traffic of the dominant kernel: dram__bytes_read + dram__bytes_write of one launch at this size from the
-    # committed `ncu --set full` capture (profiles/r01_v15_traffic.json), scaled to this rank's launch
+    # committed `ncu --set full` capture (profiles/r01_v16_traffic.json), scaled to this rank's launch
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v15_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_v16_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_trajectory"] * (n_traj / world)
     except Exception:
         pass
@@ -364,12 +364,12 @@ def run_ours(args):
                 "alg_flops_per_traj": fl / (n_traj / world), "alg_transcendentals_per_traj": tr / (n_traj / world),
                 "peak_source": "measured live: DFMA micro-benchmark (cude_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_register_operands": peak_rrr,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_v15_traffic.json): "
-                                  "56 B per trajectory against 29 B algorithmic; HBM is not the bound",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_v16_traffic.json): "
+                                  "52 B per trajectory against 29 B algorithmic; HBM is not the bound",
                 "note": "peak = DFMA chains whose other operands come from the uniform path (upper bound); "
                         "peak_register_operands = DFMA with three register operands, the shape of real code. One FP64 "
                         "tanh/exp/log costs 8-25 FP64 instructions but counts once in `achieved`; ncu "
-                        "(profiles/r01_v12_*) shows the FP64 pipe 56 % active and 60 % of the issue slots used.",
+                        "(profiles/r01_v16_*) shows the FP64 pipe 58 % active and 60 % of the issue slots used.",
                 "n_acc_per_traj": n_acc / n_traj, "n_rej_per_traj": n_rej / n_traj}
 
     if rank == 0:

@@ -160,7 +160,7 @@ struct NetShape {
 //    it recomputes anyway.  1: the record also keeps d = 1 + exp(z_out) of the step's 5 nodes (7 doubles), which takes
 //    the sigmoid off the adjoint's dependent chain: +0.9 % throughput on B200, but the records (1.2 KB per trajectory
 //    in local memory) no longer stay in L2 and every one is written back: 76 GB of DRAM traffic per 64 M-trajectory
-//    launch instead of 3.6 GB (ncu, profiles/r01_v15_traffic.json).  Not worth it.
+//    launch instead of 3.6 GB (ncu, profiles/r01_v16_traffic.json).  Not worth it.
 #define CUDE_STASH_D 0
 #endif
 #ifndef CUDE_REC_CAP
