@@ -173,3 +173,46 @@ def test_lane_balancing_changes_the_grouping_not_the_results(ctx):
     # a different number of starts resets the state
     b3 = pop.loss_grad(neural2[:2], cond2[:2], opts=ob, mean=False, return_sse=True)
     assert np.array_equal(b3[3], r2[3][:2])
+
+
+def test_config5_synthetic_population_1m_individuals_x_64_starts(ctx):
+    """BASELINE config 5 at full size (64 M trajectories, loss + gradient through the host-buffer C-ABI call).
+    (a) oracle on a random subsample; (b) a checksum of checksums: the per-start sums of four shards of the
+    individuals add up to the sums of the whole population, and the shards' d/d beta are the whole's, bit for bit."""
+    import bench
+    N, S, P = 1_000_000, 64, 37
+    pk = bench.synthetic_population(N, seed=1)
+    neural, cond = bench.synthetic_starts(N, S, seed_shared=11, seed_rank=12)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    sums, gc = pop.loss_grad_sums(neural, cond, cond_scale=1.0)
+    assert np.isfinite(sums).all() and np.isfinite(gc).all() and np.all(sums[:, 0] > 0)
+    # (a) 1500 random trajectories against the oracle: d sse/d beta directly, the sse through a loss-only pass on
+    # the picked individuals
+    rng = np.random.default_rng(3)
+    ss, ii = rng.integers(0, S, 1500), rng.integers(0, N, 1500)
+    want, wantg = np.empty(1500), np.empty(1500)
+    for s in np.unique(ss):
+        m = ss == s
+        sub = {k: (v[ii[m]] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in pk.items()}
+        sub["n_ind"] = int(m.sum())
+        r = oracle.OraclePopulation(sub).eval(neural[s], cond[s, ii[m]][None], grad_mode=0)
+        want[m], wantg[m] = r["sse"][0], r["g_cond"][0]
+    assert noise_ok(np.abs(gc[ss, ii] - wantg) / np.abs(wantg).max(), 1e-4)
+    # (b) shards of the individuals (the multi-GPU decomposition, here one after the other on one GPU)
+    total = np.zeros_like(sums)
+    sse_sub = None
+    for lo, hi in ((0, 250_000), (250_000, 500_000), (500_000, 750_000), (750_000, N)):
+        sub = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in pk.items()}
+        sub["n_ind"] = hi - lo
+        shard = cu.Population(packed=sub, ctx=ctx)
+        s_k, gc_k = shard.loss_grad_sums(neural, np.ascontiguousarray(cond[:, lo:hi]), cond_scale=1.0)
+        assert np.array_equal(gc_k, gc[:, lo:hi])
+        total += s_k
+        if lo == 0:                                            # per-trajectory sse of the first shard for (a)
+            sse_sub = shard.loss(neural, np.ascontiguousarray(cond[:, lo:hi]), return_sse=True)[1]
+        del shard
+    assert np.allclose(total[:, 0], sums[:, 0], rtol=1e-12, atol=0)
+    scale = np.abs(sums[:, 1:]).max(axis=1, keepdims=True)
+    assert np.max(np.abs(total[:, 1:] - sums[:, 1:]) / scale) < 1e-11
+    m = ii < 250_000
+    assert noise_ok(np.abs(sse_sub[ss[m], ii[m]] - want[m]) / want[m], 1e-5)
