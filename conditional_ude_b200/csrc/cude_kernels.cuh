@@ -155,19 +155,15 @@ struct NetShape {
 #endif
 #define CUDE_PRAGMA(x) _Pragma(#x)
 #define CUDE_UNROLL(n) CUDE_PRAGMA(unroll n)
-#ifndef CUDE_STASH_D
-// 0 (default): an accepted-step record is (t, dt); the adjoint recomputes z_out and its sigmoid from the activations
-//    it recomputes anyway.  1: the record also keeps d = 1 + exp(z_out) of the step's 5 nodes (7 doubles), which takes
-//    the sigmoid off the adjoint's dependent chain: +0.9 % throughput on B200, but the records (1.2 KB per trajectory
-//    in local memory) no longer stay in L2 and every one is written back: 76 GB of DRAM traffic per 64 M-trajectory
-//    launch instead of 3.6 GB (ncu, profiles/r01_v16_traffic.json).  Not worth it.
-#define CUDE_STASH_D 0
-#endif
 #ifndef CUDE_REC_CAP
 #define CUDE_REC_CAP 48
 #endif
 constexpr int REC_CAP = CUDE_REC_CAP;
-constexpr int REC_W = CUDE_STASH_D ? 7 : 2;   // doubles per record  // ring of accepted-step records kept per thread (local memory)
+// Ring of accepted-step records kept per thread (local memory).  A record is (t, dt): the adjoint recomputes z_out and
+// its sigmoid from the activations it recomputes anyway.  Keeping d = 1 + exp(z_out) of the step's 5 nodes as well
+// (7 doubles) took the sigmoid off the adjoint's dependent chain for +0.9 %, but the records then no longer stay in L2:
+// 76 GB of DRAM traffic per 64 M-trajectory launch instead of 3.6 GB (profiles/README.md).
+constexpr int REC_W = 2;   // doubles per record
 
 // per-thread view of the staged glucose knots in shared memory, layout [k][tid]
 struct Knots {
@@ -329,7 +325,7 @@ __device__ __forceinline__ void softplus_d_mixed(double z, const double* __restr
 // Adjoint at one time node: acc += dz * d z_out/d(params), dz = (node weight) * sigmoid(z_out).  The hidden activations
 // are recomputed (8 tanh): keeping them from the forward pass (9 doubles per node, ~7 KB per trajectory in local memory)
 // was measured slower on B200 (1.05e8 vs 1.30e8 evals/s) — the footprint of all resident threads exceeds L2 and the
-// kernel has too few warps to hide the HBM latency (see also CUDE_STASH_D).
+// kernel has too few warps to hide the HBM latency (see also REC_W).
 // The accumulators g[] stay in registers during the adjoint sweep (updating them in shared memory
 // serialised on the LDS latency: ncu v2 short_scoreboard); they are parked in shared memory only around a
 // forward replay and for the final block reduction.  Layout:
@@ -368,7 +364,7 @@ __device__ __forceinline__ void mlp_backward(const R* __restrict__ sW, const dou
         }
         off += NS::LH;
     }
-    if (!CUDE_STASH_D) {   // dz arrives as the bare node weight: times d softplus(z_out) = sigmoid(z_out)
+    {   // dz arrives as the bare node weight: times d softplus(z_out) = sigmoid(z_out)
         R z = sW[off + W];
 #pragma unroll
         for (int i = 0; i < W; ++i) z = fma(sW[off + i], a[D - 1][i], z);
@@ -573,8 +569,7 @@ cude_eval_kernel(const EvalArgs A) {
         const double dtmin = fmax(nextafter(at0, CUDART_INF) - at0, nextafter(at1, CUDART_INF) - at1);
         const double snap = 100.0 * (nextafter(at1, CUDART_INF) - at1);
 
-        double rec[GRAD ? REC_CAP * REC_W : 1];   // accepted-step records {t, dt} (+ d[5] = 1 + exp(z_out) of the step's nodes with CUDE_STASH_D)
-        double d_nn0 = 1.0;                   // d at the node t0, dG = 0: the NN([0;beta]) term
+        double rec[GRAD ? REC_CAP * REC_W : 1];   // accepted-step records {t, dt}
         RB acc[GRAD ? NS::NACC : 1];          // gradient accumulators (compressed layout, see mlp_backward): registers during the adjoint sweep
         volatile double park[GRAD ? NS::NACC : 1];   // ... local memory across a forward replay (solves longer than REC_CAP
                                                      // steps: rare); volatile keeps it out of the register allocation
@@ -658,7 +653,6 @@ cude_eval_kernel(const EvalArgs A) {
                     // ---- Hairer, part 2: probe f(u0 + dt0 f0, t0 + dt0) ----
                     init = false;
                     nn0 = sp[0];                                  // network([0; beta]) — identical at every call
-                    d_nn0 = dd[0];
                     if (BSENS) dnn0 = fma(-1.0, m_rcp(dd[0]), 1.0) * myDG[0];   // d network([0; beta]) / d beta
                     const double pe = sp[1] - nn0;
                     double f0, f1;
@@ -775,8 +769,6 @@ cude_eval_kernel(const EvalArgs A) {
                     if (GRAD) {
                         double* const r7 = rec + (na % REC_CAP) * REC_W;
                         r7[0] = t; r7[1] = dt;
-#pragma unroll
-                        for (int q = 0; q < (CUDE_STASH_D ? 5 : 0); ++q) r7[2 + q] = dd[q];
                     }
                     ++na;
                     lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
@@ -816,15 +808,9 @@ cude_eval_kernel(const EvalArgs A) {
                 double tn, h;
                 if (n < 0) {
                     nq = 1; cn = CN_INIT; tn = t0; h = 0.0;
-                    myNode[0] = CUDE_STASH_D ? -wsum * fma(-1.0, m_rcp(d_nn0), 1.0) : -wsum;
+                    myNode[0] = -wsum;
                 } else {
                     tn = rn_t; h = rn_h;
-                    double dd[5];                                  // needed after the stage recursion: the loads overlap it
-                    {
-                        const double* const r7 = rec + (n % REC_CAP) * REC_W;
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) dd[q] = CUDE_STASH_D ? r7[2 + q] : 0.0;
-                    }
                     if (n > lo) { rn_t = rec[((n - 1) % REC_CAP) * REC_W]; rn_h = rec[((n - 1) % REC_CAP) * REC_W + 1]; }
                     nq = 5; cn = CN_STEP;
                     double kb[7][2];
@@ -888,14 +874,8 @@ cude_eval_kernel(const EvalArgs A) {
                     (void)hg0; (void)hg1;
                     // node weights, in CN_STEP order; node tn+h serves stages 6, 7 and the next step's stage 1
                     const double w6 = pb6 + pb7 + wnode;
-                    // dz = node weight * d softplus(z_out) = w * (1 - 1/d)
-                    if (CUDE_STASH_D) {
-                        myNode[0] = pb2 * fma(-1.0, m_rcp(dd[0]), 1.0); myNode[B] = pb3 * fma(-1.0, m_rcp(dd[1]), 1.0);
-                        myNode[2 * B] = pb4 * fma(-1.0, m_rcp(dd[2]), 1.0); myNode[3 * B] = pb5 * fma(-1.0, m_rcp(dd[3]), 1.0);
-                        myNode[4 * B] = w6 * fma(-1.0, m_rcp(dd[4]), 1.0);
-                    } else {
-                        myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
-                    }
+                    // the bare node weights; mlp_backward multiplies by d softplus(z_out)
+                    myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
                     wsum += w6 + pb5 + pb4 + pb3 + pb2;
                     wnode = pb1;
                     lam0 = ub0; lam1 = ub1;
