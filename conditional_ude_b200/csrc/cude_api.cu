@@ -24,7 +24,10 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-#define CUDE_MAX_CHUNKS 16
+#ifndef CUDE_MAX_CHUNKS
+#define CUDE_MAX_CHUNKS 6    // pipeline depth of a host-buffer call; measured at 64 M trajectories: 3 / 4 / 5 / 6 / 8 / 16 / 32 chunks
+                             // -> e2e 2.112 / 2.118 / 2.122 / 2.115 / 2.108 / 2.10 / 2.055e8 evals/s (kernel tails vs exposed first/last copy)
+#endif
 #ifndef CUDE_WEIGHTS_IN_CONSTANT_MEMORY
 #define CUDE_WEIGHTS_IN_CONSTANT_MEMORY 1   // weights of the FP64 adjoint kernel as uniform operands from constant memory when they fit (0: shared memory)
 #endif
