@@ -31,8 +31,10 @@ LN2 = float(np.log(2.0))
 
 
 # ----------------------------------------------------------------------------- synthetic population
-def synthetic_population(n, seed):
-    """Ohashi-like OGTT individuals (5 knots on [0,120] min)."""
+def synthetic_individuals(n, seed):
+    """Ohashi-like OGTT individuals (5 knots on [0,120] min): age ~ U(20,80), T2DM ~ Bernoulli(0.44),
+    c0 ~ LogNormal clipped to [0.2,1.5] nmol/L, glucose = G0 + A*shape(t) with G0 ~ U(4,8), peak dG ~ U(1,15) mmol/L.
+    Returns the packed population with placeholder observations and the generator (for the observation noise)."""
     from conditional_ude_b200 import chain
     rng = np.random.default_rng(seed)
     age = rng.uniform(20.0, 80.0, n)
@@ -50,20 +52,58 @@ def synthetic_population(n, seed):
     shape = np.stack([np.zeros(n), 0.6 + 0.4 * rng.random(n), 0.8 + 0.2 * rng.random(n),
                       0.4 + 0.5 * rng.random(n), 0.1 + 0.4 * rng.random(n)], axis=1)
     glucose = g0[:, None] + peak[:, None] * shape
-    gain = rng.uniform(1.0, 4.0, n)
-    y = c0[:, None] * (1.0 + gain[:, None] * shape * (peak[:, None] / 8.0)) + rng.normal(0.0, 0.1, (n, 5))
-    y = np.maximum(y, 0.05)
-    y[:, 0] = c0                                                  # c0 = cpeptide_data[1], c-peptide-models.jl:174
-    return dict(n_ind=n, max_knots=5, max_obs=5, n_knots=np.full(n, 5, np.int32), knot_t=np.tile(t, (n, 1)),
-                knot_g=glucose, n_obs=np.full(n, 5, np.int32), obs_t=np.tile(t, (n, 1)), obs_y=y,
-                kin=np.stack([k0, k1, k2, c0], axis=1), cov=None, chain=chain(4, 2, "tanh"))
+    y = np.repeat(c0[:, None], 5, axis=1)                         # placeholder; c0 = cpeptide_data[1], c-peptide-models.jl:174
+    pk = dict(n_ind=n, max_knots=5, max_obs=5, n_knots=np.full(n, 5, np.int32), knot_t=np.tile(t, (n, 1)),
+              knot_g=glucose, n_obs=np.full(n, 5, np.int32), obs_t=np.tile(t, (n, 1)), obs_y=y,
+              kin=np.stack([k0, k1, k2, c0], axis=1), cov=None, chain=chain(4, 2, "tanh"))
+    return pk, rng
+
+
+def stored_network():
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz"))
+    return np.ascontiguousarray(fx["cude_neural"][int(fx["cude_best_model_index"]) - 1])
+
+
+def synthetic_population(n, seed, simulate=None):
+    """SURVEY.md 8(d) config 5, observations included: the model's own solution at "true" parameters (the reference's stored
+    network, set 14, and beta_true ~ N(-1, 0.6)) at the observation times + N(0, 0.1^2) noise; the first observation is c0
+    (it is the initial condition, c-peptide-models.jl:174,185).  `simulate(pk, neural, beta[n]) -> yhat[n x 5]` is the
+    product's cude_simulate in the GPU arm and the oracle in the CPU arms."""
+    pk, rng = synthetic_individuals(n, seed)
+    beta_true = rng.normal(-1.0, 0.6, n)
+    if simulate is None:                       # default: the product path on this process's GPU
+        import conditional_ude_b200 as cu
+        simulate = simulate_gpu(cu.default_context())
+    yhat = simulate(pk, stored_network(), beta_true)
+    y = np.maximum(yhat + rng.normal(0.0, 0.1, yhat.shape), 0.01)
+    y[:, 0] = pk["kin"][:, 3]
+    pk["obs_y"] = np.ascontiguousarray(y)
+    pk["beta_true"] = beta_true
+    return pk
+
+
+def simulate_gpu(ctx):
+    def f(pk, neural, beta):
+        import conditional_ude_b200 as cu
+        return cu.Population(packed=pk, ctx=ctx).simulate(neural, beta[None, :])[0]
+    return f
+
+
+def simulate_oracle(threads):
+    def f(pk, neural, beta):
+        from oracle import oracle
+        return oracle.OraclePopulation(pk).eval(neural, beta[None, :], n_threads=threads, want_yhat=True)["yhat"][0]
+    return f
 
 
 def synthetic_starts(n_ind, n_starts, seed_shared, seed_rank):
-    fx = np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz"))
-    nn = fx["cude_neural"][int(fx["cude_best_model_index"]) - 1]
+    """Starts: the stored network perturbed by N(0, 0.1^2) per start, beta ~ Latin hypercube on [-2, 0] per individual
+    (the LHS range of train, parameter-estimation.jl:343-344)."""
+    nn = stored_network()
     neural = nn[None, :] + 0.1 * np.random.default_rng(seed_shared).standard_normal((n_starts, nn.size))
-    cond = np.random.default_rng(seed_rank).uniform(-2.0, 0.0, (n_starts, n_ind))   # LHS range, parameter-estimation.jl:343-344
+    rng = np.random.default_rng(seed_rank)
+    strata = rng.permuted(np.tile(np.arange(n_starts, dtype=np.int8 if n_starts < 128 else np.int32), (n_ind, 1)), axis=1)
+    cond = -2.0 + 2.0 * (strata.T + rng.random((n_starts, n_ind))) / n_starts
     return np.ascontiguousarray(neural), np.ascontiguousarray(cond)
 
 
@@ -147,14 +187,41 @@ def cpu_baseline(n_ind, n_starts, threads, seed=7):
     """Times the oracle (C++ restatement of the reference path, forward-mode gradient like the reference's
     AutoForwardDiff) on a bounded sample of the same synthetic workload."""
     from oracle import oracle
-    pk = synthetic_population(n_ind, seed)
+    pk = synthetic_population(n_ind, seed, simulate_oracle(threads))
     neural, cond = synthetic_starts(n_ind, n_starts, 11, seed + 1)
     op = oracle.OraclePopulation(pk)
     op.population_loss(neural[:1], cond[:1], with_grad=True, n_threads=threads)   # warm-up
     t0 = time.perf_counter()
     r = op.population_loss(neural, cond, with_grad=True, n_threads=threads)
     dt = time.perf_counter() - t0
-    return n_ind * n_starts / dt, dt, r
+    return n_ind * n_starts / dt, dt, (pk, neural, cond, op)
+
+
+def parity_sample(ctx, sample, threads, n_sub=250, n_starts=20):
+    """Inside the cpu_baseline leg (the one place the bench may run the oracle — as the checker): the CUDA path against the
+    oracle (frozen-step tangents, the CUDA kernel's twin) on n_sub x n_starts trajectories of the timed CPU sample, at the
+    reference's tolerances: how many trajectories sit outside the contract (1e-5 on sse, 1e-4 on d sse/d cond, relative to
+    the gradient scale of the sample) and by how much.  An adaptive solve puts every second implementation on a noise
+    floor of rare accept/reject flips: this is their measured rate."""
+    import conditional_ude_b200 as cu
+    from oracle import oracle
+    pk, neural, cond, _ = sample
+    n = min(n_sub, pk["n_ind"])
+    S = min(n_starts, cond.shape[0])
+    sub = {k: (v[:n] if isinstance(v, np.ndarray) and v.shape[:1] == (pk["n_ind"],) else v) for k, v in pk.items()}
+    sub["n_ind"] = n
+    ref = oracle.OraclePopulation(sub).eval(neural[:S], cond[:S, :n], grad_mode=0, n_threads=threads)
+    _, gn, gc, sse = cu.Population(packed=sub, ctx=ctx).loss_grad(neural[:S], cond[:S, :n], mean=False, return_sse=True)
+    e_sse = np.abs(sse - ref["sse"]) / np.abs(ref["sse"])
+    gscale = np.abs(ref["g_cond"]).max()
+    e_gc = np.abs(gc - ref["g_cond"]) / gscale
+    gn_ref = ref["g_neural"].sum(axis=1)
+    e_gn = np.abs(gn - gn_ref).max(axis=1) / np.abs(gn_ref).max(axis=1)
+    return {"trajectories": int(n * S), "oracle": "frozen-step tangents (grad_mode 0), reference tolerances",
+            "sse_frac_beyond_1e-5": float((e_sse > 1e-5).mean()), "sse_max_rel": float(e_sse.max()), "sse_median_rel": float(np.median(e_sse)),
+            "dcond_frac_beyond_1e-4": float((e_gc > 1e-4).mean()), "dcond_max_rel_to_scale": float(e_gc.max()),
+            "dcond_median_rel_to_scale": float(np.median(e_gc)),
+            "dneural_per_start_max_rel_to_row_max": float(e_gn.max())}
 
 
 def host_threads():
@@ -174,7 +241,7 @@ def run_reference(args):
     from oracle import oracle
     threads = host_threads()       # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     n_ind, n_starts = args.ref_individuals, args.ref_starts
-    pk = synthetic_population(n_ind, 7)
+    pk = synthetic_population(n_ind, 7, simulate_oracle(threads))
     neural, cond = synthetic_starts(n_ind, n_starts, 11, 8)
     op = oracle.OraclePopulation(pk)
     for _ in range(args.warmup):
@@ -229,7 +296,7 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     from conditional_ude_b200.distributed import DevicePopulationShard
-    pk = synthetic_population(n_loc, 1000 + rank)
+    pk = synthetic_population(n_loc, 1000 + rank, simulate_gpu(ctx))
     pop = cu.Population(packed=pk, ctx=ctx)
     P = pop.n_params
     neural_h, cond_h = synthetic_starts(n_loc, S, 11, 2000 + rank)
@@ -237,8 +304,14 @@ def run_ours(args):
     neural_p = torch.from_numpy(neural_h).pin_memory()
     cond_p = torch.from_numpy(cond_h).pin_memory()
     gcond_p = torch.empty((S, n_loc), dtype=torch.float64).pin_memory()
-    sums_p = torch.empty((S, P + 1), dtype=torch.float64).pin_memory()
-    shard = DevicePopulationShard(pop, N_total, S, dev, stream=stream)      # device tensors + kernel/reduce/all-reduce sequence
+    gneural_p = torch.empty((S, P), dtype=torch.float64).pin_memory()
+    loss_p = torch.empty((S,), dtype=torch.float64).pin_memory()
+    # device tensors + the launch sequence of a step: loss+gradient kernel(s) -> partial-row reduction -> (N > 1) the library's
+    # own ncclAllReduce (cude_allreduce_dev) on the same stream.  The communicator lives inside libcude_b200.so
+    # (cude_comm_init_rank; the 128-byte id is broadcast over torch.distributed, which is otherwise only the launcher's
+    # rendezvous and the barrier / max-over-ranks of the timing).
+    shard = DevicePopulationShard(pop, N_total, S, dev, stream=stream)
+    assert world == 1 or (shard.lib_comm and ctx.comm_size == world)
     shard.neural.copy_(neural_p)
     shard.cond.copy_(cond_p)
     d_sums = shard.sums
@@ -251,20 +324,16 @@ def run_ours(args):
         # loss+gradient kernel -> block-partial reduction into `sums` -> NCCL all-reduce of `sums` (N > 1)
         shard.step(opts)
 
-    sums_dev = torch.empty((S, P + 1), dtype=torch.float64, device=dev)
-    neural_np, cond_np, gcond_np, sums_np = neural_p.numpy(), cond_p.numpy(), gcond_p.numpy(), sums_p.numpy()
+    neural_np, cond_np, gcond_np, gneural_np, loss_np = (x.numpy() for x in (neural_p, cond_p, gcond_p, gneural_p, loss_p))
 
     def step_e2e():
-        # the C-ABI host-buffer call (cude_loss_grad_sums): page-locked host arrays in, page-locked host arrays out; inside,
-        # the H2D of the step's conditional parameters and the D2H of their gradients are pipelined against the kernels
-        # in chunks of starts.  N > 1: the [S x (P+1)] shard sums take one more round trip through the NCCL all-reduce.
-        pop.loss_grad_sums(neural_np, cond_np, 1.0 / N_total, opts, out_sums=sums_np, out_g_cond=gcond_np)
-        if world > 1:
-            sums_dev.copy_(sums_p, non_blocking=True)
-            dist.all_reduce(sums_dev)
-            sums_p.copy_(sums_dev, non_blocking=True)
-            stream.synchronize()
-        return sums_np[:, 0] / N_total   # the step's result: loss per start
+        # the reference-facing C-ABI call with HOST buffers (cude_loss_grad_sharded; with one rank it is cude_loss_grad):
+        # page-locked host arrays in (this rank's [n_loc x S] conditional parameters, the S networks), host arrays out
+        # (global loss[S], global d loss/d neural [P x S], this rank's d loss/d cond [n_loc x S]).  Inside: H2D of the step's
+        # inputs and D2H of its gradients pipelined against the kernels in chunks of starts, the all-reduce of the
+        # per-start sums over NCCL between the last kernel and the read-back.
+        pop.loss_grad_sharded(neural_np, cond_np, N_total, opts, out_loss=loss_np, out_g_neural=gneural_np, out_g_cond=gcond_np)
+        return loss_np   # the step's result: loss per start
 
     def barrier():
         if world > 1:
@@ -331,7 +400,7 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, max(2, args.steps // 2)) / max(2, args.steps // 2)
     e2e_value = N_total * S / (ms_e2e * 1e-3)
     h2d = (neural_p.numel() + cond_p.numel()) * 8
-    d2h = (sums_p.numel() + gcond_p.numel()) * 8
+    d2h = (loss_p.numel() + gneural_p.numel() + gcond_p.numel()) * 8
 
     # roofline of the dominant kernel (cude_eval_kernel<..., GRAD>): FP64 CUDA-core pipe
     peak = ctx.fp64_peak_tflops()
@@ -381,7 +450,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "individuals": N_total, "starts": S, "trajectories_per_step": N_total * S,
                        "abstol": opts.abstol, "reltol": opts.reltol, "network": "chain(4,2,tanh): 37 parameters",
-                       "sharding": f"individuals over {world} rank(s); all-reduce of {S}x{P + 1} f64",
+                       "sharding": f"individuals over {world} rank(s); all-reduce of {S}x{P + 1} f64 inside libcude_b200.so "
+                                   f"(cude_allreduce_dev / cude_loss_grad_sharded, NCCL {ctx._lib.cude_nccl_version()})",
+                       "observations": "model solution (cude_simulate) at the stored network 14 and beta_true ~ N(-1, 0.6) "
+                                       "+ N(0, 0.1^2) noise (SURVEY 8d config 5); starts: network + N(0, 0.1^2), beta ~ LHS[-2, 0]",
                        "l2": "inputs larger than L2 (cond + g_cond = %.0f MB per rank)" % (2 * S * n_loc * 8 / 1e6),
                        "lane_balance": "on (cude_opts.balance = 1)" if args.balance else "off (natural order)",
                        "lane_balanced_evals_per_s": balanced_value,
@@ -404,10 +476,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            v, secs, _ = cpu_baseline(args.cpu_individuals, args.cpu_starts, threads)
+            v, secs, sample = cpu_baseline(args.cpu_individuals, args.cpu_starts, threads)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{args.cpu_individuals} individuals x {args.cpu_starts} starts, {secs:.1f} s "
                                              "(oracle: C++ port of the reference algorithm, forward-mode gradient)"}
+            out["parity_sample"] = parity_sample(cu.Context(local), sample, threads)
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

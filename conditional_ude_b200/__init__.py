@@ -7,7 +7,8 @@ There is no CPU fallback.
 """
 from .models import (Chain, chain, softplus, van_cauter_parameters, CPeptideConditionalUDEModel, CPeptideUDEModel,
                      CPeptideConditionalCovariateUDEModel, pack_models)
-from .population import Context, Population, SolverOptions, default_context
+from .population import (Context, Population, SolverOptions, default_context, MultiContext, MultiPopulation,
+                         comm_unique_id, pick_device)
 from .losses import loss, loss_sigma, loss_and_gradient, ComponentVector
 from .profiles import likelihood_profile, likelihood_profile_population, find_confidence_intervals
 from .estimation import (initial_parameters, train, train_with_sigma, evaluate_model, stratified_split, argmedian,
@@ -23,7 +24,7 @@ __all__ = [
     "SuppressionPopulation", "neural_network_model", "suppression_loss", "fit_suppression_model", "validate_suppression_model",
     "Chain", "chain", "softplus", "van_cauter_parameters", "CPeptideConditionalUDEModel", "CPeptideUDEModel",
     "CPeptideConditionalCovariateUDEModel", "pack_models", "Context", "Population", "SolverOptions",
-    "default_context", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",
+    "default_context", "MultiContext", "MultiPopulation", "comm_unique_id", "pick_device", "loss", "loss_sigma", "loss_and_gradient", "ComponentVector",
     "likelihood_profile", "likelihood_profile_population", "find_confidence_intervals",
     "initial_parameters", "train", "train_with_sigma", "evaluate_model", "stratified_split", "argmedian",
     "OptimizationSolution",

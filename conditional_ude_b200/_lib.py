@@ -12,7 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CUDE_B200_LIB") or os.path.join(_HERE, "csrc", "libcude_b200.so")
 
 CUDE_OK = 0
-CUDE_EINVAL, CUDE_ENODEVICE, CUDE_ECUDA, CUDE_ENOMEM, CUDE_EUNSUPPORTED = -1, -2, -3, -4, -5
+CUDE_EINVAL, CUDE_ENODEVICE, CUDE_ECUDA, CUDE_ENOMEM, CUDE_EUNSUPPORTED, CUDE_ENCCL = -1, -2, -3, -4, -5, -6
+CUDE_SHARD_STARTS, CUDE_SHARD_INDIVIDUALS = 0, 1
+CUDE_UNIQUE_ID_BYTES = 128
+ABI_VERSION = 3
 
 
 class CudeError(RuntimeError):
@@ -56,6 +59,7 @@ SYMBOLS = {
     "cude_population_destroy": (C.c_int, [_P]),
     "cude_population_size": (C.c_int, [_P]),
     "cude_loss": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, _D, _D]),
+    "cude_simulate": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, _D, _D]),
     "cude_loss_grad": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
                                  C.c_int, _D, _D, _D, _D]),
     "cude_loss_grad_sums": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
@@ -67,6 +71,33 @@ SYMBOLS = {
     "cude_math_probe": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "cude_adam_dev": (C.c_int, [_P, C.c_longlong, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_double, _P, C.c_longlong, C.c_longlong]),
+    # multi-GPU: one process per GPU (communicator on a context) ...
+    "cude_device_count": (C.c_int, []),
+    "cude_nccl_version": (C.c_int, []),
+    "cude_comm_get_unique_id": (C.c_int, [_P]),
+    "cude_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "cude_comm_destroy": (C.c_int, [_P]),
+    "cude_comm_size": (C.c_int, [_P]),
+    "cude_comm_rank": (C.c_int, [_P]),
+    "cude_allreduce_dev": (C.c_int, [_P, _P, C.c_longlong]),
+    "cude_loss_sharded": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, C.c_longlong,
+                                    C.c_longlong, _D, _D]),
+    "cude_loss_grad_sharded": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, C.c_longlong,
+                                         C.c_longlong, C.c_int, _D, _D, _D, _D]),
+    # ... and one process driving all GPUs
+    "cude_mctx_create": (C.c_int, [C.c_int, _I, C.POINTER(_P)]),
+    "cude_mctx_destroy": (C.c_int, [_P]),
+    "cude_mctx_size": (C.c_int, [_P]),
+    "cude_mctx_ctx": (_P, [_P, C.c_int]),
+    "cude_mlast_error": (C.c_char_p, [_P]),
+    "cude_mpopulation_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.POINTER(_P)]),
+    "cude_mpopulation_destroy": (C.c_int, [_P]),
+    "cude_mpopulation_size": (C.c_int, [_P]),
+    "cude_mpopulation_mode": (C.c_int, [_P]),
+    "cude_mloss": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, _D, _D]),
+    "cude_mloss_grad": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D,
+                                  C.c_int, _D, _D, _D, _D]),
+    "cude_mget_stats": (C.c_int, [_P, C.POINTER(cude_stats)]),
     "cude_sup_population_create": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.POINTER(_P)]),
     "cude_sup_population_destroy": (C.c_int, [_P]),
     "cude_sup_loss_grad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(cude_opts), C.c_int, _D, C.c_longlong, _D, C.c_double,
@@ -90,7 +121,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.cude_abi_version() != 2:
+    if lib.cude_abi_version() != ABI_VERSION:
         raise ImportError("libcude_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -99,4 +130,10 @@ def load():
 def check(rc, ctx=None):
     if rc != CUDE_OK:
         msg = load().cude_last_error(ctx)
+        raise CudeError(rc, msg.decode() if msg else "?")
+
+
+def mcheck(rc, mctx=None):
+    if rc != CUDE_OK:
+        msg = load().cude_mlast_error(mctx)
         raise CudeError(rc, msg.decode() if msg else "?")

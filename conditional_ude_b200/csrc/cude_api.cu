@@ -64,6 +64,10 @@ struct cude_ctx {
     const void* carve_kern = nullptr;   // last kernel configuration whose shared-memory carve-out was set
     size_t carve_smem = 0;
     int carve_block = 0;
+    // NCCL communicator of a sharded population (cude_comm_init_rank, or the ranks of a cude_mctx): the per-start sums
+    // are all-reduced in place on `stream` (cude_multi.inl)
+    void* comm = nullptr;
+    int comm_nranks = 1, comm_rank = 0;
 };
 
 struct cude_population {
@@ -88,7 +92,7 @@ static thread_local std::string g_err;
 // last user of the per-device constant weight array (CW_CONST): uploads are ordered behind its kernel
 struct WConstUse { cudaEvent_t ev = nullptr; cudaStream_t stream = nullptr; bool used = false; };
 static std::mutex g_wconst_mutex;
-static WConstUse g_wconst_use[16];
+static std::vector<WConstUse> g_wconst_use;   // one entry per device, sized on first use
 
 static int fail(cude_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -122,7 +126,7 @@ extern "C" void cude_default_opts(cude_opts* o) {
     if (!o) return;
     o->abstol = 1e-6;   // OrdinaryDiffEq defaults used by parameter-estimation.jl:59
     o->reltol = 1e-3;
-    o->maxiters = 100000;
+    o->maxiters = 1000000;   // OrdinaryDiffEq's __init: maxiters = anyadaptive(alg) ? 1000000 : typemax(Int)
     o->precision = 0;
     o->block = 0;
     o->balance = 0;
@@ -149,9 +153,16 @@ extern "C" void cude_van_cauter_parameters(double age, int t2dm, double* k0, dou
     if (k2) *k2 = kk2;
 }
 
+extern "C" int cude_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
 extern "C" const char* cude_last_error(const cude_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
 // ---------------------------------------------------------------- context
+static void comm_release(cude_ctx* ctx);   // cude_multi.inl
 extern "C" int cude_ctx_create(int device, cude_ctx** out) {
     if (!out) return fail(nullptr, CUDE_EINVAL, "cude_ctx_create: out is NULL");
     *out = nullptr;
@@ -166,12 +177,17 @@ extern "C" int cude_ctx_create(int device, cude_ctx** out) {
     cude_ctx* ctx = new (std::nothrow) cude_ctx();
     if (!ctx) return fail(nullptr, CUDE_ENOMEM, "out of host memory");
     ctx->device = device;
-    CU_TRY(ctx, cudaSetDevice(device));
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    cudaError_t ce;
+    if ((ce = cudaSetDevice(device)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (ce = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (ce = cudaMallocHost(&ctx->h_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) {
+        const std::string msg = std::string("cude_ctx_create: ") + cudaGetErrorString(ce);
+        ctx->stream = ctx->own_stream;
+        cude_ctx_destroy(ctx);   // releases whatever was created
+        return fail(nullptr, ce == cudaErrorMemoryAllocation ? CUDE_ENOMEM : CUDE_ECUDA, msg);
+    }
     ctx->stream = ctx->own_stream;
-    CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
-    CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
-    CU_TRY(ctx, cudaMallocHost(&ctx->h_counters, 3 * sizeof(unsigned long long)));
     *out = ctx;
     return CUDE_OK;
 }
@@ -180,6 +196,7 @@ extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
     if (!ctx) return CUDE_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
     DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
@@ -299,10 +316,13 @@ extern "C" int cude_population_create(cude_ctx* ctx, int n_ind,
         cude_population_destroy(pop);
         return fail(ctx, CUDE_ENOMEM, std::string("cude_population_create: cudaMalloc failed: ") + cudaGetErrorString(e));
     }
-    CU_TRY(ctx, cudaMemcpyAsync(pop->block, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(pop->n_knots, n_knots, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(pop->n_obs, n_obs, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((e = cudaMemcpyAsync(pop->block, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(pop->n_knots, n_knots, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(pop->n_obs, n_obs, N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        cude_population_destroy(pop);
+        return fail(ctx, CUDE_ECUDA, std::string("cude_population_create: upload failed: ") + cudaGetErrorString(e));
+    }
     PopDev& d = pop->dev;
     d.n_ind = n_ind; d.max_knots = max_knots; d.max_obs = max_obs;
     d.n_knots = pop->n_knots; d.n_obs = pop->n_obs;
@@ -409,10 +429,23 @@ static int balance_finish(cude_ctx* ctx, const cude_population* pop, int n_start
     return CUDE_OK;
 }
 
+static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
+                         int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
+                         int want_grad, double cond_scale,
+                         double* d_sse_out, double* d_sums_out, double* d_g_cond, double* d_yhat);
+
 extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
                              int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
                              int want_grad, double cond_scale,
                              double* d_sse_out, double* d_sums_out, double* d_g_cond) {
+    return eval_dev_impl(ctx, pop, net, opts_in, n_starts, d_neural, neural_stride, d_cond, want_grad, cond_scale,
+                         d_sse_out, d_sums_out, d_g_cond, nullptr);
+}
+
+static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
+                         int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
+                         int want_grad, double cond_scale,
+                         double* d_sse_out, double* d_sums_out, double* d_g_cond, double* d_yhat) {
     if (!ctx || !pop || !net || !d_neural || !d_cond) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: NULL argument");
     if (pop->ctx != ctx) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: population belongs to another context");
     if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: n_starts < 1");
@@ -484,6 +517,7 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     a.counters = (unsigned long long*)ctx->counters.p;
     a.order = bal ? ctx->bal_order : nullptr;
     a.keys_out = bal ? ctx->bal_keys_out : nullptr;
+    a.yhat_out = grad ? nullptr : d_yhat;
 
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
@@ -511,7 +545,8 @@ extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cu
     if (wc) {
         // the constant array is one per device and process: order this upload + launch after the last launch that read it
         std::lock_guard<std::mutex> lk(g_wconst_mutex);
-        WConstUse& u = g_wconst_use[ctx->device % 16];
+        if ((int)g_wconst_use.size() <= ctx->device) g_wconst_use.resize((size_t)ctx->device + 1);
+        WConstUse& u = g_wconst_use[ctx->device];
         if (!u.ev) CU_TRY(ctx, cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
         if (u.used && u.stream != ctx->stream) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, u.ev, 0));
         CU_TRY(ctx, cudaMemcpyToSymbolAsync(CW_CONST, d_neural, n_w * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -561,11 +596,18 @@ static int host_chunks(int n_starts, size_t ntraj) {
 
 // raw_sums != NULL: raw_sums[(P+1) x S] = {sum_i sse, sum_i d sse/d neural} unscaled and g_cond scaled by cond_scale
 // (the sharded-population form); otherwise loss_out / g_neural / g_cond as documented for cude_loss / cude_loss_grad.
+// Sharded populations (cude_multi.inl): `ld` = column stride of the host matrices cond / sse_out / g_cond (0 = n_ind:
+// contiguous; a rank that owns rows [lo, hi) of a global [N_total x S] matrix passes the matrix + lo and ld = N_total),
+// `n_total` > 0 = global number of individuals: the per-start sums are all-reduced over the context's communicator
+// before they are read back, and means are taken over n_total.
+struct HostShard { long long ld = 0; long long n_total = 0; int want_neural = -1; /* -1: network gradient iff g_neural is given */ };
+static int comm_allreduce(cude_ctx* ctx, double* d_buf, size_t count);   // cude_multi.inl
+
 static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
                      int n_starts, const double* neural, long long neural_stride, const double* cond,
                      int want_grad, int mean_over_individuals,
                      double* sse_out, double* loss_out, double* g_neural, double* g_cond,
-                     double* raw_sums = nullptr, double cond_scale = 1.0) {
+                     double* raw_sums = nullptr, double cond_scale = 1.0, HostShard shard = HostShard()) {
     if (!ctx || !pop || !net || !neural || !cond) return fail(ctx, CUDE_EINVAL, "cude_loss: NULL argument");
     if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_loss: n_starts < 1");
     const int P = cude_net_nparams(net);
@@ -588,9 +630,26 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         ctx->h_sums_cap = (size_t)np1 * n_starts;
     }
     int wg = 0;
-    if (want_grad) wg = ((g_neural || raw_sums) ? 2 : 0) | 1;
-    const double scale = raw_sums ? 1.0 : (mean_over_individuals ? 1.0 / N : 1.0);
+    if (want_grad) wg = ((shard.want_neural >= 0 ? shard.want_neural > 0 : (g_neural || raw_sums)) ? 2 : 0) | 1;
+    const size_t ld = shard.ld > 0 ? (size_t)shard.ld : (size_t)N;   // host column stride
+    if (ld < (size_t)N) return fail(ctx, CUDE_EINVAL, "cude_loss: host leading dimension smaller than the population");
+    const bool sharded = shard.n_total > 0;
+    if (sharded && shard.n_total != N && !ctx->comm)
+        return fail(ctx, CUDE_EINVAL, "cude_loss: sharded call without a communicator (cude_comm_init_rank / cude_mctx_create)");
+    const double n_mean = sharded ? (double)shard.n_total : (double)N;
+    const double scale = raw_sums ? 1.0 : (mean_over_individuals ? 1.0 / n_mean : 1.0);
     const double cscale = raw_sums ? cond_scale : scale;
+    // column blocks of a host matrix with leading dimension ld <-> the contiguous [N x ns] device block
+    auto copy_in = [&](double* d, const double* h, size_t ns, cudaStream_t st) {
+        return ld == (size_t)N ? cudaMemcpyAsync(d, h, ns * N * sizeof(double), cudaMemcpyHostToDevice, st)
+                               : cudaMemcpy2DAsync(d, (size_t)N * sizeof(double), h, ld * sizeof(double), (size_t)N * sizeof(double), ns,
+                                                   cudaMemcpyHostToDevice, st);
+    };
+    auto copy_out = [&](double* h, const double* d, size_t ns, cudaStream_t st) {
+        return ld == (size_t)N ? cudaMemcpyAsync(h, d, ns * N * sizeof(double), cudaMemcpyDeviceToHost, st)
+                               : cudaMemcpy2DAsync(h, ld * sizeof(double), d, (size_t)N * sizeof(double), (size_t)N * sizeof(double), ns,
+                                                   cudaMemcpyDeviceToHost, st);
+    };
     double* const d_neural = (double*)ctx->neural.p;
     double* const d_cond = (double*)ctx->cond.p;
     double* const d_sums = (double*)ctx->sums.p;
@@ -599,11 +658,11 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
     const int nch = host_chunks(n_starts, ntraj);
     CU_TRY(ctx, cudaMemcpyAsync(d_neural, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (nch == 1) {
-        CU_TRY(ctx, cudaMemcpyAsync(d_cond, cond, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, copy_in(d_cond, cond, (size_t)n_starts, ctx->stream));
         rc = cude_eval_dev(ctx, pop, net, opts, n_starts, d_neural, neural_stride, d_cond, wg, cscale, d_sse, d_sums, d_gc);
         if (rc) return rc;
-        if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, d_sse, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond, d_gc, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sse_out) CU_TRY(ctx, copy_out(sse_out, d_sse, (size_t)n_starts, ctx->stream));
+        if (g_cond) CU_TRY(ctx, copy_out(g_cond, d_gc, (size_t)n_starts, ctx->stream));
     } else {
         if (!ctx->s_in) {
             CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -623,8 +682,8 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         unsigned int* const keys0 = bal ? ctx->bal_keys_out : nullptr;
         auto lo = [&](int k) { return (int)((long long)n_starts * k / nch); };
         auto h2d = [&](int k) -> int {
-            const size_t o = (size_t)lo(k) * N, n = (size_t)(lo(k + 1) - lo(k)) * N;
-            CU_TRY(ctx, cudaMemcpyAsync(d_cond + o, cond + o, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_in));
+            const size_t s0 = (size_t)lo(k), ns = (size_t)(lo(k + 1) - lo(k));
+            CU_TRY(ctx, copy_in(d_cond + s0 * N, cond + s0 * ld, ns, ctx->s_in));
             CU_TRY(ctx, cudaEventRecord(ctx->ev_in[k], ctx->s_in));
             return CUDE_OK;
         };
@@ -643,10 +702,10 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
             return CUDE_OK;
         };
         auto d2h = [&](int k) -> int {
-            const size_t o = (size_t)lo(k) * N, n = (size_t)(lo(k + 1) - lo(k)) * N;
+            const size_t s0 = (size_t)lo(k), ns = (size_t)(lo(k + 1) - lo(k));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[k], 0));
-            if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out + o, d_sse + o, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
-            if (g_cond) CU_TRY(ctx, cudaMemcpyAsync(g_cond + o, d_gc + o, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+            if (sse_out) CU_TRY(ctx, copy_out(sse_out + s0 * ld, d_sse + s0 * N, ns, ctx->s_out));
+            if (g_cond) CU_TRY(ctx, copy_out(g_cond + s0 * ld, d_gc + s0 * N, ns, ctx->s_out));
             return CUDE_OK;
         };
         if ((rc = h2d(0)) || (rc = run(0))) return rc;
@@ -659,6 +718,8 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
             if ((rc = balance_finish(ctx, pop, n_starts, nullptr))) return rc;
         }
     }
+    // sharded population: the only exchange of the path — sum the shards' {sum sse, sum d sse/d neural} rows in place
+    if (sharded && ctx->comm && ctx->comm_nranks > 1 && (rc = comm_allreduce(ctx, d_sums, (size_t)np1 * n_starts))) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, d_sums, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (nch > 1) CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
@@ -675,8 +736,37 @@ static int eval_host(cude_ctx* ctx, const cude_population* pop, const cude_net* 
         const bool ok = std::isfinite(row[0]);
         if (loss_out) loss_out[s] = row[0] * scale;   // Inf stays Inf (parameter-estimation.jl:134-136)
         if (g_neural) for (int p = 0; p < P; ++p) g_neural[(size_t)s * P + p] = ok ? row[1 + p] * scale : 0.0;
-        if (g_cond && !ok) for (int i = 0; i < N; ++i) g_cond[(size_t)s * N + i] = 0.0;
+        if (g_cond && !ok) for (int i = 0; i < N; ++i) g_cond[(size_t)s * ld + i] = 0.0;
     }
+    return CUDE_OK;
+}
+
+// model prediction at the observation times: the `solve(...; saveat=timepoints, save_idxs=1)` of the loss (:59) by itself
+extern "C" int cude_simulate(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                             int n_starts, const double* neural, long long neural_stride, const double* cond,
+                             double* yhat_out, double* sse_out) {
+    if (!ctx || !pop || !net || !neural || !cond || !yhat_out) return fail(ctx, CUDE_EINVAL, "cude_simulate: NULL argument");
+    if (n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_simulate: n_starts < 1");
+    const int P = cude_net_nparams(net);
+    if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_simulate: bad network description");
+    if (neural_stride != 0 && neural_stride < P) return fail(ctx, CUDE_EINVAL, "cude_simulate: neural_stride < n_params");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)pop->n_ind, M = (size_t)pop->max_obs, ntraj = N * n_starts;
+    const size_t n_neural = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
+    int rc;
+    if ((rc = ensure(ctx, ctx->neural, n_neural * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->cond, ntraj * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->sse, ntraj * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->scratch, ntraj * M * sizeof(double)))) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->neural.p, neural, n_neural * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cond.p, cond, ntraj * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->scratch.p, 0xFF, ntraj * M * sizeof(double), ctx->stream));   // NaN where nothing is observed
+    rc = eval_dev_impl(ctx, pop, net, opts, n_starts, (const double*)ctx->neural.p, neural_stride, (const double*)ctx->cond.p, 0, 1.0,
+                       (double*)ctx->sse.p, nullptr, nullptr, (double*)ctx->scratch.p);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(yhat_out, ctx->scratch.p, ntraj * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, ctx->sse.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CUDE_OK;
 }
 
@@ -943,3 +1033,5 @@ extern "C" int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops) {
     *tflops = best;
     return CUDE_OK;
 }
+
+#include "cude_multi.inl"

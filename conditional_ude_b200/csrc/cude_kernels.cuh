@@ -121,6 +121,8 @@ struct EvalArgs {
     // warps of a block) finish together; keys_out[s*N + i] = (min(steps, 255) << 24) | i feeds the next sort.
     const unsigned int* order;     // [N x S] or nullptr (natural order)
     unsigned int* keys_out;        // [N x S] or nullptr
+    double* yhat_out;              // [M][N x S] -> yhat_out[k + M*j]: the solution at the observation times (cude_simulate;
+                                   // loss-only instantiations), or nullptr
 };
 
 // ---------------------------------------------------------------- network shape
@@ -593,6 +595,7 @@ cude_eval_kernel(const EvalArgs A) {
             while (iobs < nobs && next_ot <= t0) {
                 const double r = u0 - obs_y[iobs * B];
                 if (GRAD) sRes[iobs * B + tid] = r;
+                if constexpr (!GRAD && !BSENS) { if (A.yhat_out) A.yhat_out[(size_t)j * M + iobs] = u0; }
                 fsse = fma(r, r, fsse);
                 ++iobs;
                 next_ot = (iobs < nobs) ? obs_t[iobs * B] : CUDART_INF;
@@ -751,6 +754,7 @@ cude_eval_kernel(const EvalArgs A) {
                         }
                         const double r = y - obs_y[iobs * B];
                         if (GRAD) sRes[iobs * B + tid] = r;
+                        if constexpr (!GRAD && !BSENS) { if (A.yhat_out) A.yhat_out[(size_t)j * M + iobs] = y; }
                         if constexpr (BSENS) {
                             double dy;
                             if (next_ot == tnew) dy = sn0;
@@ -940,6 +944,9 @@ cude_eval_kernel(const EvalArgs A) {
             A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
         }
         if (A.sse_out) A.sse_out[j] = sse;
+        if constexpr (!GRAD && !BSENS) {
+            if (A.yhat_out && failed) for (int k = 0; k < M; ++k) A.yhat_out[(size_t)j * M + k] = CUDART_NAN;   // no solution
+        }
         if ((GRAD || BSENS) && A.g_cond) A.g_cond[j] = failed ? 0.0 : gcond * A.cond_scale;
     }
     // ---- warp reduction: {sse, d sse/d neural[0..P)}; one partial row per WARP, no block barrier (warps of a

@@ -6,11 +6,36 @@ block of them and the only exchange is the all-reduce of the per-start sums
 {sum_i sse_i, sum_i d sse_i / d neural} — (P+1) x S doubles (19 KB for 64 starts).  Every other
 workload (multi-start screening, beta-only fits, profiles) shards with no communication at all.
 
-One process per GPU, `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests)
-is the plumbing.  The kernel's second stage writes the sums straight into the tensor that is
-all-reduced in place.
+One process per GPU.  On the GPU the exchange happens INSIDE the library: `init_library_comm` hands the context an
+NCCL communicator (the unique id travels over whatever the host already has — here torch.distributed, in Julia
+`Distributed` — and that is torch's only role), after which `cude_allreduce_dev` / `cude_loss_grad_sharded` sum the
+rows in place on the buffer and stream the reduction kernel used.  The host-level helpers below (`sharded_loss_grad`,
+gloo) cover hosts that keep their buffers on the CPU and the CPU tests.
 """
 import numpy as np
+
+
+def init_library_comm(ctx, group=None):
+    """Give `ctx` (a Context on this rank's GPU) the library-side NCCL communicator of the torch.distributed group:
+    rank 0 draws the unique id (cude_comm_get_unique_id), the 128 bytes are broadcast through torch.distributed, every
+    rank joins (cude_comm_init_rank).  Returns the communicator size; a no-op (1) outside a distributed run."""
+    import torch
+    import torch.distributed as dist
+    from .population import comm_unique_id
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1
+    if ctx.comm_size > 1:
+        return ctx.comm_size
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).clone()
+    if on_gpu:
+        t = t.cuda(ctx.device)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+    return world
 
 
 def shard_bounds(n_total, world, rank):
@@ -59,14 +84,23 @@ class DevicePopulationShard:
 
     def __init__(self, population, n_total, n_starts, device, group=None, stream=None):
         import torch
+        from .population import _default_ctx
         self.torch = torch
         self.pop, self.n_total, self.S, self.group = population, int(n_total), int(n_starts), group
         self.P = population.n_params
         self.n_loc = population.n_ind
-        # one explicit stream for the kernels, the torch ops on the shard's tensors and the NCCL ordering
+        if any(population.ctx is c for c in _default_ctx.values()):
+            raise ValueError("DevicePopulationShard re-points its context's stream: give the shard's Population its own "
+                             "Context(device), not the process-wide default_context()")
+        # one explicit stream for the kernels, the torch ops on the shard's tensors and the all-reduce; the stream object is
+        # kept alive for as long as the context points at it and the context's own stream is restored by close()
         cur = torch.cuda.current_stream(device)
         self.stream = stream or (cur if cur.cuda_stream != 0 else torch.cuda.Stream(device=device))
         population.ctx.set_stream(self.stream.cuda_stream)
+        import weakref
+        self._restore = weakref.finalize(self, population.ctx.set_stream, 0)
+        # the exchange runs inside the library (NCCL communicator on the context) when the job has more than one rank
+        self.lib_comm = init_library_comm(population.ctx, group) > 1
         f64 = dict(dtype=torch.float64, device=device)
         with torch.cuda.stream(self.stream):
             self.neural = torch.empty((self.S, self.P), **f64)
@@ -84,8 +118,13 @@ class DevicePopulationShard:
         with self.torch.cuda.stream(self.stream):
             self.pop.eval_dev(self.S, self.neural.data_ptr(), self.P, self.cond.data_ptr(), 3 if want_grad else 0,
                               1.0 / self.n_total, 0, self.sums.data_ptr(), self.g_cond.data_ptr() if want_grad else 0, opts)
-            allreduce_sums(self.sums, self.group)
+            if self.lib_comm:      # cude_allreduce_dev: ncclAllReduce in place, same stream as the kernels
+                self.pop.ctx.allreduce_dev(self.sums.data_ptr(), self.sums.numel())
         return self.sums
+
+    def close(self):
+        """Hand the context back its own stream (the shard's stream may then be released)."""
+        self._restore()
 
     # ---- device-resident Adam (population-scale training: the N x S conditional parameters stay in HBM) ----
     def adam_init(self):

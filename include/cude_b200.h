@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CUDE_B200_ABI_VERSION 2
+#define CUDE_B200_ABI_VERSION 3
 
 enum {
     CUDE_OK = 0,
@@ -31,7 +31,8 @@ enum {
     CUDE_ENODEVICE = -2,  /* no usable CUDA device (no CPU fallback) */
     CUDE_ECUDA = -3,      /* CUDA runtime error, see cude_last_error */
     CUDE_ENOMEM = -4,
-    CUDE_EUNSUPPORTED = -5 /* network shape / option not compiled in */
+    CUDE_EUNSUPPORTED = -5, /* network shape / option not compiled in */
+    CUDE_ENCCL = -6         /* NCCL missing or a collective failed (multi-GPU entry points only) */
 };
 
 typedef struct cude_ctx cude_ctx;
@@ -49,7 +50,7 @@ typedef struct {
 
 /* Solver options of `solve(model.problem, p=theta, saveat=timepoints, save_idxs=1)`
  * (src/parameter-estimation.jl:59): OrdinaryDiffEq defaults -> Tsit5, abstol 1e-6, reltol 1e-3,
- * maxiters 1e5.  cude_default_opts() fills these. */
+ * maxiters 1000000 (OrdinaryDiffEq's __init default for adaptive algorithms).  cude_default_opts() fills these. */
 typedef struct {
     double abstol;
     double reltol;
@@ -87,6 +88,7 @@ int cude_net_nparams(const cude_net* net);
 void cude_van_cauter_parameters(double age, int t2dm, double* k0, double* k1, double* k2);
 
 /* ---- context ---- */
+int cude_device_count(void);   /* visible CUDA devices; 0 when there is none (or no driver) */
 int cude_ctx_create(int device, cude_ctx** out);
 int cude_ctx_destroy(cude_ctx* ctx);
 /* message of the last error on this context (ctx may be NULL for creation errors) */
@@ -125,6 +127,14 @@ int cude_population_size(const cude_population* pop);
 int cude_loss(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
               int n_starts, const double* neural, long long neural_stride, const double* cond,
               double* sse_out, double* loss_out);
+
+/* ---- model prediction: the `solve(model.problem, p=theta, saveat=timepoints, save_idxs=1)` inside the loss (:59) by
+ * itself — what the scripts plot against the data (e.g. c-peptide/02-conditional.jl:170) and what generates synthetic
+ * observations.  yhat_out[k + max_obs*(i + n_ind*s)] = plasma c-peptide of individual i under start s at its k-th
+ * observation time; NaN for k >= n_obs[i] and for failed solves.  sse_out [n_ind x n_starts] may be NULL. */
+int cude_simulate(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                  int n_starts, const double* neural, long long neural_stride, const double* cond,
+                  double* yhat_out, double* sse_out);
 
 /* ---- loss + gradient: replaces OptimizationFunction(loss, AutoForwardDiff()) :231,:281,:299,:370.
  *   g_neural[P x n_starts] (may be NULL: beta-only estimation, :272-288): d loss[s] / d neural
@@ -190,6 +200,80 @@ int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth,
 int cude_adam_dev(cude_ctx* ctx, long long n, double* d_x, const double* d_g, double* d_m, double* d_v,
                   double lr, double beta1, double beta2, double eps, int t, double grad_scale,
                   const double* d_row_flag, long long row_len, long long flag_stride);
+
+/* =====================================================================================
+ * Multi-GPU (one B200 box, NCCL over NVLink / NVSwitch).  The reference runs every loop of the path on one CPU thread;
+ * here the independent trajectories are partitioned over the GPUs:
+ *   - starts / initial guesses / profile grid points (src/parameter-estimation.jl:362-366, :374-376, :272-288,
+ *     src/likelihood-profiles.jl:11-14) shard with NO communication: every device holds the whole population;
+ *   - the individuals of a large population (the loop of :126-140) shard with ONE exchange per call: the all-reduce
+ *     (sum, FP64) of the per-start rows {sum_i sse_i, sum_i d sse_i/d neural[0..P)} — (P+1) x n_starts doubles —
+ *     issued inside the library on the stream and buffer the reduction kernel wrote.  d/d cond needs no exchange.
+ * NCCL is loaded at run time (libnccl.so.2; override with the environment variable CUDE_NCCL_LIB); without it the
+ * entry points below that need a communicator return CUDE_ENCCL, everything else keeps working.
+ * ===================================================================================== */
+
+/* ---- (1) one process per GPU: torchrun, MPI, Julia Distributed workers ----
+ * Rank 0 calls cude_comm_get_unique_id and the host broadcasts the CUDE_UNIQUE_ID_BYTES bytes by its own means; then
+ * every rank calls cude_comm_init_rank on its context (collective, like ncclCommInitRank). */
+#define CUDE_UNIQUE_ID_BYTES 128
+int cude_nccl_version(void);                        /* e.g. 22703; 0 when NCCL cannot be loaded */
+int cude_comm_get_unique_id(void* id_out);
+int cude_comm_init_rank(cude_ctx* ctx, int nranks, int rank, const void* id);
+int cude_comm_destroy(cude_ctx* ctx);               /* also done by cude_ctx_destroy */
+int cude_comm_size(const cude_ctx* ctx);            /* 1 without a communicator */
+int cude_comm_rank(const cude_ctx* ctx);
+/* in-place sum of a device buffer over the ranks, asynchronous on the context's stream (what follows cude_eval_dev in
+ * device-resident population training); a no-op without a communicator */
+int cude_allreduce_dev(cude_ctx* ctx, double* d_buf, long long count);
+/* Population loss (:126-140) and its gradient when `pop` holds this rank's contiguous block of the n_total individuals.
+ * Collective: every rank calls it with the same n_starts and networks.  cond / sse_out / g_cond are this rank's rows of
+ * the global [n_total x n_starts] matrices: pass the address of the rank's first row and ld = the column stride in
+ * elements (n_total when the host holds the global matrix, 0 = this rank's n_ind when it holds only its block).
+ * loss_out[s] and g_neural[P x n_starts] are the global values on every rank (mean over n_total when
+ * mean_over_individuals != 0, sums otherwise); g_cond = d loss[s] / d cond[i,s] for the rank's individuals. */
+int cude_loss_sharded(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                      int n_starts, const double* neural, long long neural_stride,
+                      const double* cond, long long ld, long long n_total, double* sse_out, double* loss_out);
+int cude_loss_grad_sharded(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                           int n_starts, const double* neural, long long neural_stride,
+                           const double* cond, long long ld, long long n_total, int mean_over_individuals,
+                           double* sse_out, double* loss_out, double* g_neural, double* g_cond);
+
+/* ---- (2) one process, all GPUs: what a single Julia session uses ----
+ * cude_mctx_create(n_gpus, device_ids) owns one context + stream + host worker thread per device
+ * (device_ids NULL = 0..n_gpus-1; n_gpus 0 = all visible devices).  cude_mpopulation_create takes the arguments of
+ * cude_population_create plus the partition:
+ *   CUDE_SHARD_STARTS       every device holds the whole population; a call's starts are split into contiguous blocks
+ *                           (screening, selected starts, beta-only fits, profiles — no communication)
+ *   CUDE_SHARD_INDIVIDUALS  device k holds individuals [N k / n, N (k+1) / n); every call ends with the all-reduce
+ *                           of the per-start rows (population training; ncclCommInitAll on first use)
+ * cude_mloss / cude_mloss_grad take the same GLOBAL host matrices as cude_loss / cude_loss_grad and fill the same
+ * outputs; results do not depend on the number of devices beyond the summation order of the per-start sums
+ * (per-trajectory sse and d/d cond are bit-identical).  One host thread per cude_mctx at a time. */
+typedef struct cude_mctx cude_mctx;
+typedef struct cude_mpopulation cude_mpopulation;
+enum { CUDE_SHARD_STARTS = 0, CUDE_SHARD_INDIVIDUALS = 1 };
+int cude_mctx_create(int n_gpus, const int* device_ids, cude_mctx** out);
+int cude_mctx_destroy(cude_mctx* mctx);
+int cude_mctx_size(const cude_mctx* mctx);
+cude_ctx* cude_mctx_ctx(cude_mctx* mctx, int k);    /* the k-th device's context (stats, stream, device-pointer calls) */
+const char* cude_mlast_error(const cude_mctx* mctx);
+int cude_mpopulation_create(cude_mctx* mctx, int mode, int n_ind,
+                            int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                            int max_obs, const int* n_obs, const double* obs_t, const double* obs_y,
+                            const double* kin, const double* covariate, cude_mpopulation** out);
+int cude_mpopulation_destroy(cude_mpopulation* mpop);
+int cude_mpopulation_size(const cude_mpopulation* mpop);
+int cude_mpopulation_mode(const cude_mpopulation* mpop);
+int cude_mloss(cude_mctx* mctx, const cude_mpopulation* mpop, const cude_net* net, const cude_opts* opts,
+               int n_starts, const double* neural, long long neural_stride, const double* cond,
+               double* sse_out, double* loss_out);
+int cude_mloss_grad(cude_mctx* mctx, const cude_mpopulation* mpop, const cude_net* net, const cude_opts* opts,
+                    int n_starts, const double* neural, long long neural_stride, const double* cond,
+                    int mean_over_individuals, double* sse_out, double* loss_out, double* g_neural, double* g_cond);
+/* statistics of the last cude_mloss / cude_mloss_grad: counts summed over the devices, kernel_ms of the slowest */
+int cude_mget_stats(cude_mctx* mctx, cude_stats* out);
 
 /* Test hook: evaluates the kernels' own branch-free FP64 elementary functions on the device
  * (which: 0 tanh, 1 softplus, 2 sigmoid, 3 exp clamped to +-40, 4 log of a positive normal, 5 reciprocal). */

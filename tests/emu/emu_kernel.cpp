@@ -20,6 +20,7 @@ using std::isfinite;
 #define __constant__ static const
 #define __host__
 #define CUDART_INF INFINITY
+#define CUDART_NAN NAN
 struct emu_dim3 { int x, y, z; };
 static emu_dim3 blockIdx, threadIdx, blockDim;
 struct double2 { double x, y; };

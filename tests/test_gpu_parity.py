@@ -41,8 +41,10 @@ def test_config1_stored_weights(fx, ctx):
     assert abs(loss[0] - ref["loss"][0]) / ref["loss"][0] < 1e-6
     # at the stored optimum the net gradient is a near-cancellation of O(1) terms: the adaptive noise floor
     # (test_oracle.py::test_noise_floor: up to ~5e-5 under a 1-ulp perturbation) is visible relative to it
-    assert relmax(gn, ref["g_neural"]) < 1e-3
-    assert relmax(gc, ref["g_cond"]) < 1e-3
+    # measured 5e-6 / 1.6e-5 (round 1): gated at the contract (1e-4), a few flips of head-room and no more
+    print(f"config 1: grad rel err neural {relmax(gn, ref['g_neural']):.2e}, cond {relmax(gc, ref['g_cond']):.2e}")
+    assert relmax(gn, ref["g_neural"]) < 1e-4
+    assert relmax(gc, ref["g_cond"]) < 1e-4
     st = ctx.stats()
     assert st["n_traj"] == 57 and st["n_fail"] == 0
     assert abs(int(st["n_acc"]) - ref["n_acc"]) <= 2 and abs(int(st["n_rej"]) - ref["n_rej"]) <= 2
@@ -94,7 +96,13 @@ def test_default_tolerance_statistics(fx, ctx):
     assert _noise_ok(dc, 1e-4), (np.median(dc), np.percentile(dc, 99), dc.max())
     # per-start aggregates (what the optimiser sees)
     assert relmax(loss, r["sse"].sum(axis=1)) < 1e-5
-    assert relmax(gn, r["g_neural"].sum(axis=1)) < 1e-3
+    gsum = r["g_neural"].sum(axis=1)
+    e_gn = (np.abs(gn - gsum) / np.abs(gsum).max(axis=1, keepdims=True)).max()
+    # the flip rate itself (what `noise_ok` tolerates up to 1 %): share of trajectories outside the contract
+    print(f"default tolerances, {d.size} trajectories: sse beyond 1e-5: {(d > 1e-5).mean():.4f} (max {d.max():.1e}); "
+          f"d/dcond beyond 1e-4: {(dc > 1e-4).mean():.4f} (max {dc.max():.1e}); per-start g_neural max {e_gn:.1e}")
+    assert (d > 1e-5).mean() < 0.005 and (dc > 1e-4).mean() < 0.005
+    assert e_gn < 1e-4
     st = ctx.stats()
     assert abs(int(st["n_acc"]) - int(r["stats"][..., 0].sum())) <= 0.001 * st["n_acc"]
 
@@ -143,7 +151,34 @@ def test_covariate_network(fx, ctx):
     assert relmax(loss, rp["loss"]) < 1e-10 and relmax(gn, rp["g_neural"]) < 1e-9 and relmax(gc, rp["g_cond"]) < 1e-9
     rp = ref.population_loss(nn, betas[None], with_grad=True)
     loss, gn, gc = pop.loss_grad(nn, betas[None])
-    assert relmax(loss, rp["loss"]) < 1e-5 and relmax(gn, rp["g_neural"]) < 1e-3 and relmax(gc, rp["g_cond"]) < 1e-3
+    print(f"covariate net: loss {relmax(loss, rp['loss']):.1e} g_neural {relmax(gn, rp['g_neural']):.1e} g_cond {relmax(gc, rp['g_cond']):.1e}")
+    assert relmax(loss, rp["loss"]) < 1e-5 and relmax(gn, rp["g_neural"]) < 1e-4 and relmax(gc, rp["g_cond"]) < 1e-4
+
+
+def test_simulate_equals_the_oracle_solution(fx, ctx):
+    """cude_simulate: the `solve(...; saveat=timepoints, save_idxs=1)` of the loss by itself, on the ragged population
+    (5 and 14 observation times): the oracle's dense-output values; NaN where an individual has no observation; and
+    sum((yhat - y)^2) is the loss kernel's sse."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(4)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 3)
+    r = oracle.OraclePopulation(pk).eval(neural, cond, want_yhat=True, **DET)
+    yhat = pop.simulate(neural, cond, opts=SolverOptions(**DET))
+    assert yhat.shape == r["yhat"].shape
+    obs = np.arange(pk["max_obs"])[None, None, :] < np.asarray(pk["n_obs"])[None, :, None]
+    obs = np.broadcast_to(obs, yhat.shape)
+    assert np.isnan(yhat[~obs]).all() and np.isfinite(yhat[obs]).all()
+    assert np.abs(yhat[obs] - r["yhat"][obs]).max() < 1e-10 * np.abs(r["yhat"][obs]).max()
+    sse = pop.loss(neural, cond, opts=SolverOptions(**DET), return_sse=True)[1]
+    y = np.broadcast_to(np.asarray(pk["obs_y"])[None], yhat.shape)
+    assert np.allclose(np.where(obs, (yhat - y) ** 2, 0.0).sum(axis=2), sse, rtol=1e-12)
+    # default tolerances: same values up to the adaptive noise floor; a shared network (flat indexing) works too
+    y1 = pop.simulate(neural[0], cond[:1])
+    r1 = oracle.OraclePopulation(pk).eval(neural[0], cond[:1], want_yhat=True)
+    e = np.abs(y1[obs[:1]] - r1["yhat"][obs[:1]]) / np.abs(r1["yhat"][obs[:1]])
+    assert _noise_ok(e, 1e-5)
 
 
 def test_tight_tolerance_replay(fx, ctx):

@@ -20,10 +20,10 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.cude_abi_version() == 2
+    assert lib.cude_abi_version() == 3
     o = _lib.cude_opts()
     lib.cude_default_opts(C.byref(o))
-    assert (o.abstol, o.reltol, o.maxiters) == (1e-6, 1e-3, 100000)     # OrdinaryDiffEq defaults
+    assert (o.abstol, o.reltol, o.maxiters) == (1e-6, 1e-3, 1000000)    # OrdinaryDiffEq defaults (maxiters: __init, adaptive)
     assert lib.cude_net_nparams(C.byref(_lib.cude_net(2, 2, 4))) == 37
     assert lib.cude_net_nparams(C.byref(_lib.cude_net(3, 2, 4))) == 41
     k = [C.c_double() for _ in range(3)]
@@ -43,6 +43,32 @@ def test_no_cpu_fallback():
     models, t, c = ohashi_models({k: v for k, v in np.load(os.path.join(ROOT, "tests", "golden", "cpeptide_fixtures.npz")).items()})
     with pytest.raises(_lib.CudeError):
         cu.loss(-1.0, (models[0], t, c[0], np.zeros(37)))
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_device():
+    """The multi-GPU half of the ABI has no CPU fallback either: cude_mctx_create reports CUDE_ENODEVICE, and the NCCL
+    loader (run-time dlopen) finds the library of the image."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    lib = _lib.load()
+    assert lib.cude_device_count() == 0
+    with pytest.raises(_lib.CudeError) as ei:
+        cu.MultiContext(2)
+    assert ei.value.code == _lib.CUDE_ENODEVICE and "no CPU fallback" in str(ei.value)
+    assert lib.cude_nccl_version() >= 20000            # libnccl.so.2 of the image, loaded on demand
+    assert lib.cude_comm_size(None) == _lib.CUDE_EINVAL
+
+
+def test_default_device_follows_the_local_rank():
+    """One process per GPU: a rank that names no device takes the one of its LOCAL_RANK (torchrun does not narrow
+    CUDA_VISIBLE_DEVICES), never silently device 0 for everybody; two ranks on one device is an error."""
+    from conditional_ude_b200.population import pick_device
+    assert [pick_device(8, r) for r in range(8)] == list(range(8))          # distinct devices
+    assert pick_device(8, None, None) == 0 and pick_device(8, None, 5) == 5   # no launcher: torch's current device, else 0
+    assert pick_device(1, 3, None, one_visible=True) == 0                     # launcher narrowed the visibility per rank
+    with pytest.raises(RuntimeError):
+        pick_device(2, 3)                                                     # ranks would share a GPU
 
 
 def test_product_package_does_not_import_the_oracle():
