@@ -30,7 +30,7 @@ class cude_net(C.Structure):
 
 class cude_opts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiters", C.c_int),
-                ("precision", C.c_int), ("block", C.c_int), ("balance", C.c_int)]
+                ("precision", C.c_int), ("block", C.c_int), ("balance", C.c_int), ("split", C.c_int)]
 
 
 class cude_stats(C.Structure):

@@ -14,6 +14,7 @@
 #include "../../include/cude_b200.h"
 #include <cub/device/device_radix_sort.cuh>
 #include "cude_kernels.cuh"
+#include "cude_split.cuh"
 #include "cude_sup_kernel.cuh"
 
 using namespace cude;
@@ -40,6 +41,12 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
+#ifndef CUDE_SPLIT_MIN_TRAJ
+#define CUDE_SPLIT_MIN_TRAJ 200000          // opts.split = 0 (auto): the split gradient pipeline (6 launches) from this many trajectories per call
+#endif
+#ifndef CUDE_SPLIT_BYTES
+#define CUDE_SPLIT_BYTES (20ull << 30)      // device memory the split pipeline's step records may take per group of starts
+#endif
 #ifndef CUDE_BETA_FORWARD_SENSITIVITY
 #define CUDE_BETA_FORWARD_SENSITIVITY 1   // 0: beta-only gradients through the adjoint kernel (comparison builds)
 #endif
@@ -61,9 +68,10 @@ struct cude_ctx {
     const unsigned int* bal_order = nullptr;   // lane-balancing pointers of the call in flight (set by balance_prepare)
     unsigned int* bal_keys_out = nullptr;
     int chunk_mode = 0;                 // 0: single call; 1: first chunk of a pipelined call; 2: later chunk (counters/timer accumulate)
-    const void* carve_kern = nullptr;   // last kernel configuration whose shared-memory carve-out was set
-    size_t carve_smem = 0;
-    int carve_block = 0;
+    struct KernCfg { const void* kern; size_t smem; int block; };
+    std::vector<KernCfg> kern_cfg;      // kernel configurations whose shared-memory attributes have been set
+    int sm_count = 0;
+    DevBuf sp_rec, sp_w, sp_misc, sp_map, sp_gc;   // split gradient pipeline: step records, node weights, per-trajectory arrays, record map, per-record d/d beta
     // NCCL communicator of a sharded population (cude_comm_init_rank, or the ranks of a cude_mctx): the per-start sums
     // are all-reduced in place on `stream` (cude_multi.inl)
     void* comm = nullptr;
@@ -130,6 +138,7 @@ extern "C" void cude_default_opts(cude_opts* o) {
     o->precision = 0;
     o->block = 0;
     o->balance = 0;
+    o->split = 0;
 }
 
 extern "C" int cude_net_nparams(const cude_net* net) {
@@ -197,7 +206,8 @@ extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
-    DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch};
+    DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch,
+                      &ctx->sp_rec, &ctx->sp_w, &ctx->sp_misc, &ctx->sp_map, &ctx->sp_gc};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -434,6 +444,201 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
                          int want_grad, double cond_scale,
                          double* d_sse_out, double* d_sums_out, double* d_g_cond, double* d_yhat);
 
+// Shared-memory attributes of a kernel configuration, set once: dynamic size above 48 KB, and a carve-out of what the
+// resident blocks need and no more — the rest of the 256 KB stays L1, which serves the per-thread step ring and the
+// register spills of the gradient kernels.
+static int prep_kernel(cude_ctx* ctx, const void* kern, int B, size_t smem) {
+    for (const auto& k : ctx->kern_cfg) if (k.kern == kern && k.smem == smem && k.block == B) return CUDE_OK;
+    if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
+    if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, B, smem));
+    if (nb < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: kernel does not fit on an SM with this block size");
+    const size_t need = (size_t)nb * (smem + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    // entries of a kernel with another configuration are replaced (the attribute is per kernel)
+    for (auto& k : ctx->kern_cfg) if (k.kern == kern) { k.smem = smem; k.block = B; return CUDE_OK; }
+    ctx->kern_cfg.push_back({kern, smem, B});
+    return CUDE_OK;
+}
+
+// the per-device constant weight array (CW_CONST): upload ordered behind the last launch that read it, also across contexts
+static int wconst_upload(cude_ctx* ctx, const double* d_w, size_t n) {
+    std::lock_guard<std::mutex> lk(g_wconst_mutex);
+    if ((int)g_wconst_use.size() <= ctx->device) g_wconst_use.resize((size_t)ctx->device + 1);
+    WConstUse& u = g_wconst_use[ctx->device];
+    if (!u.ev) CU_TRY(ctx, cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+    if (u.used && u.stream != ctx->stream) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, u.ev, 0));
+    CU_TRY(ctx, cudaMemcpyToSymbolAsync(CW_CONST, d_w, n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CUDE_OK;
+}
+static int wconst_used(cude_ctx* ctx) {      // after the launches that read the array
+    std::lock_guard<std::mutex> lk(g_wconst_mutex);
+    WConstUse& u = g_wconst_use[ctx->device];
+    CU_TRY(ctx, cudaEventRecord(u.ev, ctx->stream));
+    u.used = true; u.stream = ctx->stream;
+    return CUDE_OK;
+}
+
+// ---------------------------------------------------------------- split gradient pipeline (cude_split.cuh)
+typedef void (*node_kernel_t)(const NodeArgs);
+typedef void (*final_kernel_t)(const FinalArgs);
+struct SplitKernels { eval_kernel_t k1 = nullptr; node_kernel_t k3 = nullptr; final_kernel_t k4 = nullptr; };
+
+template <class NS>
+static SplitKernels pick_split(bool fbwd, bool wc) {
+    SplitKernels k;
+    k.k1 = wc ? cude_eval_kernel<NS, false, false, false, false, true, true> : cude_eval_kernel<NS, false, false, false, false, false, true>;
+    if (fbwd) { k.k3 = wc ? cude_node_kernel<NS, float, true> : cude_node_kernel<NS, float, false>; k.k4 = cude_final_kernel<NS, float>; }
+    else { k.k3 = wc ? cude_node_kernel<NS, double, true> : cude_node_kernel<NS, double, false>; k.k4 = cude_final_kernel<NS, double>; }
+    return k;
+}
+static SplitKernels select_split(const cude_net* net, bool fbwd, bool wc) {
+    if (net->depth == 2 && net->width == 4) {
+        if (net->n_in == 2) return pick_split<NetShape<2, 2, 4>>(fbwd, wc);
+        if (net->n_in == 3) return pick_split<NetShape<3, 2, 4>>(fbwd, wc);
+    }
+    return SplitKernels();
+}
+
+// Loss + full gradient of n_starts starts through the five stages, in groups of starts whose step records fit the
+// memory budget.  `a` carries the call's arguments (pointers to start 0); `fused` is the fused gradient kernel, launched
+// once per group as the fallback for trajectories with more than SPLIT_CAP accepted steps (its blocks return at once
+// when the block has none).  All launches go to ctx->stream; nothing synchronises.
+static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int nchunks, bool fbwd, bool wc,
+                     eval_kernel_t fused, size_t smem_fused, double* d_sums_out, int* launches) {
+    const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
+    const int M = a.pop.max_obs, K = a.pop.max_knots;
+    const SplitKernels sk = select_split(net, fbwd, wc);
+    if (!sk.k1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
+    if (!ctx->sm_count) {
+        cudaDeviceProp prop;
+        CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+        ctx->sm_count = prop.multiProcessorCount;
+    }
+    // ---- groups of starts ----
+    const size_t per_traj = (size_t)(SPLIT_W + SPLIT_WW) * SPLIT_CAP * 8 + (size_t)SPLIT_CAP * (4 + 8) + (size_t)M * 8 + 4 * 8 + 8 + 3 * (size_t)np1 * 8 / 32 + 64;
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = CUDE_SPLIT_BYTES;
+    const size_t have = ctx->sp_rec.cap + ctx->sp_w.cap + ctx->sp_misc.cap + ctx->sp_map.cap + ctx->sp_gc.cap;
+    if (budget > (free_b + have) / 2) budget = (free_b + have) / 2;
+    long long sg = (long long)(budget / (per_traj * (size_t)N));
+    if (sg < 1) sg = 1;
+    if (sg > S) sg = S;
+    while ((long long)N * sg * SPLIT_CAP > 0x7fffffffLL && sg > 1) --sg;      // 32-bit record offsets
+    if ((long long)N * SPLIT_CAP > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: population too large for one call; shard the individuals");
+    const int ngroups = (int)((S + sg - 1) / sg);
+    const int Sg = (S + ngroups - 1) / ngroups;
+    const size_t ntg = (size_t)N * Sg;
+    const int nscan = (int)((ntg + SCAN_TILE - 1) / SCAN_TILE);
+    int G = (4 * ctx->sm_count * CUDE_NODE_MIN_BLOCKS) / Sg;               // stage-4 blocks per start: at most 4 full waves of resident blocks per group
+    const long long max_tiles = ((long long)N * SPLIT_CAP + CUDE_NODE_THREADS - 1) / CUDE_NODE_THREADS;
+    if (G > max_tiles) G = (int)max_tiles;
+    if (G < 1) G = 1;
+    const int nwn = CUDE_NODE_THREADS / 32;
+    const int nA = G * nwn, nB = nchunks * nw;
+    const size_t rowsA = (size_t)Sg * nA, rowsB = (size_t)Sg * nB;
+    int nseg = (nA + 2 * nB + 2047) / 2048;                                 // second-stage reduction: ~2048 rows per block
+    if (nseg > 64) nseg = 64;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sp_rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->sp_w, ntg * SPLIT_WW * SPLIT_CAP * sizeof(double)))) return rc;
+    // per-trajectory arrays: res [M] , beta, wsum, sse (double), off (uint, +1), nrec (int); then bsum (uint, nscan + 1), blkflag (int),
+    // segment sums of the reduction
+    const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_wsum = o_beta + ntg * 8, o_sse = o_wsum + ntg * 8, o_off = o_sse + ntg * 8,
+                 o_nrec = o_off + ((ntg + 2) * 4 + 7) / 8 * 8, o_bsum = o_nrec + (ntg * 4 + 7) / 8 * 8,
+                 o_flag = o_bsum + (((size_t)nscan + 2) * 4 + 7) / 8 * 8, o_seg = o_flag + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8,
+                 misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
+    if ((rc = ensure(ctx, ctx->sp_misc, misc_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->sp_map, ntg * SPLIT_CAP * sizeof(unsigned int)))) return rc;
+    if ((rc = ensure(ctx, ctx->sp_gc, ntg * SPLIT_CAP * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->partials, (rowsA + 2 * rowsB) * np1 * sizeof(double)))) return rc;
+    char* const misc = (char*)ctx->sp_misc.p;
+    double* const pA = (double*)ctx->partials.p;
+    double* const pB = pA + rowsA * np1;
+    double* const pC = pB + rowsB * np1;
+    // ---- kernel attributes ----
+    const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
+    const size_t smem1 = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, false, false, true);    // loss-only rows + the 5 dG rows
+    const size_t smem3 = sizeof(double) * node_smem_doubles(P, CUDE_NODE_THREADS, fbwd, wc);
+    if ((rc = prep_kernel(ctx, (const void*)sk.k1, B, smem1))) return rc;
+    if ((rc = prep_kernel(ctx, (const void*)sk.k3, CUDE_NODE_THREADS, smem3))) return rc;
+    if ((rc = prep_kernel(ctx, (const void*)fused, B, smem_fused))) return rc;
+
+    for (int g0 = 0; g0 < S; g0 += Sg) {
+        const int ns = (S - g0 < Sg) ? S - g0 : Sg;
+        const size_t nt = (size_t)N * ns;
+        EvalArgs e = a;
+        e.n_starts = ns;
+        e.neural = a.neural + (size_t)g0 * a.neural_stride;
+        e.cond = a.cond + (size_t)g0 * N;
+        e.sse_out = a.sse_out ? a.sse_out + (size_t)g0 * N : nullptr;
+        e.g_cond = a.g_cond + (size_t)g0 * N;
+        e.order = a.order ? a.order + (size_t)g0 * N : nullptr;
+        e.keys_out = a.keys_out ? a.keys_out + (size_t)g0 * N : nullptr;
+        e.partials = nullptr;
+        e.sp_rec = (double*)ctx->sp_rec.p;
+        e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
+        e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
+        double* const d_wsum = (double*)(misc + o_wsum);
+        unsigned int* const d_off = (unsigned int*)(misc + o_off);
+        unsigned int* const d_bsum = (unsigned int*)(misc + o_bsum);
+        double* const d_seg = (double*)(misc + o_seg);
+        const unsigned nblk = (unsigned)((size_t)ns * nchunks);
+        CU_TRY(ctx, cudaMemsetAsync(e.sp_blkflag, 0, (size_t)nblk * sizeof(int), ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(pC, 0, (size_t)ns * nB * np1 * sizeof(double), ctx->stream));
+        if (wc) {
+            const size_t n_w = (size_t)a.neural_stride * (ns - 1) + P;
+            if ((rc = wconst_upload(ctx, e.neural, n_w))) return rc;
+        }
+        // stage 1: forward solve -> step records {t, h, dG[5]}, residuals
+        sk.k1<<<nblk, B, smem1, ctx->stream>>>(e);
+        CU_TRY(ctx, cudaGetLastError());
+        // stage 2: adjoint recursion -> node weights
+        RecurArgs ra{};
+        ra.pop = a.pop; ra.ntraj = (long long)nt; ra.sp_rec = e.sp_rec; ra.sp_w = (double*)ctx->sp_w.p; ra.sp_res = e.sp_res; ra.sp_nrec = e.sp_nrec; ra.sp_wsum = d_wsum;
+        cude_recur_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ra);
+        CU_TRY(ctx, cudaGetLastError());
+        // stage 3: flat record list
+        const int nsc = (int)((nt + SCAN_TILE - 1) / SCAN_TILE);
+        cude_scan_sums<<<nsc, SCAN_T, 0, ctx->stream>>>(e.sp_nrec, (long long)nt, d_bsum);
+        cude_scan_bsums<<<1, 1024, 0, ctx->stream>>>(d_bsum, nsc);
+        cude_scan_final<<<nsc, SCAN_T, 0, ctx->stream>>>(e.sp_nrec, (long long)nt, d_bsum, d_off, (unsigned int*)ctx->sp_map.p);
+        CU_TRY(ctx, cudaGetLastError());
+        // stage 4: network forward + backward, one thread per record
+        NodeArgs na{};
+        na.pop = a.pop; na.neural = e.neural; na.neural_stride = a.neural_stride;
+        na.sp_rec = e.sp_rec; na.sp_w = (const double*)ctx->sp_w.p; na.off = d_off; na.map = (const unsigned int*)ctx->sp_map.p; na.sp_beta = e.sp_beta;
+        na.gc_rec = (double*)ctx->sp_gc.p; na.partials = pA;
+        sk.k3<<<dim3((unsigned)G, (unsigned)ns), CUDE_NODE_THREADS, smem3, ctx->stream>>>(na);
+        CU_TRY(ctx, cudaGetLastError());
+        // stage 5: NN([0;beta]) node, d/d cond, sse rows
+        FinalArgs fa{};
+        fa.pop = a.pop; fa.n_starts = ns; fa.nchunks = nchunks; fa.neural = e.neural; fa.neural_stride = a.neural_stride;
+        fa.sp_nrec = e.sp_nrec; fa.sp_beta = e.sp_beta; fa.sp_wsum = d_wsum; fa.sp_sse = e.sp_sse; fa.off = d_off;
+        fa.gc_rec = (const double*)ctx->sp_gc.p; fa.cond_scale = a.cond_scale; fa.g_cond = e.g_cond; fa.partials = pB;
+        sk.k4<<<nblk, B, 0, ctx->stream>>>(fa);
+        CU_TRY(ctx, cudaGetLastError());
+        // fallback: trajectories with more than SPLIT_CAP accepted steps through the fused kernel (flagged blocks only)
+        EvalArgs f = e;
+        f.partials = pC; f.only_flag = e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
+        fused<<<nblk, B, smem_fused, ctx->stream>>>(f);
+        CU_TRY(ctx, cudaGetLastError());
+        if (wc && (rc = wconst_used(ctx))) return rc;
+        *launches += 8;
+        if (d_sums_out) {
+            cude_reduce_rows<<<dim3((unsigned)nseg, (unsigned)ns), RED_T, 0, ctx->stream>>>(pA, nA, pB, pC, nB, np1, nseg * np1, d_seg);
+            cude_reduce_rows<<<dim3(1, (unsigned)ns), RED_T, 0, ctx->stream>>>(d_seg, nseg, nullptr, nullptr, 0, np1, np1, d_sums_out + (size_t)g0 * np1);
+            CU_TRY(ctx, cudaGetLastError());
+            *launches += 2;
+        }
+    }
+    return CUDE_OK;
+}
+
 extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
                              int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
                              int want_grad, double cond_scale,
@@ -522,44 +727,27 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     const int K = pop->max_knots, M = pop->max_obs;
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
     const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, adj, mixed || (fbwd && adj), bsens);
-    if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots/observations for shared memory; lower opts.block");
-    if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if ((const void*)kern != ctx->carve_kern || smem != ctx->carve_smem || B != ctx->carve_block) {
-        // Shared-memory carve-out = what the resident blocks need and no more: the rest of the 256 KB stays L1, which
-        // serves the per-thread step ring and the register spills of the gradient kernel.
-        int nb = 0;
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kern, B, smem));
-        if (nb < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: kernel does not fit on an SM with this block size");
-        const size_t need = (size_t)nb * (smem + 1024);
-        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-        if (pct > 100) pct = 100;
-        CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        ctx->carve_kern = (const void*)kern; ctx->carve_smem = smem; ctx->carve_block = B;
-    }
+    if ((rc = prep_kernel(ctx, (const void*)kern, B, smem))) return rc;
 
+    // loss + full gradient of a large batch: the split pipeline (opts.split: 0 auto, 1 never, 2 always)
+    const bool use_split = adj && !flat && !mixed && want_neural_grad && d_g_cond && o.split != 1 &&
+                           (o.split == 2 || ntraj >= CUDE_SPLIT_MIN_TRAJ);
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
-    if (wc) {
-        // the constant array is one per device and process: order this upload + launch after the last launch that read it
-        std::lock_guard<std::mutex> lk(g_wconst_mutex);
-        if ((int)g_wconst_use.size() <= ctx->device) g_wconst_use.resize((size_t)ctx->device + 1);
-        WConstUse& u = g_wconst_use[ctx->device];
-        if (!u.ev) CU_TRY(ctx, cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
-        if (u.used && u.stream != ctx->stream) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, u.ev, 0));
-        CU_TRY(ctx, cudaMemcpyToSymbolAsync(CW_CONST, d_neural, n_w * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
-        kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
-        CU_TRY(ctx, cudaGetLastError());
-        CU_TRY(ctx, cudaEventRecord(u.ev, ctx->stream));
-        u.used = true; u.stream = ctx->stream;
+    int launches = 0;
+    if (use_split) {
+        if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, kern, smem, d_sums_out, &launches))) return rc;
     } else {
+        if (wc && (rc = wconst_upload(ctx, d_neural, n_w))) return rc;
         kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
         CU_TRY(ctx, cudaGetLastError());
+        if (wc && (rc = wconst_used(ctx))) return rc;
+        launches = 1;
     }
-    int launches = 1;
-    if (d_sums_out) {
+    if (d_sums_out && !use_split) {
         if (flat) {
             const int wpb = 8;
             cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);

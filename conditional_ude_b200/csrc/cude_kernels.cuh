@@ -123,6 +123,14 @@ struct EvalArgs {
     unsigned int* keys_out;        // [N x S] or nullptr
     double* yhat_out;              // [M][N x S] -> yhat_out[k + M*j]: the solution at the observation times (cude_simulate;
                                    // loss-only instantiations), or nullptr
+    // split gradient pipeline (SPLIT instantiation = stage 1; see "split gradient pipeline" below)
+    double* sp_rec;                // [N x S][SPLIT_CAP][SPLIT_W] one record per accepted step: {t, h, dG at the 5 nodes, 0}
+    double* sp_res;                // [M][N x S] residuals yhat_k - y_k
+    int* sp_nrec;                  // [N x S] accepted steps recorded; 0 = failed trajectory, -1 = more than SPLIT_CAP steps
+    double* sp_beta;               // [N x S] beta = exp(cond)
+    double* sp_sse;                // [N x S] sse (Inf when failed)
+    int* sp_blkflag;               // [blocks] set when a trajectory of the block overflowed SPLIT_CAP (fused-kernel fallback)
+    const int* only_flag;          // fused GRAD kernel as that fallback: run only the trajectories with only_flag[j] < 0 of flagged blocks
 };
 
 // ---------------------------------------------------------------- network shape
@@ -166,6 +174,28 @@ constexpr int REC_CAP = CUDE_REC_CAP;
 // (7 doubles) took the sigmoid off the adjoint's dependent chain for +0.9 %, but the records then no longer stay in L2:
 // 76 GB of DRAM traffic per 64 M-trajectory launch instead of 3.6 GB (profiles/README.md).
 constexpr int REC_W = 2;   // doubles per record
+
+// ---------------------------------------------------------------- split gradient pipeline
+// The adjoint has a cheap sequential part — the 2-vector recursion backwards through the accepted steps, which only
+// produces the *weights* of the network's output at the 5 nodes of every step — and an expensive part that is
+// embarrassingly parallel once the weights exist: network forward + backward at every (trajectory, step, node), about
+// 100 node evaluations per trajectory, whose results are merely *summed*.  The fused kernel does everything in one thread
+// per trajectory: 33 FP64 accumulators stay live across 70 KB of code, and a warp waits for its longest trajectory in
+// every phase.  The split pipeline separates the phases (cude_split.cuh):
+//   stage 1  cude_eval_kernel<.., SPLIT>   the loss-only forward solve, one thread per trajectory; per accepted step it
+//                                          leaves a record {t, h, dG at the step's 5 nodes}, per observation a residual
+//   stage 2  cude_recur_kernel             adjoint recursion per trajectory (no network): the 5 node weights per record
+//   stage 3  cude_scan_*                   exclusive scan of the step counts -> a flat list of (trajectory, step) records
+//   stage 4  cude_node_kernel              one thread per RECORD: 5 network forward+backward evaluations into per-thread
+//                                          accumulators (all lanes busy, no divergence, a few KB of hot code)
+//   stage 5  cude_final_kernel             per trajectory: the NN([0;beta]) node, d sse/d cond, partial rows
+// Trajectories with more than SPLIT_CAP accepted steps (tight tolerances) take the fused kernel instead (only_flag).
+#ifndef CUDE_SPLIT_CAP
+#define CUDE_SPLIT_CAP 32
+#endif
+constexpr int SPLIT_CAP = CUDE_SPLIT_CAP;
+constexpr int SPLIT_W = 8;    // doubles per step record of stage 1 (64 B = 2 sectors, written whole): t, h, dG[5], 0
+constexpr int SPLIT_WW = 6;   // doubles per weight record of stage 2 (48 B, written whole): w[5], 0
 
 // per-thread view of the staged glucose knots in shared memory, layout [k][tid]
 struct Knots {
@@ -448,9 +478,10 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 // the same steps (frozen step sequence => the same derivative the adjoint produces), no step ring, no backward sweep.
 // FBWD (with GRAD): the forward pass — loss, step sequence — stays FP64 bit for bit, only the adjoint's network
 // evaluations and gradient accumulators are FP32 (opts.precision = 2): gradients to ~1e-6 instead of ~1e-13.
-template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false>
+template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false, bool SPLIT = false>
 __global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : ((WC && !BSENS) ? CUDE_MIN_BLOCKS_LOSS_WC : CUDE_MIN_BLOCKS_LOSS))
 cude_eval_kernel(const EvalArgs A) {
+    static_assert(!SPLIT || (!GRAD && !MIXED && !BSENS), "SPLIT (stage 1 of the split gradient pipeline) is a variant of the FP64 loss-only kernel");
     static_assert(!WC || !MIXED, "WC (weights in constant memory) needs an FP64 forward network");
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
     static_assert(!FBWD || (GRAD && !MIXED), "FBWD is a variant of the FP64 gradient kernel");
@@ -472,8 +503,8 @@ cude_eval_kernel(const EvalArgs A) {
     double* sOt = sSl + (size_t)K * B;               // [M][B] observation times
     double* sOy = sOt + (size_t)M * B;               // [M][B] observed c-peptide
     double* sNode = sOy + (size_t)M * B;             // [5][B] network outputs (forward) / node weights (adjoint)
-    double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD) / d z_out/d beta at the nodes (BSENS)
-    double* sRes = sDG + ((GRAD || BSENS) ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
+    double* sDG = sNode + (size_t)5 * B;             // [5][B] dG at the adjoint's nodes (GRAD) / d z_out/d beta at the nodes (BSENS) / dG copy (SPLIT)
+    double* sRes = sDG + ((GRAD || BSENS || SPLIT) ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
 
     // ---- which trajectory ----
     long long j, prow = blockIdx.x;   // prow: this block's row group in `partials`, [start][chunk] order
@@ -496,6 +527,13 @@ cude_eval_kernel(const EvalArgs A) {
         if (!active) i = 0;
         else if (A.order) i = (int)(A.order[(size_t)s * N + i] & 0xffffffu);
         j = (long long)s * N + i;
+        if constexpr (GRAD) {
+            // fallback of the split pipeline: only the trajectories stage 1 could not record (block-uniform early exit first)
+            if (A.only_flag) {
+                if (!A.sp_blkflag[prow]) return;
+                active = active && A.only_flag[j] < 0;
+            }
+        }
     }
     // ---- the start's weights: staged in shared memory (block-uniform), or read from constant memory (WC) ----
     // (offset from block-uniform values only, so that the compiler keeps it — and the weight loads — on the uniform path)
@@ -595,6 +633,7 @@ cude_eval_kernel(const EvalArgs A) {
             while (iobs < nobs && next_ot <= t0) {
                 const double r = u0 - obs_y[iobs * B];
                 if (GRAD) sRes[iobs * B + tid] = r;
+                if constexpr (SPLIT) A.sp_res[(size_t)iobs * ((size_t)N * A.n_starts) + j] = r;
                 if constexpr (!GRAD && !BSENS) { if (A.yhat_out) A.yhat_out[(size_t)j * M + iobs] = u0; }
                 fsse = fma(r, r, fsse);
                 ++iobs;
@@ -635,6 +674,10 @@ cude_eval_kernel(const EvalArgs A) {
 #pragma unroll
                     for (int q = 0; q < 5; ++q) tau[q] = fma(cn[q], dt, t);
                     kn.dG5(tau, myNode, B, kbase, klast);         // dG of the node times, staged in myNode
+                    if constexpr (SPLIT) {                         // kept for the step record (myNode is overwritten by z_out)
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) myDG[q * B] = myNode[q * B];
+                    }
                 }
                 if constexpr (BSENS) {
 #pragma unroll 1
@@ -754,6 +797,7 @@ cude_eval_kernel(const EvalArgs A) {
                         }
                         const double r = y - obs_y[iobs * B];
                         if (GRAD) sRes[iobs * B + tid] = r;
+                        if constexpr (SPLIT) A.sp_res[(size_t)iobs * ((size_t)N * A.n_starts) + j] = r;
                         if constexpr (!GRAD && !BSENS) { if (A.yhat_out) A.yhat_out[(size_t)j * M + iobs] = y; }
                         if constexpr (BSENS) {
                             double dy;
@@ -773,6 +817,15 @@ cude_eval_kernel(const EvalArgs A) {
                     if (GRAD) {
                         double* const r7 = rec + (na % REC_CAP) * REC_W;
                         r7[0] = t; r7[1] = dt;
+                    }
+                    if constexpr (SPLIT) {
+                        if (na < SPLIT_CAP) {      // 64-byte record = 2 whole sectors: {t, h}, {dG0, dG1}, {dG2, dG3}, {dG4, 0}
+                            double2* const r = reinterpret_cast<double2*>(A.sp_rec + ((size_t)j * SPLIT_CAP + na) * SPLIT_W);
+                            r[0] = make_double2(t, dt);
+                            r[1] = make_double2(myDG[0], myDG[B]);
+                            r[2] = make_double2(myDG[2 * B], myDG[3 * B]);
+                            r[3] = make_double2(myDG[4 * B], 0.0);
+                        }
                     }
                     ++na;
                     lnqold = fmax(lnE, -9.210340371976182);        // qold = max(EEst, qoldinit)
@@ -944,6 +997,12 @@ cude_eval_kernel(const EvalArgs A) {
             A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
         }
         if (A.sse_out) A.sse_out[j] = sse;
+        if constexpr (SPLIT) {
+            A.sp_nrec[j] = failed ? 0 : (nacc > SPLIT_CAP ? -1 : nacc);
+            A.sp_beta[j] = beta;
+            A.sp_sse[j] = sse;
+            if (!failed && nacc > SPLIT_CAP) A.sp_blkflag[prow] = 1;
+        }
         if constexpr (!GRAD && !BSENS) {
             if (A.yhat_out && failed) for (int k = 0; k < M; ++k) A.yhat_out[(size_t)j * M + k] = CUDART_NAN;   // no solution
         }
@@ -952,7 +1011,7 @@ cude_eval_kernel(const EvalArgs A) {
     // ---- warp reduction: {sse, d sse/d neural[0..P)}; one partial row per WARP, no block barrier (warps of a
     //      block finish at different times; a barrier here idled their slots: ncu v4 epilogue 45 % barrier) ----
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
-    if (A.partials) {
+    if (A.partials && !SPLIT) {
         double* const row = A.partials + ((size_t)prow * nw + wid) * (P + 1);
         if constexpr (GRAD) {
             // rows [q][tid] of this warp's 32 columns -> lane l sums row l (and row 32 + l): 32 shared loads and adds

@@ -1,0 +1,520 @@
+// =====================================================================================
+// cude_split.cuh — stages 2-5 of the split gradient pipeline (stage 1 is cude_eval_kernel<.., SPLIT>, see the
+// "split gradient pipeline" note in cude_kernels.cuh).
+//
+// What the split buys on B200 (measured against the fused kernel, profiles/README.md):
+//   * the network forward+backward evaluations — ~60 % of the fused kernel's instructions — run one thread per
+//     (trajectory, accepted step) record: every lane of every warp has exactly 5 node evaluations per tile, so the
+//     12 % of lane-cycles the fused kernel loses there to trajectories of different length are recovered, the hot loop
+//     is a few KB of straight code instead of 70 KB, and its register budget is its own;
+//   * the forward solve runs as the loss-only kernel (128 registers, 4 blocks per SM instead of 168 / 3) and the
+//     adjoint recursion as a small kernel at full occupancy;
+//   * the price is one 96-byte step record per accepted step through HBM (~250 GB per 64 M-trajectory call, ~1 TB/s at
+//     the rate the kernels produce and consume it: far below the 6.5 TB/s the device moves, and prefetched with
+//     cp.async one tile ahead in stage 4).
+// Reference semantics are unchanged: the same discrete adjoint of the same Tsit5 solve (src/parameter-estimation.jl:59,
+// gradient of :126-140 in place of AutoForwardDiff :370); only the order in which node contributions are summed differs.
+// =====================================================================================
+#pragma once
+#include "cude_kernels.cuh"
+
+namespace cude {
+
+// ---------------------------------------------------------------- stage 2: adjoint recursion, one thread per trajectory
+// The discrete adjoint of the linear stage recursion (the same arithmetic, in the same order, as the fused kernel's
+// sweep): walks the accepted steps backwards, carries the 2-vector adjoint, and leaves in every step record the weights
+// of the production term at the step's 5 nodes {c2, c3, c4, c5, 1}; sp_wsum = -(sum of all weights) is the weight of the
+// NN([0; beta]) node.
+struct RecurArgs {
+    PopDev pop;
+    long long ntraj;               // N x S
+    const double* sp_rec;          // stage 1's records {t, h, dG[5], 0}
+    double* sp_w;                  // [ntraj][SPLIT_CAP][SPLIT_WW] node weights {w(c2), w(c3), w(c4), w(c5), w(1), 0}
+    const double* sp_res;          // [M][ntraj]
+    const int* sp_nrec;
+    double* sp_wsum;               // [ntraj]
+};
+
+__global__ void __launch_bounds__(128) cude_recur_kernel(const RecurArgs A) {
+    using namespace tab;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.ntraj) return;
+    const int nrec = A.sp_nrec[j];
+    if (nrec <= 0) { A.sp_wsum[j] = 0.0; return; }
+    const int N = A.pop.n_ind;
+    const int i = (int)(j % N);
+    const double k0 = A.pop.k0[i], k1 = A.pop.k1[i], k2 = A.pop.k2[i];
+    const double d00 = -(k0 + k2);
+    const int nobs = A.pop.n_obs[i];
+    const double tend = A.pop.knot_t[(size_t)(A.pop.n_knots[i] - 1) * N + i];
+    const double* const obs_t = A.pop.obs_t + i;
+    const double* const res = A.sp_res + j;
+    double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
+    int kobs_top = nobs - 1;
+    double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;
+    const double* rec = A.sp_rec + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_W;
+    double* wrec = A.sp_w + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_WW;
+    double2 th_next = *reinterpret_cast<const double2*>(rec);       // (t, h) fetched one step ahead of its use
+    for (int n = nrec - 1; n >= 0; --n, rec -= SPLIT_W, wrec -= SPLIT_WW) {
+        const double2 th = th_next;
+        if (n > 0) th_next = *reinterpret_cast<const double2*>(rec - SPLIT_W);
+        const double tn = th.x, h = th.y;
+        double kb[7][2];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
+        double ub0 = 0.0, ub1 = 0.0;
+        // observations in (tn, t_next]
+        while (kobs_top >= 0) {
+            const double ts = top_ot;
+            if (!(ts > tn)) break;
+            const double wr = 2.0 * res[(size_t)kobs_top * A.ntraj];
+            if (ts == t_next) lam0 += wr;
+            else {
+                double bw[7];
+                dense_weights((ts - tn) * m_rcp(h), bw);
+                ub0 += wr;
+                const double wh = wr * h;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
+            }
+            --kobs_top;
+            top_ot = (kobs_top >= 0) ? obs_t[(size_t)kobs_top * N] : -CUDART_INF;
+        }
+        // k7 = A un + b + e1 p7 (dense output only): lam += A^T kb7
+        const double pb7 = kb[6][0];
+        lam0 = fma(d00, kb[6][0], lam0);   // kb7[1] == 0
+        lam1 = fma(k1, kb[6][0], lam1);
+        // un = u + h sum b_j k_j
+        ub0 += lam0; ub1 += lam1;
+        {
+            const double hl0 = h * lam0, hl1 = h * lam1;
+            kb[0][0] = fma(b1, hl0, kb[0][0]); kb[0][1] = fma(b1, hl1, kb[0][1]);
+            kb[1][0] = fma(b2, hl0, kb[1][0]); kb[1][1] = fma(b2, hl1, kb[1][1]);
+            kb[2][0] = fma(b3, hl0, kb[2][0]); kb[2][1] = fma(b3, hl1, kb[2][1]);
+            kb[3][0] = fma(b4, hl0, kb[3][0]); kb[3][1] = fma(b4, hl1, kb[3][1]);
+            kb[4][0] = fma(b5, hl0, kb[4][0]); kb[4][1] = fma(b5, hl1, kb[4][1]);
+            kb[5][0] = fma(b6, hl0, kb[5][0]); kb[5][1] = fma(b6, hl1, kb[5][1]);
+        }
+        // stage i: k_i = A g_i + b + e1 p_i, g_i = u + h sum_{j<i} a_ij k_j;  gb = A^T kb_i
+        double gb0, gb1, hg0, hg1;
+#define CUDE_STAGE_BACK(I)                                                    \
+    gb0 = fma(d00, kb[I][0], k2 * kb[I][1]);                                  \
+    gb1 = k1 * (kb[I][0] - kb[I][1]);                                         \
+    ub0 += gb0; ub1 += gb1; hg0 = h * gb0; hg1 = h * gb1;
+#define CUDE_PUSH(J, COEF) kb[J][0] = fma(COEF, hg0, kb[J][0]); kb[J][1] = fma(COEF, hg1, kb[J][1]);
+        const double pb6 = kb[5][0];
+        CUDE_STAGE_BACK(5) CUDE_PUSH(0, a61) CUDE_PUSH(1, a62) CUDE_PUSH(2, a63) CUDE_PUSH(3, a64) CUDE_PUSH(4, a65)
+        const double pb5 = kb[4][0];
+        CUDE_STAGE_BACK(4) CUDE_PUSH(0, a51) CUDE_PUSH(1, a52) CUDE_PUSH(2, a53) CUDE_PUSH(3, a54)
+        const double pb4 = kb[3][0];
+        CUDE_STAGE_BACK(3) CUDE_PUSH(0, a41) CUDE_PUSH(1, a42) CUDE_PUSH(2, a43)
+        const double pb3 = kb[2][0];
+        CUDE_STAGE_BACK(2) CUDE_PUSH(0, a31) CUDE_PUSH(1, a32)
+        const double pb2 = kb[1][0];
+        CUDE_STAGE_BACK(1) CUDE_PUSH(0, a21)
+        const double pb1 = kb[0][0];
+        CUDE_STAGE_BACK(0)
+#undef CUDE_STAGE_BACK
+#undef CUDE_PUSH
+        (void)hg0; (void)hg1;
+        // node weights in CN_STEP order; node tn+h serves stages 6, 7 and the next step's stage 1
+        const double w6 = pb6 + pb7 + wnode;
+        reinterpret_cast<double2*>(wrec)[0] = make_double2(pb2, pb3);
+        reinterpret_cast<double2*>(wrec)[1] = make_double2(pb4, pb5);
+        reinterpret_cast<double2*>(wrec)[2] = make_double2(w6, 0.0);
+        wsum += w6 + pb5 + pb4 + pb3 + pb2;
+        wnode = pb1;
+        lam0 = ub0; lam1 = ub1;
+        t_next = tn;
+    }
+    A.sp_wsum[j] = -wsum;      // the node t0 itself has dG = 0 and cancels against its share of the NN([0;beta]) term
+}
+
+// ---------------------------------------------------------------- stage 3: scan of the step counts
+// off[j] = sum_{j' < j} max(nrec[j'], 0), off[n] = total; map[off[j] + q] = j for q < nrec[j].
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_TILE = SCAN_T * SCAN_E;
+
+#ifndef CUDE_HOST_EMU
+__device__ __forceinline__ unsigned int scan_block_exclusive(unsigned int v, unsigned int* sh /*[33]*/, unsigned int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        sh[lane] = w;     // inclusive over the warps
+    }
+    __syncthreads();
+    total = sh[(blockDim.x >> 5) - 1];
+    const unsigned int wbase = wid ? sh[wid - 1] : 0u;
+    __syncthreads();
+    return wbase + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) cude_scan_sums(const int* __restrict__ nrec, long long n, unsigned int* __restrict__ bsum) {
+    __shared__ unsigned int sh[33];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_E;
+    unsigned int v = 0;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; ++e) {
+        const long long idx = base + e;
+        if (idx < n) { const int c = nrec[idx]; v += c > 0 ? (unsigned int)c : 0u; }
+    }
+    unsigned int total;
+    (void)scan_block_exclusive(v, sh, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// exclusive scan of the block sums in place (one block); bsum[nb] = grand total
+__global__ void __launch_bounds__(1024) cude_scan_bsums(unsigned int* __restrict__ bsum, int nb) {
+    __shared__ unsigned int sh[33];
+    unsigned int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const unsigned int v = b < nb ? bsum[b] : 0u;
+        unsigned int total;
+        const unsigned int ex = scan_block_exclusive(v, sh, total);
+        if (b < nb) bsum[b] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T) cude_scan_final(const int* __restrict__ nrec, long long n, const unsigned int* __restrict__ bsum,
+                                                          unsigned int* __restrict__ off, unsigned int* __restrict__ map) {
+    __shared__ unsigned int sh[33];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_E;
+    unsigned int c[SCAN_E], v = 0;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; ++e) {
+        const long long idx = base + e;
+        const int x = idx < n ? nrec[idx] : 0;
+        c[e] = x > 0 ? (unsigned int)x : 0u;
+        v += c[e];
+    }
+    unsigned int total;
+    unsigned int o = bsum[blockIdx.x] + scan_block_exclusive(v, sh, total);
+#pragma unroll
+    for (int e = 0; e < SCAN_E; ++e) {
+        const long long idx = base + e;
+        if (idx < n) {
+            off[idx] = o;
+            for (unsigned int q = 0; q < c[e]; ++q) map[o + q] = (unsigned int)idx;
+            o += c[e];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) off[n] = bsum[gridDim.x];
+}
+#endif  // CUDE_HOST_EMU
+
+// ---------------------------------------------------------------- stage 4: one thread per step record
+struct NodeArgs {
+    PopDev pop;
+    const double* neural;          // the group's first start: start s uses neural + s*neural_stride
+    long long neural_stride;
+    const double* sp_rec;          // [N x S][SPLIT_CAP][SPLIT_W]  {t, h, dG[5], 0}
+    const double* sp_w;            // [N x S][SPLIT_CAP][SPLIT_WW] {w[5], 0}
+    const unsigned int* off;       // [N x S + 1]
+    const unsigned int* map;       // [records] -> trajectory
+    const double* sp_beta;         // [N x S]
+    double* gc_rec;                // [records] sum_j (sum over the record's nodes of dz1_j) * W1[j, beta column]
+    double* partials;              // [S][gridDim.x * warps][P+1] (row 0 unused = 0)
+};
+
+#ifndef CUDE_NODE_THREADS
+#define CUDE_NODE_THREADS 128
+#endif
+#ifndef CUDE_NODE_MIN_BLOCKS
+#define CUDE_NODE_MIN_BLOCKS 3
+#endif
+#ifndef CUDE_NODE_UNROLL
+#define CUDE_NODE_UNROLL 1      // unroll factor of the 5-node loop
+#endif
+
+// asynchronous global -> shared copies (LDGSTS): the next tile's records land in shared memory while this tile computes
+#ifdef CUDE_HOST_EMU
+static inline void cp_async16(void* s, const void* g) { memcpy(s, g, 16); }
+static inline void cp_async8(void* s, const void* g) { memcpy(s, g, 8); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async16(void* s, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* s, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
+// dynamic shared memory (doubles) of cude_node_kernel: exp table, weights (unless uniform operands), 2 buffers of
+// {6 x 16-byte record chunks, beta, covariate} per thread
+constexpr int NODE_BUF_D = 14;    // doubles per thread and buffer
+__host__ __device__ inline size_t node_smem_doubles(int P, int B, bool f32copy, bool wc) {
+    return (size_t)256 + ((wc && !f32copy) ? 0 : (size_t)((P + 1) & ~1)) + (size_t)2 * NODE_BUF_D * B;
+}
+
+template <class NS, class RB, bool WC>
+__global__ void __launch_bounds__(CUDE_NODE_THREADS, CUDE_NODE_MIN_BLOCKS) cude_node_kernel(const NodeArgs A) {
+    constexpr int W = NS::W, P = NS::P;
+    constexpr bool F32 = std::is_same<RB, float>::value;
+    extern __shared__ double smem[];
+    const int B = blockDim.x, tid = threadIdx.x;
+    const int s = blockIdx.y, N = A.pop.n_ind;
+    double* sTab = smem;                                       // [256]
+    double* sWs = sTab + 256;                                  // weights as RB (unused with WC in FP64)
+    double* sBuf = sWs + ((WC && !F32) ? 0 : ((P + 1) & ~1));   // [2][NODE_BUF_D][B]: chunks 0..5 as double2 [c][tid], then beta[tid], cov[tid]
+    for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
+    const long long wofs = (long long)s * A.neural_stride;
+    double wuni[(WC && !F32) ? P : 1];
+    if constexpr (WC && !F32) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[wofs + p];
+    } else {
+        RB* const w = reinterpret_cast<RB*>(sWs);
+        for (int p = tid; p < P; p += B) w[p] = (RB)A.neural[wofs + p];
+    }
+    const RB* const sW = (WC && !F32) ? reinterpret_cast<const RB*>(wuni) : reinterpret_cast<const RB*>(sWs);
+    __syncthreads();
+    // FP64 copies of the first layer's beta / covariate columns and bias for the per-record constants
+    double w1b[W], w1c[W], b1[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        w1b[q] = (double)sW[W + q];
+        w1c[q] = NS::NIN > 2 ? (double)sW[2 * W + q] : 0.0;
+        b1[q] = (double)sW[NS::NIN * W + q];
+    }
+
+    RB g[NS::NACC];                 // compressed accumulators of mlp_backward; [W, 2W) is per record
+    RB gb[W], gbeta[W], gcov[NS::NIN > 2 ? W : 1];
+#pragma unroll
+    for (int k = 0; k < NS::NACC; ++k) g[k] = RB(0);
+#pragma unroll
+    for (int q = 0; q < W; ++q) { gb[q] = RB(0); gbeta[q] = RB(0); if (NS::NIN > 2) gcov[q] = RB(0); }
+
+    const size_t r_lo = A.off[(size_t)s * N], r_hi = A.off[(size_t)(s + 1) * N];
+    const size_t stride = (size_t)gridDim.x * B;
+    const size_t jbase = (size_t)s * N;
+    // this thread's slots of buffer b: chunk c -> (double2*)(sBuf + b*NODE_BUF_D*B) + c*B + tid; beta / cov behind the chunks
+    auto buf = [&](int b) { return sBuf + (size_t)b * NODE_BUF_D * B; };
+    auto issue = [&](int b, bool act, unsigned int j, unsigned int o, size_t k) {
+        double* const bb = buf(b);
+        double2* const ch = reinterpret_cast<double2*>(bb) + tid;
+        if (act) {
+            const size_t slot = (size_t)j * SPLIT_CAP + (unsigned int)(k - o);
+            const double* const r = A.sp_rec + slot * SPLIT_W;
+            const double* const w = A.sp_w + slot * SPLIT_WW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cp_async16(ch + c * B, r + 2 + 2 * c);      // {dG0,dG1} {dG2,dG3} {dG4,0}
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cp_async16(ch + (3 + c) * B, w + 2 * c);    // {w0,w1} {w2,w3} {w4,0}
+            cp_async8(bb + 12 * B + tid, A.sp_beta + j);
+            if (NS::NIN > 2) cp_async8(bb + 13 * B + tid, A.pop.cov + (j - jbase));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ch[c * B] = make_double2(0.0, 0.0);
+            bb[12 * B + tid] = 0.0;
+            bb[13 * B + tid] = 0.0;
+        }
+        cp_async_commit();
+    };
+    // software pipeline over the block's tiles: records of tile t+1 in flight (cp.async), trajectory index of tile t+2
+    // and its record offset one load behind each other
+    size_t k = r_lo + (size_t)blockIdx.x * B + tid;          // this thread's record in tile t
+    {
+        const bool a0 = k < r_hi;
+        unsigned int j0 = 0, o0 = 0;
+        if (a0) { j0 = A.map[k]; o0 = A.off[j0]; }
+        issue(0, a0, j0, o0, k);
+    }
+    unsigned int jA = 0, oA = 0, jB = 0;
+    if (k + stride < r_hi) { jA = A.map[k + stride]; oA = A.off[jA]; }
+    if (k + 2 * stride < r_hi) jB = A.map[k + 2 * stride];
+    int cur = 0;
+    for (size_t kb0 = r_lo + (size_t)blockIdx.x * B; kb0 < r_hi; kb0 += stride, k += stride, cur ^= 1) {
+        issue(cur ^ 1, k + stride < r_hi, jA, oA, k + stride);              // tile t+1
+        unsigned int oB = 0, jC = 0;
+        if (k + 2 * stride < r_hi) oB = A.off[jB];
+        if (k + 3 * stride < r_hi) jC = A.map[k + 3 * stride];
+        cp_async_wait<1>();                                                  // tile t has landed (own copies only: no barrier)
+        const double* const bb = buf(cur);
+        const double* const rd = bb + 2 * tid;                               // double index of chunk c, component e: (c*B)*2 + e
+        const double beta = bb[12 * B + tid];
+        const double covv = NS::NIN > 2 ? bb[13 * B + tid] : 0.0;
+        RB cb[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            double z = fma(w1b[q], beta, b1[q]);
+            if (NS::NIN > 2) z = fma(w1c[q], covv, z);
+            cb[q] = (RB)z;
+            g[W + q] = RB(0);
+        }
+        CUDE_UNROLL(CUDE_NODE_UNROLL)
+        for (int q = 0; q < 5; ++q) {
+            const int id = q, iw = 6 + q;                                    // positions in the sequence dG[5], 0, w[5], 0
+            const double dG = rd[(size_t)(id >> 1) * 2 * B + (id & 1)];
+            const double wq = rd[(size_t)(iw >> 1) * 2 * B + (iw & 1)];
+            mlp_backward<NS, RB>(sW, sTab, cb, (RB)dG, (RB)wq, g);
+        }
+        double dc = 0.0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const RB tq = g[W + q];
+            gb[q] += tq;
+            gbeta[q] = fma((RB)beta, tq, gbeta[q]);
+            if (NS::NIN > 2) gcov[q] = fma((RB)covv, tq, gcov[q]);
+            dc = fma((double)tq, w1b[q], dc);
+        }
+        if (k < r_hi) A.gc_rec[k] = dc;
+        jA = jB; oA = oB; jB = jC;
+    }
+    cp_async_wait<0>();
+    // ---- one partial row per warp, SimpleChains layout: rows 1..P (row 0, the sse, belongs to stage 5) ----
+    const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
+    double* const row = A.partials + (((size_t)s * gridDim.x + blockIdx.x) * nw + wid) * (P + 1);
+    if (lane == 0) row[0] = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        double v;
+        if (p < W) v = (double)g[p];                                        // W1[:,0]  (dG column)
+        else if (p < 2 * W) v = (double)gbeta[p - W];                       // W1[:,1]  (beta column)
+        else if (NS::NIN > 2 && p < 3 * W) v = (double)gcov[p - 2 * W];     // W1[:,2]  (covariate)
+        else if (p < NS::L1) v = (double)gb[p - NS::NIN * W];               // b1
+        else v = (double)g[2 * W + (p - NS::L1)];                           // hidden + output layers
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) row[1 + p] = v;
+    }
+}
+
+// ---------------------------------------------------------------- stage 5: per trajectory
+struct FinalArgs {
+    PopDev pop;
+    int n_starts, nchunks;
+    const double* neural;
+    long long neural_stride;
+    const int* sp_nrec;
+    const double* sp_beta;
+    const double* sp_wsum;
+    const double* sp_sse;
+    const unsigned int* off;
+    const double* gc_rec;
+    double cond_scale;
+    double* g_cond;                // [N x S]
+    double* partials;              // [S*nchunks*warps][P+1]
+};
+
+template <class NS, class RB>
+__global__ void __launch_bounds__(128) cude_final_kernel(const FinalArgs A) {
+    constexpr int W = NS::W, P = NS::P;
+    __shared__ double sTab[256];
+    __shared__ double sWd[(P + 1) & ~1];
+    __shared__ RB sWr[(P + 1) & ~1];
+    const int B = blockDim.x, tid = threadIdx.x, N = A.pop.n_ind;
+    const int c = blockIdx.x / A.n_starts, s = blockIdx.x - c * A.n_starts;      // chunk-major like stage 1
+    const long long prow = (long long)s * A.nchunks + c;
+    for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
+    for (int p = tid; p < P; p += B) { const double w = A.neural[(long long)s * A.neural_stride + p]; sWd[p] = w; sWr[p] = (RB)w; }
+    __syncthreads();
+    const int i = c * B + tid;
+    const bool inb = i < N;
+    const size_t j = (size_t)s * N + (inb ? i : 0);
+    const int nrec = inb ? A.sp_nrec[j] : 0;
+    RB g[NS::NACC];
+#pragma unroll
+    for (int k = 0; k < NS::NACC; ++k) g[k] = RB(0);
+    double beta = 0.0, covv = 0.0, sse = 0.0;
+    if (inb && nrec >= 0) sse = A.sp_sse[j];          // failed: Inf; overflowed trajectories are the fallback's
+    if (nrec > 0) {
+        beta = A.sp_beta[j];
+        if (NS::NIN > 2) covv = A.pop.cov[i];
+        RB cb[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            double z = fma(sWd[W + q], beta, sWd[NS::NIN * W + q]);
+            if (NS::NIN > 2) z = fma(sWd[2 * W + q], covv, z);
+            cb[q] = (RB)z;
+        }
+        // the NN([0; beta]) term of conditional_production (c-peptide-models.jl:91): one node at dG = 0, weight -sum(w)
+        mlp_backward<NS, RB>(sWr, sTab, cb, RB(0), (RB)A.sp_wsum[j], g);
+        double dc = 0.0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) dc = fma((double)g[W + q], sWd[W + q], dc);
+        const double* const gr = A.gc_rec + A.off[j];
+        for (int n = 0; n < nrec; ++n) dc += gr[n];
+        A.g_cond[j] = dc * beta * A.cond_scale;       // d sse / d cond = beta * d sse / d beta
+    } else if (inb && nrec == 0) {
+        A.g_cond[j] = 0.0;
+    }
+    const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
+    double* const row = A.partials + ((size_t)prow * nw + wid) * (P + 1);
+#pragma unroll
+    for (int p = -1; p < P; ++p) {
+        double v;
+        if (p < 0) v = sse;
+        else if (p < W) v = (double)g[p];
+        else if (p < 2 * W) v = (double)g[W + (p - W)] * beta;
+        else if (NS::NIN > 2 && p < 3 * W) v = (double)g[W + (p - 2 * W)] * covv;
+        else if (p < NS::L1) v = (double)g[W + (p - NS::NIN * W)];
+        else v = (double)g[2 * W + (p - NS::L1)];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) row[1 + p] = v;
+    }
+}
+
+// ---------------------------------------------------------------- second-stage reduction over the three row sets
+// Per start s: rows of stage 4 (A: nA), stage 5 (B: nB) and the fused-kernel fallback (C: nB, zero-filled before the
+// launch, written only by flagged blocks), each [np1] wide.  Pass 1: block (seg, s) sums its share of the rows
+// (thread = column q x row group, coalesced row reads) into seg_out[s][seg][np1]; pass 2 (nseg_in rows of A only) sums the
+// segments.  Fixed order throughout: run-to-run deterministic.
+constexpr int RED_T = 256, RED_Q = 64;      // 4 row groups x up to 64 columns
+__device__ __forceinline__ double reduce_region(const double* __restrict__ p, int n, int lo, int hi, int np1, int q, int rg, int nrg) {
+    // rows [lo, hi) intersected with [0, n) of a region, column q, rows rg, rg + nrg, ...: 4 independent chains
+    lo = lo < 0 ? 0 : lo; hi = hi > n ? n : hi;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int r = lo + rg;
+    for (; r + 3 * nrg < hi; r += 4 * nrg) {
+        v0 += p[(size_t)r * np1 + q]; v1 += p[(size_t)(r + nrg) * np1 + q];
+        v2 += p[(size_t)(r + 2 * nrg) * np1 + q]; v3 += p[(size_t)(r + 3 * nrg) * np1 + q];
+    }
+    for (; r < hi; r += nrg) v0 += p[(size_t)r * np1 + q];
+    return (v0 + v1) + (v2 + v3);
+}
+__global__ void __launch_bounds__(RED_T) cude_reduce_rows(const double* __restrict__ pA, int nA, const double* __restrict__ pB,
+                                                          const double* __restrict__ pC, int nB, int np1, int out_stride,
+                                                          double* __restrict__ out) {
+    __shared__ double sh[RED_T];
+    const int s = blockIdx.y, seg = blockIdx.x, nseg = gridDim.x;
+    const int q = threadIdx.x % RED_Q, rg = threadIdx.x / RED_Q, nrg = RED_T / RED_Q;
+    const int total = nA + 2 * nB;
+    const int lo = (int)((long long)total * seg / nseg), hi = (int)((long long)total * (seg + 1) / nseg);
+    double v = 0.0;
+    if (q < np1) {
+        v = reduce_region(pA + (size_t)s * nA * np1, nA, lo, hi, np1, q, rg, nrg);
+        if (nB > 0) {
+            v += reduce_region(pB + (size_t)s * nB * np1, nB, lo - nA, hi - nA, np1, q, rg, nrg);
+            v += reduce_region(pC + (size_t)s * nB * np1, nB, lo - nA - nB, hi - nA - nB, np1, q, rg, nrg);
+        }
+    }
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    if (rg == 0 && q < np1) {
+        double t = sh[q];
+        for (int g2 = 1; g2 < nrg; ++g2) t += sh[g2 * RED_Q + q];
+        out[(size_t)s * out_stride + (size_t)seg * np1 + q] = t;
+    }
+}
+
+}  // namespace cude

@@ -25,13 +25,14 @@ def _iptr(a):
 class SolverOptions:
     """abstol / reltol / maxiters of the reference's `solve` call (OrdinaryDiffEq defaults)."""
 
-    def __init__(self, abstol=1e-6, reltol=1e-3, maxiters=1000000, block=0, precision=0, balance=0):
+    def __init__(self, abstol=1e-6, reltol=1e-3, maxiters=1000000, block=0, precision=0, balance=0, split=0):
         self.abstol, self.reltol, self.maxiters, self.block, self.precision = abstol, reltol, maxiters, block, precision
         self.balance = balance      # 1: regroup each start's individuals by earlier step counts (iterative workloads)
+        self.split = split          # gradient pipeline: 0 automatic, 1 fused kernel, 2 split pipeline (cude_b200.h)
 
     def c(self):
         return _lib.cude_opts(self.abstol, self.reltol, int(self.maxiters), int(self.precision), int(self.block),
-                              int(self.balance))
+                              int(self.balance), int(self.split))
 
 
 class Context:

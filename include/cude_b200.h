@@ -67,6 +67,14 @@ typedef struct {
                     * 32 lanes of a warp finish together (~12 % fewer warp-steps).  Per-trajectory results (sse,
                     * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping.
                     * Costs 8 bytes of device memory per trajectory on the population (two key buffers). */
+    int split;     /* gradient pipeline of loss + full-gradient calls with per-start networks:
+                    * 0 (default) = automatic: batches of >= 200 000 trajectories run the split pipeline (forward solve +
+                    *     adjoint recursion per trajectory -> one thread per accepted step for the network's forward +
+                    *     backward evaluations -> per-trajectory finish; needs ~2.2 KB of device memory per trajectory of a
+                    *     group of starts, the library sizes the groups), smaller ones the fused single-kernel adjoint;
+                    * 1 = always the fused kernel; 2 = always the split pipeline.
+                    * Same discrete adjoint either way: per-trajectory sse bit-identical, gradients equal to summation
+                    * order (1e-15). */
 } cude_opts;
 
 typedef struct {
