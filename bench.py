@@ -318,7 +318,7 @@ def run_ours(args):
     # headline: natural lane order (cude_opts.balance = 0).  Lane balancing (each start's individuals grouped by the step
     # counts of an earlier call) is reported as a secondary figure only: on this bench's *repeated identical inputs* the
     # prediction is perfect (+12 %), under real Adam training it is worth +3 % (profiles/r01_adam_balance.json)
-    opts = cu.SolverOptions(block=args.block, precision=args.precision, balance=args.balance)
+    opts = cu.SolverOptions(block=args.block, precision=args.precision, balance=args.balance, split=args.split)
 
     def step_resident():
         # loss+gradient kernel -> block-partial reduction into `sums` -> NCCL all-reduce of `sums` (N > 1)
@@ -378,7 +378,7 @@ def run_ours(args):
     loss_only_value = N_total * S / (timed(step_loss_only, 2) / 2 * 1e-3)
 
     # secondary figure: the same step with lane balancing on (see the note at `opts`)
-    opts_bal = cu.SolverOptions(block=args.block, precision=args.precision, balance=1)
+    opts_bal = cu.SolverOptions(block=args.block, precision=args.precision, balance=1, split=args.split)
     def step_balanced():
         shard.step(opts_bal)
     for _ in range(2):
@@ -388,7 +388,7 @@ def run_ours(args):
     # secondary figure: opts.precision = 2 (forward pass FP64 bit for bit, FP32 network only in the adjoint sweep)
     fp32adj_value = None
     if args.precision == 0:
-        opts_p2 = cu.SolverOptions(block=args.block, precision=2)
+        opts_p2 = cu.SolverOptions(block=args.block, precision=2, split=args.split)
         def step_p2():
             shard.step(opts_p2)
         step_p2()
@@ -515,6 +515,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--precision", type=int, default=0, help="0 = FP64 (headline, parity-gated); 1 = FP32 network (looser bound); 2 = FP64 forward, FP32 adjoint network")
     ap.add_argument("--balance", type=int, default=0, help="cude_opts.balance for the headline: 0 = natural lane order (default), 1 = regroup lanes by earlier step counts")
+    ap.add_argument("--split", type=int, default=0, help="cude_opts.split: 0 = automatic (split gradient pipeline for large batches), 1 = fused kernel, 2 = split pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-individuals", type=int, default=4000)
     ap.add_argument("--cpu-starts", type=int, default=64)

@@ -41,9 +41,6 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
-#ifndef CUDE_SPLIT_MIN_TRAJ
-#define CUDE_SPLIT_MIN_TRAJ 200000          // opts.split = 0 (auto): the split gradient pipeline (6 launches) from this many trajectories per call
-#endif
 #ifndef CUDE_SPLIT_BYTES
 #define CUDE_SPLIT_BYTES (20ull << 30)      // device memory the split pipeline's step records may take per group of starts
 #endif
@@ -71,7 +68,13 @@ struct cude_ctx {
     struct KernCfg { const void* kern; size_t smem; int block; };
     std::vector<KernCfg> kern_cfg;      // kernel configurations whose shared-memory attributes have been set
     int sm_count = 0;
-    DevBuf sp_rec, sp_w, sp_misc, sp_map, sp_gc;   // split gradient pipeline: step records, node weights, per-trajectory arrays, record map, per-record d/d beta
+    // split gradient pipeline: three sets of {step records, node weights, per-trajectory arrays, record map, per-record
+    // d/d beta, partial rows} so that consecutive groups of starts are in different stages at the same time; the
+    // memory-bound stages run on the high-priority side stream s_hi next to the compute-bound ones on `stream`
+    struct SplitSet { DevBuf rec, w, misc, map, gc, part; cudaEvent_t ev_k1 = nullptr, ev_scan = nullptr, ev_k3 = nullptr, ev_free = nullptr; };
+    SplitSet sp[3];
+    cudaStream_t s_hi = nullptr;
+    cudaEvent_t ev_fork = nullptr;
     // NCCL communicator of a sharded population (cude_comm_init_rank, or the ranks of a cude_mctx): the per-start sums
     // are all-reduced in place on `stream` (cude_multi.inl)
     void* comm = nullptr;
@@ -206,9 +209,17 @@ extern "C" int cude_ctx_destroy(cude_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
-    DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch,
-                      &ctx->sp_rec, &ctx->sp_w, &ctx->sp_misc, &ctx->sp_map, &ctx->sp_gc};
+    DevBuf* bufs[] = {&ctx->neural, &ctx->cond, &ctx->sse, &ctx->partials, &ctx->sums, &ctx->gcond, &ctx->counters, &ctx->scratch};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->s_hi) cudaStreamSynchronize(ctx->s_hi);
+    for (auto& st : ctx->sp) {
+        DevBuf* sb[] = {&st.rec, &st.w, &st.misc, &st.map, &st.gc, &st.part};
+        for (DevBuf* b : sb) if (b->p) cudaFree(b->p);
+        cudaEvent_t* ev[] = {&st.ev_k1, &st.ev_scan, &st.ev_k3, &st.ev_free};
+        for (cudaEvent_t* e : ev) if (*e) cudaEventDestroy(*e);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->s_hi) cudaStreamDestroy(ctx->s_hi);
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -234,6 +245,7 @@ extern "C" int cude_ctx_set_stream(cude_ctx* ctx, void* cuda_stream) {
     return CUDE_OK;
 }
 
+static void trace_dump();
 static int collect_stats(cude_ctx* ctx) {
     if (!ctx->stats_pending) return CUDE_OK;
     CU_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -246,6 +258,7 @@ static int collect_stats(cude_ctx* ctx) {
     ctx->stats.n_rhs = 6ull * (ctx->stats.n_acc + ctx->stats.n_rej) + 2ull * ctx->stats.n_traj;
     ctx->stats.kernel_ms = ms;
     ctx->stats_pending = false;
+    trace_dump();
     return CUDE_OK;
 }
 
@@ -397,7 +410,10 @@ static int choose_block(const cude_opts* o, int n_ind, bool flat) {
 // ---- lane balancing (cude_opts.balance): per start, the individuals sorted by the step counts of an earlier call.
 // The kernel writes keys (steps << 24 | individual) in natural order on refresh calls; a stable radix sort over the top
 // 8 bits of each start's segment yields the order the following calls run in.
-static const int BAL_REFRESH = 8;            // refresh the grouping every this many balanced calls
+#ifndef CUDE_BAL_REFRESH
+#define CUDE_BAL_REFRESH 8
+#endif
+static const int BAL_REFRESH = CUDE_BAL_REFRESH;            // refresh the grouping every this many balanced calls
 static bool balance_applies(const cude_opts& o, const cude_population* pop, bool grad, bool flat, int n_starts) {
     return o.balance == 1 && grad && !flat && pop->n_ind >= 4096 && pop->n_ind < (1 << 24) && n_starts <= 65536;
 }
@@ -506,8 +522,42 @@ static SplitKernels select_split(const cude_net* net, bool fbwd, bool wc) {
 // Loss + full gradient of n_starts starts through the five stages, in groups of starts whose step records fit the
 // memory budget.  `a` carries the call's arguments (pointers to start 0); `fused` is the fused gradient kernel, launched
 // once per group as the fallback for trajectories with more than SPLIT_CAP accepted steps (its blocks return at once
-// when the block has none).  All launches go to ctx->stream; nothing synchronises.
-static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int nchunks, bool fbwd, bool wc,
+// when the block has none).  Nothing synchronises with the host.
+//
+// Two streams: the compute-bound stages 1 and 4 (and the fallback) run back to back on ctx->stream; the memory-bound
+// stages 2, 3 and 5 and the second-stage reduction run on a high-priority side stream with small grids, so that they
+// share the SMs with the compute stages of the neighbouring groups (three buffer sets keep three groups in flight):
+//   ctx->stream : K1(0) K1(1) K4(0) K1(2) K4(1) K1(3) ...
+//   side stream :       K2(0) K2(1) K5(0) K2(2) K5(1) ...
+#ifndef CUDE_RECUR_BLOCKS
+#define CUDE_RECUR_BLOCKS 2      // blocks of 128 threads per SM for the adjoint recursion (stage 2)
+#endif
+// Diagnostic timeline (environment variable CUDE_SPLIT_TRACE=1): timing events around every stage on both streams, printed
+// to stderr by the next cude_get_stats.  Off in normal operation.
+struct TraceEv { const char* name; int group; cudaEvent_t a, b; };
+static std::vector<TraceEv> g_trace;
+static cudaEvent_t g_trace_base = nullptr;
+static bool trace_on() { static int on = -1; if (on < 0) { const char* e = getenv("CUDE_SPLIT_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on == 1; }
+static void trace_begin(cudaStream_t s, const char* name, int g) {
+    if (!trace_on()) return;
+    TraceEv t{name, g, nullptr, nullptr};
+    cudaEventCreate(&t.a); cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, s);
+    g_trace.push_back(t);
+}
+static void trace_end(cudaStream_t s) { if (trace_on() && !g_trace.empty()) cudaEventRecord(g_trace.back().b, s); }
+static void trace_dump() {
+    if (!trace_on() || g_trace.empty()) return;
+    for (auto& t : g_trace) {
+        float t0 = 0, t1 = 0;
+        cudaEventSynchronize(t.b);
+        cudaEventElapsedTime(&t0, g_trace_base, t.a); cudaEventElapsedTime(&t1, g_trace_base, t.b);
+        fprintf(stderr, "trace %-8s g%-3d %9.3f -> %9.3f  (%7.3f ms)\n", t.name, t.group, t0, t1, t1 - t0);
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    g_trace.clear();
+}
+static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int nchunks, bool fbwd, bool wc, size_t n_w,
                      eval_kernel_t fused, size_t smem_fused, double* d_sums_out, int* launches) {
     const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
     const int M = a.pop.max_obs, K = a.pop.max_knots;
@@ -518,16 +568,30 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
         ctx->sm_count = prop.multiProcessorCount;
     }
-    // ---- groups of starts ----
+    if (!ctx->s_hi) {
+        int least = 0, greatest = 0;
+        CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU_TRY(ctx, cudaStreamCreateWithPriority(&ctx->s_hi, cudaStreamNonBlocking, greatest));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (auto& st : ctx->sp) {
+            CU_TRY(ctx, cudaEventCreateWithFlags(&st.ev_k1, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&st.ev_scan, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&st.ev_k3, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&st.ev_free, cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t sM = ctx->stream, sH = ctx->s_hi;
+    // ---- groups of starts: three sets of buffers share the budget ----
     const size_t per_traj = (size_t)(SPLIT_W + SPLIT_WW) * SPLIT_CAP * 8 + (size_t)SPLIT_CAP * (4 + 8) + (size_t)M * 8 + 4 * 8 + 8 + 3 * (size_t)np1 * 8 / 32 + 64;
     size_t free_b = 0, total_b = 0;
     CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t have = 0;
+    for (auto& st : ctx->sp) have += st.rec.cap + st.w.cap + st.misc.cap + st.map.cap + st.gc.cap + st.part.cap;
     size_t budget = CUDE_SPLIT_BYTES;
-    const size_t have = ctx->sp_rec.cap + ctx->sp_w.cap + ctx->sp_misc.cap + ctx->sp_map.cap + ctx->sp_gc.cap;
     if (budget > (free_b + have) / 2) budget = (free_b + have) / 2;
-    long long sg = (long long)(budget / (per_traj * (size_t)N));
+    long long sg = (long long)(budget / 3 / (per_traj * (size_t)N));
     if (sg < 1) sg = 1;
-    if (sg > S) sg = S;
+    if (sg > (S + 2) / 3) sg = (S + 2) / 3;                                   // at least three groups when there are three starts
     while ((long long)N * sg * SPLIT_CAP > 0x7fffffffLL && sg > 1) --sg;      // 32-bit record offsets
     if ((long long)N * SPLIT_CAP > 0x7fffffffLL) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: population too large for one call; shard the individuals");
     const int ngroups = (int)((S + sg - 1) / sg);
@@ -543,23 +607,23 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     const size_t rowsA = (size_t)Sg * nA, rowsB = (size_t)Sg * nB;
     int nseg = (nA + 2 * nB + 2047) / 2048;                                 // second-stage reduction: ~2048 rows per block
     if (nseg > 64) nseg = 64;
-    int rc;
-    if ((rc = ensure(ctx, ctx->sp_rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->sp_w, ntg * SPLIT_WW * SPLIT_CAP * sizeof(double)))) return rc;
-    // per-trajectory arrays: res [M] , beta, wsum, sse (double), off (uint, +1), nrec (int); then bsum (uint, nscan + 1), blkflag (int),
-    // segment sums of the reduction
+    // per-trajectory arrays of a set: res [M] , beta, wsum, sse (double), off (uint, +1), nrec (int); then bsum (uint, nscan + 1),
+    // blkflag (int), segment sums of the reduction
     const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_wsum = o_beta + ntg * 8, o_sse = o_wsum + ntg * 8, o_off = o_sse + ntg * 8,
                  o_nrec = o_off + ((ntg + 2) * 4 + 7) / 8 * 8, o_bsum = o_nrec + (ntg * 4 + 7) / 8 * 8,
                  o_flag = o_bsum + (((size_t)nscan + 2) * 4 + 7) / 8 * 8, o_seg = o_flag + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8,
                  misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
-    if ((rc = ensure(ctx, ctx->sp_misc, misc_bytes))) return rc;
-    if ((rc = ensure(ctx, ctx->sp_map, ntg * SPLIT_CAP * sizeof(unsigned int)))) return rc;
-    if ((rc = ensure(ctx, ctx->sp_gc, ntg * SPLIT_CAP * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->partials, (rowsA + 2 * rowsB) * np1 * sizeof(double)))) return rc;
-    char* const misc = (char*)ctx->sp_misc.p;
-    double* const pA = (double*)ctx->partials.p;
-    double* const pB = pA + rowsA * np1;
-    double* const pC = pB + rowsB * np1;
+    int rc;
+    const int nsets = ngroups < 3 ? ngroups : 3;
+    for (int k = 0; k < nsets; ++k) {
+        cude_ctx::SplitSet& st = ctx->sp[k];
+        if ((rc = ensure(ctx, st.rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, st.w, ntg * SPLIT_WW * SPLIT_CAP * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, st.misc, misc_bytes))) return rc;
+        if ((rc = ensure(ctx, st.map, ntg * SPLIT_CAP * sizeof(unsigned int)))) return rc;
+        if ((rc = ensure(ctx, st.gc, ntg * SPLIT_CAP * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, st.part, (rowsA + 2 * rowsB) * np1 * sizeof(double)))) return rc;
+    }
     // ---- kernel attributes ----
     const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
     const size_t smem1 = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, false, false, true);    // loss-only rows + the 5 dG rows
@@ -567,75 +631,115 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     if ((rc = prep_kernel(ctx, (const void*)sk.k1, B, smem1))) return rc;
     if ((rc = prep_kernel(ctx, (const void*)sk.k3, CUDE_NODE_THREADS, smem3))) return rc;
     if ((rc = prep_kernel(ctx, (const void*)fused, B, smem_fused))) return rc;
+    if (wc && (rc = wconst_upload(ctx, a.neural, n_w))) return rc;          // the whole call's weights; groups index it by wc_base
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, sM));
+    CU_TRY(ctx, cudaStreamWaitEvent(sH, ctx->ev_fork, 0));
+    if (trace_on()) { if (!g_trace_base) cudaEventCreate(&g_trace_base); cudaEventRecord(g_trace_base, sM); }
 
-    for (int g0 = 0; g0 < S; g0 += Sg) {
-        const int ns = (S - g0 < Sg) ? S - g0 : Sg;
-        const size_t nt = (size_t)N * ns;
+    struct GroupView { EvalArgs e; double *wsum, *seg, *pA, *pB, *pC; unsigned int *off, *bsum; int ns, g0; size_t nt; unsigned nblk; };
+    auto view = [&](int g) {
+        cude_ctx::SplitSet& st = ctx->sp[g % 3];
+        GroupView v;
+        v.g0 = g * Sg;
+        v.ns = (S - v.g0 < Sg) ? S - v.g0 : Sg;
+        v.nt = (size_t)N * v.ns;
+        v.nblk = (unsigned)((size_t)v.ns * nchunks);
+        char* const misc = (char*)st.misc.p;
         EvalArgs e = a;
-        e.n_starts = ns;
-        e.neural = a.neural + (size_t)g0 * a.neural_stride;
-        e.cond = a.cond + (size_t)g0 * N;
-        e.sse_out = a.sse_out ? a.sse_out + (size_t)g0 * N : nullptr;
-        e.g_cond = a.g_cond + (size_t)g0 * N;
-        e.order = a.order ? a.order + (size_t)g0 * N : nullptr;
-        e.keys_out = a.keys_out ? a.keys_out + (size_t)g0 * N : nullptr;
+        e.n_starts = v.ns;
+        e.neural = a.neural + (size_t)v.g0 * a.neural_stride;
+        e.wc_base = a.wc_base + (long long)v.g0 * a.neural_stride;
+        e.cond = a.cond + (size_t)v.g0 * N;
+        e.sse_out = a.sse_out ? a.sse_out + (size_t)v.g0 * N : nullptr;
+        e.g_cond = a.g_cond + (size_t)v.g0 * N;
+        e.order = a.order ? a.order + (size_t)v.g0 * N : nullptr;
+        e.keys_out = a.keys_out ? a.keys_out + (size_t)v.g0 * N : nullptr;
         e.partials = nullptr;
-        e.sp_rec = (double*)ctx->sp_rec.p;
+        e.sp_rec = (double*)st.rec.p;
         e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
         e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
-        double* const d_wsum = (double*)(misc + o_wsum);
-        unsigned int* const d_off = (unsigned int*)(misc + o_off);
-        unsigned int* const d_bsum = (unsigned int*)(misc + o_bsum);
-        double* const d_seg = (double*)(misc + o_seg);
-        const unsigned nblk = (unsigned)((size_t)ns * nchunks);
-        CU_TRY(ctx, cudaMemsetAsync(e.sp_blkflag, 0, (size_t)nblk * sizeof(int), ctx->stream));
-        CU_TRY(ctx, cudaMemsetAsync(pC, 0, (size_t)ns * nB * np1 * sizeof(double), ctx->stream));
-        if (wc) {
-            const size_t n_w = (size_t)a.neural_stride * (ns - 1) + P;
-            if ((rc = wconst_upload(ctx, e.neural, n_w))) return rc;
-        }
-        // stage 1: forward solve -> step records {t, h, dG[5]}, residuals
-        sk.k1<<<nblk, B, smem1, ctx->stream>>>(e);
-        CU_TRY(ctx, cudaGetLastError());
-        // stage 2: adjoint recursion -> node weights
-        RecurArgs ra{};
-        ra.pop = a.pop; ra.ntraj = (long long)nt; ra.sp_rec = e.sp_rec; ra.sp_w = (double*)ctx->sp_w.p; ra.sp_res = e.sp_res; ra.sp_nrec = e.sp_nrec; ra.sp_wsum = d_wsum;
-        cude_recur_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ra);
-        CU_TRY(ctx, cudaGetLastError());
-        // stage 3: flat record list
-        const int nsc = (int)((nt + SCAN_TILE - 1) / SCAN_TILE);
-        cude_scan_sums<<<nsc, SCAN_T, 0, ctx->stream>>>(e.sp_nrec, (long long)nt, d_bsum);
-        cude_scan_bsums<<<1, 1024, 0, ctx->stream>>>(d_bsum, nsc);
-        cude_scan_final<<<nsc, SCAN_T, 0, ctx->stream>>>(e.sp_nrec, (long long)nt, d_bsum, d_off, (unsigned int*)ctx->sp_map.p);
-        CU_TRY(ctx, cudaGetLastError());
-        // stage 4: network forward + backward, one thread per record
-        NodeArgs na{};
-        na.pop = a.pop; na.neural = e.neural; na.neural_stride = a.neural_stride;
-        na.sp_rec = e.sp_rec; na.sp_w = (const double*)ctx->sp_w.p; na.off = d_off; na.map = (const unsigned int*)ctx->sp_map.p; na.sp_beta = e.sp_beta;
-        na.gc_rec = (double*)ctx->sp_gc.p; na.partials = pA;
-        sk.k3<<<dim3((unsigned)G, (unsigned)ns), CUDE_NODE_THREADS, smem3, ctx->stream>>>(na);
-        CU_TRY(ctx, cudaGetLastError());
-        // stage 5: NN([0;beta]) node, d/d cond, sse rows
-        FinalArgs fa{};
-        fa.pop = a.pop; fa.n_starts = ns; fa.nchunks = nchunks; fa.neural = e.neural; fa.neural_stride = a.neural_stride;
-        fa.sp_nrec = e.sp_nrec; fa.sp_beta = e.sp_beta; fa.sp_wsum = d_wsum; fa.sp_sse = e.sp_sse; fa.off = d_off;
-        fa.gc_rec = (const double*)ctx->sp_gc.p; fa.cond_scale = a.cond_scale; fa.g_cond = e.g_cond; fa.partials = pB;
-        sk.k4<<<nblk, B, 0, ctx->stream>>>(fa);
-        CU_TRY(ctx, cudaGetLastError());
-        // fallback: trajectories with more than SPLIT_CAP accepted steps through the fused kernel (flagged blocks only)
-        EvalArgs f = e;
-        f.partials = pC; f.only_flag = e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
-        fused<<<nblk, B, smem_fused, ctx->stream>>>(f);
-        CU_TRY(ctx, cudaGetLastError());
-        if (wc && (rc = wconst_used(ctx))) return rc;
-        *launches += 8;
-        if (d_sums_out) {
-            cude_reduce_rows<<<dim3((unsigned)nseg, (unsigned)ns), RED_T, 0, ctx->stream>>>(pA, nA, pB, pC, nB, np1, nseg * np1, d_seg);
-            cude_reduce_rows<<<dim3(1, (unsigned)ns), RED_T, 0, ctx->stream>>>(d_seg, nseg, nullptr, nullptr, 0, np1, np1, d_sums_out + (size_t)g0 * np1);
+        v.e = e;
+        v.wsum = (double*)(misc + o_wsum); v.off = (unsigned int*)(misc + o_off); v.bsum = (unsigned int*)(misc + o_bsum);
+        v.seg = (double*)(misc + o_seg);
+        v.pA = (double*)st.part.p; v.pB = v.pA + rowsA * np1; v.pC = v.pB + rowsB * np1;
+        return v;
+    };
+    for (int g = 0; g <= ngroups; ++g) {
+        if (g < ngroups) {
+            cude_ctx::SplitSet& st = ctx->sp[g % 3];
+            const GroupView v = view(g);
+            if (g >= 3) CU_TRY(ctx, cudaStreamWaitEvent(sM, st.ev_free, 0));          // the set's previous group has been finished
+            CU_TRY(ctx, cudaMemsetAsync(v.e.sp_blkflag, 0, (size_t)v.nblk * sizeof(int), sM));
+            CU_TRY(ctx, cudaMemsetAsync(v.pC, 0, (size_t)v.ns * nB * np1 * sizeof(double), sM));
+            // stage 1: forward solve -> step records {t, h, dG[5]}, residuals
+            trace_begin(sM, "fwd", g);
+            sk.k1<<<v.nblk, B, smem1, sM>>>(v.e);
+            trace_end(sM);
             CU_TRY(ctx, cudaGetLastError());
-            *launches += 2;
+            CU_TRY(ctx, cudaEventRecord(st.ev_k1, sM));
+            CU_TRY(ctx, cudaStreamWaitEvent(sH, st.ev_k1, 0));
+            // stage 2: adjoint recursion -> node weights
+            RecurArgs ra{};
+            ra.pop = a.pop; ra.ntraj = (long long)v.nt; ra.sp_rec = v.e.sp_rec; ra.sp_w = (double*)st.w.p; ra.sp_res = v.e.sp_res;
+            ra.sp_nrec = v.e.sp_nrec; ra.sp_wsum = v.wsum;
+            long long rblocks = (long long)(v.nt + 127) / 128;
+            if (rblocks > (long long)ctx->sm_count * CUDE_RECUR_BLOCKS) rblocks = (long long)ctx->sm_count * CUDE_RECUR_BLOCKS;
+            trace_begin(sH, "recur", g);
+            cude_recur_kernel<<<(unsigned)rblocks, 128, 0, sH>>>(ra);
+            trace_end(sH);
+            CU_TRY(ctx, cudaGetLastError());
+            trace_begin(sH, "scan", g);
+            // stage 3: flat record list
+            const int nsc = (int)((v.nt + SCAN_TILE - 1) / SCAN_TILE);
+            cude_scan_sums<<<nsc, SCAN_T, 0, sH>>>(v.e.sp_nrec, (long long)v.nt, v.bsum);
+            cude_scan_bsums<<<1, 1024, 0, sH>>>(v.bsum, nsc);
+            cude_scan_final<<<nsc, SCAN_T, 0, sH>>>(v.e.sp_nrec, (long long)v.nt, v.bsum, v.off, (unsigned int*)st.map.p);
+            trace_end(sH);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaEventRecord(st.ev_scan, sH));
+            *launches += 5;
+        }
+        if (g >= 1) {
+            cude_ctx::SplitSet& st = ctx->sp[(g - 1) % 3];
+            const GroupView v = view(g - 1);
+            CU_TRY(ctx, cudaStreamWaitEvent(sM, st.ev_scan, 0));
+            // stage 4: network forward + backward, one thread per record
+            NodeArgs na{};
+            na.pop = a.pop; na.neural = v.e.neural; na.neural_stride = a.neural_stride; na.wc_base = v.e.wc_base;
+            na.sp_rec = v.e.sp_rec; na.sp_w = (const double*)st.w.p; na.off = v.off; na.map = (const unsigned int*)st.map.p;
+            na.sp_beta = v.e.sp_beta; na.gc_rec = (double*)st.gc.p; na.partials = v.pA;
+            trace_begin(sM, "node", g - 1);
+            sk.k3<<<dim3((unsigned)G, (unsigned)v.ns), CUDE_NODE_THREADS, smem3, sM>>>(na);
+            trace_end(sM);
+            CU_TRY(ctx, cudaGetLastError());
+            // fallback: trajectories with more than SPLIT_CAP accepted steps through the fused kernel (flagged blocks only)
+            EvalArgs f = v.e;
+            f.partials = v.pC; f.only_flag = v.e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
+            fused<<<v.nblk, B, smem_fused, sM>>>(f);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaEventRecord(st.ev_k3, sM));
+            CU_TRY(ctx, cudaStreamWaitEvent(sH, st.ev_k3, 0));
+            // stage 5: NN([0;beta]) node, d/d cond, sse rows; then the second-stage reduction
+            FinalArgs fa{};
+            fa.pop = a.pop; fa.n_starts = v.ns; fa.nchunks = nchunks; fa.neural = v.e.neural; fa.neural_stride = a.neural_stride;
+            fa.sp_nrec = v.e.sp_nrec; fa.sp_beta = v.e.sp_beta; fa.sp_wsum = v.wsum; fa.sp_sse = v.e.sp_sse; fa.off = v.off;
+            fa.gc_rec = (const double*)st.gc.p; fa.cond_scale = a.cond_scale; fa.g_cond = v.e.g_cond; fa.partials = v.pB;
+            trace_begin(sH, "final", g - 1);
+            sk.k4<<<v.nblk, B, 0, sH>>>(fa);
+            CU_TRY(ctx, cudaGetLastError());
+            *launches += 3;
+            if (d_sums_out) {
+                cude_reduce_rows<<<dim3((unsigned)nseg, (unsigned)v.ns), RED_T, 0, sH>>>(v.pA, nA, v.pB, v.pC, nB, np1, nseg * np1, v.seg);
+                cude_reduce_rows<<<dim3(1, (unsigned)v.ns), RED_T, 0, sH>>>(v.seg, nseg, nullptr, nullptr, 0, np1, np1, d_sums_out + (size_t)v.g0 * np1);
+                CU_TRY(ctx, cudaGetLastError());
+                *launches += 2;
+            }
+            trace_end(sH);
+            CU_TRY(ctx, cudaEventRecord(st.ev_free, sH));
         }
     }
+    CU_TRY(ctx, cudaStreamWaitEvent(sM, ctx->sp[(ngroups - 1) % 3].ev_free, 0));    // join: the side stream is in order
+    if (wc && (rc = wconst_used(ctx))) return rc;
     return CUDE_OK;
 }
 
@@ -729,9 +833,9 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     const size_t smem = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, adj, mixed || (fbwd && adj), bsens);
     if ((rc = prep_kernel(ctx, (const void*)kern, B, smem))) return rc;
 
-    // loss + full gradient of a large batch: the split pipeline (opts.split: 0 auto, 1 never, 2 always)
-    const bool use_split = adj && !flat && !mixed && want_neural_grad && d_g_cond && o.split != 1 &&
-                           (o.split == 2 || ntraj >= CUDE_SPLIT_MIN_TRAJ);
+    // loss + full gradient through the split pipeline only on request (opts.split = 2): measured 5 - 15 % slower than the
+    // fused kernel on B200 (profiles/README.md, round 2), kept as a parity-tested alternative
+    const bool use_split = adj && !flat && !mixed && want_neural_grad && d_g_cond && o.split == 2;
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
@@ -739,7 +843,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
     int launches = 0;
     if (use_split) {
-        if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, kern, smem, d_sums_out, &launches))) return rc;
+        if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
     } else {
         if (wc && (rc = wconst_upload(ctx, d_neural, n_w))) return rc;
         kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);

@@ -130,6 +130,7 @@ struct EvalArgs {
     double* sp_beta;               // [N x S] beta = exp(cond)
     double* sp_sse;                // [N x S] sse (Inf when failed)
     int* sp_blkflag;               // [blocks] set when a trajectory of the block overflowed SPLIT_CAP (fused-kernel fallback)
+    long long wc_base;             // offset of the call's first start in the constant weight array (WC instantiations)
     const int* only_flag;          // fused GRAD kernel as that fallback: run only the trajectories with only_flag[j] < 0 of flagged blocks
 };
 
@@ -541,7 +542,7 @@ cude_eval_kernel(const EvalArgs A) {
     double wuni[WC ? P : 1];         // WC: the weights as block-uniform values, loaded here in convergent code
     if constexpr (WC) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[wofs + p];
+        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[A.wc_base + wofs + p];
     }
     const double* const sW = WC ? wuni : sWs;
     R* const sWr = MIXED ? reinterpret_cast<R*>(sWs + ((P + 1) & ~1)) : reinterpret_cast<R*>(const_cast<double*>(sW));   // network weights as R

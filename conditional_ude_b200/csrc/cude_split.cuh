@@ -35,12 +35,16 @@ struct RecurArgs {
     double* sp_wsum;               // [ntraj]
 };
 
+#ifndef CUDE_RECUR_PF
+#define CUDE_RECUR_PF 4        // (t, h) of this many steps in flight per thread (the kernel is bound by the latency of that load)
+#endif
 __global__ void __launch_bounds__(128) cude_recur_kernel(const RecurArgs A) {
     using namespace tab;
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= A.ntraj) return;
+    // grid-stride over the trajectories: launched with a few blocks per SM on a side stream, so that it shares the SMs
+    // with the compute-bound stages of the neighbouring groups instead of displacing them
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < A.ntraj; j += (long long)gridDim.x * blockDim.x) {
     const int nrec = A.sp_nrec[j];
-    if (nrec <= 0) { A.sp_wsum[j] = 0.0; return; }
+    if (nrec <= 0) { A.sp_wsum[j] = 0.0; continue; }
     const int N = A.pop.n_ind;
     const int i = (int)(j % N);
     const double k0 = A.pop.k0[i], k1 = A.pop.k1[i], k2 = A.pop.k2[i];
@@ -54,10 +58,15 @@ __global__ void __launch_bounds__(128) cude_recur_kernel(const RecurArgs A) {
     double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;
     const double* rec = A.sp_rec + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_W;
     double* wrec = A.sp_w + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_WW;
-    double2 th_next = *reinterpret_cast<const double2*>(rec);       // (t, h) fetched one step ahead of its use
+    double2 pf[CUDE_RECUR_PF];                                       // (t, h) of steps n, n-1, ..: fetched ahead of their use
+#pragma unroll
+    for (int q = 0; q < CUDE_RECUR_PF; ++q)
+        pf[q] = (nrec - 1 - q >= 0) ? *reinterpret_cast<const double2*>(rec - (size_t)q * SPLIT_W) : make_double2(0.0, 0.0);
     for (int n = nrec - 1; n >= 0; --n, rec -= SPLIT_W, wrec -= SPLIT_WW) {
-        const double2 th = th_next;
-        if (n > 0) th_next = *reinterpret_cast<const double2*>(rec - SPLIT_W);
+        const double2 th = pf[0];
+#pragma unroll
+        for (int q = 0; q + 1 < CUDE_RECUR_PF; ++q) pf[q] = pf[q + 1];
+        if (n - CUDE_RECUR_PF >= 0) pf[CUDE_RECUR_PF - 1] = *reinterpret_cast<const double2*>(rec - (size_t)CUDE_RECUR_PF * SPLIT_W);
         const double tn = th.x, h = th.y;
         double kb[7][2];
 #pragma unroll
@@ -128,6 +137,7 @@ __global__ void __launch_bounds__(128) cude_recur_kernel(const RecurArgs A) {
         t_next = tn;
     }
     A.sp_wsum[j] = -wsum;      // the node t0 itself has dG = 0 and cancels against its share of the NN([0;beta]) term
+    }
 }
 
 // ---------------------------------------------------------------- stage 3: scan of the step counts
@@ -222,6 +232,7 @@ struct NodeArgs {
     PopDev pop;
     const double* neural;          // the group's first start: start s uses neural + s*neural_stride
     long long neural_stride;
+    long long wc_base;             // offset of the group's first start in the constant weight array (WC)
     const double* sp_rec;          // [N x S][SPLIT_CAP][SPLIT_W]  {t, h, dG[5], 0}
     const double* sp_w;            // [N x S][SPLIT_CAP][SPLIT_WW] {w[5], 0}
     const unsigned int* off;       // [N x S + 1]
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(CUDE_NODE_THREADS, CUDE_NODE_MIN_BLOCKS) cude_
     double wuni[(WC && !F32) ? P : 1];
     if constexpr (WC && !F32) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[wofs + p];
+        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[A.wc_base + wofs + p];
     } else {
         RB* const w = reinterpret_cast<RB*>(sWs);
         for (int p = tid; p < P; p += B) w[p] = (RB)A.neural[wofs + p];

@@ -68,13 +68,13 @@ typedef struct {
                     * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping.
                     * Costs 8 bytes of device memory per trajectory on the population (two key buffers). */
     int split;     /* gradient pipeline of loss + full-gradient calls with per-start networks:
-                    * 0 (default) = automatic: batches of >= 200 000 trajectories run the split pipeline (forward solve +
-                    *     adjoint recursion per trajectory -> one thread per accepted step for the network's forward +
-                    *     backward evaluations -> per-trajectory finish; needs ~2.2 KB of device memory per trajectory of a
-                    *     group of starts, the library sizes the groups), smaller ones the fused single-kernel adjoint;
-                    * 1 = always the fused kernel; 2 = always the split pipeline.
-                    * Same discrete adjoint either way: per-trajectory sse bit-identical, gradients equal to summation
-                    * order (1e-15). */
+                    * 0, 1 = the fused single-kernel adjoint (default);
+                    * 2 = the split pipeline: forward solve leaving one record per accepted step -> adjoint recursion
+                    *     per trajectory -> one thread per step record for the network's forward + backward evaluations ->
+                    *     per-trajectory finish (needs ~2.3 KB of device memory per trajectory of a group of starts; the
+                    *     library sizes the groups).  Same discrete adjoint: per-trajectory sse bit-identical, gradients
+                    *     equal to summation order (1e-15).  Measured 5-15 % slower than the fused kernel on B200
+                    *     (profiles/README.md): kept as a tested alternative, not the default. */
 } cude_opts;
 
 typedef struct {

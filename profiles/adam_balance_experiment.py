@@ -17,12 +17,13 @@ dev = torch.device("cuda", 0)
 out = {}
 for bal in (0, 1):
     ctx = cu.Context(0)
-    pop = cu.Population(packed=bench.synthetic_population(n, 1000), ctx=ctx)
+    pop = cu.Population(packed=bench.synthetic_population(n, 1000, bench.simulate_gpu(ctx)), ctx=ctx)
     neural, cond = bench.synthetic_starts(n, S, 11, 2000)
     shard = DevicePopulationShard(pop, n, S, dev)
+    split = int(os.environ.get("CUDE_EXP_SPLIT", "1"))
     with torch.cuda.stream(shard.stream):
         shard.neural.copy_(torch.from_numpy(neural)); shard.cond.copy_(torch.from_numpy(cond))
-    opts = cu.SolverOptions(balance=bal)
+    opts = cu.SolverOptions(balance=bal, split=split)
     ms, losses = [], []
     for it in range(iters):
         shard.adam_step(lr=1e-2, opts=opts)
