@@ -68,6 +68,7 @@ SYMBOLS = {
                                 C.c_int, C.c_double, _P, _P, _P]),
     "cude_measure_fp64_peak": (C.c_int, [_P, _D]),
     "cude_measure_fp64_peak_rrr": (C.c_int, [_P, _D]),
+    "cude_measure_fp32_peak": (C.c_int, [_P, _D, _D]),
     "cude_math_probe": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "cude_adam_dev": (C.c_int, [_P, C.c_longlong, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_double, _P, C.c_longlong, C.c_longlong]),

@@ -1299,6 +1299,39 @@ extern "C" int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops) {
     return CUDE_OK;
 }
 
+// FP32 FMA peak (TFLOP/s) and MUFU peak (G transcendental ops / s): denominators of the FP32-network modes
+extern "C" int cude_measure_fp32_peak(cude_ctx* ctx, double* tflops, double* mufu_gops) {
+    if (!ctx || !tflops) return CUDE_EINVAL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    int rc = ensure(ctx, ctx->scratch, (size_t)threads * blocks * sizeof(double));
+    if (rc) return rc;
+    double best[2] = {0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+        if (which == 1 && !mufu_gops) break;
+        for (int rep = 0; rep < 5; ++rep) {
+            CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            (void)cudaGetLastError();
+            if (which == 0) cude_ffma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((float*)ctx->scratch.p, iters, 0.999999f, 1e-6f);
+            else cude_mufu_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((float*)ctx->scratch.p, iters);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            const double ops = 64.0 * (double)iters * threads * blocks;      // FFMA resp. ex2 instructions (thread level)
+            const double v = (which == 0 ? 2.0 * ops / 1e12 : ops / 1e9) / (ms * 1e-3);
+            if (rep > 0 && v > best[which]) best[which] = v;
+        }
+    }
+    ctx->stats_pending = false;
+    *tflops = best[0];
+    if (mufu_gops) *mufu_gops = best[1];
+    return CUDE_OK;
+}
+
 // diagnostic: DFMA rate with three register operands per instruction
 extern "C" int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return CUDE_EINVAL;

@@ -1166,4 +1166,29 @@ __global__ void cude_dfma_peak_rrr_kernel(double* out, int iters, double a, doub
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// FP32 FMA peak (8 independent FFMA chains per thread) and MUFU peak (8 independent ex2.approx chains): the denominators of
+// the optional FP32-network modes (cude_opts.precision = 1, 2).
+__global__ void cude_ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+__global__ void cude_mufu_peak_kernel(float* out, int iters) {
+    float x0 = 1e-3f * threadIdx.x, x1 = x0 + 0.1f, x2 = x0 + 0.2f, x3 = x0 + 0.3f, x4 = x0 + 0.4f, x5 = x0 + 0.5f, x6 = x0 + 0.6f, x7 = x0 + 0.7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {      // ex2 of a value in [0, 1] stays in [1, 2]: subtract 1 on the FMA pipe to keep the chain bounded
+            x0 = f_ex2(x0) - 1.0f; x1 = f_ex2(x1) - 1.0f; x2 = f_ex2(x2) - 1.0f; x3 = f_ex2(x3) - 1.0f;
+            x4 = f_ex2(x4) - 1.0f; x5 = f_ex2(x5) - 1.0f; x6 = f_ex2(x6) - 1.0f; x7 = f_ex2(x7) - 1.0f;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace cude

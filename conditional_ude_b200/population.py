@@ -146,6 +146,15 @@ def auto_device():
     return pick_device(_lib.load().cude_device_count(), int(lr) if lr is not None and lr.strip().isdigit() else None, td, one)
 
 
+def _fp32_peaks(self):
+    """(FP32 FMA peak in TFLOP/s, MUFU ex2 rate in 1e9 ops/s) measured on this context's device."""
+    a, b = C.c_double(), C.c_double()
+    _lib.check(self._lib.cude_measure_fp32_peak(self._h, C.byref(a), C.byref(b)), self._h)
+    return a.value, b.value
+
+
+Context.fp32_peaks = _fp32_peaks
+
 _default_ctx = {}
 
 

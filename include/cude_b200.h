@@ -290,6 +290,9 @@ int cude_math_probe(cude_ctx* ctx, int which, int n, const double* x, double* y)
 /* Measured FP64 FMA peak of the context's device (dependent-chain-free DFMA micro-benchmark),
  * the denominator of the roofline.  Returns TFLOP/s in *tflops. */
 int cude_measure_fp64_peak(cude_ctx* ctx, double* tflops);
+/* Same for the optional FP32-network modes (opts.precision = 1, 2): FP32 FMA peak in TFLOP/s and, if mufu_gops is not
+ * NULL, the MUFU (ex2.approx) rate in 1e9 operations / s. */
+int cude_measure_fp32_peak(cude_ctx* ctx, double* tflops, double* mufu_gops);
 /* Diagnostic: the same with three distinct register operands per DFMA (register-file-bandwidth bound shape). */
 int cude_measure_fp64_peak_rrr(cude_ctx* ctx, double* tflops);
 
