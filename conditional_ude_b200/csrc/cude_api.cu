@@ -1197,7 +1197,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     sup_kernel_t kern = grad ? cude_sup_kernel<SN, true> : cude_sup_kernel<SN, false>;
     const size_t smem = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, grad, spb);
     if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: too many observations for shared memory; lower opts.block");
-    if (smem > 48 * 1024) CU_TRY(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc = prep_kernel(ctx, (const void*)kern, B, smem))) return rc;     // dynamic size + a carve-out that fits all resident blocks
     CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)

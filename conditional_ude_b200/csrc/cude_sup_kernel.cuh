@@ -11,8 +11,11 @@
 // the backward sweep replays the step's stages (keeping only the stage inputs g_i), then walks the stages in
 // reverse, re-evaluating the network (forward + backward) at each g_i with the scalar seed kb_i[3] - kb_i[2].
 // Stages, stage inputs and stage adjoints live in shared memory so that the stage loops stay rolled (one inlined
-// network site per phase); the 64 compressed gradient accumulators live in shared memory and are updated in
-// per-layer batches.
+// network site per phase); the 64 compressed gradient accumulators live in REGISTERS during the adjoint sweep (round 2:
+// in shared memory every network evaluation re-read and re-wrote all of them — 128 shared accesses per evaluation —
+// and their 64 rows held the kernel at one 128-thread block per SM; now 87 rows = 2 blocks per SM) and are parked in
+// the dead stage rows only for the final reduction.  Solves with more accepted steps than the step ring holds replay
+// the forward pass in chunks, like the c-peptide kernel.
 // =====================================================================================
 #pragma once
 #include "cude_kernels.cuh"
@@ -63,8 +66,13 @@ __constant__ double SUP_E[7] = {-0.00178001105222577714, -0.0008164344596567469,
                                 0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
 
 // network forward at state (u0,u1,u2); c[] = first-layer constant part (theta column + bias)
+// One copy of the forward network per kernel instead of one per call site (5 in the gradient instantiation): 7056 -> 4904
+// SASS instructions and +9 % (ncu round 2: `no_instruction` was the second largest stall, 1.16 per issue).
+#ifndef CUDE_SUP_FWD_INLINE
+#define CUDE_SUP_FWD_INLINE __noinline__
+#endif
 template <class SN>
-__device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, const double* __restrict__ tab,
+__device__ CUDE_SUP_FWD_INLINE double sup_nn_forward(const double* __restrict__ sW, const double* __restrict__ tab,
                                                  const double (&c)[SN::W], double u0, double u1, double u2) {
     constexpr int W = SN::W;
     int nanmax = 0;
@@ -94,11 +102,11 @@ __device__ __forceinline__ double sup_nn_forward(const double* __restrict__ sW, 
 }
 
 // forward + backward with scalar seed s: returns d(u_hat)/d(u) * s in du[], accumulates parameter gradients
-// into acc (shared memory, [k][tid], stride as) in per-layer batches.
+// into acc (registers; every index below is a compile-time constant after unrolling).
 template <class SN>
 __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, const double* __restrict__ tab,
                                                 const double (&c)[SN::W], double u0, double u1, double u2, double s,
-                                                double* __restrict__ acc, int as, double (&du)[3]) {
+                                                double (&acc)[SN::NACC], double (&du)[3]) {
     constexpr int W = SN::W, D = SN::DEPTH;
     int nanmax = 0;   // the forward pass succeeded on the same inputs
     double a[D][W];
@@ -122,23 +130,14 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
     const double dz = s * t_sigmoid(z, tab);
     int aoff = 4 * W + (D - 1) * SN::LH;
     double da[W];
-    {   // output layer batch
-        double g[W + 1];
 #pragma unroll
-        for (int i = 0; i <= W; ++i) g[i] = acc[(aoff + i) * as];
-#pragma unroll
-        for (int i = 0; i < W; ++i) { g[i] = fma(dz, a[D - 1][i], g[i]); da[i] = dz * sW[off + i]; }
-        g[W] += dz;
-#pragma unroll
-        for (int i = 0; i <= W; ++i) acc[(aoff + i) * as] = g[i];
-    }
+    for (int i = 0; i < W; ++i) { acc[aoff + i] = fma(dz, a[D - 1][i], acc[aoff + i]); da[i] = dz * sW[off + i]; }
+    acc[aoff + W] += dz;
 #pragma unroll
     for (int l = D - 1; l >= 1; --l) {
         off -= SN::LH;
         aoff -= SN::LH;
-        double dzl[W], dprev[W], g[SN::LH];
-#pragma unroll
-        for (int k = 0; k < SN::LH; ++k) g[k] = acc[(aoff + k) * as];
+        double dzl[W], dprev[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) dzl[j] = da[j] * fma(-a[l][j], a[l][j], 1.0);
 #pragma unroll
@@ -146,30 +145,24 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
             double sum = 0.0;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                g[i * W + j] = fma(dzl[j], a[l - 1][i], g[i * W + j]);
+                acc[aoff + i * W + j] = fma(dzl[j], a[l - 1][i], acc[aoff + i * W + j]);
                 sum = fma(sW[off + i * W + j], dzl[j], sum);
             }
             dprev[i] = sum;
         }
 #pragma unroll
-        for (int j = 0; j < W; ++j) { g[W * W + j] += dzl[j]; da[j] = dprev[j]; }
-#pragma unroll
-        for (int k = 0; k < SN::LH; ++k) acc[(aoff + k) * as] = g[k];
+        for (int j = 0; j < W; ++j) { acc[aoff + W * W + j] += dzl[j]; da[j] = dprev[j]; }
     }
-    {   // first layer batch: dW1[:,0:3] and sum dz1
-        double g[4 * W], dz1[W];
-#pragma unroll
-        for (int k = 0; k < 4 * W; ++k) g[k] = acc[k * as];
+    {   // first layer: dW1[:,0:3] and sum dz1
+        double dz1[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             dz1[j] = da[j] * fma(-a[0][j], a[0][j], 1.0);
-            g[j] = fma(dz1[j], u0, g[j]);
-            g[W + j] = fma(dz1[j], u1, g[W + j]);
-            g[2 * W + j] = fma(dz1[j], u2, g[2 * W + j]);
-            g[3 * W + j] += dz1[j];
+            acc[j] = fma(dz1[j], u0, acc[j]);
+            acc[W + j] = fma(dz1[j], u1, acc[W + j]);
+            acc[2 * W + j] = fma(dz1[j], u2, acc[2 * W + j]);
+            acc[3 * W + j] += dz1[j];
         }
-#pragma unroll
-        for (int k = 0; k < 4 * W; ++k) acc[k * as] = g[k];
         du[0] = du[1] = du[2] = 0.0;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
@@ -182,16 +175,24 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
 
 __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad, int spb = 0) {
     // exp table, weights (one copy per start of the block), per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] +
-    // residuals M*3 + accumulators); the packed reduction re-uses the rows as [P+1][B]
-    size_t rows = (size_t)21 + (grad ? (size_t)(42 + 3 * M + NACC) : 0);
-    if (spb > 0 && grad && rows < (size_t)P + 1) rows = (size_t)P + 1;
+    // residuals M*3); the accumulators are parked in these rows for the reduction ([NACC][B], then expanded to [P+1][B])
+    size_t rows = (size_t)21 + (grad ? (size_t)(42 + 3 * M) : 0);
+    if (grad && rows < (size_t)P + 1) rows = (size_t)P + 1;
+    if (grad && rows < (size_t)NACC) rows = (size_t)NACC;
     return (size_t)256 + (size_t)(spb > 0 ? spb : 1) * ((P + 1) & ~1) + rows * B;
 }
 
-constexpr int SUP_REC_CAP = 512;  // accepted-step records (t, dt, u[3]) kept per thread in local memory (20 KB)
+#ifndef CUDE_SUP_REC_CAP
+#define CUDE_SUP_REC_CAP 64
+#endif
+constexpr int SUP_REC_CAP = CUDE_SUP_REC_CAP;  // ring of accepted-step records (t, dt, u[3]) per thread in local memory (2.5 KB); longer
+                                               // solves replay the forward pass in chunks of this many steps
+#ifndef CUDE_SUP_MIN_BLOCKS
+#define CUDE_SUP_MIN_BLOCKS 2
+#endif
 
 template <class SN, bool GRAD>
-__global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
+__global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_kernel(const SupArgs A) {
     using namespace tab;
     constexpr int W = SN::W, P = SN::P;
     extern __shared__ double smem[];
@@ -205,7 +206,6 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
     double* sG = sK + (size_t)21 * B;                 // [7][3][B] stage inputs (GRAD)
     double* sKb = sG + (GRAD ? (size_t)21 * B : 0);   // [7][3][B] stage adjoints (GRAD)
     double* sRes = sKb + (GRAD ? (size_t)21 * B : 0); // [M][3][B] weighted residuals (GRAD)
-    double* sAcc = sRes + (GRAD ? (size_t)3 * M * B : 0);   // [NACC][B]
 
     int s, i, sloc = 0;
     bool active;
@@ -234,11 +234,10 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
     double* const myG = sG + tid;
     double* const myKb = sKb + tid;
     double* const myRes = sRes + tid;
-    double* const myAcc = sAcc + tid;
-    if (GRAD) {
-#pragma unroll 1
-        for (int q = 0; q < SN::NACC; ++q) myAcc[q * B] = 0.0;
-    }
+    double* const myAcc = sK + tid;          // the accumulators' parking rows for the reduction (the stage rows, dead by then)
+    double acc[GRAD ? SN::NACC : 1];         // gradient accumulators (compressed layout): registers
+#pragma unroll
+    for (int q = 0; q < (GRAD ? SN::NACC : 1); ++q) acc[q] = 0.0;
     __syncthreads();
 
     double sse = 0.0, gtheta = 0.0, etheta = 0.0;
@@ -267,16 +266,23 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
         struct Rec { double t, h, u0, u1, u2; };
         Rec rec[GRAD ? SUP_REC_CAP : 1];
 
-        // ---------------- forward pass ----------------
+        // adjoint carry across replay chunks
+        double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0, t_next = tend;
+        int kobs = M - 1;
+        int stop_at = 0x7fffffff;      // accepted steps the (re)played forward pass runs for
+        bool first_pass = true;
+        do {
+        // ---------------- forward pass (first pass: the solve; later passes: replay up to stop_at accepted steps) ----------------
         double u0 = yd[0], u1 = yd[(size_t)N], u2 = yd[(size_t)2 * N];      // u0 = data[:,1,i]
         double t = t0;
-        int iobs = 0, ret = 0;
-        while (iobs < M && A.obs_t[iobs] <= t0) {                            // save_start: residual at t0 is 0 by construction
+        int iobs = 0, ret = 0, na = 0, nr = 0;
+        double fsse = 0.0;
+        while (first_pass && iobs < M && A.obs_t[iobs] <= t0) {              // save_start: residual at t0 is 0 by construction
             const double r0 = (u0 - yd[(size_t)(iobs * 3) * N]) * A.iscale[0];
             const double r1 = (u1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
             const double r2 = (u2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
             if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
-            sse += m_sumsq(r0, r1, r2);
+            fsse += m_sumsq(r0, r1, r2);
             ++iobs;
         }
         double k10, k11, k12;
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
         myK[0] = k10; myK[B] = k11; myK[2 * B] = k12;
         double lnqold = -9.210340371976182;
         int iter = 0;
-        while (ret == 0 && t < tend) {
+        while (ret == 0 && t < tend && na < stop_at) {
             if (++iter > A.maxiters) { ret = 1; break; }
             dt = fmin(dt, tend - t);
             if (!(dt > dtmin)) { ret = (dt != dt) ? 3 : 2; break; }
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                 const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, t_exp_sat(fma(beta1, lnE, -beta2 * lnqold), sTab) * (1.0 / gamma)));
                 double tnew = t + dt;
                 if (fabs(tnew - tend) < snap) tnew = tend;
-                while (iobs < M && A.obs_t[iobs] <= tnew) {
+                while (first_pass && iobs < M && A.obs_t[iobs] <= tnew) {
                     const double ts = A.obs_t[iobs];
                     double y0, y1, y2;
                     if (ts == tnew) { y0 = un0; y1 = un1; y2 = un2; }
@@ -355,33 +361,35 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                     const double r1 = (y1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
                     const double r2 = (y2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
                     if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
-                    sse += m_sumsq(r0, r1, r2);
+                    fsse += m_sumsq(r0, r1, r2);
                     ++iobs;
                 }
-                if (GRAD) {
-                    if (nacc < SUP_REC_CAP) { Rec r; r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2; rec[nacc] = r; }
-                }
-                ++nacc;
+                if (GRAD) { Rec r; r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2; rec[na % SUP_REC_CAP] = r; }
+                ++na;
                 lnqold = fmax(lnE, -9.210340371976182);
                 dt = fmin(dt * m_rcp(q), dtmax);
                 t = tnew; u0 = un0; u1 = un1; u2 = un2;
                 myK[0] = myK[18 * B]; myK[B] = myK[19 * B]; myK[2 * B] = myK[20 * B];      // FSAL: k1 <- k7
             } else {
-                ++nrej;
+                ++nr;
                 dt = dt * m_rcp(fmin(1.0 / qmin, t_exp_sat(beta1 * lnE, sTab) * (1.0 / gamma)));
             }
         }
-        if (ret == 0 && iobs < M) ret = 3;
-        if (GRAD && ret == 0 && nacc > SUP_REC_CAP) ret = 4;      // more accepted steps than the ring holds: not supported (Inf)
-        failed = (ret != 0);
-        if (failed) sse = CUDART_INF;
+        if (first_pass) {
+            if (ret == 0 && iobs < M) ret = 3;
+            failed = (ret != 0);
+            sse = failed ? CUDART_INF : fsse;
+            nacc = na; nrej = nr;
+            stop_at = na;
+        }
+        first_pass = false;
+        if (!GRAD || failed) break;
 
-        if constexpr (GRAD) if (!failed) {
-            // ---------------- discrete adjoint ----------------
-            double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0, t_next = tend;
-            int kobs = M - 1;
-            for (int n = nacc - 1; n >= 0; --n) {
-                const Rec r = rec[n];
+        if constexpr (GRAD) {
+            // ---------------- discrete adjoint over the steps [lo, stop_at) held in the ring ----------------
+            const int lo = (stop_at > SUP_REC_CAP) ? stop_at - SUP_REC_CAP : 0;
+            for (int n = stop_at - 1; n >= lo; --n) {
+                const Rec r = rec[n % SUP_REC_CAP];
                 const double tn = r.t, h = r.h;
                 // replay the stages of step n from u_n, keeping the stage inputs g_1..g_7
                 myG[0] = r.u0; myG[B] = r.u1; myG[2 * B] = r.u2;
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                     } else {
                         const double v0 = myKb[(st * 3) * B], v1 = myKb[(st * 3 + 1) * B], v2 = myKb[(st * 3 + 2) * B];
                         double du[3];
-                        sup_nn_backward<SN>(sW, sTab, c, myG[(st * 3) * B], myG[(st * 3 + 1) * B], myG[(st * 3 + 2) * B], v2 - v1, myAcc, B, du);
+                        sup_nn_backward<SN>(sW, sTab, c, myG[(st * 3) * B], myG[(st * 3 + 1) * B], myG[(st * 3 + 2) * B], v2 - v1, acc, du);
                         // gb = J^T v = [-p1 v0 + p1 v1, 0, -p3 v2] + grad_u(u_hat) (v2 - v1)
                         const double gb0 = fma(p1, v1 - v0, du[0]), gb1 = du[1], gb2 = fma(-p3, v2, du[2]);
                         if (st == 6) { lam0 += gb0; lam1 += gb1; lam2 += gb2; }
@@ -466,13 +474,21 @@ __global__ void __launch_bounds__(128) cude_sup_kernel(const SupArgs A) {
                 lam0 = ub0; lam1 = ub1; lam2 = ub2;
                 t_next = tn;
             }
+            stop_at = lo;          // steps below lo still to do: replay the forward pass up to lo
+        }
+        } while (stop_at > 0);
+        if constexpr (GRAD) if (!failed) {
             // d sse / d theta = (sum_j dz1_j W1[j,3]) * exp(theta)
             double db = 0.0;
 #pragma unroll
-            for (int q = 0; q < W; ++q) db = fma(myAcc[(3 * W + q) * B], sW[3 * W + q], db);
+            for (int q = 0; q < W; ++q) db = fma(acc[3 * W + q], sW[3 * W + q], db);
             gtheta = db * etheta;
         }
 #undef SUP_RHS
+    }
+    if constexpr (GRAD) {      // park the accumulators in the (dead) stage rows for the reduction below
+#pragma unroll
+        for (int q = 0; q < SN::NACC; ++q) myAcc[q * B] = acc[q];
     }
 
     if (active) {

@@ -193,8 +193,7 @@ int cude_sup_population_destroy(cude_sup_population* pop);
  *   loss_out[s] = sum_i sse_i / N + lambda * sum(neural_s .^ 2)   (Inf if a trajectory failed)
  *   g_neural[P x n_starts] (may be NULL), g_theta[n_ind x n_starts] (may be NULL => loss only)
  *   sse_out [n_ind x n_starts] (may be NULL): per-individual scaled SSE
- * Limitation: the gradient pass keeps at most 512 accepted steps per trajectory (default tolerances take ~25);
- * a longer trajectory is reported as failed (Inf).                                                              */
+ * Solves with more accepted steps than the kernel's step ring (64) replay the forward pass in chunks: any tolerance works. */
 int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth, int width, const cude_opts* opts,
                        int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
                        double* sse_out, double* loss_out, double* g_neural, double* g_theta);

@@ -57,6 +57,49 @@ def test_emulated_packed_block_path(sup):
     assert noise_ok(np.abs(e["g_neural"] - g["g_neural"]) / np.abs(g["g_neural"]).max(axis=-1, keepdims=True), 1e-4)
 
 
+def test_emulated_step_ring_replay(sup, tmp_path):
+    """The gradient pass keeps a ring of accepted-step records and replays the forward pass in chunks when a solve has more
+    steps than the ring (round 1 returned Inf beyond 512 steps).  Rebuilt with a 4-entry ring, the ~25-step solves need
+    six replays; gradients must equal the 64-entry build's bit for bit (same arithmetic, same order)."""
+    import ctypes as C
+    import importlib
+    import os
+    import subprocess
+    lib = str(tmp_path / "libcude_emu_supcap4.so")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                           "-DCUDE_SUP_REC_CAP=4", "-o", lib, os.path.join(emu_wrap._HERE, "emu_kernel.cpp")])
+    data, t = sup["group_data"][:, :, :6], sup["timepoints"]
+    nns, th = _starts(sup, 2)
+    th = th[:, :6]
+    sc = oracle.suppression_scale(sup["group_data"])
+    ref = emu_wrap.emu_sup_eval(data, t, nns, th, scale=sc)
+    assert ref["n_acc"] > 12 * 20
+    old = emu_wrap.LIB
+    try:
+        emu_wrap.LIB = lib
+        emu_wrap.build = lambda: lib
+        e = emu_wrap.emu_sup_eval(data, t, nns, th, scale=sc)
+    finally:
+        emu_wrap.LIB = old
+        importlib.reload(emu_wrap)
+    assert np.array_equal(e["sse"], ref["sse"]) and e["n_acc"] == ref["n_acc"]
+    assert np.array_equal(e["g_theta"], ref["g_theta"]) and np.array_equal(e["g_neural"], ref["g_neural"])
+
+
+@pytest.mark.gpu
+def test_gpu_tight_tolerance_replays_instead_of_failing(sup):
+    """reltol 1e-9: ~300 accepted steps per trajectory, several ring lengths: finite and equal to the oracle's gradient."""
+    data, t = sup["group_data"], sup["timepoints"]
+    nns, th = _starts(sup, 2)
+    o = dict(abstol=1e-11, reltol=1e-9)
+    g = oracle.sup_eval(data, t, nns, th, with_grad=True, **o)
+    pop = cu.SuppressionPopulation(data, t, ctx=cu.Context(0))
+    loss, gn, gt, sse = pop.loss_grad(nns, th, lam=0.0, opts=cu.SolverOptions(**o), return_sse=True)
+    assert g["stats"][..., 0].min() > 64 and np.isfinite(loss).all()
+    assert relmax(sse, g["sse"]) < 1e-6
+    assert relmax(gt * 37, g["g_theta"]) < 1e-4 and relmax(gn * 37, g["g_neural"].sum(axis=1)) < 1e-4
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_stored_reference_losses(sup):
     """All 25 stored training and validation losses of suppression/results/lambda=1.0.jld2 on the B200."""
