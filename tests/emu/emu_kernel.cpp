@@ -14,6 +14,7 @@ using std::isfinite;
 #define __global__
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__
