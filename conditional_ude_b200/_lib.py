@@ -33,6 +33,12 @@ class cude_opts(C.Structure):
                 ("precision", C.c_int), ("block", C.c_int), ("balance", C.c_int), ("split", C.c_int)]
 
 
+class cude_train_opts(C.Structure):
+    _fields_ = [("adam_iters", C.c_int), ("adam_lr", C.c_double), ("adam_beta1", C.c_double), ("adam_beta2", C.c_double),
+                ("adam_eps", C.c_double), ("lbfgs_iters", C.c_int), ("lbfgs_m", C.c_int), ("g_tol", C.c_double), ("c1", C.c_double),
+                ("rho_hi", C.c_double), ("rho_lo", C.c_double), ("ls_maxiter", C.c_int), ("check_every", C.c_int)]
+
+
 class cude_stats(C.Structure):
     _fields_ = [("n_traj", C.c_ulonglong), ("n_acc", C.c_ulonglong), ("n_rej", C.c_ulonglong),
                 ("n_rhs", C.c_ulonglong), ("n_fail", C.c_ulonglong), ("kernel_ms", C.c_float),
@@ -70,6 +76,8 @@ SYMBOLS = {
     "cude_measure_fp64_peak_rrr": (C.c_int, [_P, _D]),
     "cude_measure_fp32_peak": (C.c_int, [_P, _D, _D]),
     "cude_math_probe": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "cude_train_default_opts": (None, [C.POINTER(cude_train_opts)]),
+    "cude_train": (C.c_int, [_P, _P, C.POINTER(cude_net), C.POINTER(cude_opts), C.POINTER(cude_train_opts), C.c_int, _D, _D, _D, _I, _I, _I]),
     "cude_adam_dev": (C.c_int, [_P, C.c_longlong, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_double, _P, C.c_longlong, C.c_longlong]),
     # multi-GPU: one process per GPU (communicator on a context) ...

@@ -16,6 +16,7 @@
 #include "cude_kernels.cuh"
 #include "cude_split.cuh"
 #include "cude_sup_kernel.cuh"
+#include "cude_train.cuh"
 
 using namespace cude;
 
@@ -1233,6 +1234,118 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
         if (g_neural) for (int p = 0; p < P; ++p) g_neural[(size_t)s * P + p] = ok ? row[1 + p] / N + 2.0 * lambda * w[p] : 0.0;
         if (g_theta && !ok) for (int i = 0; i < N; ++i) g_theta[(size_t)s * N + i] = 0.0;
     }
+    return CUDE_OK;
+}
+
+// ---------------------------------------------------------------- device-resident multi-start training
+extern "C" void cude_train_default_opts(cude_train_opts* t) {
+    if (!t) return;
+    t->adam_iters = 1000; t->adam_lr = 1e-2; t->adam_beta1 = 0.9; t->adam_beta2 = 0.999; t->adam_eps = 1e-8;   // :346-348, Optimisers.Adam
+    t->lbfgs_iters = 1000; t->lbfgs_m = 10; t->g_tol = 1e-8;                                                 // Optim.LBFGS defaults
+    t->c1 = 1e-4; t->rho_hi = 0.5; t->rho_lo = 0.1; t->ls_maxiter = 50;                                      // LineSearches.BackTracking (1000 iterations upstream)
+    t->check_every = 16;
+}
+
+extern "C" int cude_train(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+                          const cude_train_opts* topts, int n_starts, double* neural, double* cond,
+                          double* objective_out, int* iters_out, int* status_out, int* evals_out) {
+    if (!ctx || !pop || !net || !neural || !cond || n_starts < 1) return fail(ctx, CUDE_EINVAL, "cude_train: bad argument");
+    if (pop->ctx != ctx) return fail(ctx, CUDE_EINVAL, "cude_train: population belongs to another context");
+    cude_train_opts t;
+    if (topts) t = *topts; else cude_train_default_opts(&t);
+    if (t.adam_iters < 0 || t.lbfgs_iters < 0 || t.lbfgs_m < 1 || t.lbfgs_m > 16 || t.ls_maxiter < 1 || t.check_every < 1)
+        return fail(ctx, CUDE_EINVAL, "cude_train: bad optimiser options (history length 1..16)");
+    const int P = cude_net_nparams(net);
+    if (P < 0) return fail(ctx, CUDE_EINVAL, "cude_train: bad network description");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t S = (size_t)n_starts, N = (size_t)pop->n_ind, D = (size_t)P + N, m = (size_t)t.lbfgs_m;
+    // one allocation: doubles first, then ints
+    const size_t n_d = S * P + S * N + S * (P + 1) + S * N + 6 * S * D + 2 * m * S * D + m * S + S * SC_N;
+    const size_t n_i = S * IC_N + 2;
+    double* base = nullptr;
+    CU_TRY(ctx, cudaMalloc(&base, n_d * sizeof(double) + n_i * sizeof(int)));
+    struct Free { double* p; ~Free() { if (p) cudaFree(p); } } guard{base};
+    TrainArgs A{};
+    A.S = n_starts; A.P = P; A.N = (int)N; A.D = (int)D; A.m = t.lbfgs_m;
+    double* q = base;
+    A.xt_n = q; q += S * P;
+    A.xt_c = q; q += S * N;
+    double* d_sums = q; q += S * (P + 1);
+    double* d_gc = q; q += S * N;
+    A.sums = d_sums; A.g_cond = d_gc; A.scale = 1.0 / (double)N;
+    A.x = q; q += S * D; A.g = q; q += S * D; A.d = q; q += S * D; A.best_x = q; q += S * D; A.am = q; q += S * D; A.av = q; q += S * D;
+    A.hs = q; q += m * S * D; A.hy = q; q += m * S * D; A.rho = q; q += m * S; A.sc = q; q += S * SC_N;
+    A.ic = (int*)q; A.status_count = A.ic + S * IC_N;
+    A.lr = t.adam_lr; A.b1 = t.adam_beta1; A.b2 = t.adam_beta2; A.eps = t.adam_eps;
+    A.g_tol = t.g_tol; A.c1 = t.c1; A.rho_hi = t.rho_hi; A.rho_lo = t.rho_lo; A.ls_maxiter = t.ls_maxiter; A.maxiters = t.lbfgs_iters;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemsetAsync(base, 0, n_d * sizeof(double) + n_i * sizeof(int), st));
+    CU_TRY(ctx, cudaMemcpyAsync(A.xt_n, neural, S * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(A.xt_c, cond, S * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpy2DAsync(A.x, D * sizeof(double), A.xt_n, P * sizeof(double), P * sizeof(double), S, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(ctx, cudaMemcpy2DAsync(A.x + P, D * sizeof(double), A.xt_c, N * sizeof(double), N * sizeof(double), S, cudaMemcpyDeviceToDevice, st));
+    {
+        std::vector<double> sc(S * SC_N, 0.0);
+        for (size_t s = 0; s < S; ++s) { sc[s * SC_N + SC_BESTF] = INFINITY; sc[s * SC_N + SC_ALPHA] = 1.0; sc[s * SC_N + SC_APREV] = 1.0; }
+        CU_TRY(ctx, cudaMemcpyAsync(A.sc, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));      // sc goes out of scope
+    }
+    int rc, evals = 0;
+    auto eval = [&]() -> int {
+        ++evals;
+        return eval_dev_impl(ctx, pop, net, opts, n_starts, A.xt_n, P, A.xt_c, 3, A.scale, nullptr, d_sums, d_gc, nullptr);
+    };
+    // ---- training step 1: Adam (:172-176) ----
+    double b1t = 1.0, b2t = 1.0;
+    for (int it = 0; it < t.adam_iters; ++it) {
+        if ((rc = eval())) return rc;
+        b1t *= t.adam_beta1; b2t *= t.adam_beta2;
+        A.b1t = b1t; A.b2t = b2t;
+        cude_adam_step_kernel<<<n_starts, TRAIN_T, 0, st>>>(A, 0);
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    if (t.adam_iters > 0) {
+        if ((rc = eval())) return rc;
+        cude_adam_step_kernel<<<n_starts, TRAIN_T, 0, st>>>(A, 1);      // best iterate -> x, xt
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    // ---- training step 2: L-BFGS with BackTracking (:178-182) ----
+    int h_count[2] = {0, 0};
+    if (t.lbfgs_iters > 0) {
+        if ((rc = eval())) return rc;
+        cude_lbfgs_step_kernel<<<n_starts, TRAIN_T, 0, st>>>(A, 1);
+        CU_TRY(ctx, cudaGetLastError());
+        // every start ends by itself (converged, line search exhausted after ls_maxiter trials, or lbfgs_iters accepted
+        // iterations): the bound below is the worst case, the status check leaves the loop long before
+        const long long max_micro = (long long)t.lbfgs_iters * (t.ls_maxiter + 1) + t.check_every;
+        for (long long k = 0; k < max_micro; ++k) {
+            if ((rc = eval())) return rc;
+            const bool check = ((k + 1) % t.check_every == 0);
+            if (check) CU_TRY(ctx, cudaMemsetAsync(A.status_count, 0, 2 * sizeof(int), st));
+            cude_lbfgs_step_kernel<<<n_starts, TRAIN_T, 0, st>>>(A, 0);
+            CU_TRY(ctx, cudaGetLastError());
+            if (check) {       // 8 bytes every `check_every` micro-steps: are any starts still searching?
+                CU_TRY(ctx, cudaMemcpyAsync(h_count, A.status_count, sizeof h_count, cudaMemcpyDeviceToHost, st));
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+                if (h_count[0] == 0) break;
+            }
+        }
+    }
+    // ---- results ----
+    std::vector<double> h_x(S * D), h_sc(S * SC_N);
+    std::vector<int> h_ic(S * IC_N);
+    CU_TRY(ctx, cudaMemcpyAsync(h_x.data(), A.x, S * D * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(h_sc.data(), A.sc, S * SC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(h_ic.data(), A.ic, S * IC_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    for (size_t s = 0; s < S; ++s) {
+        memcpy(neural + s * P, h_x.data() + s * D, P * sizeof(double));
+        memcpy(cond + s * N, h_x.data() + s * D + P, N * sizeof(double));
+        if (objective_out) objective_out[s] = t.lbfgs_iters > 0 ? h_sc[s * SC_N + SC_FX] : h_sc[s * SC_N + SC_BESTF];
+        if (iters_out) iters_out[s] = h_ic[s * IC_N + IC_ITERS];
+        if (status_out) status_out[s] = h_ic[s * IC_N + IC_STATUS];
+    }
+    if (evals_out) *evals_out = evals;
     return CUDE_OK;
 }
 

@@ -16,7 +16,9 @@ loops over [n_problems x n_dims] arrays (host bookkeeping, no trajectory arithme
 Parity note.  Optimisers.Adam / Optim.LBFGS / LineSearches.BackTracking / Fminbox are third-party Julia packages that
 cannot be run here; the restatements below follow their published algorithms (Adam beta=(0.9,0.999), eps=1e-8, best
 iterate kept; L-BFGS m=10 two-loop recursion, BackTracking c1=1e-4, rho in [0.1,0.5] with quadratic/cubic
-interpolation, g_tol=1e-8).  Box constraints use projection instead of Fminbox's log-barrier (documented deviation).
+interpolation, g_tol=1e-8).
+Box constraints: `fminbox_batched` restates Optim.Fminbox's log-barrier method (the default for the bounded beta fits);
+projection is kept as an option.  Training steps 1 and 2 of the multi-start training run on the device (cude_train).
 Julia's RNG streams (StableRNG, QuasiMonteCarlo, SimpleChains.init_params) are not reproducible: sampling uses numpy.
 The end-to-end check is on *results*: re-fitting beta on the Ohashi train split with the stored weights recovers the
 stored betas (tests/test_estimation_gpu.py).
@@ -207,6 +209,61 @@ def lbfgs_batched(f, fg, x0, maxiters=1000, m=10, g_tol=1e-8, lb=None, ub=None, 
     return x, fx, iters, conv
 
 
+def fminbox_batched(f, fg, x0, lb, ub, maxiters=1000, mufactor=1e-3, outer_iterations=8, g_tol=1e-8, x_tol=1e-10):
+    """Optim.Fminbox(LBFGS(linesearch = BackTracking())) on S independent problems in lock-step — what Optimization.jl runs
+    when `lb` / `ub` are given (reference src/parameter-estimation.jl:159-168).  Logarithmic-barrier method: the inner
+    L-BFGS minimises f(x) + mu * sum(-log(x - lb) - log(ub - x)) over the open box (trial points outside the box have an
+    infinite objective, so the backtracking line search keeps the iterates inside), mu starts at
+    mufactor * |grad f|_1 / |grad barrier|_1 (Optim's mu0 = :auto) and is multiplied by mufactor after every outer
+    iteration; it stops when the projected gradient of f is below g_tol, the iterate stops moving, or after
+    `outer_iterations` (mu has then shrunk by 1e-24).  Infinite bounds carry no barrier.  A start on the boundary is moved
+    inside by 1 % of the box like Optim does.  Returns (x, f(x), inner iterations, converged)."""
+    x = np.array(x0, dtype=np.float64)
+    S, D = x.shape
+    lbv = np.broadcast_to(np.asarray(-np.inf if lb is None else lb, dtype=np.float64), (D,)).copy()
+    ubv = np.broadcast_to(np.asarray(np.inf if ub is None else ub, dtype=np.float64), (D,)).copy()
+    fl, fu = np.isfinite(lbv), np.isfinite(ubv)
+    width = np.where(fl & fu, ubv - lbv, 1.0)
+    x = np.where(fl & (x <= lbv), lbv + 0.01 * width, x)
+    x = np.where(fu & (x >= ubv), ubv - 0.01 * width, x)
+
+    def barrier(z):
+        with np.errstate(all="ignore"):
+            b = np.where(fl, -np.log(z - lbv), 0.0).sum(axis=1) + np.where(fu, -np.log(ubv - z), 0.0).sum(axis=1)
+            gb = np.where(fl, -1.0 / (z - lbv), 0.0) + np.where(fu, 1.0 / (ubv - z), 0.0)
+        inside = np.all((~fl | (z > lbv)) & (~fu | (z < ubv)), axis=1)
+        return np.where(inside, b, np.inf), np.where(inside[:, None], gb, 0.0), inside
+
+    f0, g0 = fg(x)
+    _, gb0, _ = barrier(x)
+    n1f, n1b = np.abs(g0).sum(axis=1), np.abs(gb0).sum(axis=1)
+    mu = np.where((n1f > 0) & (n1b > 0), mufactor * n1f / np.where(n1b > 0, n1b, 1.0), 1e-3 * mufactor)
+    iters = np.zeros(S, dtype=int)
+    conv = np.zeros(S, dtype=bool)
+    for _ in range(outer_iterations):
+        def fb(z):
+            b, _, inside = barrier(z)
+            val = f(np.where(inside[:, None], z, x))
+            return np.where(inside, val + mu * b, np.inf)
+
+        def fgb(z):
+            b, gb, inside = barrier(z)
+            val, grad = fg(np.where(inside[:, None], z, x))
+            return np.where(inside, val + mu * b, np.inf), np.where(inside[:, None], grad + mu[:, None] * gb, 0.0)
+
+        xn, _, it, _ = lbfgs_batched(fb, fgb, x, maxiters=maxiters, g_tol=g_tol)
+        iters += it
+        moved = np.abs(xn - x).max(axis=1)
+        x = xn
+        fx, g = fg(x)
+        pg = np.where((fl & (x - lbv <= 1e-8 * width) & (g > 0)) | (fu & (ubv - x <= 1e-8 * width) & (g < 0)), 0.0, g)
+        conv = (np.abs(pg).max(axis=1) <= g_tol) | (moved <= x_tol)
+        mu = mu * mufactor
+        if conv.all():
+            break
+    return x, f(x), iters, conv
+
+
 # ----------------------------------------------------------------------------- beta-only estimation
 def _as_population(models, timepoints, cpeptide_data, ctx=None):
     if isinstance(models, Population) or (hasattr(models, "loss_grad") and hasattr(models, "n_params")):
@@ -215,10 +272,12 @@ def _as_population(models, timepoints, cpeptide_data, ctx=None):
 
 
 def train_conditional(models, timepoints, cpeptide_data, neural_network_parameters, initial_beta=-2.0,
-                      lbfgs_lower_bound=-4.0, lbfgs_upper_bound=1.0, lbfgs_iterations=1000, opts=None):
+                      lbfgs_lower_bound=-4.0, lbfgs_upper_bound=1.0, lbfgs_iterations=1000, opts=None, bounds="fminbox"):
     """train(models, timepoints, cpeptide_data, neural_network_parameters; initial_beta, bounds) — :272-288:
     per-individual beta with the network fixed.  All individuals are fitted simultaneously: one GPU call per
-    optimiser iteration (shared network => flat trajectory indexing)."""
+    optimiser iteration (shared network => flat trajectory indexing).  bounds="fminbox" (default): the reference's
+    Fminbox(LBFGS) barrier method; "projection": projected L-BFGS (round 1; same solutions on the reference's data, see
+    tests/test_estimation_gpu.py::test_bounded_beta_fits_fminbox_and_projection_agree)."""
     pop = _as_population(models, timepoints, cpeptide_data)
     nn = np.asarray(neural_network_parameters, dtype=np.float64)
     n = pop.n_ind
@@ -233,12 +292,15 @@ def train_conditional(models, timepoints, cpeptide_data, neural_network_paramete
         return sse[0], gc[0].reshape(n, 1)
 
     x0 = np.broadcast_to(np.asarray(initial_beta, dtype=np.float64), (n,)).reshape(n, 1).copy()
-    x, fx, iters, conv = lbfgs_batched(f, fg, x0, maxiters=lbfgs_iterations, lb=lb, ub=ub)
+    if bounds == "fminbox" and (lb is not None or ub is not None):
+        x, fx, iters, conv = fminbox_batched(f, fg, x0, lb, ub, maxiters=lbfgs_iterations)
+    else:
+        x, fx, iters, conv = lbfgs_batched(f, fg, x0, maxiters=lbfgs_iterations, lb=lb, ub=ub)
     return [OptimizationSolution(np.array([x[i, 0]]), fx[i], iters[i], conv[i]) for i in range(n)]
 
 
 def train_with_sigma(models, timepoints, cpeptide_data, neural_network_parameters, initial_beta=-2.0,
-                     lbfgs_lower_bound=-4.0, lbfgs_upper_bound=1.0, lbfgs_iterations=1000, opts=None):
+                     lbfgs_lower_bound=-4.0, lbfgs_upper_bound=1.0, lbfgs_iterations=1000, opts=None, bounds="fminbox"):
     """:290-307 — theta = (ode=[beta], sigma=1.0), objective (n/2) log sigma^2 + sse/(2 sigma^2), bounds on beta only."""
     pop = _as_population(models, timepoints, cpeptide_data)
     nn = np.asarray(neural_network_parameters, dtype=np.float64)
@@ -261,7 +323,10 @@ def train_with_sigma(models, timepoints, cpeptide_data, neural_network_parameter
         return val, np.stack([gb / (2 * s2), nobs / sig - sse / sig ** 3], axis=1)
 
     x0 = np.stack([np.broadcast_to(np.asarray(initial_beta, dtype=np.float64), (n,)), np.ones(n)], axis=1)
-    x, fx, iters, conv = lbfgs_batched(f, fg, x0, maxiters=lbfgs_iterations, lb=lbv, ub=ubv)
+    if bounds == "fminbox":
+        x, fx, iters, conv = fminbox_batched(f, fg, x0, lbv, ubv, maxiters=lbfgs_iterations)
+    else:
+        x, fx, iters, conv = lbfgs_batched(f, fg, x0, maxiters=lbfgs_iterations, lb=lbv, ub=ubv)
     return [OptimizationSolution(ComponentVector(ode=np.array([x[i, 0]]), sigma=float(x[i, 1])), fx[i], iters[i], conv[i])
             for i in range(n)]
 
@@ -301,7 +366,8 @@ class _Comm:
 
 def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=None, selected_initials=None,
           lhs_lower_bound=-2.0, lhs_upper_bound=0.0, n_conditional_parameters=1, number_of_iterations_adam=1000,
-          number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None, distributed=False, group=None, **kw):
+          number_of_iterations_lbfgs=1000, learning_rate_adam=1e-2, opts=None, distributed=False, group=None,
+          device_optimizer=True, **kw):
     """The `train` methods of the reference, dispatched like Julia on the first and 4th argument:
       train(model::CPeptideUDEModel, t, y, rng; ...)  non-conditional UDE on one individual (:211-247; 10 000 / 10)
       train(models, t, Y, rng::Generator; ...)  full cUDE training (:340-386; 25 000 guesses / 25 selected)
@@ -309,7 +375,10 @@ def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=None, se
     distributed=True (one process per GPU under torch.distributed; BASELINE config "starts sharded over 8 x B200"):
     every rank draws the same initial guesses from an identically seeded `rng`, screens its slice of them, the losses
     are all-gathered, the globally best `selected_initials` starts are split over the ranks and optimised there, and
-    every rank returns all solutions in selection order.  No communication on the data path."""
+    every rank returns all solutions in selection order.  No communication on the data path.
+    device_optimizer=True (default, on a device Population): training steps 1 and 2 (:170-183) run in the library's
+    device-resident lock-step optimisers (cude_train: parameters, Adam moments and L-BFGS history stay in HBM, the host only
+    enqueues kernels); False keeps the host numpy optimisers of this module (same algorithms, one GPU call per evaluation)."""
     from .models import CPeptideUDEModel
     if isinstance(models, CPeptideUDEModel):           # train(model::CPeptideUDEModel, t, y, rng; ...) :211-247, its own defaults
         return train_ude(models, timepoints, cpeptide_data, rng_or_nn,
@@ -347,7 +416,11 @@ def train(models, timepoints, cpeptide_data, rng_or_nn, initial_guesses=None, se
     k = x0.shape[0]
     lo, hi = comm.bounds(k)
     res = np.full((hi - lo, P + n + 3), np.nan)
-    if hi > lo:
+    if hi > lo and device_optimizer and type(pop) is Population:
+        nn2, cc2, fx, iters, status, _ = pop.train_starts(x0[lo:hi, :P], x0[lo:hi, P:], adam_iters=number_of_iterations_adam,
+                                                          lr=learning_rate_adam, lbfgs_iters=number_of_iterations_lbfgs, opts=opts)
+        res = np.concatenate([nn2, cc2, fx[:, None], iters.astype(np.float64)[:, None], (status == 1).astype(np.float64)[:, None]], axis=1)
+    elif hi > lo:
         x1, _ = adam_batched(fg, x0[lo:hi], lr=learning_rate_adam, maxiters=number_of_iterations_adam)
         x2, fx, iters, conv = lbfgs_batched(f, fg, x1, maxiters=number_of_iterations_lbfgs)
         res = np.concatenate([x2, fx[:, None], np.asarray(iters, dtype=np.float64)[:, None],

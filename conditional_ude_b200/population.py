@@ -267,6 +267,28 @@ class Population:
                                                  _dptr(cond), float(cond_scale), _dptr(sums), _dptr(gc)), self.ctx.handle)
         return sums, gc
 
+    def train_starts(self, neural, cond, adam_iters=1000, lr=1e-2, lbfgs_iters=1000, opts=None, **kw):
+        """`_optimize` (src/parameter-estimation.jl:170-183) for S starts in lock-step on the device (cude_train): Adam, then
+        L-BFGS with BackTracking; parameters, moments and history stay in HBM.  neural[S x P], cond[S x N] -> (neural,
+        cond, objective[S], lbfgs_iterations[S], status[S], evaluations)."""
+        neural, stride, cond, S = self._prep(neural, cond)
+        if stride == 0:
+            raise ValueError("train_starts needs one network per start")
+        neural, cond = neural.copy(), cond.copy()
+        o = (opts or SolverOptions()).c()
+        t = _lib.cude_train_opts()
+        self._lib.cude_train_default_opts(C.byref(t))
+        t.adam_iters, t.adam_lr, t.lbfgs_iters = int(adam_iters), float(lr), int(lbfgs_iters)
+        for k, v in kw.items():
+            setattr(t, k, v)
+        obj = np.empty(S)
+        iters = np.zeros(S, dtype=np.int32)
+        status = np.zeros(S, dtype=np.int32)
+        ev = C.c_int(0)
+        _lib.check(self._lib.cude_train(self.ctx.handle, self._h, C.byref(self.net), C.byref(o), C.byref(t), S, _dptr(neural),
+                                        _dptr(cond), _dptr(obj), _iptr(iters), _iptr(status), C.byref(ev)), self.ctx.handle)
+        return neural, cond, obj, iters, status, ev.value
+
     def loss_grad_sharded(self, neural, cond, n_total, opts=None, neural_grad=True, mean=True, loss_only=False,
                           out_loss=None, out_g_neural=None, out_g_cond=None):
         """Collective population loss / gradient when this Population holds one rank's block of `n_total` individuals
@@ -391,7 +413,7 @@ class MultiPopulation(Population):
     def loss_grad_sums(self, *a, **k):
         raise NotImplementedError("device-level sums belong to one device: use Population on MultiContext.device_context(k)")
 
-    eval_dev = simulate = loss_grad_sharded = loss_grad_sums
+    eval_dev = simulate = loss_grad_sharded = train_starts = loss_grad_sums
 
 
 _pop_cache = {}

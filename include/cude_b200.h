@@ -198,6 +198,26 @@ int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth,
                        int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
                        double* sse_out, double* loss_out, double* g_neural, double* g_theta);
 
+/* ---- device-resident multi-start training: `_optimize` (src/parameter-estimation.jl:170-183) for all selected starts of
+ * `train` (:374-376) in lock-step — Optimisers.Adam(adam_lr) for adam_iters iterations (best iterate kept), then
+ * Optim.LBFGS(m, linesearch = BackTracking(order 3: c1, rho_lo, rho_hi)) for at most lbfgs_iters iterations, objective =
+ * the population loss (:126-140).  Parameters, gradients, moments and the L-BFGS history never leave the device; per
+ * iteration the host only enqueues the loss+gradient kernel, its reduction and one optimiser kernel (one block per
+ * start), and reads 8 bytes every `check_every` line-search steps to stop when every start has finished.
+ *   neural[P x n_starts], cond[n_ind x n_starts]: initial parameters on entry, solutions on exit (host memory)
+ *   objective_out[s]: final loss; iters_out[s]: accepted L-BFGS iterations; status_out[s]: 0 = stopped by the step budget,
+ *   1 = converged (|g|_inf <= g_tol, or no change), 2 = line search failed, 3 = lbfgs_iters reached; evals_out: loss+gradient
+ *   evaluations of the whole batch. */
+typedef struct {
+    int adam_iters; double adam_lr, adam_beta1, adam_beta2, adam_eps;
+    int lbfgs_iters, lbfgs_m; double g_tol, c1, rho_hi, rho_lo; int ls_maxiter;
+    int check_every;
+} cude_train_opts;
+void cude_train_default_opts(cude_train_opts* t);
+int cude_train(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts,
+               const cude_train_opts* topts, int n_starts, double* neural, double* cond,
+               double* objective_out, int* iters_out, int* status_out, int* evals_out);
+
 /* Device-resident Adam step (Optimisers.Adam(eta, (beta1, beta2), eps), `_optimize` step 1,
  * src/parameter-estimation.jl:170-183) for population-scale training, where the parameter vector (one beta per
  * individual per start) never leaves HBM:  g <- grad_scale * d_g;  m, v moments;  x -= lr * mhat / (sqrt(vhat) + eps)

@@ -41,6 +41,29 @@ def test_lbfgs_batched_bounds_and_nonfinite():
     assert np.all(x <= 1.0) and np.all(x > 0.9) and np.isfinite(fx).all()
 
 
+def test_fminbox_batched_barrier_method():
+    """Optim.Fminbox restated: interior minima are found exactly, minima outside the box end on the bound (approached from
+    inside: every iterate is feasible), one-sided and infinite bounds work, a start on the boundary is moved inside."""
+    c = np.array([[-5.0], [0.3], [4.0], [-3.9999]])
+    evals = []
+    def fg(z):
+        evals.append(z.copy())
+        return ((z - c) ** 2).sum(axis=1), 2 * (z - c)
+    x, fx, iters, conv = est.fminbox_batched(lambda z: fg(z)[0], fg, np.full((4, 1), -2.0), -4.0, 1.0)
+    assert np.allclose(x[:, 0], [-4.0, 0.3, 1.0, -3.9999], atol=2e-6) and conv.all()
+    assert all(np.all((e > -4.0) & (e < 1.0)) for e in evals)                  # never leaves the open box
+    assert np.allclose(fx, ((x - c) ** 2).sum(axis=1))
+    # same answers as projection on these problems
+    xp, _, _, _ = est.lbfgs_batched(lambda z: fg(z)[0], fg, np.full((4, 1), -2.0), lb=-4.0, ub=1.0)
+    assert np.abs(x - xp).max() < 2e-6
+    # two parameters, only the first bounded (train_with_sigma: bounds [lb, -Inf], [ub, Inf], :295-296); start on the bound
+    c2 = np.array([[3.0, 7.0], [0.0, -2.0]])
+    fg2 = lambda z: (((z - c2) ** 2).sum(axis=1), 2 * (z - c2))
+    x, fx, _, conv = est.fminbox_batched(lambda z: fg2(z)[0], fg2, np.array([[1.0, 1.0], [-4.0, 1.0]]), np.array([-4.0, -np.inf]),
+                                         np.array([1.0, np.inf]))
+    assert np.allclose(x, [[1.0, 7.0], [0.0, -2.0]], atol=2e-6) and conv.all()
+
+
 def test_adam_batched_keeps_best_iterate():
     c = np.array([[1.0, -2.0], [0.5, 0.5]])
     fg = lambda z: (((z - c) ** 2).sum(axis=1), 2 * (z - c))
@@ -81,7 +104,7 @@ def test_beta_refit_recovers_stored_betas_with_oracle_backend(fx):
     assert np.median(np.abs(got - betas)) < 5e-3 and np.percentile(np.abs(got - betas), 90) < 5e-2
     # the reltol=1e-3 objective is rough at the 1e-3 level (solver error): compare within that
     assert np.mean(obj <= stored + 2e-3 * np.maximum(1.0, stored)) > 0.9 and abs(obj.mean() - stored.mean()) < 2e-3
-    assert pop.calls < 1000          # ~all individuals advance together: a few hundred batched calls, not 57 x 1000
+    assert pop.calls < 2500          # all individuals advance together: batched calls (8 barrier rounds of L-BFGS), not 57 x 1000
 
 
 def test_multi_start_training_with_oracle_backend(fx):
