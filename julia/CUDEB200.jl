@@ -7,14 +7,16 @@
 # Drop-in usage inside the reference repository (after `include("src/parameter-estimation.jl")`):
 #
 #     include("CUDEB200.jl"); using .CUDEB200
-#     idx  = indices_train
-#     pop  = CUDEB200.Population(train_data.glucose[idx, :], train_data.timepoints, train_data.ages[idx],
-#                                train_data.types[idx] .== "T2DM", train_data.timepoints, train_data.cpeptide[idx, :])
+#     include("cude_overrides.jl")      # re-defines the reference's own `loss` / `likelihood_profile` methods (same signatures)
+#                                       # on top of this module: `train`, `train_with_sigma`, `evaluate_model` and the scripts
+#                                       # then run UNMODIFIED, AutoForwardDiff() included (see cude_overrides.jl)
+#
+# or explicitly:
+#     pop  = CUDEB200.Population(models, timepoints, cpeptide_data)   # from the reference's own model vector
 #     optf = CUDEB200.optimization_function(pop)          # replaces OptimizationFunction(loss, AutoForwardDiff())
 #     prob = OptimizationProblem(optf, θ0, nothing)       # θ0::ComponentArray(neural=…, conditional=…)
-#
-# and `CUDEB200.loss(θ, (pop, timepoints, cpeptide_data[, nn]))` evaluates the tuple shapes of
-# src/parameter-estimation.jl:56, :93, :126 on the GPU (the Population stands in for the model vector).
+#     mctx = CUDEB200.Context([0, 1, 2, 3, 4, 5, 6, 7])   # all GPUs of the box from this one Julia session
+#     mpop = CUDEB200.MultiPopulation(models, timepoints, cpeptide_data; ctx=mctx, shard=:individuals)
 module CUDEB200
 
 using ComponentArrays: ComponentArray
@@ -35,8 +37,10 @@ struct CudeOpts
     precision::Cint
     block::Cint
     balance::Cint     # 1: regroup each start's individuals by earlier step counts (iterative workloads)
+    split::Cint       # 2: split gradient pipeline instead of the fused adjoint kernel (include/cude_b200.h)
 end
-CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=100_000, precision=0, balance=0) = CudeOpts(abstol, reltol, maxiters, precision, 0, balance)
+CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=1_000_000, precision=0, balance=0, split=0) =
+    CudeOpts(abstol, reltol, maxiters, precision, 0, balance, split)
 
 check(rc::Cint, ctx=C_NULL) = rc == 0 ? nothing :
     error("cude_b200 error $rc: " * unsafe_string(ccall((:cude_last_error, libcude), Cstring, (Ptr{Cvoid},), ctx)))
@@ -54,6 +58,46 @@ end
 
 const default_context = Ref{Union{Nothing,Context}}(nothing)
 context() = (default_context[] === nothing && (default_context[] = Context(0)); default_context[])
+
+"""
+    MultiContext(devices)   /   Context(devices::AbstractVector)
+
+All (or some) GPUs of the box driven from this one Julia session (`cude_mctx_create`): one context, stream and host
+worker thread per device inside the library; NCCL (loaded by the library at run time) all-reduces the per-start sums of
+individual-sharded populations.  `MultiContext()` takes every visible device.
+"""
+mutable struct MultiContext
+    handle::Ptr{Cvoid}
+    n_gpus::Int
+    function MultiContext(devices::AbstractVector{<:Integer}=Int[])
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        ids = Cint.(devices)
+        rc = ccall((:cude_mctx_create, libcude), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(ids), isempty(ids) ? C_NULL : ids, h)
+        rc == 0 || error("cude_b200 error $rc: " * unsafe_string(ccall((:cude_mlast_error, libcude), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(h[], Int(ccall((:cude_mctx_size, libcude), Cint, (Ptr{Cvoid},), h[])))
+        finalizer(c -> ccall((:cude_mctx_destroy, libcude), Cint, (Ptr{Cvoid},), c.handle), m)
+        m
+    end
+end
+Context(devices::AbstractVector{<:Integer}) = MultiContext(devices)
+mcheck(rc::Cint, m::MultiContext) = rc == 0 ? nothing :
+    error("cude_b200 error $rc: " * unsafe_string(ccall((:cude_mlast_error, libcude), Cstring, (Ptr{Cvoid},), m.handle)))
+
+"""
+Constants of one reference model object, read out of the closures the reference's own constructor built
+(src/c-peptide-models.jl:170-194 / :196-220): `model.problem.f.f` is `combined!` (`combine`, :108-114) capturing
+`kinetics!` — the `ode!` closure of `van_cauter_model` (:56-64) with `k0, k1, k2, c_peptide_0` — and `production`, which
+captures the `LinearInterpolation` `glucose` (`.t` knots, `.u` values) and, for the covariate model, `age`.
+"""
+function model_constants(model)
+    comb = model.problem.f.f
+    kin = getfield(comb, Symbol("kinetics!"))
+    prod = getfield(comb, :production)
+    g = getfield(prod, :glucose)
+    age = :age in fieldnames(typeof(prod)) ? Float64(getfield(prod, :age)) : nothing
+    (k0 = Float64(kin.k0), k1 = Float64(kin.k1), k2 = Float64(kin.k2), c0 = Float64(kin.c_peptide_0),
+     knot_t = collect(Float64, g.t), knot_g = collect(Float64, g.u), covariate = age)
+end
 
 """
 Device-resident image of a vector of `CPeptideConditionalUDEModel` (src/c-peptide-models.jl:170-194) and
@@ -95,6 +139,103 @@ function Population(glucose::AbstractMatrix, glucose_timepoints::AbstractVector,
     pop = Population(h[], ctx, n, net, P)
     finalizer(x -> ccall((:cude_population_destroy, libcude), Cint, (Ptr{Cvoid},), x.handle), pop)
     pop
+end
+
+"""
+    Population(models, timepoints, cpeptide_data; ctx)
+
+From the reference's own vector of `CPeptideConditionalUDEModel` (or covariate models) and the `(timepoints, cpeptide_data)`
+of the loss tuple (:126): nothing else is needed, the model constants come from `model_constants`.
+"""
+function _pack(models::AbstractVector, timepoints::AbstractVector, cpeptide::AbstractVecOrMat)
+    cs = [model_constants(m) for m in models]
+    n = length(models)
+    K = maximum(length(c.knot_t) for c in cs); M = length(timepoints)
+    knot_t = zeros(K, n); knot_g = zeros(K, n); nk = Vector{Cint}(undef, n)
+    for (i, c) in enumerate(cs)
+        nk[i] = length(c.knot_t)
+        knot_t[1:nk[i], i] .= c.knot_t; knot_g[1:nk[i], i] .= c.knot_g
+    end
+    Y = cpeptide isa AbstractVector ? reshape(Float64.(cpeptide), 1, :) : Float64.(cpeptide)       # [n x M]
+    kin = [getfield(c, f) for f in (:k0, :k1, :k2, :c0), c in cs]                                   # [4 x n]
+    cov = cs[1].covariate === nothing ? nothing : Float64[c.covariate for c in cs]
+    net = CudeNet(cov === nothing ? 2 : 3, 2, 4)                                                    # chain(4, 2, tanh; input_dims)
+    (; n, K, M, nk, knot_t, knot_g, obs_t = repeat(Float64.(timepoints), 1, n), obs_y = permutedims(Y), kin, cov, net)
+end
+
+function Population(models::AbstractVector, timepoints::AbstractVector, cpeptide::AbstractVecOrMat; ctx::Context=context())
+    p = _pack(models, timepoints, cpeptide)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cude_population_create, libcude), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                ctx.handle, p.n, p.K, p.nk, p.knot_t, p.knot_g, p.M, fill(Cint(p.M), p.n), p.obs_t, p.obs_y, p.kin,
+                p.cov === nothing ? C_NULL : p.cov, h), ctx.handle)
+    pop = Population(h[], ctx, p.n, p.net, Int(ccall((:cude_net_nparams, libcude), Cint, (Ref{CudeNet},), p.net)))
+    finalizer(x -> ccall((:cude_population_destroy, libcude), Cint, (Ptr{Cvoid},), x.handle), pop)
+    pop
+end
+
+"""
+Population on a `MultiContext`.  `shard = :starts`: every device holds the whole population and a call's starts are split
+over the devices (screening :362-366, selected starts :374-376, beta-only fits :272-288, profiles): no communication.
+`shard = :individuals`: the individuals (loop of :126-140) are split and every call ends with the library's NCCL
+all-reduce of the per-start sums.  Same `loss` / `loss_grad` methods and results as `Population`.
+"""
+mutable struct MultiPopulation
+    handle::Ptr{Cvoid}
+    ctx::MultiContext
+    n::Int
+    net::CudeNet
+    nparams::Int
+end
+function MultiPopulation(models::AbstractVector, timepoints::AbstractVector, cpeptide::AbstractVecOrMat;
+                         ctx::MultiContext=MultiContext(), shard::Symbol=:starts)
+    p = _pack(models, timepoints, cpeptide)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mode = shard === :individuals ? 1 : 0          # CUDE_SHARD_INDIVIDUALS / CUDE_SHARD_STARTS
+    mcheck(ccall((:cude_mpopulation_create, libcude), Cint,
+                 (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble},
+                  Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                 ctx.handle, mode, p.n, p.K, p.nk, p.knot_t, p.knot_g, p.M, fill(Cint(p.M), p.n), p.obs_t, p.obs_y, p.kin,
+                 p.cov === nothing ? C_NULL : p.cov, h), ctx)
+    mp = MultiPopulation(h[], ctx, p.n, p.net, Int(ccall((:cude_net_nparams, libcude), Cint, (Ref{CudeNet},), p.net)))
+    finalizer(x -> ccall((:cude_mpopulation_destroy, libcude), Cint, (Ptr{Cvoid},), x.handle), mp)
+    mp
+end
+
+function loss(pop::MultiPopulation, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}; opts=CudeOpts())
+    S = size(cond, 2)
+    out = Vector{Float64}(undef, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    mcheck(ccall((:cude_mloss, libcude), Cint,
+                 (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                 pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, C_NULL, out), pop.ctx)
+    out
+end
+
+function loss_grad(pop::MultiPopulation, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}; opts=CudeOpts(),
+                   mean::Bool=true, neural_grad::Bool=true)
+    S = size(cond, 2)
+    l = Vector{Float64}(undef, S)
+    gn = neural_grad ? Matrix{Float64}(undef, pop.nparams, S) : nothing
+    gc = Matrix{Float64}(undef, pop.n, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    mcheck(ccall((:cude_mloss_grad, libcude), Cint,
+                 (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Cint,
+                  Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                 pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, mean ? 1 : 0,
+                 C_NULL, l, gn === nothing ? C_NULL : gn, gc), pop.ctx)
+    l, gn, gc
+end
+
+# one device population per (model vector, data) the reference passes around: built on first use, then re-used by every
+# `loss(θ, (models, t, Y))` call of an optimisation (the reference re-creates nothing between calls either)
+const _pop_cache = IdDict{Any,Any}()
+function cached_population(models, timepoints, cpeptide)
+    get!(_pop_cache, models) do
+        (Population(models isa AbstractVector ? models : [models], timepoints, cpeptide), copy(cpeptide))
+    end[1]
 end
 
 """
