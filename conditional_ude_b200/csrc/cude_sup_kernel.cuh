@@ -185,8 +185,11 @@ __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B
 #ifndef CUDE_SUP_REC_CAP
 #define CUDE_SUP_REC_CAP 64
 #endif
-constexpr int SUP_REC_CAP = CUDE_SUP_REC_CAP;  // ring of accepted-step records (t, dt, u[3]) per thread in local memory (2.5 KB); longer
+constexpr int SUP_REC_CAP = CUDE_SUP_REC_CAP;  // ring of accepted-step records (t, dt, u[3], k1..k6: 184 B) per thread in local memory; longer
                                                // solves replay the forward pass in chunks of this many steps
+#ifndef CUDE_SUP_KEEP_STAGES
+#define CUDE_SUP_KEEP_STAGES 1
+#endif
 #ifndef CUDE_SUP_MIN_BLOCKS
 #define CUDE_SUP_MIN_BLOCKS 2
 #endif
@@ -263,7 +266,9 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         const double uh__ = sup_nn_forward<SN>(sW, sTab, c, U0, U1, U2);  \
         F0 = -p1 * (U0); F1 = fma(p1, (U0), -uh__); F2 = fma(-p3, (U2), uh__); \
     }
-        struct Rec { double t, h, u0, u1, u2; };
+        // accepted-step record: (t, dt, u) and — CUDE_SUP_KEEP_STAGES — the step's stage derivatives k1..k6, so that the
+        // adjoint rebuilds the stage inputs g_i = u + dt sum a_ij k_j without re-evaluating the network 6 times per step
+        struct Rec { double t, h, u0, u1, u2; double k[CUDE_SUP_KEEP_STAGES ? 18 : 1]; };
         Rec rec[GRAD ? SUP_REC_CAP : 1];
 
         // adjoint carry across replay chunks
@@ -364,7 +369,14 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                     fsse += m_sumsq(r0, r1, r2);
                     ++iobs;
                 }
-                if (GRAD) { Rec r; r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2; rec[na % SUP_REC_CAP] = r; }
+                if (GRAD) {
+                    Rec& r = rec[na % SUP_REC_CAP];
+                    r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2;
+                    if (CUDE_SUP_KEEP_STAGES) {
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) r.k[q] = myK[q * B];
+                    }
+                }
                 ++na;
                 lnqold = fmax(lnE, -9.210340371976182);
                 dt = fmin(dt * m_rcp(q), dtmax);
@@ -389,11 +401,14 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
             // ---------------- discrete adjoint over the steps [lo, stop_at) held in the ring ----------------
             const int lo = (stop_at > SUP_REC_CAP) ? stop_at - SUP_REC_CAP : 0;
             for (int n = stop_at - 1; n >= lo; --n) {
-                const Rec r = rec[n % SUP_REC_CAP];
+                const Rec& r = rec[n % SUP_REC_CAP];
                 const double tn = r.t, h = r.h;
-                // replay the stages of step n from u_n, keeping the stage inputs g_1..g_7
+                // the stage inputs g_1..g_7 of step n from u_n and the stage derivatives (kept, or recomputed by replay)
                 myG[0] = r.u0; myG[B] = r.u1; myG[2 * B] = r.u2;
-                {
+                if (CUDE_SUP_KEEP_STAGES) {
+#pragma unroll
+                    for (int q = 0; q < 18; ++q) myK[q * B] = r.k[q];
+                } else {
                     double f0, f1, f2;
                     SUP_RHS(r.u0, r.u1, r.u2, f0, f1, f2)
                     myK[0] = f0; myK[B] = f1; myK[2 * B] = f2;
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                     }
                     const double g0 = fma(h, s0, r.u0), g1 = fma(h, s1, r.u1), g2 = fma(h, s2, r.u2);
                     myG[((st + 1) * 3) * B] = g0; myG[((st + 1) * 3 + 1) * B] = g1; myG[((st + 1) * 3 + 2) * B] = g2;
-                    if (st < 5) {     // k7 itself is not needed by the adjoint (only its input g_7 = u_{n+1})
+                    if (!CUDE_SUP_KEEP_STAGES && st < 5) {     // k7 itself is not needed by the adjoint (only its input g_7 = u_{n+1})
                         double f0, f1, f2;
                         SUP_RHS(g0, g1, g2, f0, f1, f2)
                         myK[((st + 1) * 3) * B] = f0; myK[((st + 1) * 3 + 1) * B] = f1; myK[((st + 1) * 3 + 2) * B] = f2;
