@@ -1162,9 +1162,10 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     // starts side by side (87 - 94 % of the lanes busy instead of 58 % with one start per 64-thread block)
     const int B = o.block > 0 ? o.block : (CUDE_SUP_PACK_DEFAULT && N <= 128 ? 128 : (N > 32 ? 64 : 32));
     if (B < 32 || B > 128 || (B & 31)) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: block must be 32, 64, 96 or 128");
-    const int spb = ((CUDE_SUP_PACK_DEFAULT || o.block > 0) && N <= B) ? B / N : 0;
-    const int nchunks = spb > 0 ? 1 : (N + B - 1) / B, nw = spb > 0 ? 1 : B / 32;
-    const long long nblocks = spb > 0 ? ((long long)n_starts + spb - 1) / spb : (long long)n_starts * nchunks;
+    // small populations: flat indexing over the [S x N] batch (every lane busy), at most (B-1)/N + 2 starts per block
+    const int spb = ((CUDE_SUP_PACK_DEFAULT || o.block > 0) && N <= B) ? (B - 1) / N + 2 : 0;
+    const int nchunks = spb > 0 ? 2 : (N + B - 1) / B, nw = spb > 0 ? 1 : B / 32;      // flat: a start lies in at most 2 blocks = 2 partial rows
+    const long long nblocks = spb > 0 ? ((long long)N * n_starts + B - 1) / B : (long long)n_starts * nchunks;
     const size_t ntraj = (size_t)N * n_starts;
     const size_t n_neural = neural_stride == 0 ? (size_t)P : (size_t)neural_stride * (n_starts - 1) + P;
     int rc;
@@ -1172,7 +1173,9 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     if ((rc = ensure(ctx, ctx->neural, n_neural * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->cond, ntraj * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->sums, (size_t)np1 * n_starts * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->partials, (spb > 0 ? (size_t)n_starts : (size_t)nblocks * nw) * np1 * sizeof(double)))) return rc;
+    const size_t n_prow = spb > 0 ? (size_t)n_starts * 2 : (size_t)nblocks * nw;
+    if ((rc = ensure(ctx, ctx->partials, n_prow * np1 * sizeof(double)))) return rc;
+    if (spb > 0) CU_TRY(ctx, cudaMemsetAsync(ctx->partials.p, 0, n_prow * np1 * sizeof(double), ctx->stream));   // rows of blocks a start does not reach
     if (sse_out && (rc = ensure(ctx, ctx->sse, ntraj * sizeof(double)))) return rc;
     if (g_theta && (rc = ensure(ctx, ctx->gcond, ntraj * sizeof(double)))) return rc;
     if (ctx->h_sums_cap < (size_t)np1 * n_starts) {

@@ -24,8 +24,10 @@ namespace cude {
 
 struct SupArgs {
     int n_ind, n_obs, n_starts, nchunks;
-    int spb;                    // > 0: small population (n_ind <= block): every block runs `spb` whole starts side by side
-                                // (thread = start_in_block * n_ind + individual) and writes one partial row per start
+    int spb;                    // > 0: small population (n_ind <= block): FLAT indexing — the block's B threads are B consecutive
+                                // trajectories of the [S x N] batch (all lanes busy; round 1 packed floor(B/N) whole starts per
+                                // block: 111 of 128 lanes at N = 37); spb = the most starts a block can touch, (B-1)/N + 2.  A start
+                                // lies in at most two blocks: partial rows [start][2][P+1], zero-filled by the host
     const double* obs_t;        // [M] common time grid
     const double* data;         // [M][3][N]: data[(k*3 + j)*N + i]
     double p1, p3;
@@ -212,15 +214,20 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
 
     int s, i, sloc = 0;
     bool active;
-    if (spb > 0) {                                    // packed: whole starts side by side in the block
-        sloc = tid / N;
-        i = tid - sloc * N;
-        s = blockIdx.x * spb + sloc;
-        active = sloc < spb && s < A.n_starts;
-        if (!active) { sloc = 0; s = blockIdx.x * spb; i = 0; }
-        for (int p = tid; p < spb * P; p += B) {
-            const int sl = p / P, pp = p - sl * P, ss = blockIdx.x * spb + sl;
-            if (ss < A.n_starts) sWall[sl * PP + pp] = A.neural[(long long)ss * A.neural_stride + pp];
+    const long long j0 = (long long)blockIdx.x * B, ntot = (long long)N * A.n_starts;   // flat mode: first trajectory of the block
+    int s_first = 0, nsl = 1;
+    if (spb > 0) {                                    // flat: B consecutive trajectories, up to spb starts per block
+        const long long jj = j0 + tid;
+        active = jj < ntot;
+        s_first = (int)(j0 / N);
+        s = active ? (int)(jj / N) : s_first;
+        i = active ? (int)(jj - (long long)s * N) : 0;
+        sloc = s - s_first;
+        const long long jlast = (j0 + B < ntot ? j0 + B : ntot) - 1;
+        nsl = (int)(jlast / N) - s_first + 1;
+        for (int p = tid; p < nsl * P; p += B) {
+            const int sl = p / P, pp = p - sl * P;
+            sWall[sl * PP + pp] = A.neural[(long long)(s_first + sl) * A.neural_stride + pp];
         }
     } else {
         s = blockIdx.x / A.nchunks;
@@ -513,9 +520,9 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     constexpr int nred = GRAD ? P + 1 : 1;
     if (A.partials && spb > 0) {
-        // packed blocks: a warp may hold lanes of two starts, so the rows go through shared memory: every thread writes
+        // flat blocks: a warp may hold lanes of two starts, so the rows go through shared memory: every thread writes
         // its expanded values to [q][tid] (its own column of the — now dead — stage rows), then thread (start, q) sums
-        // the start's n_ind columns in index order (deterministic) into the start's single partial row
+        // the start's columns of this block in index order (deterministic) into the start's partial row for this block
         double vals_first = active ? sse : 0.0;
         double* const myRow = sK + tid;
         if constexpr (GRAD) {
@@ -538,13 +545,17 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         }
         myRow[0] = vals_first;
         __syncthreads();
-        for (int idx = tid; idx < spb * nred; idx += B) {
-            const int sl = idx / nred, q = idx - sl * nred, ss = blockIdx.x * spb + sl;
-            if (ss >= A.n_starts) continue;
-            const double* src = sK + (size_t)q * B + sl * N;
+        for (int idx = tid; idx < nsl * nred; idx += B) {
+            const int sl = idx / nred, q = idx - sl * nred, ss = s_first + sl;
+            long long lo = (long long)ss * N - j0, hi = (long long)(ss + 1) * N - j0;      // the start's columns in this block
+            if (lo < 0) lo = 0;
+            if (hi > B) hi = B;
+            if (hi > ntot - j0) hi = ntot - j0;
+            const double* src = sK + (size_t)q * B;
             double v = 0.0;
-            for (int k = 0; k < N; ++k) v += src[k];
-            A.partials[(size_t)ss * (P + 1) + q] = v;
+            for (long long k = lo; k < hi; ++k) v += src[k];
+            const long long which = (long long)blockIdx.x - ((long long)ss * N) / B;        // 0: the start's first block, 1: its second
+            A.partials[((size_t)ss * 2 + (size_t)which) * (P + 1) + q] = v;
         }
     } else if (A.partials) {
         double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);

@@ -103,14 +103,15 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
             for (int j = 0; j < 3; ++j) h[(k * 3 + j) * N + i] = data[j + 3 * (k + M * i)];
     SupArgs a{};
     a.n_ind = n_ind; a.n_obs = n_obs; a.n_starts = n_starts; a.nchunks = n_ind;
-    a.spb = (n_ind == 1) ? 1 : 0;      // one individual: exercise the packed (starts-per-block) code path, one start per "block"
+    a.spb = (n_ind == 1) ? 1 : 0;      // one individual: exercise the flat (small-population) code path, one trajectory per "block"
+    const int prow_stride = a.spb ? 2 : 1;   // flat mode keeps two partial rows per start
     a.obs_t = obs_t; a.data = h.data(); a.p1 = p_true[0]; a.p3 = p_true[2];
     for (int j = 0; j < 3; ++j) a.iscale[j] = 1.0 / scale[j];
     a.t0 = t0; a.tend = tend; a.neural = neural; a.neural_stride = neural_stride; a.theta = theta;
     a.abstol = abstol; a.reltol = reltol; a.maxiters = maxiters; a.theta_scale = 1.0;
     a.sse_out = sse; a.g_theta = g_theta; a.counters = counters;
     const long long nblocks = (long long)n_ind * n_starts;
-    std::vector<double> partials((size_t)nblocks * (SN::P + 1), 0.0);
+    std::vector<double> partials((size_t)nblocks * prow_stride * (SN::P + 1), 0.0);
     a.partials = partials.data();
     blockDim.x = 1; threadIdx.x = 0;
     for (long long b = 0; b < nblocks; ++b) {
@@ -119,7 +120,7 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
     }
     if (grad && g_neural_traj)
         for (long long b = 0; b < nblocks; ++b)
-            for (int p = 0; p < SN::P; ++p) g_neural_traj[b * SN::P + p] = partials[b * (SN::P + 1) + 1 + p];
+            for (int p = 0; p < SN::P; ++p) g_neural_traj[b * SN::P + p] = partials[b * prow_stride * (SN::P + 1) + 1 + p];
     return 0;
 }
 
