@@ -23,7 +23,7 @@ using std::isfinite;
 #define CUDART_INF INFINITY
 #define CUDART_NAN NAN
 struct emu_dim3 { int x, y, z; };
-static emu_dim3 blockIdx, threadIdx, blockDim;
+static emu_dim3 blockIdx, threadIdx, blockDim, gridDim;
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline void __syncthreads() {}
@@ -35,6 +35,7 @@ namespace cude { double smem[1 << 16]; }   // the kernel's `extern __shared__ do
 static double* g_trace_buf = nullptr; static int g_trace_cap = 0, g_trace_n = 0;
 #define CUDE_TRACE_STEP(t, dt, eest) if (g_trace_buf && g_trace_n < g_trace_cap) { double* r_ = g_trace_buf + 4 * g_trace_n++; r_[0] = t; r_[1] = dt; r_[2] = eest; r_[3] = (eest <= 1.0) ? 1.0 : 0.0; }
 #include "../../conditional_ude_b200/csrc/cude_kernels.cuh"
+#include "../../conditional_ude_b200/csrc/cude_split.cuh"
 #include "../../conditional_ude_b200/csrc/cude_sup_kernel.cuh"
 
 using namespace cude;
@@ -85,6 +86,77 @@ extern "C" int emu_eval(int n_ind, int max_knots, const int* n_knots, const doub
     if (!flat && grad == 1 && g_neural_traj)
         for (long long b = 0; b < nblocks; ++b)   // block b = s*N + i = trajectory index
             for (int p = 0; p < P; ++p) g_neural_traj[b * P + p] = partials[b * (P + 1) + 1 + p];
+    return 0;
+}
+
+// The split gradient pipeline (csrc/cude_split.cuh) stage by stage, one thread per block: forward solve with step records
+// -> adjoint recursion -> (host) scan -> node kernel -> finish; returns per-start sums {sum sse, d sum sse / d neural} and
+// per-trajectory sse / d sse / d cond.  n_in = 2 only.
+extern "C" int emu_eval_split(int n_ind, int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                              int max_obs, const int* n_obs, const double* obs_t, const double* obs_y, const double* kin,
+                              int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters,
+                              double* sse, double* sums, double* g_cond, int* n_overflow) {
+    typedef NetShape<2, 2, 4> NS;
+    const size_t N = n_ind, K = max_knots, M = max_obs, S = n_starts, NT = N * S;
+    const int P = NS::P, np1 = P + 1;
+    std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N);
+    for (size_t i = 0; i < N; ++i) {
+        const int nk = n_knots[i], no = n_obs[i];
+        for (int k = 0; k < max_knots; ++k) {
+            const int kk = k < nk ? k : nk - 1;
+            kt[k * N + i] = knot_t[i * K + kk]; kg[k * N + i] = knot_g[i * K + kk];
+            if (k + 1 < nk) sl[k * N + i] = (knot_g[i * K + k + 1] - knot_g[i * K + k]) / (knot_t[i * K + k + 1] - knot_t[i * K + k]);
+        }
+        for (int k = 0; k < max_obs; ++k) { const int kk = k < no ? k : no - 1; ot[k * N + i] = obs_t[i * M + kk]; oy[k * N + i] = obs_y[i * M + kk]; }
+        k0[i] = kin[4 * i]; k1[i] = kin[4 * i + 1]; k2[i] = kin[4 * i + 2]; c0[i] = kin[4 * i + 3];
+    }
+    EvalArgs a{};
+    a.pop.n_ind = n_ind; a.pop.max_knots = max_knots; a.pop.max_obs = max_obs;
+    a.pop.n_knots = n_knots; a.pop.knot_t = kt.data(); a.pop.knot_g = kg.data(); a.pop.slope = sl.data();
+    a.pop.n_obs = n_obs; a.pop.obs_t = ot.data(); a.pop.obs_y = oy.data();
+    a.pop.k0 = k0.data(); a.pop.k1 = k1.data(); a.pop.k2 = k2.data(); a.pop.c0 = c0.data(); a.pop.cov = nullptr;
+    a.n_starts = n_starts; a.neural = neural; a.neural_stride = P; a.cond = cond;
+    a.abstol = abstol; a.reltol = reltol; a.maxiters = maxiters; a.flat = 0; a.nchunks = n_ind; a.cond_scale = 1.0;
+    unsigned long long counters[3] = {0, 0, 0};
+    a.sse_out = sse; a.counters = counters;
+    std::vector<double> rec(NT * SPLIT_CAP * SPLIT_W, 0.0), wrec(NT * SPLIT_CAP * SPLIT_WW, 0.0), res(M * NT, 0.0), beta(NT), spsse(NT), wsum(NT);
+    std::vector<int> nrec(NT), flag(NT, 0);
+    a.sp_rec = rec.data(); a.sp_res = res.data(); a.sp_nrec = nrec.data(); a.sp_beta = beta.data(); a.sp_sse = spsse.data(); a.sp_blkflag = flag.data();
+    blockDim.x = 1; threadIdx.x = 0; gridDim.x = (int)NT; gridDim.y = 1;
+    // stage 1 (chunk-major block order: block b = chunk c * S + s, one individual per chunk)
+    for (size_t b = 0; b < NT; ++b) { blockIdx.x = (int)b; blockIdx.y = 0; cude_eval_kernel<NS, false, false, false, false, false, true>(a); }
+    // stage 2
+    RecurArgs ra{};
+    ra.pop = a.pop; ra.ntraj = (long long)NT; ra.sp_rec = rec.data(); ra.sp_w = wrec.data(); ra.sp_res = res.data(); ra.sp_nrec = nrec.data(); ra.sp_wsum = wsum.data();
+    for (size_t b = 0; b < NT; ++b) { blockIdx.x = (int)b; cude_recur_kernel(ra); }
+    // stage 3 (host)
+    std::vector<unsigned int> off(NT + 1), map;
+    unsigned int o = 0; int novf = 0;
+    for (size_t j = 0; j < NT; ++j) { off[j] = o; const int c = nrec[j] > 0 ? nrec[j] : 0; if (nrec[j] < 0) ++novf; for (int q = 0; q < c; ++q) map.push_back((unsigned int)j); o += c; }
+    off[NT] = o;
+    if (map.empty()) map.push_back(0);
+    if (n_overflow) *n_overflow = novf;
+    // stage 4: one "block" per start
+    std::vector<double> gc(map.size(), 0.0), pA(S * np1, 0.0), pB(NT * np1, 0.0);
+    NodeArgs na{};
+    na.pop = a.pop; na.neural = neural; na.neural_stride = P; na.wc_base = 0; na.sp_rec = rec.data(); na.sp_w = wrec.data();
+    na.off = off.data(); na.map = map.data(); na.sp_beta = beta.data(); na.gc_rec = gc.data(); na.partials = pA.data();
+    gridDim.x = 1; gridDim.y = (int)S;
+    for (size_t s = 0; s < S; ++s) { blockIdx.x = 0; blockIdx.y = (int)s; cude_node_kernel<NS, double, false>(na); }
+    // stage 5
+    FinalArgs fa{};
+    fa.pop = a.pop; fa.n_starts = n_starts; fa.nchunks = n_ind; fa.neural = neural; fa.neural_stride = P; fa.sp_nrec = nrec.data();
+    fa.sp_beta = beta.data(); fa.sp_wsum = wsum.data(); fa.sp_sse = spsse.data(); fa.off = off.data(); fa.gc_rec = gc.data();
+    fa.cond_scale = 1.0; fa.g_cond = g_cond; fa.partials = pB.data();
+    gridDim.x = (int)NT; gridDim.y = 1;
+    for (size_t b = 0; b < NT; ++b) { blockIdx.x = (int)b; blockIdx.y = 0; cude_final_kernel<NS, double>(fa); }
+    // second-stage reduction: stage-4 row of the start + the stage-5 rows of its trajectories (row group s * nchunks + c)
+    for (size_t s = 0; s < S; ++s)
+        for (int q = 0; q < np1; ++q) {
+            double v = pA[s * np1 + q];
+            for (size_t c = 0; c < N; ++c) v += pB[(s * N + c) * np1 + q];
+            sums[s * np1 + q] = v;
+        }
     return 0;
 }
 

@@ -14,7 +14,7 @@ _I = C.POINTER(C.c_int)
 def build():
     src = [os.path.join(_HERE, "emu_kernel.cpp")] + [
         os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f)
-        for f in ("cude_kernels.cuh", "cude_math.cuh", "cude_sup_kernel.cuh")]
+        for f in ("cude_kernels.cuh", "cude_math.cuh", "cude_sup_kernel.cuh", "cude_split.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in src):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-o", LIB, src[0]])
@@ -49,6 +49,30 @@ def emu_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, gr
                     _dp(sse), _dp(gn), _dp(gc), cnt, int(mixed))
     assert rc == 0
     return dict(sse=sse, g_neural=gn, g_cond=gc, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
+
+
+def emu_eval_split(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000):
+    """The split gradient pipeline (csrc/cude_split.cuh) through the host-compiled kernel sources, stage by stage.
+    Returns dict(sse[S,N], sums[S,P+1] = {sum sse, d sum sse/d neural}, g_cond[S,N], n_overflow)."""
+    L = C.CDLL(build())
+    L.emu_eval_split.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, C.c_int, _D, _D, C.c_double, C.c_double,
+                                 C.c_int, _D, _D, _D, _I]
+    ch = packed["chain"]
+    N, P = int(packed["n_ind"]), ch.n_params
+    a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
+    nk = np.ascontiguousarray(packed["n_knots"], dtype=np.int32)
+    no = np.ascontiguousarray(packed["n_obs"], dtype=np.int32)
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float64).reshape(-1, N))
+    S = cond.shape[0]
+    assert neural.shape == (S, P) and ch.input_dims == 2
+    sse, sums, gc = np.empty((S, N)), np.zeros((S, P + 1)), np.zeros((S, N))
+    novf = C.c_int(0)
+    rc = L.emu_eval_split(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
+                          int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]),
+                          S, _dp(neural), _dp(cond), abstol, reltol, maxiters, _dp(sse), _dp(sums), _dp(gc), C.byref(novf))
+    assert rc == 0
+    return dict(sse=sse, sums=sums, g_cond=gc, n_overflow=novf.value)
 
 
 def emu_sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), scale=None, abstol=1e-6, reltol=1e-3,

@@ -209,3 +209,34 @@ def test_fp32_adjoint_network_mode(fx):
     gn_a, gn_b = a["g_neural"].sum(axis=1), b["g_neural"].sum(axis=1)        # population gradient per start
     assert np.abs(gn_b - gn_a).max() < 1e-5 * np.abs(gn_a).max()
     assert np.abs(b["g_neural"] - a["g_neural"]).max() < 2e-5 * np.abs(a["g_neural"]).max()
+
+
+def test_split_gradient_pipeline_stages(fx):
+    """csrc/cude_split.cuh compiled for the host: forward solve with step records -> adjoint recursion -> scan -> node kernel
+    (one thread per step record) -> finish.  Same discrete adjoint as the fused kernel: sse bit for bit, gradients to
+    summation order; and the oracle's in the deterministic regime.  Ragged population (5 and 14 knots / observations)."""
+    models, ts, ys = mixed_population(fx)
+    pick = [0, 3, 50, 100, 120, 130, 136]
+    pk = cu.pack_models([models[i] for i in pick], [ts[i] for i in pick], [ys[i] for i in pick])
+    rng = np.random.default_rng(6)
+    neural, cond = random_starts(rng, pk["chain"], len(pick), 3)
+    pk5 = cu.pack_models([models[i] for i in pick[:4]], [ts[i] for i in pick[:4]], [ys[i] for i in pick[:4]])   # Ohashi only: <= 32 steps
+    for pkx, cx, o in ((pk, cond, DET), (pk5, cond[:, :4], dict())):
+        f = emu_wrap.emu_eval(pkx, neural, cx, **o)
+        s = emu_wrap.emu_eval_split(pkx, neural, cx, **o)
+        assert s["n_overflow"] == 0
+        assert np.array_equal(s["sse"], f["sse"])
+        assert relmax(s["g_cond"], f["g_cond"]) < 1e-12
+        assert relmax(s["sums"][:, 0], f["sse"].sum(axis=1)) < 1e-14
+        assert relmax(s["sums"][:, 1:], f["g_neural"].sum(axis=1)) < 1e-12
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    s = emu_wrap.emu_eval_split(pk, neural, cond, **DET)
+    assert relmax(s["sse"], g["sse"]) < 1e-10 and relmax(s["g_cond"], g["g_cond"]) < 1e-9
+    assert relmax(s["sums"][:, 1:], g["g_neural"].sum(axis=1)) < 1e-9
+    # a failed trajectory: Inf in the start's sse sum, zero gradient contribution, the others untouched
+    bad = cond.copy(); bad[1, 2] = np.nan
+    s2 = emu_wrap.emu_eval_split(pk, neural, bad, **DET)
+    assert np.isinf(s2["sums"][1, 0]) and s2["g_cond"][1, 2] == 0 and np.allclose(s2["sums"][[0, 2]], s["sums"][[0, 2]], rtol=1e-14)
+    # more accepted steps than a record block holds (tight tolerance): flagged for the fused-kernel fallback, not recorded
+    s3 = emu_wrap.emu_eval_split(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
+    assert s3["n_overflow"] == len(pick)
