@@ -10,7 +10,12 @@ over the ranks (strong scaling: the population size is fixed).
   python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
   python bench.py --impl reference ...                   # CPU restatement of the reference path (oracle)
 
-One JSON line on stdout (rank 0).
+One JSON line on stdout (rank 0).  Besides the contract's keys it carries: `roofline` (FP64 CUDA-core pipe, peak measured live),
+`e2e` (the host-buffer C-ABI call cude_loss_grad_sharded on page-locked arrays), `cpu_baseline` + `parity_sample` (the oracle on a
+bounded sample of the same workload: its throughput, and the share of trajectories on which the CUDA path differs from it beyond
+the contract), `fp32_modes` (the optional FP32-network modes against measured FP32 / MUFU peaks) and `secondary` (BASELINE
+configs 1-4 and the suppression example as kernel measurements).  N > 1: the all-reduce of the per-start sums runs inside
+libcude_b200.so (NCCL communicator on the context); torch.distributed is the launcher's rendezvous and the timing barrier.
 """
 import argparse
 import json
