@@ -2,16 +2,17 @@
 // cude_split.cuh — stages 2-5 of the split gradient pipeline (stage 1 is cude_eval_kernel<.., SPLIT>, see the
 // "split gradient pipeline" note in cude_kernels.cuh).
 //
-// What the split buys on B200 (measured against the fused kernel, profiles/README.md):
+// Intent and outcome on B200 (measured against the fused kernel, profiles/README.md round 2):
 //   * the network forward+backward evaluations — ~60 % of the fused kernel's instructions — run one thread per
-//     (trajectory, accepted step) record: every lane of every warp has exactly 5 node evaluations per tile, so the
-//     12 % of lane-cycles the fused kernel loses there to trajectories of different length are recovered, the hot loop
-//     is a few KB of straight code instead of 70 KB, and its register budget is its own;
+//     (trajectory, accepted step) record: every lane of every warp has exactly 5 node evaluations per tile (32.0 of 32
+//     lanes active against 27.6), the hot loop is a few KB of straight code instead of 70 KB, its register budget is its own;
 //   * the forward solve runs as the loss-only kernel (128 registers, 4 blocks per SM instead of 168 / 3) and the
-//     adjoint recursion as a small kernel at full occupancy;
-//   * the price is one 96-byte step record per accepted step through HBM (~250 GB per 64 M-trajectory call, ~1 TB/s at
-//     the rate the kernels produce and consume it: far below the 6.5 TB/s the device moves, and prefetched with
-//     cp.async one tile ahead in stage 4).
+//     adjoint recursion as a small kernel;
+//   * the price is one 64-byte step record + one 48-byte weight record per accepted step through HBM (written whole-sector,
+//     prefetched with cp.async one tile ahead in stage 4), the recursion's load latency and five more launches per group.
+//   Outcome: the node kernel saturates the FP64 pipe (68 % active, math-pipe throttled) and is 13 % faster per evaluation
+//   than the fused kernel's loop, but the pipeline as a whole is 5-15 % SLOWER than the fused kernel.  It is therefore an
+//   option (cude_opts.split = 2), parity-tested against the fused kernel, not the default.
 // Reference semantics are unchanged: the same discrete adjoint of the same Tsit5 solve (src/parameter-estimation.jl:59,
 // gradient of :126-140 in place of AutoForwardDiff :370); only the order in which node contributions are summed differs.
 // =====================================================================================
