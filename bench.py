@@ -422,9 +422,10 @@ def run_ours(args):
     shard.neural.copy_(neural_p)
     shard.cond.copy_(cond_p)
     d_sums = shard.sums
-    # headline: natural lane order (cude_opts.balance = 0).  Lane balancing (each start's individuals grouped by the step
-    # counts of an earlier call) is reported as a secondary figure only: on this bench's *repeated identical inputs* the
-    # prediction is perfect (+12 %), under real Adam training it is worth +3 % (profiles/r01_adam_balance.json)
+    # headline: the library's default (cude_opts.balance = 0): for a population this large the two-kernel gradient — forward
+    # solve with step records, each start's trajectories sorted by their accepted-step count, adjoint sweep in sorted order.
+    # It uses nothing from earlier calls (the bench repeats its inputs; a history-based regrouping, balance = 1, would profit
+    # from that and is reported as a secondary figure only, as is the fused single-kernel adjoint, balance = 3).
     opts = cu.SolverOptions(block=args.block, precision=args.precision, balance=args.balance, split=args.split)
 
     def step_resident():
@@ -484,7 +485,11 @@ def run_ours(args):
     step_loss_only()
     loss_only_value = N_total * S / (timed(step_loss_only, 2) / 2 * 1e-3)
 
-    # secondary figure: the same step with lane balancing on (see the note at `opts`)
+    # secondary figures: the fused single-kernel adjoint in natural lane order (the round-1 headline path), and the same with
+    # history-based lane regrouping (see the note at `opts`)
+    opts_fused = cu.SolverOptions(block=args.block, precision=args.precision, balance=3, split=args.split)
+    shard.step(opts_fused)
+    fused_value = N_total * S / (timed(lambda: shard.step(opts_fused), 3) / 3 * 1e-3)
     opts_bal = cu.SolverOptions(block=args.block, precision=args.precision, balance=1, split=args.split)
     def step_balanced():
         shard.step(opts_bal)
@@ -550,7 +555,7 @@ def run_ours(args):
     # committed `ncu --set full` capture (profiles/r01_v16_traffic.json), scaled to this rank's launch
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v16_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json" if args.balance in (0, 2) else "r01_v16_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_trajectory"] * (n_traj / world)
     except Exception:
         pass
@@ -567,16 +572,22 @@ def run_ours(args):
            "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
            "measured_dram_gbs": (traffic / kernel_s / 1e9) if traffic else None}
     roofline = {"bound": "fp64", "hbm": hbm, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "cude_eval_kernel<NetShape<2,2,4>,GRAD>", "kernel_ms": float(kms.item()),
+                "traffic": traffic,
+                "kernel": ("cude_eval_kernel<NetShape<2,2,4>,SPLIT> (forward solve + step records) + cude_adjoint_kernel<NetShape<2,2,4>> "
+                           "(adjoint sweep in step-count order): the two kernels of a step, timed together"
+                           if args.balance in (0, 2) else "cude_eval_kernel<NetShape<2,2,4>,GRAD>"),
+                "kernel_ms": float(kms.item()),
                 "alg_flops_per_traj": fl / (n_traj / world), "alg_transcendentals_per_traj": tr / (n_traj / world),
                 "peak_source": "measured live: DFMA micro-benchmark (cude_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_register_operands": peak_rrr,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_v16_traffic.json): "
-                                  "52 B per trajectory against 29 B algorithmic; HBM is not the bound",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of each kernel (profiles/r02_traffic.json; "
+                                  "fused kernel: profiles/r01_v16_traffic.json, 52 B per trajectory against 29 B algorithmic): the step "
+                                  "records add ~1.3 KB written + read per trajectory; HBM is still not the bound",
                 "note": "peak = DFMA chains whose other operands come from the uniform path (upper bound); "
                         "peak_register_operands = DFMA with three register operands, the shape of real code. One FP64 "
                         "tanh/exp/log costs 8-25 FP64 instructions but counts once in `achieved`; ncu "
-                        "(profiles/r01_v16_*) shows the FP64 pipe 58 % active and 60 % of the issue slots used.",
+                        "(profiles/r02_*_kernel_ncu_summary.txt) shows the FP64 pipe 56-68 % active in these kernels, which is "
+                        "what DFMAs with three register operands sustain.",
                 "n_acc_per_traj": n_acc / n_traj, "n_rej_per_traj": n_rej / n_traj}
 
     if rank == 0:
@@ -593,23 +604,26 @@ def run_ours(args):
                        "observations": "model solution (cude_simulate) at the stored network 14 and beta_true ~ N(-1, 0.6) "
                                        "+ N(0, 0.1^2) noise (SURVEY 8d config 5); starts: network + N(0, 0.1^2), beta ~ LHS[-2, 0]",
                        "l2": "inputs larger than L2 (cond + g_cond = %.0f MB per rank)" % (2 * S * n_loc * 8 / 1e6),
-                       "lane_balance": "on (cude_opts.balance = 1)" if args.balance else "off (natural order)",
+                       "gradient_path": {0: "automatic (balance = 0): two-kernel gradient, adjoint in exact step-count order",
+                                         1: "fused kernel, history-based lane regrouping (balance = 1)",
+                                         2: "two-kernel gradient, adjoint in exact step-count order (balance = 2)",
+                                         3: "fused single-kernel adjoint, natural lane order (balance = 3)"}[args.balance],
+                       "fused_kernel_natural_order_evals_per_s": fused_value,
                        "lane_balanced_evals_per_s": balanced_value,
                        "fp32_adjoint_evals_per_s": fp32adj_value,
                        "fp32_adjoint_note": "secondary: cude_opts.precision = 2 — loss and step sequence bitwise those of the FP64 "
                                             "headline, FP32 network only in the adjoint sweep (gradients to 1e-5 of their scale)",
-                       "lane_balanced_note": "secondary: individuals of each start grouped by the step counts of an earlier "
-                                             "call; exact prediction here because the bench repeats its inputs (under Adam "
-                                             "training the measured gain is +3 %, profiles/r01_adam_balance.json)",
+                       "lane_balanced_note": "secondary (balance = 1): fused kernel, individuals of each start grouped by the step counts "
+                                             "of an earlier call; exact prediction here because the bench repeats its inputs (under "
+                                             "Adam training the measured gain is +2 %, profiles/README.md round 2)",
                        "n_fail": n_fail, "mean_loss_start0": float(loss0[0]),
                        "loss_only_evals_per_s": loss_only_value},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e},
-            # per step: loss+gradient kernel + partial-row reduction; on the lane-balancing refresh steps (every 8th call
-            # on the population) one radix-sort call per start on top (counted once each)
-            "gpu_launches": 2 * args.steps + (S * sum(1 for c in range(args.warmup, args.warmup + args.steps) if c % 8 == 0)
-                                              if args.balance else 0),
+            # kernels launched per step, counted by the library (cude_stats.launches of one step): forward-with-records kernel,
+            # one stable radix sort per start, adjoint kernel, fallback launch and two reduction kernels per group of starts
+            "gpu_launches": int(st["launches"]) * args.steps,
             "roofline": roofline,
         }
         if fp32_modes is not None:
@@ -656,7 +670,7 @@ def main():
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--precision", type=int, default=0, help="0 = FP64 (headline, parity-gated); 1 = FP32 network (looser bound); 2 = FP64 forward, FP32 adjoint network")
-    ap.add_argument("--balance", type=int, default=0, help="cude_opts.balance for the headline: 0 = natural lane order (default), 1 = regroup lanes by earlier step counts")
+    ap.add_argument("--balance", type=int, default=0, help="cude_opts.balance for the headline: 0 = library default (two-kernel gradient with exact lane balance for large populations), 1 = fused kernel with history-based regrouping, 2 = two-kernel always, 3 = fused kernel in natural order")
     ap.add_argument("--split", type=int, default=0, help="cude_opts.split: 0 = automatic (split gradient pipeline for large batches), 1 = fused kernel, 2 = split pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernel measurements (configs 1-4, suppression, FP32 modes)")

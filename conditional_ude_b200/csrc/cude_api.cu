@@ -42,6 +42,10 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
+#ifndef CUDE_EXACT_MIN_IND
+#define CUDE_EXACT_MIN_IND 32768            // opts.balance = 0 (automatic): populations of at least this many individuals take the two-kernel
+                                            // gradient with exact lane balance; smaller ones the fused single-kernel adjoint (lower latency)
+#endif
 #ifndef CUDE_SPLIT_BYTES
 #define CUDE_SPLIT_BYTES (20ull << 30)      // device memory the split pipeline's step records may take per group of starts
 #endif
@@ -76,6 +80,7 @@ struct cude_ctx {
     SplitSet sp[3];
     cudaStream_t s_hi = nullptr;
     cudaEvent_t ev_fork = nullptr;
+    size_t split_budget = 0;            // device memory the step records may take (decided once: cudaMemGetInfo synchronises)
     // NCCL communicator of a sharded population (cude_comm_init_rank, or the ranks of a cude_mctx): the per-start sums
     // are all-reduced in place on `stream` (cude_multi.inl)
     void* comm = nullptr;
@@ -499,17 +504,34 @@ static int wconst_used(cude_ctx* ctx) {      // after the launches that read the
     return CUDE_OK;
 }
 
+// Record-memory budget of the split / two-kernel gradient paths: CUDE_SPLIT_BYTES, at most 40 % of what was free when the
+// context first asked (asked once: cudaMemGetInfo synchronises the device, which would serialise a pipelined host call).
+static int split_budget(cude_ctx* ctx, size_t* out) {
+    if (!ctx->split_budget) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        size_t b = CUDE_SPLIT_BYTES;
+        if (b > free_b * 2 / 5) b = free_b * 2 / 5;
+        ctx->split_budget = b > (1u << 20) ? b : (1u << 20);
+    }
+    *out = ctx->split_budget;
+    return CUDE_OK;
+}
+
 // ---------------------------------------------------------------- split gradient pipeline (cude_split.cuh)
 typedef void (*node_kernel_t)(const NodeArgs);
 typedef void (*final_kernel_t)(const FinalArgs);
-struct SplitKernels { eval_kernel_t k1 = nullptr; node_kernel_t k3 = nullptr; final_kernel_t k4 = nullptr; };
+typedef void (*adj_kernel_t)(const AdjArgs);
+struct SplitKernels { eval_kernel_t k1 = nullptr; node_kernel_t k3 = nullptr; final_kernel_t k4 = nullptr; adj_kernel_t ka = nullptr; };
 
 template <class NS>
 static SplitKernels pick_split(bool fbwd, bool wc) {
     SplitKernels k;
     k.k1 = wc ? cude_eval_kernel<NS, false, false, false, false, true, true> : cude_eval_kernel<NS, false, false, false, false, false, true>;
-    if (fbwd) { k.k3 = wc ? cude_node_kernel<NS, float, true> : cude_node_kernel<NS, float, false>; k.k4 = cude_final_kernel<NS, float>; }
-    else { k.k3 = wc ? cude_node_kernel<NS, double, true> : cude_node_kernel<NS, double, false>; k.k4 = cude_final_kernel<NS, double>; }
+    if (fbwd) { k.k3 = wc ? cude_node_kernel<NS, float, true> : cude_node_kernel<NS, float, false>; k.k4 = cude_final_kernel<NS, float>;
+                k.ka = wc ? cude_adjoint_kernel<NS, float, true> : cude_adjoint_kernel<NS, float, false>; }
+    else { k.k3 = wc ? cude_node_kernel<NS, double, true> : cude_node_kernel<NS, double, false>; k.k4 = cude_final_kernel<NS, double>;
+           k.ka = wc ? cude_adjoint_kernel<NS, double, true> : cude_adjoint_kernel<NS, double, false>; }
     return k;
 }
 static SplitKernels select_split(const cude_net* net, bool fbwd, bool wc) {
@@ -584,12 +606,9 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     cudaStream_t sM = ctx->stream, sH = ctx->s_hi;
     // ---- groups of starts: three sets of buffers share the budget ----
     const size_t per_traj = (size_t)(SPLIT_W + SPLIT_WW) * SPLIT_CAP * 8 + (size_t)SPLIT_CAP * (4 + 8) + (size_t)M * 8 + 4 * 8 + 8 + 3 * (size_t)np1 * 8 / 32 + 64;
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    size_t have = 0;
-    for (auto& st : ctx->sp) have += st.rec.cap + st.w.cap + st.misc.cap + st.map.cap + st.gc.cap + st.part.cap;
-    size_t budget = CUDE_SPLIT_BYTES;
-    if (budget > (free_b + have) / 2) budget = (free_b + have) / 2;
+    size_t budget = 0;
+    int rc0 = split_budget(ctx, &budget);
+    if (rc0) return rc0;
     long long sg = (long long)(budget / 3 / (per_traj * (size_t)N));
     if (sg < 1) sg = 1;
     if (sg > (S + 2) / 3) sg = (S + 2) / 3;                                   // at least three groups when there are three starts
@@ -744,6 +763,102 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     return CUDE_OK;
 }
 
+// Two-kernel gradient with exact lane balance (opts.balance = 2): stage 1 (forward solve + step records + keys) -> every
+// start's trajectories sorted by their accepted-step count (stable radix sort over the count byte: deterministic) -> the
+// adjoint kernel in sorted order -> fused-kernel fallback for trajectories beyond SPLIT_CAP steps -> row reduction.  One
+// stream, groups of starts sized by the record memory (set 0 of the split pipeline's buffers).
+static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int nchunks, bool fbwd, bool wc, size_t n_w,
+                     eval_kernel_t fused, size_t smem_fused, double* d_sums_out, int* launches) {
+    const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
+    const int M = a.pop.max_obs, K = a.pop.max_knots;
+    if (N >= (1 << 24)) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: balance = 2 supports up to 2^24 individuals per population");
+    const SplitKernels sk = select_split(net, fbwd, wc);
+    if (!sk.k1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
+    cudaStream_t st = ctx->stream;
+    const size_t per_traj = (size_t)SPLIT_W * SPLIT_CAP * 8 + (size_t)M * 8 + 2 * 8 + 4 + 2 * 4 + 2 * (size_t)np1 * 8 / 32 + 64;
+    size_t budget = 0;
+    int rc0 = split_budget(ctx, &budget);
+    if (rc0) return rc0;
+    long long sg = (long long)(budget / (per_traj * (size_t)N));
+    if (sg < 1) sg = 1;
+    if (sg > S) sg = S;
+    const int ngroups = (int)((S + sg - 1) / sg);
+    const int Sg = (S + ngroups - 1) / ngroups;
+    const size_t ntg = (size_t)N * Sg;
+    const int nB = nchunks * nw;
+    const size_t rowsB = (size_t)Sg * nB;
+    int nseg = (2 * nB + 2047) / 2048;
+    if (nseg > 64) nseg = 64;
+    cude_ctx::SplitSet& set = ctx->sp[0];
+    const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_sse = o_beta + ntg * 8, o_keys = o_sse + ntg * 8,
+                 o_nrec = o_keys + 2 * ((ntg * 4 + 7) / 8 * 8), o_flag = o_nrec + (ntg * 4 + 7) / 8 * 8,
+                 o_seg = o_flag + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8, misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
+    int rc;
+    if ((rc = ensure(ctx, set.rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, set.misc, misc_bytes))) return rc;
+    if ((rc = ensure(ctx, set.part, 2 * rowsB * np1 * sizeof(double)))) return rc;
+    size_t sort_bytes = 0;
+    CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (unsigned int*)nullptr, (unsigned int*)nullptr, N, 24, 32, st));
+    if ((rc = ensure(ctx, set.map, sort_bytes))) return rc;        // radix-sort workspace
+    char* const misc = (char*)set.misc.p;
+    double* const pB = (double*)set.part.p;
+    double* const pC = pB + rowsB * np1;
+    const int nacc = 2 * net->width + (net->depth - 1) * net->width * (net->width + 1) + net->width + 1;
+    const size_t smem1 = sizeof(double) * eval_smem_doubles(P, nacc, K, M, B, false, false, true);
+    const size_t smemA = sizeof(double) * adj_smem_doubles(P, B, fbwd, wc);
+    if ((rc = prep_kernel(ctx, (const void*)sk.k1, B, smem1))) return rc;
+    if ((rc = prep_kernel(ctx, (const void*)sk.ka, B, smemA))) return rc;
+    if ((rc = prep_kernel(ctx, (const void*)fused, B, smem_fused))) return rc;
+    if (wc && (rc = wconst_upload(ctx, a.neural, n_w))) return rc;
+    for (int g0 = 0; g0 < S; g0 += Sg) {
+        const int ns = (S - g0 < Sg) ? S - g0 : Sg;
+        const unsigned nblk = (unsigned)((size_t)ns * nchunks);
+        EvalArgs e = a;
+        e.n_starts = ns;
+        e.neural = a.neural + (size_t)g0 * a.neural_stride;
+        e.wc_base = a.wc_base + (long long)g0 * a.neural_stride;
+        e.cond = a.cond + (size_t)g0 * N;
+        e.sse_out = a.sse_out ? a.sse_out + (size_t)g0 * N : nullptr;
+        e.g_cond = a.g_cond + (size_t)g0 * N;
+        e.order = nullptr;
+        e.partials = nullptr;
+        unsigned int* const keys_raw = (unsigned int*)(misc + o_keys);
+        unsigned int* const keys_sorted = keys_raw + (ntg * 4 + 7) / 8 * 2;
+        e.keys_out = keys_raw;
+        e.sp_rec = (double*)set.rec.p;
+        e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
+        e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
+        CU_TRY(ctx, cudaMemsetAsync(e.sp_blkflag, 0, (size_t)nblk * sizeof(int), st));
+        CU_TRY(ctx, cudaMemsetAsync(pC, 0, (size_t)ns * nB * np1 * sizeof(double), st));
+        sk.k1<<<nblk, B, smem1, st>>>(e);                                     // forward solve, step records, keys
+        CU_TRY(ctx, cudaGetLastError());
+        for (int s = 0; s < ns; ++s) {                                        // each start's individuals by accepted steps
+            size_t b = set.map.cap;
+            CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(set.map.p, b, keys_raw + (size_t)s * N, keys_sorted + (size_t)s * N, N, 24, 32, st));
+        }
+        AdjArgs aa{};
+        aa.pop = a.pop; aa.n_starts = ns; aa.nchunks = nchunks; aa.neural = e.neural; aa.neural_stride = a.neural_stride; aa.wc_base = e.wc_base;
+        aa.sp_rec = e.sp_rec; aa.sp_res = e.sp_res; aa.sp_nrec = e.sp_nrec; aa.sp_beta = e.sp_beta; aa.sp_sse = e.sp_sse;
+        aa.order = keys_sorted; aa.cond_scale = a.cond_scale; aa.g_cond = e.g_cond; aa.partials = pB;
+        sk.ka<<<nblk, B, smemA, st>>>(aa);                                    // adjoint sweep in sorted order
+        CU_TRY(ctx, cudaGetLastError());
+        EvalArgs f = e;
+        f.partials = pC; f.only_flag = e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
+        fused<<<nblk, B, smem_fused, st>>>(f);                                // trajectories beyond SPLIT_CAP steps
+        CU_TRY(ctx, cudaGetLastError());
+        *launches += 3 + ns;
+        if (d_sums_out) {
+            double* const d_seg = (double*)(misc + o_seg);
+            cude_reduce_rows<<<dim3((unsigned)nseg, (unsigned)ns), RED_T, 0, st>>>(nullptr, 0, pB, pC, nB, np1, nseg * np1, d_seg);
+            cude_reduce_rows<<<dim3(1, (unsigned)ns), RED_T, 0, st>>>(d_seg, nseg, nullptr, nullptr, 0, np1, np1, d_sums_out + (size_t)g0 * np1);
+            CU_TRY(ctx, cudaGetLastError());
+            *launches += 2;
+        }
+    }
+    if (wc && (rc = wconst_used(ctx))) return rc;
+    return CUDE_OK;
+}
+
 extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
                              int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
                              int want_grad, double cond_scale,
@@ -762,6 +877,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     cude_opts o;
     if (opts_in) o = *opts_in; else cude_default_opts(&o);
     if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad solver options");
+    if (o.balance < 0 || o.balance > 3) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: balance must be 0 (automatic), 1 (history), 2 (exact) or 3 (off)");
     if (o.precision < 0 || o.precision > 2) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: precision must be 0 (FP64), 1 (FP32 network, FP64 integrator) or 2 (FP64 forward pass, FP32 network in the adjoint)");
     const bool mixed = o.precision == 1;
     const bool fbwd = o.precision == 2;
@@ -837,6 +953,11 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     // loss + full gradient through the split pipeline only on request (opts.split = 2): measured 5 - 15 % slower than the
     // fused kernel on B200 (profiles/README.md, round 2), kept as a parity-tested alternative
     const bool use_split = adj && !flat && !mixed && want_neural_grad && d_g_cond && o.split == 2;
+    // the two-kernel gradient whose adjoint runs every start's trajectories sorted by their exact step count: on request
+    // (opts.balance = 2) or automatically for large populations (opts.balance = 0).  The choice depends on the population
+    // only, never on the number of starts, so that a start's sums do not depend on how a batch is split into calls.
+    const bool use_exact = !use_split && adj && !flat && !mixed && want_neural_grad && d_g_cond && N < (1 << 24) &&
+                           (o.balance == 2 || (o.balance == 0 && N >= CUDE_EXACT_MIN_IND));
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
@@ -845,6 +966,8 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     int launches = 0;
     if (use_split) {
         if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
+    } else if (use_exact) {
+        if ((rc = run_exact(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
     } else {
         if (wc && (rc = wconst_upload(ctx, d_neural, n_w))) return rc;
         kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
@@ -852,7 +975,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
         if (wc && (rc = wconst_used(ctx))) return rc;
         launches = 1;
     }
-    if (d_sums_out && !use_split) {
+    if (d_sums_out && !use_split && !use_exact) {
         if (flat) {
             const int wpb = 8;
             cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);

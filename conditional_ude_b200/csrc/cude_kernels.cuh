@@ -994,7 +994,7 @@ cude_eval_kernel(const EvalArgs A) {
     // ---- outputs ----
     if (active) {
         if (A.keys_out) {
-            const int ns = nacc + nrej;
+            const int ns = SPLIT ? nacc : nacc + nrej;      // stage 1 of the two-kernel gradient: the adjoint's length (accepted steps)
             A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
         }
         if (A.sse_out) A.sse_out[j] = sse;

@@ -486,6 +486,187 @@ __global__ void __launch_bounds__(128) cude_final_kernel(const FinalArgs A) {
     }
 }
 
+// ---------------------------------------------------------------- two-kernel gradient with exact lane balance (opts.balance = 2)
+// Stage 1 (the forward solve with step records) -> every start's trajectories sorted by their number of accepted steps ->
+// this kernel: the adjoint sweep of one trajectory per thread, in the sorted order.  The 32 lanes of a warp (and the 4
+// warps of a block) then walk the same number of steps, so the sweep has no idle lanes — what history-based regrouping
+// (opts.balance = 1) cannot deliver once the parameters move (profiles/README.md) — and the kernel carries only the adjoint's
+// code and registers.  Arithmetic and accumulation order per trajectory are the fused kernel's (recursion, then the 5 node
+// evaluations of the step, accumulators in registers, NN([0;beta]) node last); glucose at the nodes comes from the record.
+struct AdjArgs {
+    PopDev pop;
+    int n_starts, nchunks;
+    const double* neural;          // the group's first start
+    long long neural_stride, wc_base;
+    const double* sp_rec;          // [N x S][SPLIT_CAP][SPLIT_W]  {t, h, dG[5], 0}
+    const double* sp_res;          // [M][N x S]
+    const int* sp_nrec;
+    const double* sp_beta;
+    const double* sp_sse;
+    const unsigned int* order;     // [N x S]: position pos of start s runs individual order[s*N + pos] & 0xffffff
+    double cond_scale;
+    double* g_cond;                // [N x S]
+    double* partials;              // [S*nchunks*warps][P+1]
+};
+#ifndef CUDE_ADJ_MIN_BLOCKS
+#define CUDE_ADJ_MIN_BLOCKS 4      // 128 registers, 16 warps per SM: 2.38e8 evals/s; 3 blocks (168 registers) 2.36e8, 2 blocks 2.30e8
+#endif
+__host__ __device__ inline size_t adj_smem_doubles(int P, int B, bool f32copy, bool wc) {
+    return (size_t)256 + ((wc && !f32copy) ? 0 : (size_t)((P + 1) & ~1)) + (size_t)10 * B;
+}
+
+template <class NS, class RB, bool WC>
+__global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(const AdjArgs A) {
+    using namespace tab;
+    constexpr int W = NS::W, P = NS::P;
+    constexpr bool F32 = std::is_same<RB, float>::value;
+    extern __shared__ double smem[];
+    const int B = blockDim.x, tid = threadIdx.x, N = A.pop.n_ind;
+    double* sTab = smem;
+    double* sWs = sTab + 256;
+    double* sNode = sWs + ((WC && !F32) ? 0 : ((P + 1) & ~1));   // [5][B] node weights
+    double* sDG = sNode + (size_t)5 * B;                        // [5][B] dG at the nodes
+    const int c = blockIdx.x / A.n_starts, s = blockIdx.x - c * A.n_starts;      // chunk-major like stage 1
+    const long long prow = (long long)s * A.nchunks + c;
+    for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
+    const long long wofs = (long long)(blockIdx.x % (unsigned)A.n_starts) * A.neural_stride;
+    double wuni[(WC && !F32) ? P : 1];
+    if constexpr (WC && !F32) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) wuni[p] = CW_CONST[A.wc_base + wofs + p];
+    } else {
+        RB* const w = reinterpret_cast<RB*>(sWs);
+        for (int p = tid; p < P; p += B) w[p] = (RB)A.neural[wofs + p];
+    }
+    const RB* const sW = (WC && !F32) ? reinterpret_cast<const RB*>(wuni) : reinterpret_cast<const RB*>(sWs);
+    __syncthreads();
+    const int pos = c * B + tid;
+    const bool inb = pos < N;
+    const int i = inb ? (A.order ? (int)(A.order[(size_t)s * N + pos] & 0xffffffu) : pos) : 0;
+    const size_t j = (size_t)s * N + i;
+    const size_t ntraj = (size_t)N * A.n_starts;
+    const int nrec = inb ? A.sp_nrec[j] : 0;
+    RB acc[NS::NACC];
+#pragma unroll
+    for (int k = 0; k < NS::NACC; ++k) acc[k] = RB(0);
+    double beta = 0.0, covv = 0.0, sse = 0.0;
+    if (inb && nrec >= 0) sse = A.sp_sse[j];          // failed: Inf; overflowed trajectories belong to the fallback
+    double* const myNode = sNode + tid;
+    double* const myDG = sDG + tid;
+    if (nrec > 0) {
+        const double k0 = A.pop.k0[i], k1 = A.pop.k1[i], k2 = A.pop.k2[i];
+        const double d00 = -(k0 + k2);
+        const int nobs = A.pop.n_obs[i];
+        const double tend = A.pop.knot_t[(size_t)(A.pop.n_knots[i] - 1) * N + i];
+        const double* const obs_t = A.pop.obs_t + i;
+        const double* const res = A.sp_res + j;
+        beta = A.sp_beta[j];
+        if (NS::NIN > 2) covv = A.pop.cov[i];
+        RB cb[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            double z = fma((double)sW[W + q], beta, (double)sW[NS::NIN * W + q]);
+            if (NS::NIN > 2) z = fma((double)sW[2 * W + q], covv, z);
+            cb[q] = (RB)z;
+        }
+        double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
+        int kobs_top = nobs - 1;
+        double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;
+        const double2* rec = reinterpret_cast<const double2*>(A.sp_rec + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_W);
+        double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];      // the step's record, fetched one step ahead
+        for (int n = nrec - 1; n >= 0; --n, rec -= SPLIT_W / 2) {
+            const double tn = r0.x, h = r0.y;
+            myDG[0] = r1.x; myDG[B] = r1.y; myDG[2 * B] = r2.x; myDG[3 * B] = r2.y; myDG[4 * B] = r3.x;
+            if (n > 0) { r0 = rec[-(SPLIT_W / 2)]; r1 = rec[1 - SPLIT_W / 2]; r2 = rec[2 - SPLIT_W / 2]; r3 = rec[3 - SPLIT_W / 2]; }
+            double kb[7][2];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
+            double ub0 = 0.0, ub1 = 0.0;
+            while (kobs_top >= 0) {                      // observations in (tn, t_next]
+                const double ts = top_ot;
+                if (!(ts > tn)) break;
+                const double wr = 2.0 * res[(size_t)kobs_top * ntraj];
+                if (ts == t_next) lam0 += wr;
+                else {
+                    double bw[7];
+                    dense_weights((ts - tn) * m_rcp(h), bw);
+                    ub0 += wr;
+                    const double wh = wr * h;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
+                }
+                --kobs_top;
+                top_ot = (kobs_top >= 0) ? obs_t[(size_t)kobs_top * N] : -CUDART_INF;
+            }
+            const double pb7 = kb[6][0];
+            lam0 = fma(d00, kb[6][0], lam0);
+            lam1 = fma(k1, kb[6][0], lam1);
+            ub0 += lam0; ub1 += lam1;
+            {
+                const double hl0 = h * lam0, hl1 = h * lam1;
+                kb[0][0] = fma(b1, hl0, kb[0][0]); kb[0][1] = fma(b1, hl1, kb[0][1]);
+                kb[1][0] = fma(b2, hl0, kb[1][0]); kb[1][1] = fma(b2, hl1, kb[1][1]);
+                kb[2][0] = fma(b3, hl0, kb[2][0]); kb[2][1] = fma(b3, hl1, kb[2][1]);
+                kb[3][0] = fma(b4, hl0, kb[3][0]); kb[3][1] = fma(b4, hl1, kb[3][1]);
+                kb[4][0] = fma(b5, hl0, kb[4][0]); kb[4][1] = fma(b5, hl1, kb[4][1]);
+                kb[5][0] = fma(b6, hl0, kb[5][0]); kb[5][1] = fma(b6, hl1, kb[5][1]);
+            }
+            double gb0, gb1, hg0, hg1;
+#define CUDE_STAGE_BACK(I)                                                    \
+    gb0 = fma(d00, kb[I][0], k2 * kb[I][1]);                                  \
+    gb1 = k1 * (kb[I][0] - kb[I][1]);                                         \
+    ub0 += gb0; ub1 += gb1; hg0 = h * gb0; hg1 = h * gb1;
+#define CUDE_PUSH(J, COEF) kb[J][0] = fma(COEF, hg0, kb[J][0]); kb[J][1] = fma(COEF, hg1, kb[J][1]);
+            const double pb6 = kb[5][0];
+            CUDE_STAGE_BACK(5) CUDE_PUSH(0, a61) CUDE_PUSH(1, a62) CUDE_PUSH(2, a63) CUDE_PUSH(3, a64) CUDE_PUSH(4, a65)
+            const double pb5 = kb[4][0];
+            CUDE_STAGE_BACK(4) CUDE_PUSH(0, a51) CUDE_PUSH(1, a52) CUDE_PUSH(2, a53) CUDE_PUSH(3, a54)
+            const double pb4 = kb[3][0];
+            CUDE_STAGE_BACK(3) CUDE_PUSH(0, a41) CUDE_PUSH(1, a42) CUDE_PUSH(2, a43)
+            const double pb3 = kb[2][0];
+            CUDE_STAGE_BACK(2) CUDE_PUSH(0, a31) CUDE_PUSH(1, a32)
+            const double pb2 = kb[1][0];
+            CUDE_STAGE_BACK(1) CUDE_PUSH(0, a21)
+            const double pb1 = kb[0][0];
+            CUDE_STAGE_BACK(0)
+#undef CUDE_STAGE_BACK
+#undef CUDE_PUSH
+            (void)hg0; (void)hg1;
+            const double w6 = pb6 + pb7 + wnode;
+            myNode[0] = pb2; myNode[B] = pb3; myNode[2 * B] = pb4; myNode[3 * B] = pb5; myNode[4 * B] = w6;
+            wsum += w6 + pb5 + pb4 + pb3 + pb2;
+            wnode = pb1;
+            lam0 = ub0; lam1 = ub1;
+            t_next = tn;
+#pragma unroll 1
+            for (int q = 0; q < 5; ++q) mlp_backward<NS, RB>(sW, sTab, cb, (RB)myDG[q * B], (RB)myNode[q * B], acc);
+        }
+        // the NN([0; beta]) term (c-peptide-models.jl:91): one node at dG = 0 with weight -sum(w)
+        mlp_backward<NS, RB>(sW, sTab, cb, RB(0), (RB)(-wsum), acc);
+        double db = 0.0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) db = fma((double)acc[W + q], (double)sW[W + q], db);
+        A.g_cond[j] = db * beta * A.cond_scale;
+    } else if (inb && nrec == 0) {
+        A.g_cond[j] = 0.0;
+    }
+    const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
+    double* const row = A.partials + ((size_t)prow * nw + wid) * (P + 1);
+#pragma unroll
+    for (int p = -1; p < P; ++p) {
+        double v;
+        if (p < 0) v = sse;
+        else if (p < W) v = (double)acc[p];
+        else if (p < 2 * W) v = (double)acc[W + (p - W)] * beta;
+        else if (NS::NIN > 2 && p < 3 * W) v = (double)acc[W + (p - 2 * W)] * covv;
+        else if (p < NS::L1) v = (double)acc[W + (p - NS::NIN * W)];
+        else v = (double)acc[2 * W + (p - NS::L1)];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) row[1 + p] = v;
+    }
+}
+
 // ---------------------------------------------------------------- second-stage reduction over the three row sets
 // Per start s: rows of stage 4 (A: nA), stage 5 (B: nB) and the fused-kernel fallback (C: nB, zero-filled before the
 // launch, written only by flagged blocks), each [np1] wide.  Pass 1: block (seg, s) sums its share of the rows

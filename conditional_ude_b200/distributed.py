@@ -109,12 +109,11 @@ class DevicePopulationShard:
             self.g_cond = torch.empty((self.S, self.n_loc), **f64)
 
     def step(self, opts=None, want_grad=True):
-        """Asynchronous: after it returns the stream holds kernel + reduction + all-reduce.  Default options: the
-        reference's tolerances with lane balancing on (training is iterative: each start's individuals run grouped by
-        the step counts of an earlier iteration, cude_opts.balance)."""
+        """Asynchronous: after it returns the stream holds kernel(s) + reduction + all-reduce.  Default options: the
+        reference's tolerances, automatic lane balance (cude_opts.balance = 0)."""
         if opts is None:
             from .population import SolverOptions
-            opts = SolverOptions(balance=1)
+            opts = SolverOptions()
         with self.torch.cuda.stream(self.stream):
             self.pop.eval_dev(self.S, self.neural.data_ptr(), self.P, self.cond.data_ptr(), 3 if want_grad else 0,
                               1.0 / self.n_total, 0, self.sums.data_ptr(), self.g_cond.data_ptr() if want_grad else 0, opts)

@@ -60,13 +60,18 @@ typedef struct {
                     * 2 = forward pass (loss, step sequence) in FP64 bit for bit, FP32 network and accumulators only in
                     * the adjoint sweep: loss as in mode 0, gradients to ~1e-6 relative */
     int block;     /* threads per block (individuals per tile); 0 = library default */
-    int balance;   /* 0 (default) = lanes in natural order: the per-start sums are bitwise run-to-run deterministic.
-                    * 1 = iterative workloads (training): for loss+gradient calls on >= 4096 individuals with
-                    * per-start networks, the individuals of each start are regrouped by the step counts their
-                    * trajectories took in an earlier call on this population (refreshed every 8 calls), so that the
-                    * 32 lanes of a warp finish together (~12 % fewer warp-steps).  Per-trajectory results (sse,
-                    * g_cond) are bitwise unchanged; the summation order of the per-start sums follows the grouping.
-                    * Costs 8 bytes of device memory per trajectory on the population (two key buffers). */
+    int balance;   /* lane balance of loss + full-gradient calls with per-start networks (a warp runs to its slowest lane and the
+                    * trajectories of a start take 17-26 steps, so 12 % of the lane-cycles idle in natural order):
+                    * 0 (default) = automatic: populations of >= 32768 individuals use the TWO-KERNEL gradient — forward solve
+                    *     leaving a 64-byte record per accepted step, every start's trajectories sorted by their accepted-step
+                    *     count (stable radix sort: deterministic), adjoint sweep in the sorted order with no idle lanes
+                    *     (+9 % on B200; needs ~2.1 KB of device memory per trajectory of a group of starts, the library sizes
+                    *     the groups to min(20 GB, 40 % of the free memory)); smaller populations use the fused kernel;
+                    * 1 = fused kernel, each start's individuals regrouped by the step counts of an EARLIER call on this
+                    *     population (refreshed every 8 calls; pays only when the parameters barely move between calls);
+                    * 2 = always the two-kernel gradient;  3 = always the fused kernel in natural order.
+                    * Per-trajectory results (sse, d/d cond) are bitwise the same in every mode; the per-start sums differ only
+                    * in summation order and are run-to-run deterministic in modes 0, 2 and 3. */
     int split;     /* gradient pipeline of loss + full-gradient calls with per-start networks:
                     * 0, 1 = the fused single-kernel adjoint (default);
                     * 2 = the split pipeline: forward solve leaving one record per accepted step -> adjoint recursion

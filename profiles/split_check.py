@@ -17,7 +17,8 @@ out = {"individuals": n, "starts": S}
 res = {}
 for name, o in (("fused", cu.SolverOptions(split=1)), ("split", cu.SolverOptions(split=2)),
                 ("fused_p2", cu.SolverOptions(split=1, precision=2)), ("split_p2", cu.SolverOptions(split=2, precision=2)),
-                ("split_bal", cu.SolverOptions(split=2, balance=1))):
+                ("split_bal", cu.SolverOptions(split=2, balance=1)), ("exact", cu.SolverOptions(balance=2)),
+                ("exact_p2", cu.SolverOptions(balance=2, precision=2))):
     ms = []
     for it in range(4):
         r = pop.loss_grad(neural, cond, opts=o, mean=False, return_sse=True)
@@ -29,7 +30,7 @@ for name, o in (("fused", cu.SolverOptions(split=1)), ("split", cu.SolverOptions
 def rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 f = res["fused"]
-for name in ("split", "split_bal", "split_p2"):
+for name in ("split", "split_bal", "split_p2", "exact", "exact_p2"):
     r = res[name]
     out[name]["vs_fused"] = {"sse_bitwise": bool(np.array_equal(r[3], f[3])), "loss_rel": rel(r[0], f[0]), "g_neural_rel": rel(r[1], f[1]),
                              "g_cond_rel": rel(r[2], f[2])}

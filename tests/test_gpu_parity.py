@@ -436,3 +436,60 @@ def test_split_gradient_pipeline_equals_the_fused_kernel(fx, ctx):
     f = popc.loss_grad(neural, cond, opts=SolverOptions(split=1), mean=False, return_sse=True)
     s = popc.loss_grad(neural, cond, opts=SolverOptions(split=2), mean=False, return_sse=True)
     assert np.array_equal(s[3], f[3]) and relmax(s[1], f[1]) < 1e-12 and relmax(s[2], f[2]) < 1e-12
+
+
+def test_two_kernel_gradient_with_exact_lane_balance(fx, ctx):
+    """opts.balance = 2 (and the automatic choice for >= 32768 individuals): forward solve with step records -> every start's
+    trajectories sorted by their accepted-step count -> adjoint kernel in sorted order.  Per-trajectory results are the fused
+    kernel's bit for bit, per-start sums to summation order, run-to-run deterministic; trajectories beyond 32 steps take the
+    fused kernel inside the same call; failures give Inf / zero gradients; the oracle in the deterministic regime."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(12)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 9)
+    for o in (dict(), DET, dict(abstol=1e-8, reltol=1e-5)):                    # the last one: Fujita trajectories exceed 32 steps
+        f = pop.loss_grad(neural, cond, opts=SolverOptions(balance=3, **o), mean=False, return_sse=True)
+        e = pop.loss_grad(neural, cond, opts=SolverOptions(balance=2, **o), mean=False, return_sse=True)
+        e2 = pop.loss_grad(neural, cond, opts=SolverOptions(balance=2, **o), mean=False, return_sse=True)
+        assert np.array_equal(e[3], f[3]) and np.array_equal(e[2], f[2])       # sse and d/d cond: bit for bit
+        assert relmax(e[0], f[0]) < 1e-14 and relmax(e[1], f[1]) < 1e-12
+        assert all(np.array_equal(a, b) for a, b in zip(e, e2))                 # deterministic
+        assert ctx.stats()["launches"] > 2 and ctx.stats()["n_fail"] == 0
+    r = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    e = pop.loss_grad(neural, cond, opts=SolverOptions(balance=2, **DET), mean=False)
+    assert relmax(e[1], r["g_neural"].sum(axis=1)) < 1e-9 and relmax(e[2], r["g_cond"]) < 1e-9
+    bad = cond.copy(); bad[2, 5] = np.nan
+    e = pop.loss_grad(neural, bad, opts=SolverOptions(balance=2))
+    f = pop.loss_grad(neural, bad, opts=SolverOptions(balance=3))
+    assert np.isinf(e[0][2]) and np.all(e[1][2] == 0) and np.all(e[2][2] == 0) and np.allclose(e[0][[0, 1, 3]], f[0][[0, 1, 3]], rtol=1e-14)
+    # FP32 adjoint network, covariate network
+    p2 = pop.loss_grad(neural, cond, opts=SolverOptions(balance=2, precision=2), mean=False)
+    f = pop.loss_grad(neural, cond, opts=SolverOptions(balance=3), mean=False)
+    assert np.array_equal(p2[0], pop.loss_grad(neural, cond, opts=SolverOptions(balance=2), mean=False)[0])
+    assert relmax(p2[1], f[1]) < 1e-5 and relmax(p2[2], f[2]) < 1e-5
+    models, t, c = ohashi_models(fx, "train", covariate=True)
+    pkc = cu.pack_models(models, t, c)
+    popc = cu.Population(packed=pkc, ctx=ctx)
+    neural, cond = random_starts(rng, pkc["chain"], len(models), 4)
+    f = popc.loss_grad(neural, cond, opts=SolverOptions(balance=3), mean=False, return_sse=True)
+    e = popc.loss_grad(neural, cond, opts=SolverOptions(balance=2), mean=False, return_sse=True)
+    assert np.array_equal(e[3], f[3]) and np.array_equal(e[2], f[2]) and relmax(e[1], f[1]) < 1e-12
+
+
+def test_automatic_gradient_path_depends_on_the_population_only(ctx):
+    """The default (balance = 0) picks the two-kernel gradient from 32768 individuals on — by the population, never by the
+    number of starts, so that a start's sums do not depend on how a batch is cut into calls (bitwise)."""
+    import bench
+    n = 40_000
+    pk = bench.synthetic_population(n, 21, bench.simulate_gpu(ctx))
+    neural, cond = bench.synthetic_starts(n, 5, 11, 22)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    a = pop.loss_grad(neural, cond, mean=False, return_sse=True)
+    assert ctx.stats()["launches"] > 2                                         # two-kernel path
+    for s in (0, 3):
+        b = pop.loss_grad(neural[s:s + 1], cond[s:s + 1], mean=False, return_sse=True)
+        assert all(np.array_equal(x[s:s + 1], y) for x, y in zip(a, b))
+    f = pop.loss_grad(neural, cond, opts=SolverOptions(balance=3), mean=False, return_sse=True)
+    assert ctx.stats()["launches"] == 2
+    assert np.array_equal(a[3], f[3]) and np.array_equal(a[2], f[2]) and relmax(a[1], f[1]) < 1e-12
