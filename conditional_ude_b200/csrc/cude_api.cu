@@ -580,17 +580,19 @@ static void trace_dump() {
     }
     g_trace.clear();
 }
+static int sm_count(cude_ctx* ctx) {
+    if (!ctx->sm_count) CU_TRY(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+    return CUDE_OK;
+}
+
 static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int nchunks, bool fbwd, bool wc, size_t n_w,
                      eval_kernel_t fused, size_t smem_fused, double* d_sums_out, int* launches) {
     const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
     const int M = a.pop.max_obs, K = a.pop.max_knots;
     const SplitKernels sk = select_split(net, fbwd, wc);
     if (!sk.k1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
-    if (!ctx->sm_count) {
-        cudaDeviceProp prop;
-        CU_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
-        ctx->sm_count = prop.multiProcessorCount;
-    }
+    int rc_sm = sm_count(ctx);
+    if (rc_sm) return rc_sm;
     if (!ctx->s_hi) {
         int least = 0, greatest = 0;
         CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -631,8 +633,9 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     // blkflag (int), segment sums of the reduction
     const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_wsum = o_beta + ntg * 8, o_sse = o_wsum + ntg * 8, o_off = o_sse + ntg * 8,
                  o_nrec = o_off + ((ntg + 2) * 4 + 7) / 8 * 8, o_bsum = o_nrec + (ntg * 4 + 7) / 8 * 8,
-                 o_flag = o_bsum + (((size_t)nscan + 2) * 4 + 7) / 8 * 8, o_seg = o_flag + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8,
-                 misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
+                 o_flag = o_bsum + (((size_t)nscan + 2) * 4 + 7) / 8 * 8, o_list = o_flag + ((size_t)Sg * nchunks * 4 + 4 + 7) / 8 * 8,
+                 o_seg = o_list + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8, misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
+    const unsigned fb_grid = (unsigned)(ctx->sm_count * CUDE_MIN_BLOCKS);          // resident blocks walking the fallback list
     int rc;
     const int nsets = ngroups < 3 ? ngroups : 3;
     for (int k = 0; k < nsets; ++k) {
@@ -678,6 +681,7 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         e.sp_rec = (double*)st.rec.p;
         e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
         e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
+        e.sp_blklist = (int*)(misc + o_list); e.sp_blkcount = e.sp_blkflag + (size_t)Sg * nchunks;
         v.e = e;
         v.wsum = (double*)(misc + o_wsum); v.off = (unsigned int*)(misc + o_off); v.bsum = (unsigned int*)(misc + o_bsum);
         v.seg = (double*)(misc + o_seg);
@@ -689,7 +693,7 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
             cude_ctx::SplitSet& st = ctx->sp[g % 3];
             const GroupView v = view(g);
             if (g >= 3) CU_TRY(ctx, cudaStreamWaitEvent(sM, st.ev_free, 0));          // the set's previous group has been finished
-            CU_TRY(ctx, cudaMemsetAsync(v.e.sp_blkflag, 0, (size_t)v.nblk * sizeof(int), sM));
+            CU_TRY(ctx, cudaMemsetAsync(v.e.sp_blkflag, 0, ((size_t)Sg * nchunks + 1) * sizeof(int), sM));
             CU_TRY(ctx, cudaMemsetAsync(v.pC, 0, (size_t)v.ns * nB * np1 * sizeof(double), sM));
             // stage 1: forward solve -> step records {t, h, dG[5]}, residuals
             trace_begin(sM, "fwd", g);
@@ -735,7 +739,7 @@ static int run_split(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
             // fallback: trajectories with more than SPLIT_CAP accepted steps through the fused kernel (flagged blocks only)
             EvalArgs f = v.e;
             f.partials = v.pC; f.only_flag = v.e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
-            fused<<<v.nblk, B, smem_fused, sM>>>(f);
+            fused<<<(v.nblk < fb_grid ? v.nblk : fb_grid), B, smem_fused, sM>>>(f);
             CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaEventRecord(st.ev_k3, sM));
             CU_TRY(ctx, cudaStreamWaitEvent(sH, st.ev_k3, 0));
@@ -792,8 +796,11 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     cude_ctx::SplitSet& set = ctx->sp[0];
     const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_sse = o_beta + ntg * 8, o_keys = o_sse + ntg * 8,
                  o_nrec = o_keys + 2 * ((ntg * 4 + 7) / 8 * 8), o_flag = o_nrec + (ntg * 4 + 7) / 8 * 8,
-                 o_seg = o_flag + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8, misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
+                 o_list = o_flag + ((size_t)Sg * nchunks * 4 + 4 + 7) / 8 * 8,      // block flags, then the length of the list
+                 o_seg = o_list + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8, misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
     int rc;
+    if ((rc = sm_count(ctx))) return rc;
+    const unsigned fb_grid = (unsigned)(ctx->sm_count * CUDE_MIN_BLOCKS);          // resident blocks walking the fallback list
     if ((rc = ensure(ctx, set.rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, set.misc, misc_bytes))) return rc;
     if ((rc = ensure(ctx, set.part, 2 * rowsB * np1 * sizeof(double)))) return rc;
@@ -828,7 +835,8 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         e.sp_rec = (double*)set.rec.p;
         e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
         e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
-        CU_TRY(ctx, cudaMemsetAsync(e.sp_blkflag, 0, (size_t)nblk * sizeof(int), st));
+        e.sp_blklist = (int*)(misc + o_list); e.sp_blkcount = e.sp_blkflag + (size_t)Sg * nchunks;
+        CU_TRY(ctx, cudaMemsetAsync(e.sp_blkflag, 0, ((size_t)Sg * nchunks + 1) * sizeof(int), st));
         CU_TRY(ctx, cudaMemsetAsync(pC, 0, (size_t)ns * nB * np1 * sizeof(double), st));
         sk.k1<<<nblk, B, smem1, st>>>(e);                                     // forward solve, step records, keys
         CU_TRY(ctx, cudaGetLastError());
@@ -844,7 +852,7 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         CU_TRY(ctx, cudaGetLastError());
         EvalArgs f = e;
         f.partials = pC; f.only_flag = e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
-        fused<<<nblk, B, smem_fused, st>>>(f);                                // trajectories beyond SPLIT_CAP steps
+        fused<<<(nblk < fb_grid ? nblk : fb_grid), B, smem_fused, st>>>(f);   // trajectories beyond SPLIT_CAP steps (list of flagged blocks)
         CU_TRY(ctx, cudaGetLastError());
         *launches += 3 + ns;
         if (d_sums_out) {

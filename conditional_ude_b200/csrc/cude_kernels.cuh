@@ -130,6 +130,8 @@ struct EvalArgs {
     double* sp_beta;               // [N x S] beta = exp(cond)
     double* sp_sse;                // [N x S] sse (Inf when failed)
     int* sp_blkflag;               // [blocks] set when a trajectory of the block overflowed SPLIT_CAP (fused-kernel fallback)
+    int* sp_blklist;               // [blocks] the flagged blocks (their blockIdx.x, any order), appended by stage 1 ...
+    int* sp_blkcount;              // ... and how many: the fallback launch is a few resident blocks walking this list
     long long wc_base;             // offset of the call's first start in the constant weight array (WC instantiations)
     const int* only_flag;          // fused GRAD kernel as that fallback: run only the trajectories with only_flag[j] < 0 of flagged blocks
 };
@@ -479,9 +481,9 @@ __host__ __device__ inline size_t eval_smem_doubles(int P, int NACC, int K, int 
 // the same steps (frozen step sequence => the same derivative the adjoint produces), no step ring, no backward sweep.
 // FBWD (with GRAD): the forward pass — loss, step sequence — stays FP64 bit for bit, only the adjoint's network
 // evaluations and gradient accumulators are FP32 (opts.precision = 2): gradients to ~1e-6 instead of ~1e-13.
-template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false, bool SPLIT = false>
-__global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : ((WC && !BSENS) ? CUDE_MIN_BLOCKS_LOSS_WC : CUDE_MIN_BLOCKS_LOSS))
-cude_eval_kernel(const EvalArgs A) {
+// The kernel's body for block `bid` of the launch geometry (blockIdx.x, except in the fallback walk below).
+template <class NS, bool GRAD, bool MIXED, bool BSENS, bool FBWD, bool WC, bool SPLIT>
+__device__ __forceinline__ void cude_eval_block(const EvalArgs& A, const unsigned bid) {
     static_assert(!SPLIT || (!GRAD && !MIXED && !BSENS), "SPLIT (stage 1 of the split gradient pipeline) is a variant of the FP64 loss-only kernel");
     static_assert(!WC || !MIXED, "WC (weights in constant memory) needs an FP64 forward network");
     static_assert(!BSENS || (!GRAD && !MIXED), "BSENS is a variant of the FP64 loss-only kernel");
@@ -508,11 +510,11 @@ cude_eval_kernel(const EvalArgs A) {
     double* sRes = sDG + ((GRAD || BSENS || SPLIT) ? (size_t)5 * B : 0);  // [M][B] residuals (GRAD)
 
     // ---- which trajectory ----
-    long long j, prow = blockIdx.x;   // prow: this block's row group in `partials`, [start][chunk] order
+    long long j, prow = bid;   // prow: this block's row group in `partials`, [start][chunk] order
     int i, s;
     bool active;
     if (A.flat) {
-        j = (long long)blockIdx.x * B + tid;
+        j = (long long)bid * B + tid;
         active = j < (long long)N * A.n_starts;
         i = active ? (int)(j % N) : 0;
         s = active ? (int)(j / N) : 0;
@@ -520,8 +522,8 @@ cude_eval_kernel(const EvalArgs A) {
         // chunk-major block order: the blocks resident at any time cover a few chunks of individuals x all starts, so the
         // population data of a chunk is read from HBM once and served from L2 to the other starts (start-major order
         // re-read the whole population per start: 15 GB per launch at 1 M individuals x 64 starts, ncu v11)
-        const int c = blockIdx.x / A.n_starts;
-        s = blockIdx.x - c * A.n_starts;
+        const int c = bid / A.n_starts;
+        s = bid - c * A.n_starts;
         prow = (long long)s * A.nchunks + c;
         i = c * B + tid;
         active = i < N;
@@ -529,16 +531,13 @@ cude_eval_kernel(const EvalArgs A) {
         else if (A.order) i = (int)(A.order[(size_t)s * N + i] & 0xffffffu);
         j = (long long)s * N + i;
         if constexpr (GRAD) {
-            // fallback of the split pipeline: only the trajectories stage 1 could not record (block-uniform early exit first)
-            if (A.only_flag) {
-                if (!A.sp_blkflag[prow]) return;
-                active = active && A.only_flag[j] < 0;
-            }
+            // fallback of the two-kernel / split gradient: only the trajectories stage 1 could not record
+            if (A.only_flag) active = active && A.only_flag[j] < 0;
         }
     }
     // ---- the start's weights: staged in shared memory (block-uniform), or read from constant memory (WC) ----
     // (offset from block-uniform values only, so that the compiler keeps it — and the weight loads — on the uniform path)
-    const long long wofs = A.flat ? 0 : (long long)(blockIdx.x % (unsigned)A.n_starts) * A.neural_stride;
+    const long long wofs = A.flat ? 0 : (long long)(bid % (unsigned)A.n_starts) * A.neural_stride;
     double wuni[WC ? P : 1];         // WC: the weights as block-uniform values, loaded here in convergent code
     if constexpr (WC) {
 #pragma unroll
@@ -1002,7 +1001,8 @@ cude_eval_kernel(const EvalArgs A) {
             A.sp_nrec[j] = failed ? 0 : (nacc > SPLIT_CAP ? -1 : nacc);
             A.sp_beta[j] = beta;
             A.sp_sse[j] = sse;
-            if (!failed && nacc > SPLIT_CAP) A.sp_blkflag[prow] = 1;
+            if (!failed && nacc > SPLIT_CAP && atomicExch(&A.sp_blkflag[prow], 1) == 0)
+                A.sp_blklist[atomicAdd(A.sp_blkcount, 1)] = (int)bid;
         }
         if constexpr (!GRAD && !BSENS) {
             if (A.yhat_out && failed) for (int k = 0; k < M; ++k) A.yhat_out[(size_t)j * M + k] = CUDART_NAN;   // no solution
@@ -1056,6 +1056,24 @@ cude_eval_kernel(const EvalArgs A) {
             if (cf) atomicAdd(&A.counters[2], (unsigned long long)cf);
         }
     }
+}
+
+template <class NS, bool GRAD, bool MIXED = false, bool BSENS = false, bool FBWD = false, bool WC = false, bool SPLIT = false>
+__global__ void __launch_bounds__(CUDE_MAX_THREADS, GRAD ? CUDE_MIN_BLOCKS : ((WC && !BSENS) ? CUDE_MIN_BLOCKS_LOSS_WC : CUDE_MIN_BLOCKS_LOSS))
+cude_eval_kernel(const EvalArgs A) {
+    if constexpr (GRAD) {
+        if (A.only_flag) {
+            // fallback launch: a grid of resident blocks walks the list of blocks stage 1 flagged (usually empty) instead of
+            // 62 500 blocks per group looking up their flag (1.7 % of a bench step)
+            const unsigned cnt = (unsigned)*A.sp_blkcount;
+            for (unsigned v = blockIdx.x; v < cnt; v += gridDim.x) {
+                cude_eval_block<NS, GRAD, MIXED, BSENS, FBWD, WC, SPLIT>(A, (unsigned)A.sp_blklist[v]);
+                __syncthreads();
+            }
+            return;
+        }
+    }
+    cude_eval_block<NS, GRAD, MIXED, BSENS, FBWD, WC, SPLIT>(A, blockIdx.x);
 }
 
 // Second stage (tile mode): sums[(P+1) x S] column-major, sums[q + (P+1)*s] = sum over the start's

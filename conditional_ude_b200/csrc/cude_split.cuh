@@ -508,11 +508,21 @@ struct AdjArgs {
     double* g_cond;                // [N x S]
     double* partials;              // [S*nchunks*warps][P+1]
 };
+// Tuning of the adjoint kernel (bench workload, evals/s of the whole two-kernel step; profiles/README.md round 2):
+//   records through registers, 4 / 3 / 2 blocks per SM (128 / 168 / 255 registers)      2.38e8 / 2.36e8 / 2.30e8
+//   records by cp.async into shared memory (16 registers and ~200 B of spills less):   4 blocks 2.30e8, 3 blocks 2.46e8, 2 blocks 2.38e8
+//   observation loads two ahead (the exit test of the observation loop never waits)     +0.6 %
+#ifndef CUDE_ADJ_REC_ASYNC
+#define CUDE_ADJ_REC_ASYNC 1
+#endif
+#ifndef CUDE_ADJ_OBS_AHEAD
+#define CUDE_ADJ_OBS_AHEAD 1
+#endif
 #ifndef CUDE_ADJ_MIN_BLOCKS
-#define CUDE_ADJ_MIN_BLOCKS 4      // 128 registers, 16 warps per SM: 2.38e8 evals/s; 3 blocks (168 registers) 2.36e8, 2 blocks 2.30e8
+#define CUDE_ADJ_MIN_BLOCKS 3
 #endif
 __host__ __device__ inline size_t adj_smem_doubles(int P, int B, bool f32copy, bool wc) {
-    return (size_t)256 + ((wc && !f32copy) ? 0 : (size_t)((P + 1) & ~1)) + (size_t)10 * B;
+    return (size_t)256 + ((wc && !f32copy) ? 0 : (size_t)((P + 1) & ~1)) + (size_t)(5 + (CUDE_ADJ_REC_ASYNC ? 2 * 7 : 5)) * B;
 }
 
 template <class NS, class RB, bool WC>
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
     double* sTab = smem;
     double* sWs = sTab + 256;
     double* sNode = sWs + ((WC && !F32) ? 0 : ((P + 1) & ~1));   // [5][B] node weights
-    double* sDG = sNode + (size_t)5 * B;                        // [5][B] dG at the nodes
+    double* sRec = sNode + (size_t)5 * B;                       // [2][7][B] step records {t, h, dG[5]}: the current one and the next in flight
     const int c = blockIdx.x / A.n_starts, s = blockIdx.x - c * A.n_starts;      // chunk-major like stage 1
     const long long prow = (long long)s * A.nchunks + c;
     for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
@@ -552,7 +562,6 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
     double beta = 0.0, covv = 0.0, sse = 0.0;
     if (inb && nrec >= 0) sse = A.sp_sse[j];          // failed: Inf; overflowed trajectories belong to the fallback
     double* const myNode = sNode + tid;
-    double* const myDG = sDG + tid;
     if (nrec > 0) {
         const double k0 = A.pop.k0[i], k1 = A.pop.k1[i], k2 = A.pop.k2[i];
         const double d00 = -(k0 + k2);
@@ -570,14 +579,38 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
             cb[q] = (RB)z;
         }
         double lam0 = 0.0, lam1 = 0.0, wnode = 0.0, wsum = 0.0, t_next = tend;
+        // observations, last first: time and residual of the next one to meet are loaded when the one before it is consumed,
+        // and the time of the one after that as well, so that the loop's exit test never waits for memory
         int kobs_top = nobs - 1;
         double top_ot = (nobs > 0) ? obs_t[(size_t)(nobs - 1) * N] : -CUDART_INF;
-        const double2* rec = reinterpret_cast<const double2*>(A.sp_rec + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_W);
+        double top_res = (nobs > 0) ? res[(size_t)(nobs - 1) * ntraj] : 0.0;
+        double nxt_ot = (nobs > 1) ? obs_t[(size_t)(nobs - 2) * N] : -CUDART_INF;
+        // step records: cp.async into this thread's column of the double buffer, one step ahead (own copies only: no barrier)
+        const double* recg = A.sp_rec + ((size_t)j * SPLIT_CAP + (nrec - 1)) * SPLIT_W;
+        auto fetch = [&](int b, const double* g) {
+            double* const d = sRec + (size_t)b * 7 * B + tid;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) cp_async8(d + (size_t)k * B, g + k);
+        };
+#if CUDE_ADJ_REC_ASYNC
+        fetch(0, recg);
+        cp_async_commit();
+        int cur = 0;
+        for (int n = nrec - 1; n >= 0; --n, recg -= SPLIT_W, cur ^= 1) {
+            if (n > 0) fetch(cur ^ 1, recg - SPLIT_W);
+            cp_async_commit();
+            cp_async_wait<1>();                                              // this step's record has landed
+            const double* const myRec = sRec + (size_t)cur * 7 * B + tid;
+            const double tn = myRec[0], h = myRec[B];
+#else
+        const double2* rec = reinterpret_cast<const double2*>(recg);
         double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];      // the step's record, fetched one step ahead
+        double* const myRec = sRec + tid - 2 * B;                        // rows 2..6 of the record = rows 0..4 of the buffer
         for (int n = nrec - 1; n >= 0; --n, rec -= SPLIT_W / 2) {
             const double tn = r0.x, h = r0.y;
-            myDG[0] = r1.x; myDG[B] = r1.y; myDG[2 * B] = r2.x; myDG[3 * B] = r2.y; myDG[4 * B] = r3.x;
+            myRec[2 * B] = r1.x; myRec[3 * B] = r1.y; myRec[4 * B] = r2.x; myRec[5 * B] = r2.y; myRec[6 * B] = r3.x;
             if (n > 0) { r0 = rec[-(SPLIT_W / 2)]; r1 = rec[1 - SPLIT_W / 2]; r2 = rec[2 - SPLIT_W / 2]; r3 = rec[3 - SPLIT_W / 2]; }
+#endif
             double kb[7][2];
 #pragma unroll
             for (int q = 0; q < 7; ++q) { kb[q][0] = 0.0; kb[q][1] = 0.0; }
@@ -585,7 +618,7 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
             while (kobs_top >= 0) {                      // observations in (tn, t_next]
                 const double ts = top_ot;
                 if (!(ts > tn)) break;
-                const double wr = 2.0 * res[(size_t)kobs_top * ntraj];
+                const double wr = 2.0 * top_res;
                 if (ts == t_next) lam0 += wr;
                 else {
                     double bw[7];
@@ -596,7 +629,15 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
                     for (int q = 0; q < 7; ++q) kb[q][0] = fma(wh, bw[q], kb[q][0]);
                 }
                 --kobs_top;
+#if CUDE_ADJ_OBS_AHEAD
+                top_ot = nxt_ot;
+                top_res = (kobs_top >= 0) ? res[(size_t)kobs_top * ntraj] : 0.0;
+                nxt_ot = (kobs_top >= 1) ? obs_t[(size_t)(kobs_top - 1) * N] : -CUDART_INF;
+#else
                 top_ot = (kobs_top >= 0) ? obs_t[(size_t)kobs_top * N] : -CUDART_INF;
+                top_res = (kobs_top >= 0) ? res[(size_t)kobs_top * ntraj] : 0.0;
+                (void)nxt_ot;
+#endif
             }
             const double pb7 = kb[6][0];
             lam0 = fma(d00, kb[6][0], lam0);
@@ -639,8 +680,9 @@ __global__ void __launch_bounds__(128, CUDE_ADJ_MIN_BLOCKS) cude_adjoint_kernel(
             lam0 = ub0; lam1 = ub1;
             t_next = tn;
 #pragma unroll 1
-            for (int q = 0; q < 5; ++q) mlp_backward<NS, RB>(sW, sTab, cb, (RB)myDG[q * B], (RB)myNode[q * B], acc);
+            for (int q = 0; q < 5; ++q) mlp_backward<NS, RB>(sW, sTab, cb, (RB)myRec[(2 + q) * B], (RB)myNode[q * B], acc);
         }
+        cp_async_wait<0>();
         // the NN([0; beta]) term (c-peptide-models.jl:91): one node at dG = 0 with weight -sum(w)
         mlp_backward<NS, RB>(sW, sTab, cb, RB(0), (RB)(-wsum), acc);
         double db = 0.0;

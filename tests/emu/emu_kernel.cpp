@@ -30,6 +30,8 @@ static inline void __syncthreads() {}
 static inline void __syncwarp() {}
 template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }   // lanes 1..31 are empty
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 namespace cude { double smem[1 << 16]; }   // the kernel's `extern __shared__ double smem[]`
 
 static double* g_trace_buf = nullptr; static int g_trace_cap = 0, g_trace_n = 0;
@@ -120,7 +122,8 @@ extern "C" int emu_eval_split(int n_ind, int max_knots, const int* n_knots, cons
     unsigned long long counters[3] = {0, 0, 0};
     a.sse_out = sse; a.counters = counters;
     std::vector<double> rec(NT * SPLIT_CAP * SPLIT_W, 0.0), wrec(NT * SPLIT_CAP * SPLIT_WW, 0.0), res(M * NT, 0.0), beta(NT), spsse(NT), wsum(NT);
-    std::vector<int> nrec(NT), flag(NT, 0);
+    std::vector<int> nrec(NT), flag(NT, 0), blklist(NT + 1, 0);
+    a.sp_blklist = blklist.data(); a.sp_blkcount = blklist.data() + NT;
     a.sp_rec = rec.data(); a.sp_res = res.data(); a.sp_nrec = nrec.data(); a.sp_beta = beta.data(); a.sp_sse = spsse.data(); a.sp_blkflag = flag.data();
     blockDim.x = 1; threadIdx.x = 0; gridDim.x = (int)NT; gridDim.y = 1;
     // stage 1 (chunk-major block order: block b = chunk c * S + s, one individual per chunk)
