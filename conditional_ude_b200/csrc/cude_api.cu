@@ -779,13 +779,14 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     const SplitKernels sk = select_split(net, fbwd, wc);
     if (!sk.k1) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     cudaStream_t st = ctx->stream;
-    const size_t per_traj = (size_t)SPLIT_W * SPLIT_CAP * 8 + (size_t)M * 8 + 2 * 8 + 4 + 2 * 4 + 2 * (size_t)np1 * 8 / 32 + 64;
+    const size_t per_traj = (size_t)SPLIT_W * SPLIT_CAP * 8 + (size_t)M * 8 + 2 * 8 + 4 + 2 * 4 + 2 * 2 + 2 * (size_t)np1 * 8 / 32 + 64;
     size_t budget = 0;
     int rc0 = split_budget(ctx, &budget);
     if (rc0) return rc0;
     long long sg = (long long)(budget / (per_traj * (size_t)N));
     if (sg < 1) sg = 1;
     if (sg > S) sg = S;
+    if (sg > 256) sg = 256;                 // the sort key holds the start in 8 bits
     const int ngroups = (int)((S + sg - 1) / sg);
     const int Sg = (S + ngroups - 1) / ngroups;
     const size_t ntg = (size_t)N * Sg;
@@ -795,7 +796,8 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     if (nseg > 64) nseg = 64;
     cude_ctx::SplitSet& set = ctx->sp[0];
     const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_sse = o_beta + ntg * 8, o_keys = o_sse + ntg * 8,
-                 o_nrec = o_keys + 2 * ((ntg * 4 + 7) / 8 * 8), o_flag = o_nrec + (ntg * 4 + 7) / 8 * 8,
+                 o_k16 = o_keys + 2 * ((ntg * 4 + 7) / 8 * 8), o_nrec = o_k16 + 2 * ((ntg * 2 + 7) / 8 * 8),
+                 o_flag = o_nrec + (ntg * 4 + 7) / 8 * 8,
                  o_list = o_flag + ((size_t)Sg * nchunks * 4 + 4 + 7) / 8 * 8,      // block flags, then the length of the list
                  o_seg = o_list + ((size_t)Sg * nchunks * 4 + 7) / 8 * 8, misc_bytes = o_seg + (size_t)Sg * nseg * np1 * 8;
     int rc;
@@ -805,7 +807,8 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     if ((rc = ensure(ctx, set.misc, misc_bytes))) return rc;
     if ((rc = ensure(ctx, set.part, 2 * rowsB * np1 * sizeof(double)))) return rc;
     size_t sort_bytes = 0;
-    CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (unsigned int*)nullptr, (unsigned int*)nullptr, N, 24, 32, st));
+    CU_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned short*)nullptr, (unsigned short*)nullptr,
+                                                (unsigned int*)nullptr, (unsigned int*)nullptr, ntg, 0, 16, st));
     if ((rc = ensure(ctx, set.map, sort_bytes))) return rc;        // radix-sort workspace
     char* const misc = (char*)set.misc.p;
     double* const pB = (double*)set.part.p;
@@ -831,7 +834,10 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         e.partials = nullptr;
         unsigned int* const keys_raw = (unsigned int*)(misc + o_keys);
         unsigned int* const keys_sorted = keys_raw + (ntg * 4 + 7) / 8 * 2;
+        unsigned short* const k16_raw = (unsigned short*)(misc + o_k16);
+        unsigned short* const k16_sorted = k16_raw + (ntg * 2 + 7) / 8 * 4;
         e.keys_out = keys_raw;
+        e.keys16_out = k16_raw;
         e.sp_rec = (double*)set.rec.p;
         e.sp_res = (double*)(misc + o_res); e.sp_beta = (double*)(misc + o_beta); e.sp_sse = (double*)(misc + o_sse);
         e.sp_nrec = (int*)(misc + o_nrec); e.sp_blkflag = (int*)(misc + o_flag);
@@ -840,9 +846,13 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         CU_TRY(ctx, cudaMemsetAsync(pC, 0, (size_t)ns * nB * np1 * sizeof(double), st));
         sk.k1<<<nblk, B, smem1, st>>>(e);                                     // forward solve, step records, keys
         CU_TRY(ctx, cudaGetLastError());
-        for (int s = 0; s < ns; ++s) {                                        // each start's individuals by accepted steps
+        {   // every start's individuals by accepted steps: ONE stable sort of the group on the key (start, steps) — the starts stay
+            // contiguous blocks of N, ties keep the individuals' order (64 sorts per step cost 5 % of a 1/8 shard's step)
             size_t b = set.map.cap;
-            CU_TRY(ctx, cub::DeviceRadixSort::SortKeys(set.map.p, b, keys_raw + (size_t)s * N, keys_sorted + (size_t)s * N, N, 24, 32, st));
+            int bits = 8;
+            while ((1 << (bits - 8)) < ns) ++bits;
+            CU_TRY(ctx, cub::DeviceRadixSort::SortPairs(set.map.p, b, k16_raw, k16_sorted, keys_raw, keys_sorted, (size_t)N * ns, 0, bits, st));
+            *launches += 2 + (bits + 7) / 8;                                  // cub one-sweep: histogram, scan, one sweep per 8 key bits
         }
         AdjArgs aa{};
         aa.pop = a.pop; aa.n_starts = ns; aa.nchunks = nchunks; aa.neural = e.neural; aa.neural_stride = a.neural_stride; aa.wc_base = e.wc_base;
@@ -854,7 +864,7 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
         f.partials = pC; f.only_flag = e.sp_nrec; f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr;
         fused<<<(nblk < fb_grid ? nblk : fb_grid), B, smem_fused, st>>>(f);   // trajectories beyond SPLIT_CAP steps (list of flagged blocks)
         CU_TRY(ctx, cudaGetLastError());
-        *launches += 3 + ns;
+        *launches += 3;
         if (d_sums_out) {
             double* const d_seg = (double*)(misc + o_seg);
             cude_reduce_rows<<<dim3((unsigned)nseg, (unsigned)ns), RED_T, 0, st>>>(nullptr, 0, pB, pC, nB, np1, nseg * np1, d_seg);

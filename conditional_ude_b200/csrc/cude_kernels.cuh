@@ -121,6 +121,8 @@ struct EvalArgs {
     // warps of a block) finish together; keys_out[s*N + i] = (min(steps, 255) << 24) | i feeds the next sort.
     const unsigned int* order;     // [N x S] or nullptr (natural order)
     unsigned int* keys_out;        // [N x S] or nullptr
+    unsigned short* keys16_out;    // [N x S] or nullptr: (start << 8) | min(accepted steps, 255) — the key of the two-kernel gradient's one
+                                   // sort per group of (at most 256) starts, with keys_out as its payload
     double* yhat_out;              // [M][N x S] -> yhat_out[k + M*j]: the solution at the observation times (cude_simulate;
                                    // loss-only instantiations), or nullptr
     // split gradient pipeline (SPLIT instantiation = stage 1; see "split gradient pipeline" below)
@@ -995,6 +997,7 @@ __device__ __forceinline__ void cude_eval_block(const EvalArgs& A, const unsigne
         if (A.keys_out) {
             const int ns = SPLIT ? nacc : nacc + nrej;      // stage 1 of the two-kernel gradient: the adjoint's length (accepted steps)
             A.keys_out[j] = ((unsigned int)(ns < 255 ? ns : 255) << 24) | (unsigned int)i;
+            if constexpr (SPLIT) if (A.keys16_out) A.keys16_out[j] = (unsigned short)(((unsigned int)s << 8) | (unsigned int)(ns < 255 ? ns : 255));
         }
         if (A.sse_out) A.sse_out[j] = sse;
         if constexpr (SPLIT) {
