@@ -1346,8 +1346,28 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
-    kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
-    CU_TRY(ctx, cudaGetLastError());
+    int n_launch = 0;
+    {
+        // gradient calls: the step ring of every block of a launch lives in global scratch ([SUP_REC_CAP][23][B] doubles per
+        // block), so a large batch is cut into launches whose rings fit the scratch budget
+        long long per_launch = nblocks;
+        if (grad) {
+            const size_t ring_block = (size_t)SUP_REC_CAP * SUP_REC_ROWS * B * sizeof(double);
+            size_t budget = 0;
+            if ((rc = split_budget(ctx, &budget))) return rc;
+            per_launch = (long long)(budget / ring_block);
+            if (per_launch < 1) per_launch = 1;
+            if (per_launch > nblocks) per_launch = nblocks;
+            if ((rc = ensure(ctx, ctx->sp[0].rec, (size_t)per_launch * ring_block))) return rc;
+            a.ring = (double*)ctx->sp[0].rec.p;
+        }
+        for (long long b0 = 0; b0 < nblocks; b0 += per_launch, ++n_launch) {
+            a.blk0 = (int)b0;
+            const long long nb = nblocks - b0 < per_launch ? nblocks - b0 : per_launch;
+            kern<<<(unsigned)nb, B, smem, ctx->stream>>>(a);
+            CU_TRY(ctx, cudaGetLastError());
+        }
+    }
     {
         const int wpb = 8;
         const long long nwarps = (long long)n_starts * np1;
@@ -1358,7 +1378,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->stats = cude_stats{};
     ctx->stats.n_traj = (unsigned long long)ntraj;
-    ctx->stats.launches = 2;
+    ctx->stats.launches = n_launch + 1;
     ctx->stats_pending = true;
     CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sums, ctx->sums.p, (size_t)np1 * n_starts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (sse_out) CU_TRY(ctx, cudaMemcpyAsync(sse_out, ctx->sse.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -19,6 +19,7 @@
 // =====================================================================================
 #pragma once
 #include "cude_kernels.cuh"
+#include "cude_split.cuh"     // cp_async helpers
 
 namespace cude {
 
@@ -43,6 +44,9 @@ struct SupArgs {
     double* partials;           // [blocks * warps][P+1]
     double* g_theta;            // [N x S] or nullptr
     unsigned long long* counters;
+    double* ring;               // GRAD: step records of this launch's blocks, [gridDim.x][SUP_REC_CAP][SUP_REC_ROWS][B] (coalesced rows)
+    int blk0;                   // this launch covers blocks blk0 .. blk0 + gridDim.x - 1 of the batch (the host cuts a batch into
+                                // launches whose rings fit its scratch budget)
 };
 
 template <int DEPTH_, int WIDTH_>
@@ -176,9 +180,10 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
 }
 
 __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad, int spb = 0) {
-    // exp table, weights (one copy per start of the block), per-thread rows: k[7][3] + (grad: g[7][3] + kb[7][3] +
-    // residuals M*3); the accumulators are parked in these rows for the reduction ([NACC][B], then expanded to [P+1][B])
-    size_t rows = (size_t)21 + (grad ? (size_t)(42 + 3 * M) : 0);
+    // exp table, weights (one copy per start of the block), per-thread rows: k[7][3] (grad: + 2 rows = record buffer 0) +
+    // (grad: record buffer 1 [23] + kb[7][3] + residuals M*3); the accumulators are parked in these rows for the reduction
+    // ([NACC][B], then expanded to [P+1][B])
+    size_t rows = grad ? (size_t)(2 * 23 + 21 + 3 * M) : (size_t)21;     // grad: stage rows doubling as record buffer 0, buffer 1, kb, residuals
     if (grad && rows < (size_t)P + 1) rows = (size_t)P + 1;
     if (grad && rows < (size_t)NACC) rows = (size_t)NACC;
     return (size_t)256 + (size_t)(spb > 0 ? spb : 1) * ((P + 1) & ~1) + rows * B;
@@ -187,11 +192,9 @@ __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B
 #ifndef CUDE_SUP_REC_CAP
 #define CUDE_SUP_REC_CAP 64
 #endif
-constexpr int SUP_REC_CAP = CUDE_SUP_REC_CAP;  // ring of accepted-step records (t, dt, u[3], k1..k6: 184 B) per thread in local memory; longer
-                                               // solves replay the forward pass in chunks of this many steps
-#ifndef CUDE_SUP_KEEP_STAGES
-#define CUDE_SUP_KEEP_STAGES 1
-#endif
+constexpr int SUP_REC_CAP = CUDE_SUP_REC_CAP;  // ring of accepted-step records per thread, in global memory; longer solves replay
+                                               // the forward pass in chunks of this many steps
+constexpr int SUP_REC_ROWS = 23;               // a record: k1..k6 [18], t, dt, u[3] = 184 B
 #ifndef CUDE_SUP_MIN_BLOCKS
 #define CUDE_SUP_MIN_BLOCKS 2
 #endif
@@ -207,14 +210,15 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     const int spb = A.spb;
     double* sTab = smem;
     double* sWall = sTab + 256;                       // [max(spb,1)][PP] weights of the block's start(s)
-    double* sK = sWall + (size_t)(spb > 0 ? spb : 1) * PP;   // [7][3][B] stages
-    double* sG = sK + (size_t)21 * B;                 // [7][3][B] stage inputs (GRAD)
-    double* sKb = sG + (GRAD ? (size_t)21 * B : 0);   // [7][3][B] stage adjoints (GRAD)
+    double* sK = sWall + (size_t)(spb > 0 ? spb : 1) * PP;   // [7][3][B] stages; GRAD: 2 more rows = record buffer 0 of the adjoint sweep
+    double* sKb = sK + (size_t)(GRAD ? SUP_REC_ROWS : 21) * B;   // [7][3][B] stage adjoints (GRAD)
     double* sRes = sKb + (GRAD ? (size_t)21 * B : 0); // [M][3][B] weighted residuals (GRAD)
+    double* sRec1 = sRes + (GRAD ? (size_t)3 * M * B : 0);       // [23][B] record buffer 1 (GRAD)
 
     int s, i, sloc = 0;
     bool active;
-    const long long j0 = (long long)blockIdx.x * B, ntot = (long long)N * A.n_starts;   // flat mode: first trajectory of the block
+    const unsigned bid = blockIdx.x + (unsigned)A.blk0;
+    const long long j0 = (long long)bid * B, ntot = (long long)N * A.n_starts;   // flat mode: first trajectory of the block
     int s_first = 0, nsl = 1;
     if (spb > 0) {                                    // flat: B consecutive trajectories, up to spb starts per block
         const long long jj = j0 + tid;
@@ -230,8 +234,8 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
             sWall[sl * PP + pp] = A.neural[(long long)(s_first + sl) * A.neural_stride + pp];
         }
     } else {
-        s = blockIdx.x / A.nchunks;
-        const int ch = blockIdx.x - s * A.nchunks;
+        s = bid / A.nchunks;
+        const int ch = bid - s * A.nchunks;
         i = ch * B + tid;
         active = i < N;
         const double* gW = A.neural + (long long)s * A.neural_stride;
@@ -241,7 +245,6 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     const long long jt = (long long)s * N + (active ? i : 0);
     for (int p = tid; p < 256; p += B) sTab[p] = EXP_TAB256[p];
     double* const myK = sK + tid;
-    double* const myG = sG + tid;
     double* const myKb = sKb + tid;
     double* const myRes = sRes + tid;
     double* const myAcc = sK + tid;          // the accumulators' parking rows for the reduction (the stage rows, dead by then)
@@ -273,10 +276,12 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         const double uh__ = sup_nn_forward<SN>(sW, sTab, c, U0, U1, U2);  \
         F0 = -p1 * (U0); F1 = fma(p1, (U0), -uh__); F2 = fma(-p3, (U2), uh__); \
     }
-        // accepted-step record: (t, dt, u) and — CUDE_SUP_KEEP_STAGES — the step's stage derivatives k1..k6, so that the
-        // adjoint rebuilds the stage inputs g_i = u + dt sum a_ij k_j without re-evaluating the network 6 times per step
-        struct Rec { double t, h, u0, u1, u2; double k[CUDE_SUP_KEEP_STAGES ? 18 : 1]; };
-        Rec rec[GRAD ? SUP_REC_CAP : 1];
+        // accepted-step record: the step's stage derivatives k1..k6 (so that the adjoint rebuilds the stage inputs
+        // g_i = u + dt sum a_ij k_j without re-evaluating the network), then (t, dt, u).  Round 2b: the ring is an explicit
+        // global array with rows [slot][row][tid] — the forward pass writes coalesced rows, the adjoint sweep fetches the next
+        // record by cp.async into a shared-memory double buffer while it works on the current one (as a local-memory array the
+        // ring was read at the top of every step and waited for: long_scoreboard 0.81 per issue)
+        double* const ringb = GRAD ? A.ring + (size_t)blockIdx.x * SUP_REC_CAP * SUP_REC_ROWS * B + tid : nullptr;
 
         // adjoint carry across replay chunks
         double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0, t_next = tend;
@@ -377,12 +382,10 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                     ++iobs;
                 }
                 if (GRAD) {
-                    Rec& r = rec[na % SUP_REC_CAP];
-                    r.t = t; r.h = dt; r.u0 = u0; r.u1 = u1; r.u2 = u2;
-                    if (CUDE_SUP_KEEP_STAGES) {
+                    double* const r = ringb + (size_t)(na % SUP_REC_CAP) * SUP_REC_ROWS * B;
 #pragma unroll
-                        for (int q = 0; q < 18; ++q) r.k[q] = myK[q * B];
-                    }
+                    for (int q = 0; q < 18; ++q) r[q * B] = myK[q * B];
+                    r[18 * B] = t; r[19 * B] = dt; r[20 * B] = u0; r[21 * B] = u1; r[22 * B] = u2;
                 }
                 ++na;
                 lnqold = fmax(lnE, -9.210340371976182);
@@ -407,34 +410,21 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         if constexpr (GRAD) {
             // ---------------- discrete adjoint over the steps [lo, stop_at) held in the ring ----------------
             const int lo = (stop_at > SUP_REC_CAP) ? stop_at - SUP_REC_CAP : 0;
-            for (int n = stop_at - 1; n >= lo; --n) {
-                const Rec& r = rec[n % SUP_REC_CAP];
-                const double tn = r.t, h = r.h;
-                // the stage inputs g_1..g_7 of step n from u_n and the stage derivatives (kept, or recomputed by replay)
-                myG[0] = r.u0; myG[B] = r.u1; myG[2 * B] = r.u2;
-                if (CUDE_SUP_KEEP_STAGES) {
+            auto fetch = [&](int b, int n) {            // record n -> buffer b (this thread's column; own copies only: no barrier)
+                const double* const g = ringb + (size_t)(n % SUP_REC_CAP) * SUP_REC_ROWS * B;
+                double* const d = (b ? sRec1 : sK) + tid;
 #pragma unroll
-                    for (int q = 0; q < 18; ++q) myK[q * B] = r.k[q];
-                } else {
-                    double f0, f1, f2;
-                    SUP_RHS(r.u0, r.u1, r.u2, f0, f1, f2)
-                    myK[0] = f0; myK[B] = f1; myK[2 * B] = f2;
-                }
-#pragma unroll 1
-                for (int st = 0; st < 6; ++st) {
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                    for (int q = 0; q <= st; ++q) {
-                        const double a = SUP_A[st][q];
-                        s0 = fma(a, myK[(q * 3) * B], s0); s1 = fma(a, myK[(q * 3 + 1) * B], s1); s2 = fma(a, myK[(q * 3 + 2) * B], s2);
-                    }
-                    const double g0 = fma(h, s0, r.u0), g1 = fma(h, s1, r.u1), g2 = fma(h, s2, r.u2);
-                    myG[((st + 1) * 3) * B] = g0; myG[((st + 1) * 3 + 1) * B] = g1; myG[((st + 1) * 3 + 2) * B] = g2;
-                    if (!CUDE_SUP_KEEP_STAGES && st < 5) {     // k7 itself is not needed by the adjoint (only its input g_7 = u_{n+1})
-                        double f0, f1, f2;
-                        SUP_RHS(g0, g1, g2, f0, f1, f2)
-                        myK[((st + 1) * 3) * B] = f0; myK[((st + 1) * 3 + 1) * B] = f1; myK[((st + 1) * 3 + 2) * B] = f2;
-                    }
-                }
+                for (int q = 0; q < SUP_REC_ROWS; ++q) cp_async8(d + (size_t)q * B, g + (size_t)q * B);
+            };
+            int cur = 0;
+            fetch(0, stop_at - 1);
+            cp_async_commit();
+            for (int n = stop_at - 1; n >= lo; --n, cur ^= 1) {
+                if (n > lo) fetch(cur ^ 1, n - 1);
+                cp_async_commit();
+                cp_async_wait<1>();                      // record n has landed
+                const double* const rk = (cur ? sRec1 : sK) + tid;     // rows 0..17: k1..k6
+                const double tn = rk[18 * B], h = rk[19 * B], ru0 = rk[20 * B], ru1 = rk[21 * B], ru2 = rk[22 * B];
                 // stage adjoints
 #pragma unroll 1
                 for (int q = 0; q < 21; ++q) myKb[q * B] = 0.0;
@@ -467,8 +457,18 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                         // no interior observation: k7 carries no adjoint
                     } else {
                         const double v0 = myKb[(st * 3) * B], v1 = myKb[(st * 3 + 1) * B], v2 = myKb[(st * 3 + 2) * B];
+                        // the stage input g_{st+1} = u_n + h sum_{q<st} a_{st+1,q+1} k_{q+1} from the record (g_1 = u_n)
+                        double g0 = ru0, g1 = ru1, g2 = ru2;
+                        if (st > 0) {
+                            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                            for (int q = 0; q < st; ++q) {
+                                const double a = SUP_A[st - 1][q];
+                                s0 = fma(a, rk[(q * 3) * B], s0); s1 = fma(a, rk[(q * 3 + 1) * B], s1); s2 = fma(a, rk[(q * 3 + 2) * B], s2);
+                            }
+                            g0 = fma(h, s0, ru0); g1 = fma(h, s1, ru1); g2 = fma(h, s2, ru2);
+                        }
                         double du[3];
-                        sup_nn_backward<SN>(sW, sTab, c, myG[(st * 3) * B], myG[(st * 3 + 1) * B], myG[(st * 3 + 2) * B], v2 - v1, acc, du);
+                        sup_nn_backward<SN>(sW, sTab, c, g0, g1, g2, v2 - v1, acc, du);
                         // gb = J^T v = [-p1 v0 + p1 v1, 0, -p3 v2] + grad_u(u_hat) (v2 - v1)
                         const double gb0 = fma(p1, v1 - v0, du[0]), gb1 = du[1], gb2 = fma(-p3, v2, du[2]);
                         if (st == 6) { lam0 += gb0; lam1 += gb1; lam2 += gb2; }
@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                 lam0 = ub0; lam1 = ub1; lam2 = ub2;
                 t_next = tn;
             }
+            cp_async_wait<0>();
             stop_at = lo;          // steps below lo still to do: replay the forward pass up to lo
         }
         } while (stop_at > 0);
@@ -554,11 +555,11 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
             const double* src = sK + (size_t)q * B;
             double v = 0.0;
             for (long long k = lo; k < hi; ++k) v += src[k];
-            const long long which = (long long)blockIdx.x - ((long long)ss * N) / B;        // 0: the start's first block, 1: its second
+            const long long which = (long long)bid - ((long long)ss * N) / B;        // 0: the start's first block, 1: its second
             A.partials[((size_t)ss * 2 + (size_t)which) * (P + 1) + q] = v;
         }
     } else if (A.partials) {
-        double* const row = A.partials + ((size_t)blockIdx.x * nw + wid) * (P + 1);
+        double* const row = A.partials + ((size_t)bid * nw + wid) * (P + 1);
 #pragma unroll 1
         for (int q = 0; q < nred; ++q) {
             double v = 0.0;

@@ -10,10 +10,11 @@ ctx = cu.Context(0)
 spop = cu.SuppressionPopulation(sup["group_data"], sup["timepoints"], ctx=ctx)
 r = np.random.default_rng(2)
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+o = cu.SolverOptions(block=int(sys.argv[2])) if len(sys.argv) > 2 else None      # optional: threads per block
 nns = sup["neural_0p01"][r.integers(0, 25, S)] + 0.05 * r.standard_normal((S, 67))
 th = r.uniform(-1, 1, (S, 37))
 out = {}
-for name, fn in (("loss", lambda: spop.loss(nns, th, lam=0.01)), ("loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01))):
+for name, fn in (("loss", lambda: spop.loss(nns, th, lam=0.01, opts=o)), ("loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01, opts=o))):
     ms = []
     for _ in range(5):
         fn(); ms.append(ctx.stats()["kernel_ms"])

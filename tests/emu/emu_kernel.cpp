@@ -188,9 +188,11 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
     const long long nblocks = (long long)n_ind * n_starts;
     std::vector<double> partials((size_t)nblocks * prow_stride * (SN::P + 1), 0.0);
     a.partials = partials.data();
-    blockDim.x = 1; threadIdx.x = 0;
+    blockDim.x = 1; threadIdx.x = 0; gridDim.x = 1;
+    std::vector<double> ring((size_t)SUP_REC_CAP * SUP_REC_ROWS, 0.0);     // one "block" of one thread per launch
+    a.ring = ring.data();
     for (long long b = 0; b < nblocks; ++b) {
-        blockIdx.x = (int)b;
+        blockIdx.x = 0; a.blk0 = (int)b;
         if (grad) cude_sup_kernel<SN, true>(a); else cude_sup_kernel<SN, false>(a);
     }
     if (grad && g_neural_traj)
