@@ -511,6 +511,10 @@ static int split_budget(cude_ctx* ctx, size_t* out) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
         size_t b = CUDE_SPLIT_BYTES;
+        if (const char* e = getenv("CUDE_SCRATCH_BYTES")) {      // tests: force the grouped / multi-launch code paths on small batches
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v) b = (size_t)v;
+        }
         if (b > free_b * 2 / 5) b = free_b * 2 / 5;
         ctx->split_budget = b > (1u << 20) ? b : (1u << 20);
     }

@@ -477,6 +477,23 @@ def test_two_kernel_gradient_with_exact_lane_balance(fx, ctx):
     assert np.array_equal(e[3], f[3]) and np.array_equal(e[2], f[2]) and relmax(e[1], f[1]) < 1e-12
 
 
+def test_two_kernel_gradient_in_groups_of_starts(fx, monkeypatch):
+    """A call whose step records exceed the scratch budget is walked in groups of starts (bench: 8 groups of 8); forced here with
+    a 64 MB budget on 40 000 individuals x 5 starts (one start per group): results equal the single-group call bit for bit."""
+    import bench
+    n = 40_000
+    ctx0 = cu.Context(0)
+    pk = bench.synthetic_population(n, 21, bench.simulate_gpu(ctx0))
+    neural, cond = bench.synthetic_starts(n, 5, 11, 22)
+    a = cu.Population(packed=pk, ctx=ctx0).loss_grad(neural, cond, mean=False, return_sse=True)
+    l0 = ctx0.stats()["launches"]
+    monkeypatch.setenv("CUDE_SCRATCH_BYTES", str(100 << 20))
+    ctx1 = cu.Context(0)
+    b = cu.Population(packed=pk, ctx=ctx1).loss_grad(neural, cond, mean=False, return_sse=True)
+    assert ctx1.stats()["launches"] > l0
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_automatic_gradient_path_depends_on_the_population_only(ctx):
     """The default (balance = 0) picks the two-kernel gradient from 32768 individuals on — by the population, never by the
     number of starts, so that a start's sums do not depend on how a batch is cut into calls (bitwise)."""

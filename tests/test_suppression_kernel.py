@@ -140,6 +140,22 @@ def test_gpu_loss_and_gradient_match_oracle(sup):
 
 
 @pytest.mark.gpu
+def test_gpu_small_scratch_budget_cuts_the_batch_into_launches(sup, monkeypatch):
+    """The step rings of a gradient launch live in global scratch; a batch whose rings exceed the budget is cut into several
+    launches over block ranges (here: 8 MB = 5 blocks per launch, 58 blocks) — same results bit for bit."""
+    data, t = sup["group_data"], sup["timepoints"]
+    rng = np.random.default_rng(4)
+    nns = sup["neural_0p01"][rng.integers(0, 25, 200)] + 0.02 * rng.standard_normal((200, 67))
+    th = rng.uniform(-1, 1, (200, 37))
+    a = cu.SuppressionPopulation(data, t).loss_grad(nns, th, 0.01, return_sse=True)
+    monkeypatch.setenv("CUDE_SCRATCH_BYTES", str(8 << 20))
+    ctx = cu.Context(0)                                   # a fresh context decides its budget at first use
+    b = cu.SuppressionPopulation(data, t, ctx=ctx).loss_grad(nns, th, 0.01, return_sse=True)
+    assert ctx.stats()["launches"] > 5
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.gpu
 def test_gpu_fit_and_validate(sup):
     """fit_suppression_model / validate_suppression_model in miniature (reference: 10 000 initials, 2000 + 2000 iterations)."""
     data, vdata, t = sup["group_data"], sup["validation_data"], sup["timepoints"]
