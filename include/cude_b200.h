@@ -65,7 +65,7 @@ typedef struct {
                     * 0 (default) = automatic: populations of >= 32768 individuals use the TWO-KERNEL gradient — forward solve
                     *     leaving a 64-byte record per accepted step, every start's trajectories sorted by their accepted-step
                     *     count (stable radix sort: deterministic), adjoint sweep in the sorted order with no idle lanes
-                    *     (+9 % on B200; needs ~2.1 KB of device memory per trajectory of a group of starts, the library sizes
+                    *     (+14 % on B200; needs ~2.2 KB of device memory per trajectory of a group of starts, the library sizes
                     *     the groups to min(20 GB, 40 % of the free memory)); smaller populations use the fused kernel;
                     * 1 = fused kernel, each start's individuals regrouped by the step counts of an EARLIER call on this
                     *     population (refreshed every 8 calls; pays only when the parameters barely move between calls);
