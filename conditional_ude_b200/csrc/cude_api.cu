@@ -16,6 +16,7 @@
 #include "cude_kernels.cuh"
 #include "cude_split.cuh"
 #include "cude_sup_kernel.cuh"
+#include "cude_warp.cuh"
 #include "cude_train.cuh"
 
 using namespace cude;
@@ -42,6 +43,9 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
+#ifndef CUDE_WARP_MAX_TRAJ
+#define CUDE_WARP_MAX_TRAJ 4096             // opts.balance = 0 (automatic): loss + full-gradient calls of at most this many trajectories take the
+#endif                                      // warp-per-trajectory latency kernel (cude_warp.cuh): 1776 warps are resident at a time (3 blocks of 4 per SM), a wave takes ~55 us against ~210 us for the fused kernel
 #ifndef CUDE_EXACT_MIN_IND
 #define CUDE_EXACT_MIN_IND 32768            // opts.balance = 0 (automatic): populations of at least this many individuals take the two-kernel
                                             // gradient with exact lane balance; smaller ones the fused single-kernel adjoint (lower latency)
@@ -881,6 +885,55 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     return CUDE_OK;
 }
 
+
+// ---- latency form of loss + full gradient: one warp per trajectory (cude_warp.cuh), fused-kernel fallback for solves longer
+// than WARP_CAP accepted steps, per-start reduction of the trajectory rows ----
+typedef void (*warp_kernel_t)(const WarpArgs);
+static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B, int nchunks, eval_kernel_t fused, size_t smem_fused,
+                    double* d_sums_out, int* launches) {
+    const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
+    warp_kernel_t kw = nullptr;
+    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>> : nullptr);
+    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
+    const size_t ntraj = (size_t)N * S, nblk = (size_t)S * nchunks;
+    int rc;
+    if ((rc = sm_count(ctx))) return rc;
+    cude_ctx::SplitSet& set = ctx->sp[0];
+    const size_t o_ovf = 0, o_flag = o_ovf + (ntraj * 4 + 7) / 8 * 8, o_list = o_flag + ((nblk + 1) * 4 + 7) / 8 * 8,
+                 misc_bytes = o_list + (nblk * 4 + 7) / 8 * 8;
+    if ((rc = ensure(ctx, set.misc, misc_bytes))) return rc;
+    if ((rc = ensure(ctx, set.part, nblk * nw * np1 * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->partials, ntraj * np1 * sizeof(double)))) return rc;
+    char* const misc = (char*)set.misc.p;
+    WarpArgs w{};
+    w.pop = a.pop; w.n_starts = S; w.neural = a.neural; w.neural_stride = a.neural_stride; w.cond = a.cond;
+    w.abstol = a.abstol; w.reltol = a.reltol; w.maxiters = a.maxiters; w.cond_scale = a.cond_scale;
+    w.sse_out = a.sse_out; w.g_cond = a.g_cond; w.rows = (double*)ctx->partials.p; w.counters = a.counters;
+    w.ovf = (int*)(misc + o_ovf); w.blkflag = (int*)(misc + o_flag); w.blkcount = w.blkflag + nblk; w.blklist = (int*)(misc + o_list);
+    w.fb_block = B; w.nchunks = nchunks;
+    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs);
+    if (smem_w > 200 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots / observations for the warp kernel");
+    if ((rc = prep_kernel(ctx, (const void*)kw, 32 * WARP_TPB, smem_w))) return rc;
+    if ((rc = prep_kernel(ctx, (const void*)fused, B, smem_fused))) return rc;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemsetAsync(w.blkflag, 0, (nblk + 1) * sizeof(int), st));
+    kw<<<(unsigned)((ntraj + WARP_TPB - 1) / WARP_TPB), 32 * WARP_TPB, smem_w, st>>>(w);
+    CU_TRY(ctx, cudaGetLastError());
+    EvalArgs f = a;                               // trajectories beyond WARP_CAP steps: the fused kernel on the flagged blocks
+    f.partials = (double*)set.part.p; f.only_flag = w.ovf; f.sp_blkflag = w.blkflag; f.sp_blklist = w.blklist; f.sp_blkcount = w.blkcount;
+    f.counters = nullptr; f.keys_out = nullptr; f.sse_out = nullptr; f.order = nullptr; f.wc_base = 0;
+    const unsigned fb_grid = (unsigned)(ctx->sm_count * CUDE_MIN_BLOCKS);
+    fused<<<(nblk < fb_grid ? (unsigned)nblk : fb_grid), B, smem_fused, st>>>(f);
+    CU_TRY(ctx, cudaGetLastError());
+    *launches += 2;
+    if (d_sums_out) {
+        cude_warp_reduce<<<(unsigned)S, RED_T, 0, st>>>(w.rows, N, (const double*)set.part.p, w.blkflag, nchunks, nw, np1, d_sums_out);
+        CU_TRY(ctx, cudaGetLastError());
+        ++*launches;
+    }
+    return CUDE_OK;
+}
+
 extern "C" int cude_eval_dev(cude_ctx* ctx, const cude_population* pop, const cude_net* net, const cude_opts* opts_in,
                              int n_starts, const double* d_neural, long long neural_stride, const double* d_cond,
                              int want_grad, double cond_scale,
@@ -899,7 +952,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     cude_opts o;
     if (opts_in) o = *opts_in; else cude_default_opts(&o);
     if (!(o.abstol > 0.0) || !(o.reltol > 0.0) || o.maxiters < 1) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: bad solver options");
-    if (o.balance < 0 || o.balance > 3) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: balance must be 0 (automatic), 1 (history), 2 (exact) or 3 (off)");
+    if (o.balance < 0 || o.balance > 4) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: balance must be 0 (automatic), 1 (history), 2 (exact), 3 (fused kernel) or 4 (warp per trajectory)");
     if (o.precision < 0 || o.precision > 2) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: precision must be 0 (FP64), 1 (FP32 network, FP64 integrator) or 2 (FP64 forward pass, FP32 network in the adjoint)");
     const bool mixed = o.precision == 1;
     const bool fbwd = o.precision == 2;
@@ -980,6 +1033,9 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     // only, never on the number of starts, so that a start's sums do not depend on how a batch is split into calls.
     const bool use_exact = !use_split && adj && !flat && !mixed && want_neural_grad && d_g_cond && N < (1 << 24) &&
                            (o.balance == 2 || (o.balance == 0 && N >= CUDE_EXACT_MIN_IND));
+    // the latency form (one warp per trajectory): on request (opts.balance = 4) or automatically for small batches
+    const bool use_warp = !use_split && !use_exact && adj && !flat && !mixed && !fbwd && want_neural_grad && d_g_cond && !bal &&
+                          (o.balance == 4 || (o.balance == 0 && ntraj <= CUDE_WARP_MAX_TRAJ));
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
@@ -990,6 +1046,9 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
         if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
     } else if (use_exact) {
         if ((rc = run_exact(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
+    } else if (use_warp) {
+        // (fallback through the shared-memory-weights instantiation: no constant-memory upload on the latency path)
+        if ((rc = run_warp(ctx, net, a, B, nchunks, select_kernel(net, true, false, false, false, false), smem, d_sums_out, &launches))) return rc;
     } else {
         if (wc && (rc = wconst_upload(ctx, d_neural, n_w))) return rc;
         kern<<<(unsigned)nblocks, B, smem, ctx->stream>>>(a);
@@ -997,7 +1056,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
         if (wc && (rc = wconst_used(ctx))) return rc;
         launches = 1;
     }
-    if (d_sums_out && !use_split && !use_exact) {
+    if (d_sums_out && !use_split && !use_exact && !use_warp) {
         if (flat) {
             const int wpb = 8;
             cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);

@@ -27,7 +27,7 @@ class SolverOptions:
 
     def __init__(self, abstol=1e-6, reltol=1e-3, maxiters=1000000, block=0, precision=0, balance=0, split=0):
         self.abstol, self.reltol, self.maxiters, self.block, self.precision = abstol, reltol, maxiters, block, precision
-        self.balance = balance      # 0 automatic (two-kernel gradient with exact lane balance for large populations), 1 history, 2 exact, 3 off
+        self.balance = balance      # 0 automatic (<= 8192 trajectories: warp per trajectory; >= 32768 individuals: two-kernel gradient; else fused), 1 history, 2 two-kernel, 3 fused, 4 warp per trajectory
         self.split = split          # gradient pipeline: 0 automatic, 1 fused kernel, 2 split pipeline (cude_b200.h)
 
     def c(self):

@@ -62,16 +62,22 @@ typedef struct {
     int block;     /* threads per block (individuals per tile); 0 = library default */
     int balance;   /* lane balance of loss + full-gradient calls with per-start networks (a warp runs to its slowest lane and the
                     * trajectories of a start take 17-26 steps, so 12 % of the lane-cycles idle in natural order):
-                    * 0 (default) = automatic: populations of >= 32768 individuals use the TWO-KERNEL gradient — forward solve
-                    *     leaving a 64-byte record per accepted step, every start's trajectories sorted by their accepted-step
-                    *     count (stable radix sort: deterministic), adjoint sweep in the sorted order with no idle lanes
-                    *     (+14 % on B200; needs ~2.2 KB of device memory per trajectory of a group of starts, the library sizes
-                    *     the groups to min(20 GB, 40 % of the free memory)); smaller populations use the fused kernel;
+                    * 0 (default) = automatic:
+                    *     - calls of <= 4096 trajectories use the WARP-PER-TRAJECTORY latency kernel (mode 4);
+                    *     - populations of >= 32768 individuals use the TWO-KERNEL gradient (mode 2);
+                    *     - everything else the fused kernel (mode 3);
                     * 1 = fused kernel, each start's individuals regrouped by the step counts of an EARLIER call on this
                     *     population (refreshed every 8 calls; pays only when the parameters barely move between calls);
-                    * 2 = always the two-kernel gradient;  3 = always the fused kernel in natural order.
-                    * Per-trajectory results (sse, d/d cond) are bitwise the same in every mode; the per-start sums differ only
-                    * in summation order and are run-to-run deterministic in modes 0, 2 and 3. */
+                    * 2 = the two-kernel gradient: forward solve leaving a 64-byte record per accepted step, every start's
+                    *     trajectories sorted by their accepted-step count (stable radix sort: deterministic), adjoint sweep in
+                    *     the sorted order with no idle lanes (+14 % on B200; needs ~2.2 KB of device memory per trajectory of a
+                    *     group of starts, the library sizes the groups to min(20 GB, 40 % of the free memory));
+                    * 3 = the fused kernel (one thread per trajectory, forward solve + adjoint sweep) in natural order;
+                    * 4 = one warp per trajectory (small batches: config 1, the selected starts of `train`): the 5 network nodes
+                    *     of a step on 5 lanes, the adjoint's (step, node) evaluations spread over the 32 lanes — 0.06-0.09 ms
+                    *     instead of 0.2 ms per evaluation of 57-1425 trajectories.
+                    * Per-trajectory sse is bitwise the same in every mode, d/d cond in modes 0-3 (mode 4: to 1e-13); the
+                    * per-start sums differ only in summation order and are run-to-run deterministic in modes 0, 2, 3 and 4. */
     int split;     /* gradient pipeline of loss + full-gradient calls with per-start networks:
                     * 0, 1 = the fused single-kernel adjoint (default);
                     * 2 = the split pipeline: forward solve leaving one record per accepted step -> adjoint recursion

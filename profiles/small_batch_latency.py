@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Latency of one loss+gradient evaluation of the 25 selected starts (57 individuals x 25, config 3) through the device
-API, fused kernel vs split pipeline: kernel ms (events) and wall time per call in a back-to-back loop."""
+API, fused kernel vs warp-per-trajectory latency kernel vs split pipeline: kernel ms (events) and wall time per call in a back-to-back loop."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -15,8 +15,7 @@ rng = np.random.default_rng(1)
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 neural = nn[None] + 0.1 * rng.standard_normal((S, 37)); cond = np.tile(betas, (S, 1)) + 0.2 * rng.standard_normal((S, 57))
 out = {}
-for name, sp in (("fused", 1), ("split", 2)):
-    o = cu.SolverOptions(split=sp)
+for name, o in (("fused", cu.SolverOptions(balance=3)), ("warp_per_trajectory", cu.SolverOptions(balance=4)), ("split", cu.SolverOptions(balance=3, split=2))):
     for _ in range(5): pop.loss_grad(neural, cond, opts=o)
     k = []
     t0 = time.perf_counter()

@@ -477,6 +477,45 @@ def test_two_kernel_gradient_with_exact_lane_balance(fx, ctx):
     assert np.array_equal(e[3], f[3]) and np.array_equal(e[2], f[2]) and relmax(e[1], f[1]) < 1e-12
 
 
+def test_warp_per_trajectory_latency_kernel(fx, ctx):
+    """opts.balance = 4 (and the automatic choice for calls of <= 8192 trajectories): one warp per trajectory — the forward pass is
+    the fused kernel's arithmetic with the 5 network nodes of a step on 5 lanes (sse bit for bit), the adjoint's (step, node)
+    evaluations are spread over the lanes (gradients to summation order); solves beyond 64 accepted steps take the fused kernel
+    inside the same call; failures give Inf / zero gradients."""
+    models, ts, ys = mixed_population(fx)
+    pk = cu.pack_models(models, ts, ys)
+    pop = cu.Population(packed=pk, ctx=ctx)
+    rng = np.random.default_rng(13)
+    neural, cond = random_starts(rng, pk["chain"], len(models), 9)
+    for o in (dict(), DET, dict(abstol=1e-8, reltol=1e-5), dict(abstol=1e-10, reltol=1e-7)):   # the last: every solve beyond 64 steps
+        f = pop.loss_grad(neural, cond, opts=SolverOptions(balance=3, **o), mean=False, return_sse=True)
+        st_f = ctx.stats()
+        w = pop.loss_grad(neural, cond, opts=SolverOptions(balance=4, **o), mean=False, return_sse=True)
+        st_w = ctx.stats()
+        w2 = pop.loss_grad(neural, cond, opts=SolverOptions(balance=4, **o), mean=False, return_sse=True)
+        assert np.array_equal(w[3], f[3])                                        # sse: bit for bit
+        assert relmax(w[2], f[2]) < 1e-12 and relmax(w[0], f[0]) < 1e-14 and relmax(w[1], f[1]) < 1e-12
+        assert all(np.array_equal(a, b) for a, b in zip(w, w2))                   # deterministic
+        assert st_w["launches"] == 3 and all(st_w[k] == st_f[k] for k in ("n_acc", "n_rej", "n_fail", "n_traj"))
+    a = pop.loss_grad(neural, cond, mean=False, return_sse=True)                  # automatic: 9 x 137 trajectories -> warp kernel
+    assert ctx.stats()["launches"] == 3 and all(np.array_equal(x, y) for x, y in zip(a, pop.loss_grad(neural, cond, opts=SolverOptions(balance=4), mean=False, return_sse=True)))
+    r = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    w = pop.loss_grad(neural, cond, opts=SolverOptions(balance=4, **DET), mean=False, return_sse=True)
+    assert relmax(w[3], r["sse"]) < 1e-10 and relmax(w[1], r["g_neural"].sum(axis=1)) < 1e-9 and relmax(w[2], r["g_cond"]) < 1e-9
+    bad = cond.copy(); bad[2, 5] = np.nan
+    w = pop.loss_grad(neural, bad, opts=SolverOptions(balance=4))
+    f = pop.loss_grad(neural, bad, opts=SolverOptions(balance=3))
+    assert np.isinf(w[0][2]) and np.all(w[1][2] == 0) and np.all(w[2][2] == 0) and np.allclose(w[0][[0, 1, 3]], f[0][[0, 1, 3]], rtol=1e-14)
+    assert ctx.stats()["n_fail"] == 1
+    models, t, c = ohashi_models(fx, "train", covariate=True)                     # covariate network
+    pkc = cu.pack_models(models, t, c)
+    popc = cu.Population(packed=pkc, ctx=ctx)
+    neural, cond = random_starts(rng, pkc["chain"], len(models), 4)
+    f = popc.loss_grad(neural, cond, opts=SolverOptions(balance=3), mean=False, return_sse=True)
+    w = popc.loss_grad(neural, cond, opts=SolverOptions(balance=4), mean=False, return_sse=True)
+    assert np.array_equal(w[3], f[3]) and relmax(w[2], f[2]) < 1e-12 and relmax(w[1], f[1]) < 1e-12
+
+
 def test_two_kernel_gradient_in_groups_of_starts(fx, monkeypatch):
     """A call whose step records exceed the scratch budget is walked in groups of starts (bench: 8 groups of 8); forced here with
     a 64 MB budget on 40 000 individuals x 5 starts (one start per group): results equal the single-group call bit for bit."""
