@@ -339,7 +339,10 @@ def secondary_configs(ctx, peak64):
     pop57 = cu.Population(m57, fx["ohashi_timepoints"], y57, ctx=ctx)
     betas = fx["cude_betas"][int(fx["cude_best_model_index"]) - 1]
     measure("config1_ohashi_train_57x1_loss_grad", lambda: pop57.loss_grad(nn, betas[None]), 57, True,
-            "cude_eval_kernel<GRAD> (fused adjoint)", reps=20, note="two warps of work: launch latency, not throughput")
+            "cude_warp_kernel (one warp per trajectory)", reps=20, note="57 warps: latency of one trajectory's forward solve + adjoint, not throughput")
+    fused = cu.SolverOptions(balance=3)
+    measure("config1_ohashi_train_57x1_loss_grad_fused_kernel", lambda: pop57.loss_grad(nn, betas[None], opts=fused), 57, True,
+            "cude_eval_kernel<GRAD> (fused adjoint, one thread per trajectory)", reps=20, note="the round-1 path of the same call, for comparison")
     # configs[1]: beta-only estimation, all Ohashi + Fujita individuals x 1000 starts, network fixed: loss + d/d beta
     m, t, y = _fixture_models(fx, cu, ["train", "test", "fujita"])
     pop137 = cu.Population(packed=cu.pack_models(m, t, y), ctx=ctx)
@@ -354,7 +357,9 @@ def secondary_configs(ctx, peak64):
     measure("config3_screening_57x25000_loss_only", lambda: pop57.loss(neural, cond3), cond3.size, False,
             "cude_eval_kernel<loss> (per-start networks from shared memory: 25 000 networks exceed the constant bank)")
     measure("config3_selected_57x25_loss_grad", lambda: pop57.loss_grad(neural[:25], cond3[:25]), 57 * 25, True,
-            "cude_eval_kernel<GRAD> (fused adjoint)", reps=20, note="one optimiser iteration of the 25 selected starts: 45 warps, latency-bound")
+            "cude_warp_kernel (one warp per trajectory)", reps=20, note="one optimiser iteration of the 25 selected starts: 1425 warps in one wave, latency-bound")
+    measure("config3_selected_57x25_loss_grad_fused_kernel", lambda: pop57.loss_grad(neural[:25], cond3[:25], opts=fused), 57 * 25, True,
+            "cude_eval_kernel<GRAD> (fused adjoint, one thread per trajectory)", reps=20, note="the round-1 path of the same call, for comparison")
     # configs[3]: likelihood profiles, 117 individuals x 1000 / 10 000 grid points (loss only, network fixed)
     m, t, y = _fixture_models(fx, cu, ["train", "test"])
     pop117 = cu.Population(m, fx["ohashi_timepoints"], np.stack(y), ctx=ctx)
