@@ -20,7 +20,14 @@ rng = np.random.default_rng(0)
 neural, cond = random_starts(rng, pk["chain"], len(models), 3)
 l = pop.loss(neural, cond)                               # loss only, tile mode
 l2 = pop.loss(neural[0], cond)                           # loss only, flat mode
-g = pop.loss_grad(neural, cond)                          # adjoint
+g = pop.loss_grad(neural, cond)                          # adjoint: automatic = warp per trajectory (small batch)
+tight = dict(abstol=1e-10, reltol=1e-7)                  # beyond 64 / 32 recorded steps: the fused-kernel fallbacks
+for bal in (2, 3, 4):                                    # two-kernel gradient, fused kernel, warp per trajectory
+    pop.loss_grad(neural, cond, opts=cu.SolverOptions(balance=bal))
+    pop.loss_grad(neural, cond, opts=cu.SolverOptions(balance=bal, **tight))
+pop.loss_grad(neural, cond, opts=cu.SolverOptions(balance=2, precision=2))   # FP32 adjoint kernel
+pop.loss_grad(neural, cond, opts=cu.SolverOptions(balance=3, split=2))       # split pipeline
+pop.simulate(neural, cond)
 b = pop.loss_grad(neural[0], cond, neural_grad=False)    # forward sensitivity, flat
 m = pop.loss_grad(neural, cond, opts=cu.SolverOptions(precision=1))   # mixed precision
 # lane balancing + pipelined host call on a population large enough to enable both (kept small for the sanitizer)
