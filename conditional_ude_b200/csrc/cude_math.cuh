@@ -24,7 +24,7 @@ namespace cude {
 // host stand-ins (tests/emu): same bit manipulations through memcpy, a float-accurate reciprocal seed
 static inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }
 static inline int __double2loint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
-static inline double __hiloint2double(int hi, int lo) { long long b = ((long long)hi << 32) | (unsigned int)lo; double x; memcpy(&x, &b, 8); return x; }
+static inline double __hiloint2double(int hi, int lo) { unsigned long long b = ((unsigned long long)(unsigned int)hi << 32) | (unsigned int)lo; double x; memcpy(&x, &b, 8); return x; }
 static inline double rcp_seed(double d) { return (double)(float)(1.0 / d); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
@@ -125,7 +125,7 @@ __device__ __forceinline__ void t_exp_parts(double x, const double* __restrict__
     double r = fma(nf, -0.0027076061740622863 / SC, x);               // ln2/256 (division by 2 is exact)
     if (LO) r = fma(nf, -9.058776616587108e-20 / SC, r);             // ln2/256 - double(ln2/256)
     const double m = tab[n & 255];
-    M = __hiloint2double(__double2hiint(m) + ((n >> 8) << 20), __double2loint(m));
+    M = __hiloint2double(__double2hiint(m) + ((n >> 8) * (1 << 20)), __double2loint(m));
     // exp(SC r), |SC r| <= ln2/512: 1 + s + s^2/2 + s^3/6 + s^4/24 with s = SC r
     double p = fma(SC == 1 ? 0.041666666666666664 : 0.6666666666666666, r, SC == 1 ? 0.16666666666666666 : 1.3333333333333333);
     p = fma(p, r, SC == 1 ? 0.5 : 2.0);

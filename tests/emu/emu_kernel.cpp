@@ -9,6 +9,7 @@
 #include <cstddef>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 using std::isfinite;
 
 #define __global__
@@ -157,6 +158,69 @@ extern "C" int emu_eval_split(int n_ind, int max_knots, const int* n_knots, cons
     for (size_t s = 0; s < S; ++s)
         for (int q = 0; q < np1; ++q) {
             double v = pA[s * np1 + q];
+            for (size_t c = 0; c < N; ++c) v += pB[(s * N + c) * np1 + q];
+            sums[s * np1 + q] = v;
+        }
+    return 0;
+}
+
+// The two-kernel gradient (opts.balance = 2): stage 1 as above -> every start's individuals stably sorted by their number of
+// accepted steps (host) -> cude_adjoint_kernel in the sorted order, one thread per block.  Returns the same quantities as
+// emu_eval_split; trajectories beyond SPLIT_CAP steps (the fused kernel's on the device) are only counted.
+extern "C" int emu_eval_exact(int n_ind, int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
+                              int max_obs, const int* n_obs, const double* obs_t, const double* obs_y, const double* kin,
+                              int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters,
+                              double* sse, double* sums, double* g_cond, int* n_overflow) {
+    typedef NetShape<2, 2, 4> NS;
+    const size_t N = n_ind, K = max_knots, M = max_obs, S = n_starts, NT = N * S;
+    const int P = NS::P, np1 = P + 1;
+    std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N);
+    for (size_t i = 0; i < N; ++i) {
+        const int nk = n_knots[i], no = n_obs[i];
+        for (int k = 0; k < max_knots; ++k) {
+            const int kk = k < nk ? k : nk - 1;
+            kt[k * N + i] = knot_t[i * K + kk]; kg[k * N + i] = knot_g[i * K + kk];
+            if (k + 1 < nk) sl[k * N + i] = (knot_g[i * K + k + 1] - knot_g[i * K + k]) / (knot_t[i * K + k + 1] - knot_t[i * K + k]);
+        }
+        for (int k = 0; k < max_obs; ++k) { const int kk = k < no ? k : no - 1; ot[k * N + i] = obs_t[i * M + kk]; oy[k * N + i] = obs_y[i * M + kk]; }
+        k0[i] = kin[4 * i]; k1[i] = kin[4 * i + 1]; k2[i] = kin[4 * i + 2]; c0[i] = kin[4 * i + 3];
+    }
+    EvalArgs a{};
+    a.pop.n_ind = n_ind; a.pop.max_knots = max_knots; a.pop.max_obs = max_obs;
+    a.pop.n_knots = n_knots; a.pop.knot_t = kt.data(); a.pop.knot_g = kg.data(); a.pop.slope = sl.data();
+    a.pop.n_obs = n_obs; a.pop.obs_t = ot.data(); a.pop.obs_y = oy.data();
+    a.pop.k0 = k0.data(); a.pop.k1 = k1.data(); a.pop.k2 = k2.data(); a.pop.c0 = c0.data(); a.pop.cov = nullptr;
+    a.n_starts = n_starts; a.neural = neural; a.neural_stride = P; a.cond = cond;
+    a.abstol = abstol; a.reltol = reltol; a.maxiters = maxiters; a.flat = 0; a.nchunks = n_ind; a.cond_scale = 1.0;
+    unsigned long long counters[3] = {0, 0, 0};
+    a.sse_out = sse; a.counters = counters;
+    std::vector<double> rec(NT * SPLIT_CAP * SPLIT_W, 0.0), res(M * NT, 0.0), beta(NT), spsse(NT);
+    std::vector<int> nrec(NT), flag(NT, 0), blklist(NT + 1, 0);
+    std::vector<unsigned int> keys(NT), order(NT);
+    std::vector<unsigned short> k16(NT);
+    a.sp_blklist = blklist.data(); a.sp_blkcount = blklist.data() + NT;
+    a.sp_rec = rec.data(); a.sp_res = res.data(); a.sp_nrec = nrec.data(); a.sp_beta = beta.data(); a.sp_sse = spsse.data(); a.sp_blkflag = flag.data();
+    a.keys_out = keys.data(); a.keys16_out = k16.data();
+    blockDim.x = 1; threadIdx.x = 0; gridDim.x = (int)NT; gridDim.y = 1;
+    for (size_t b = 0; b < NT; ++b) { blockIdx.x = (int)b; blockIdx.y = 0; cude_eval_kernel<NS, false, false, false, false, false, true>(a); }
+    int novf = 0;
+    for (size_t s = 0; s < S; ++s) {                    // the library's one stable sort on (start, steps), restricted to a start
+        std::vector<unsigned int> idx(N);
+        for (size_t i = 0; i < N; ++i) idx[i] = keys[s * N + i];
+        std::stable_sort(idx.begin(), idx.end(), [](unsigned int x, unsigned int y) { return (x >> 24) < (y >> 24); });
+        for (size_t i = 0; i < N; ++i) { order[s * N + i] = idx[i]; if (k16[s * N + i] != (unsigned short)((s << 8) | (keys[s * N + i] >> 24))) return 2; }
+    }
+    for (size_t j = 0; j < NT; ++j) if (nrec[j] < 0) ++novf;
+    if (n_overflow) *n_overflow = novf;
+    std::vector<double> pB(NT * np1, 0.0);
+    AdjArgs aa{};
+    aa.pop = a.pop; aa.n_starts = n_starts; aa.nchunks = n_ind; aa.neural = neural; aa.neural_stride = P; aa.wc_base = 0;
+    aa.sp_rec = rec.data(); aa.sp_res = res.data(); aa.sp_nrec = nrec.data(); aa.sp_beta = beta.data(); aa.sp_sse = spsse.data();
+    aa.order = order.data(); aa.cond_scale = 1.0; aa.g_cond = g_cond; aa.partials = pB.data();
+    for (size_t b = 0; b < NT; ++b) { blockIdx.x = (int)b; cude_adjoint_kernel<NS, double, false>(aa); }
+    for (size_t s = 0; s < S; ++s)
+        for (int q = 0; q < np1; ++q) {
+            double v = 0.0;
             for (size_t c = 0; c < N; ++c) v += pB[(s * N + c) * np1 + q];
             sums[s * np1 + q] = v;
         }

@@ -6,7 +6,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
-LIB = os.path.join(_HERE, "libcude_emu.so")
+# CUDE_EMU_SANITIZE=1: build with -fsanitize=address,undefined (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+# ASAN_OPTIONS=detect_leaks=0) — the memory check of the kernel sources on this pool, where compute-sanitizer is closed
+_SAN = os.environ.get("CUDE_EMU_SANITIZE") == "1"
+LIB = os.path.join(_HERE, "libcude_emu_san.so" if _SAN else "libcude_emu.so")
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int)
 
@@ -16,8 +19,9 @@ def build():
         os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f)
         for f in ("cude_kernels.cuh", "cude_math.cuh", "cude_sup_kernel.cuh", "cude_split.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in src):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                               "-o", LIB, src[0]])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas"] +
+                              (["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if _SAN else []) +
+                              ["-o", LIB, src[0]])
     return LIB
 
 
@@ -72,6 +76,30 @@ def emu_eval_split(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=1000
                           int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]),
                           S, _dp(neural), _dp(cond), abstol, reltol, maxiters, _dp(sse), _dp(sums), _dp(gc), C.byref(novf))
     assert rc == 0
+    return dict(sse=sse, sums=sums, g_cond=gc, n_overflow=novf.value)
+
+
+def emu_eval_exact(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000):
+    """The two-kernel gradient (forward kernel with step records -> per-start sort by accepted steps -> cude_adjoint_kernel in
+    sorted order) through the host-compiled kernel sources.  Same return value as emu_eval_split."""
+    L = C.CDLL(build())
+    L.emu_eval_exact.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, C.c_int, _D, _D, C.c_double, C.c_double,
+                                 C.c_int, _D, _D, _D, _I]
+    ch = packed["chain"]
+    N, P = int(packed["n_ind"]), ch.n_params
+    a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
+    nk = np.ascontiguousarray(packed["n_knots"], dtype=np.int32)
+    no = np.ascontiguousarray(packed["n_obs"], dtype=np.int32)
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float64).reshape(-1, N))
+    S = cond.shape[0]
+    assert neural.shape == (S, P) and ch.input_dims == 2
+    sse, sums, gc = np.empty((S, N)), np.zeros((S, P + 1)), np.zeros((S, N))
+    novf = C.c_int(0)
+    rc = L.emu_eval_exact(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
+                          int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]),
+                          S, _dp(neural), _dp(cond), abstol, reltol, maxiters, _dp(sse), _dp(sums), _dp(gc), C.byref(novf))
+    assert rc == 0, rc
     return dict(sse=sse, sums=sums, g_cond=gc, n_overflow=novf.value)
 
 

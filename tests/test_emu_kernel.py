@@ -240,3 +240,32 @@ def test_split_gradient_pipeline_stages(fx):
     # more accepted steps than a record block holds (tight tolerance): flagged for the fused-kernel fallback, not recorded
     s3 = emu_wrap.emu_eval_split(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
     assert s3["n_overflow"] == len(pick)
+
+
+def test_two_kernel_gradient_stages(fx):
+    """The default gradient path of large populations compiled for the host: forward kernel with step records and sort keys ->
+    per-start stable sort by accepted steps -> cude_adjoint_kernel (records through the cp.async double buffer, observation
+    loads two ahead) in the sorted order.  Per-trajectory sse and d/d cond are the fused kernel's bit for bit, sums to
+    summation order; the oracle's in the deterministic regime."""
+    models, ts, ys = mixed_population(fx)
+    pick = [0, 3, 50, 100, 120, 130, 136]
+    pk = cu.pack_models([models[i] for i in pick], [ts[i] for i in pick], [ys[i] for i in pick])
+    rng = np.random.default_rng(7)
+    neural, cond = random_starts(rng, pk["chain"], len(pick), 3)
+    pk5 = cu.pack_models([models[i] for i in pick[:4]], [ts[i] for i in pick[:4]], [ys[i] for i in pick[:4]])   # Ohashi only: <= 32 steps
+    for pkx, cx, o in ((pk, cond, DET), (pk5, cond[:, :4], dict())):
+        f = emu_wrap.emu_eval(pkx, neural, cx, **o)
+        e = emu_wrap.emu_eval_exact(pkx, neural, cx, **o)
+        assert e["n_overflow"] == 0
+        assert np.array_equal(e["sse"], f["sse"]) and np.array_equal(e["g_cond"], f["g_cond"])
+        assert relmax(e["sums"][:, 0], f["sse"].sum(axis=1)) < 1e-14
+        assert relmax(e["sums"][:, 1:], f["g_neural"].sum(axis=1)) < 1e-12
+    g = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
+    e = emu_wrap.emu_eval_exact(pk, neural, cond, **DET)
+    assert relmax(e["sse"], g["sse"]) < 1e-10 and relmax(e["g_cond"], g["g_cond"]) < 1e-9
+    assert relmax(e["sums"][:, 1:], g["g_neural"].sum(axis=1)) < 1e-9
+    bad = cond.copy(); bad[1, 2] = np.nan
+    e2 = emu_wrap.emu_eval_exact(pk, neural, bad, **DET)
+    assert np.isinf(e2["sums"][1, 0]) and e2["g_cond"][1, 2] == 0 and np.allclose(e2["sums"][[0, 2]], e["sums"][[0, 2]], rtol=1e-14)
+    e3 = emu_wrap.emu_eval_exact(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
+    assert e3["n_overflow"] == len(pick)
