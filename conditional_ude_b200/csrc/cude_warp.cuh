@@ -56,7 +56,7 @@ __host__ __device__ inline size_t warp_per_warp_doubles(int P, int K, int M) {
 }
 __host__ __device__ inline size_t warp_smem_doubles(int P, int K, int M) { return (size_t)256 + WARP_TPB * warp_per_warp_doubles(P, K, M); }
 
-#ifndef CUDE_HOST_EMU
+#if !defined(CUDE_HOST_EMU) || defined(CUDE_HOST_EMU_WARP)      // the host emulation of this kernel needs 32 cooperating lanes (tests/emu/emu_warp.cpp)
 template <class NS>
 __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpArgs A) {
     using namespace tab;
@@ -347,10 +347,12 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
     }
     // =================== outputs ===================
     double* const row = A.rows + (size_t)j * (P + 1);
+    const bool has_grad = !failed && !overflow;               // otherwise the accumulators are zero, but beta may be NaN
 #pragma unroll
     for (int p = -1; p < P; ++p) {
         double v;
         if (p < 0) v = overflow ? 0.0 : sse;                  // an overflowed trajectory's sse and gradient come from the fallback
+        else if (!has_grad) v = 0.0;
         else if (p < W) v = acc[p];
         else if (p < 2 * W) v = acc[W + (p - W)] * beta;
         else if (NS::NIN > 2 && p < 3 * W) v = acc[W + (p - 2 * W)] * covv;
@@ -374,6 +376,8 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
     }
 }
 
+#endif
+#ifndef CUDE_HOST_EMU
 // sums[(P+1) x S]: start s = its N trajectory rows in individual order + the partial rows of its flagged fallback blocks
 // (nw rows per block, block order).  One block per start, thread = column q x row group; fixed order: deterministic.
 __global__ void __launch_bounds__(RED_T) cude_warp_reduce(const double* __restrict__ rows, int N, const double* __restrict__ pC,

@@ -103,6 +103,47 @@ def emu_eval_exact(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=1000
     return dict(sse=sse, sums=sums, g_cond=gc, n_overflow=novf.value)
 
 
+LIB_WARP = os.path.join(_HERE, "libcude_emu_warp_san.so" if _SAN else "libcude_emu_warp.so")
+
+
+def build_warp():
+    src = [os.path.join(_HERE, "emu_warp.cpp")] + [
+        os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", f)
+        for f in ("cude_kernels.cuh", "cude_math.cuh", "cude_split.cuh", "cude_warp.cuh")]
+    if not os.path.exists(LIB_WARP) or os.path.getmtime(LIB_WARP) < max(os.path.getmtime(s) for s in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas"] +
+                              (["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if _SAN else []) +
+                              ["-o", LIB_WARP, src[0]])
+    return LIB_WARP
+
+
+def emu_warp_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000):
+    """The warp-per-trajectory kernel (csrc/cude_warp.cuh) with every CUDA thread as a host thread (tests/emu/emu_warp.cpp).
+    Returns dict(sse[S,N], g_neural[S,N,P], g_cond[S,N], overflow[S,N] bool, n_acc, n_rej, n_fail)."""
+    L = C.CDLL(build_warp())
+    L.emu_warp_eval.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.c_int, C.c_int, _D, _D,
+                                C.c_double, C.c_double, C.c_int, _D, _D, _D, _I, C.POINTER(C.c_ulonglong)]
+    ch = packed["chain"]
+    N, P = int(packed["n_ind"]), ch.n_params
+    a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
+    nk = np.ascontiguousarray(packed["n_knots"], dtype=np.int32)
+    no = np.ascontiguousarray(packed["n_obs"], dtype=np.int32)
+    cov = None if packed.get("cov") is None else np.ascontiguousarray(packed["cov"], dtype=np.float64)
+    neural = np.ascontiguousarray(neural, dtype=np.float64)
+    cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float64).reshape(-1, N))
+    S = cond.shape[0]
+    assert neural.shape == (S, P)
+    sse, rows, gc = np.empty((S, N)), np.zeros((S, N, P + 1)), np.zeros((S, N))
+    ovf = np.zeros((S, N), dtype=np.int32)
+    cnt = (C.c_ulonglong * 3)()
+    rc = L.emu_warp_eval(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
+                         int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]), _dp(cov),
+                         ch.input_dims, S, _dp(neural), _dp(cond), abstol, reltol, maxiters, _dp(sse), _dp(rows), _dp(gc),
+                         ovf.ctypes.data_as(_I), cnt)
+    assert rc == 0, rc
+    return dict(sse=sse, row_sse=rows[:, :, 0], g_neural=rows[:, :, 1:], g_cond=gc, overflow=ovf < 0, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
+
+
 def emu_sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), scale=None, abstol=1e-6, reltol=1e-3,
                  maxiters=100000, grad=True):
     """Suppression variant through the host-compiled kernel source; same conventions as oracle.sup_eval."""

@@ -269,3 +269,33 @@ def test_two_kernel_gradient_stages(fx):
     assert np.isinf(e2["sums"][1, 0]) and e2["g_cond"][1, 2] == 0 and np.allclose(e2["sums"][[0, 2]], e["sums"][[0, 2]], rtol=1e-14)
     e3 = emu_wrap.emu_eval_exact(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
     assert e3["n_overflow"] == len(pick)
+
+
+def test_warp_per_trajectory_kernel_with_host_threads_as_lanes(fx):
+    """csrc/cude_warp.cuh with its 128 CUDA threads per block as host threads (shuffles = exchanges between barrier waits): the
+    forward pass on 5 lanes per step reproduces the fused kernel's sse bit for bit, the lane-parallel adjoint its gradients to
+    summation order; counters, failures and the overflow flag (more than 64 accepted steps) as on the device."""
+    models, ts, ys = mixed_population(fx)
+    pick = [0, 3, 50, 100, 120, 130, 136]
+    pk = cu.pack_models([models[i] for i in pick], [ts[i] for i in pick], [ys[i] for i in pick])
+    rng = np.random.default_rng(8)
+    neural, cond = random_starts(rng, pk["chain"], len(pick), 2)
+    for o in (dict(), DET):
+        f = emu_wrap.emu_eval(pk, neural, cond, **o)
+        w = emu_wrap.emu_warp_eval(pk, neural, cond, **o)
+        assert not w["overflow"].any()
+        assert np.array_equal(w["sse"], f["sse"]) and np.array_equal(w["row_sse"], f["sse"])
+        assert relmax(w["g_cond"], f["g_cond"]) < 1e-12 and relmax(w["g_neural"], f["g_neural"]) < 1e-12
+        assert (w["n_acc"], w["n_rej"], w["n_fail"]) == (f["n_acc"], f["n_rej"], f["n_fail"])
+    bad = cond.copy(); bad[1, 2] = np.nan
+    w = emu_wrap.emu_warp_eval(pk, neural, bad)
+    assert np.isinf(w["sse"][1, 2]) and w["g_cond"][1, 2] == 0 and np.all(w["g_neural"][1, 2] == 0) and w["n_fail"] == 1
+    w = emu_wrap.emu_warp_eval(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)      # every solve beyond 64 steps
+    f = emu_wrap.emu_eval(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
+    assert w["overflow"].all() and np.array_equal(w["sse"], f["sse"]) and np.all(w["row_sse"] == 0) and np.all(w["g_neural"] == 0)
+    models, t, c = ohashi_models(fx, "train", covariate=True)                            # covariate network, 3 individuals
+    pkc = cu.pack_models(models[:3], t, c[:3])
+    neural, cond = random_starts(rng, pkc["chain"], 3, 2)
+    f = emu_wrap.emu_eval(pkc, neural, cond)
+    w = emu_wrap.emu_warp_eval(pkc, neural, cond)
+    assert np.array_equal(w["sse"], f["sse"]) and relmax(w["g_neural"], f["g_neural"]) < 1e-12 and relmax(w["g_cond"], f["g_cond"]) < 1e-12
