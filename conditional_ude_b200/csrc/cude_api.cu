@@ -51,7 +51,7 @@ struct DevBuf {
                                             // gradient with exact lane balance; smaller ones the fused single-kernel adjoint (lower latency)
 #endif
 #ifndef CUDE_SPLIT_BYTES
-#define CUDE_SPLIT_BYTES (20ull << 30)      // device memory the split pipeline's step records may take per group of starts
+#define CUDE_SPLIT_BYTES (64ull << 30)      // device memory the step records may take per group of starts (bench: 20 / 48 / 66 GB = 8 / 4 / 3 groups: 2.461 / 2.479 / 2.486e8 evals/s)
 #endif
 #ifndef CUDE_BETA_FORWARD_SENSITIVITY
 #define CUDE_BETA_FORWARD_SENSITIVITY 1   // 0: beta-only gradients through the adjoint kernel (comparison builds)
@@ -134,7 +134,8 @@ static int fail(cude_ctx* ctx, int code, const std::string& msg) {
 static int ensure(cude_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return CUDE_OK;
     if (b.p) { CU_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
-    size_t want = bytes + bytes / 8 + 256;
+    const size_t head = bytes / 8 < ((size_t)64 << 20) ? bytes / 8 : ((size_t)64 << 20);   // headroom against regrowth, at most 64 MB
+    size_t want = bytes + head + 256;
     CU_TRY(ctx, cudaMalloc(&b.p, want));
     b.cap = want;
     return CUDE_OK;
@@ -795,14 +796,23 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     if (sg < 1) sg = 1;
     if (sg > S) sg = S;
     if (sg > 256) sg = 256;                 // the sort key holds the start in 8 bits
-    const int ngroups = (int)((S + sg - 1) / sg);
-    const int Sg = (S + ngroups - 1) / ngroups;
-    const size_t ntg = (size_t)N * Sg;
+    int ngroups, Sg;
+    size_t ntg;
+    cude_ctx::SplitSet& set = ctx->sp[0];
+    for (;;) {                              // the step records of a group: if the device cannot give that much, halve the groups
+        ngroups = (int)((S + sg - 1) / sg);
+        Sg = (S + ngroups - 1) / ngroups;
+        ntg = (size_t)N * Sg;
+        if (ensure(ctx, set.rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)) == CUDE_OK) break;
+        (void)cudaGetLastError();
+        if (sg <= 1) return fail(ctx, CUDE_ECUDA, "cude_eval_dev: no device memory for the step records of one start; use opts.balance = 3");
+        sg = (sg + 1) / 2;
+        ctx->split_budget = ctx->split_budget / 2 > ((size_t)1 << 20) ? ctx->split_budget / 2 : ((size_t)1 << 20);
+    }
     const int nB = nchunks * nw;
     const size_t rowsB = (size_t)Sg * nB;
     int nseg = (2 * nB + 2047) / 2048;
     if (nseg > 64) nseg = 64;
-    cude_ctx::SplitSet& set = ctx->sp[0];
     const size_t o_res = 0, o_beta = o_res + ntg * M * 8, o_sse = o_beta + ntg * 8, o_keys = o_sse + ntg * 8,
                  o_k16 = o_keys + 2 * ((ntg * 4 + 7) / 8 * 8), o_nrec = o_k16 + 2 * ((ntg * 2 + 7) / 8 * 8),
                  o_flag = o_nrec + (ntg * 4 + 7) / 8 * 8,
@@ -811,7 +821,6 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
     int rc;
     if ((rc = sm_count(ctx))) return rc;
     const unsigned fb_grid = (unsigned)(ctx->sm_count * CUDE_MIN_BLOCKS);          // resident blocks walking the fallback list
-    if ((rc = ensure(ctx, set.rec, ntg * SPLIT_W * SPLIT_CAP * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, set.misc, misc_bytes))) return rc;
     if ((rc = ensure(ctx, set.part, 2 * rowsB * np1 * sizeof(double)))) return rc;
     size_t sort_bytes = 0;

@@ -71,7 +71,7 @@ typedef struct {
                     * 2 = the two-kernel gradient: forward solve leaving a 64-byte record per accepted step, every start's
                     *     trajectories sorted by their accepted-step count (stable radix sort: deterministic), adjoint sweep in
                     *     the sorted order with no idle lanes (+14 % on B200; needs ~2.2 KB of device memory per trajectory of a
-                    *     group of starts, the library sizes the groups to min(20 GB, 40 % of the free memory));
+                    *     group of starts, the library sizes the groups to min(64 GB, 40 % of the free memory));
                     * 3 = the fused kernel (one thread per trajectory, forward solve + adjoint sweep) in natural order;
                     * 4 = one warp per trajectory (small batches: config 1, the selected starts of `train`): the 5 network nodes
                     *     of a step on 5 lanes, the adjoint's (step, node) evaluations spread over the 32 lanes — 0.06-0.09 ms
