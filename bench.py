@@ -375,7 +375,7 @@ def secondary_configs(ctx, peak64):
     nns = sup["neural_0p01"][r.integers(0, 25, 10000)] + 0.05 * r.standard_normal((10000, 67))
     th = r.uniform(-1, 1, (10000, 37))
     measure("suppression_37x10000_loss_only", lambda: spop.loss(nns, th, lam=0.01), 370000, False, "cude_sup_kernel<loss>", flops=sup_alg_flops)
-    measure("suppression_37x10000_loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01), 370000, True, "cude_sup_kernel<GRAD>",
+    measure("suppression_37x10000_loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01), 370000, True, "cude_sup_kernel<forward + records> + cude_sup_kernel<adjoint>",
             flops=sup_alg_flops)
     return out
 

@@ -43,6 +43,9 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
+#ifndef CUDE_SUP_TWO_KERNEL
+#define CUDE_SUP_TWO_KERNEL 1               // suppression gradient as forward-with-records + adjoint kernels (opts.split = 1: the fused kernel)
+#endif
 #ifndef CUDE_WARP_MAX_TRAJ
 #define CUDE_WARP_MAX_TRAJ 4096             // opts.balance = 0 (automatic): loss + full-gradient calls of at most this many trajectories take the
 #endif                                      // warp-per-trajectory latency kernel (cude_warp.cuh): 1776 warps are resident at a time (3 blocks of 4 per SM), a wave takes ~55 us against ~210 us for the fused kernel
@@ -1411,20 +1414,29 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
     a.partials = (double*)ctx->partials.p;
     a.g_theta = g_theta ? (double*)ctx->gcond.p : nullptr;
     a.counters = (unsigned long long*)ctx->counters.p;
-    sup_kernel_t kern = grad ? cude_sup_kernel<SN, true> : cude_sup_kernel<SN, false>;
-    const size_t smem = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, grad, spb);
-    if (smem > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: too many observations for shared memory; lower opts.block");
-    if ((rc = prep_kernel(ctx, (const void*)kern, B, smem))) return rc;     // dynamic size + a carve-out that fits all resident blocks
-    CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
-    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
+    // gradient calls: two kernels by default (opts.split = 0) — the loss kernel leaving step records (3 blocks per SM, no spills),
+    // then the adjoint sweep over them; opts.split = 1 or a solve beyond SUP_REC_CAP accepted steps: the fused kernel, which replays
+    const size_t smem_loss = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, false, spb);
+    const size_t smem_grad = sizeof(double) * sup_smem_doubles(P, SN::NACC, M, B, true, spb);
+    if ((grad ? smem_grad : smem_loss) > 227 * 1024) return fail(ctx, CUDE_EINVAL, "cude_sup_loss_grad: too many observations for shared memory; lower opts.block");
     int n_launch = 0;
-    {
-        // gradient calls: the step ring of every block of a launch lives in global scratch ([SUP_REC_CAP][23][B] doubles per
-        // block), so a large batch is cut into launches whose rings fit the scratch budget
+    int h_ovf = 0;
+    for (int attempt = (grad && o.split != 1 && CUDE_SUP_TWO_KERNEL) ? 0 : 1; attempt < 2; ++attempt) {
+        const bool two = grad && attempt == 0;
+        sup_kernel_t k_main = !grad ? cude_sup_kernel<SN, SUP_LOSS> : (two ? cude_sup_kernel<SN, SUP_FWD_REC> : cude_sup_kernel<SN, SUP_FUSED>);
+        sup_kernel_t k_adj = cude_sup_kernel<SN, SUP_ADJ>;
+        if ((rc = prep_kernel(ctx, (const void*)k_main, B, (grad && !two) ? smem_grad : smem_loss))) return rc;   // dynamic size + a carve-out that fits all resident blocks
+        if (two && (rc = prep_kernel(ctx, (const void*)k_adj, B, smem_grad))) return rc;
+        if (spb > 0 && attempt == 1 && n_launch > 0) CU_TRY(ctx, cudaMemsetAsync(ctx->partials.p, 0, n_prow * np1 * sizeof(double), ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        if (n_launch == 0) CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        (void)cudaGetLastError();   // drop stale non-sticky errors of other runtime users in this process (e.g. torch)
+        // the step ring of every block of a launch lives in global scratch ([SUP_REC_CAP][23][B] doubles per block, + [3 M][B]
+        // residuals in the two-kernel form), so a large batch is cut into launches whose rings fit the scratch budget
         long long per_launch = nblocks;
+        int* d_ovf = nullptr;
         if (grad) {
-            const size_t ring_block = (size_t)SUP_REC_CAP * SUP_REC_ROWS * B * sizeof(double);
+            const size_t ring_block = (size_t)(SUP_REC_CAP * SUP_REC_ROWS + (two ? 3 * M : 0)) * B * sizeof(double);
             size_t budget = 0;
             if ((rc = split_budget(ctx, &budget))) return rc;
             per_launch = (long long)(budget / ring_block);
@@ -1432,12 +1444,39 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
             if (per_launch > nblocks) per_launch = nblocks;
             if ((rc = ensure(ctx, ctx->sp[0].rec, (size_t)per_launch * ring_block))) return rc;
             a.ring = (double*)ctx->sp[0].rec.p;
+            a.res_g = a.ring + (size_t)per_launch * SUP_REC_CAP * SUP_REC_ROWS * B;
+            if (two) {
+                if ((rc = ensure(ctx, ctx->sp[0].misc, ntraj * 12 + 16))) return rc;
+                a.sp_sse = (double*)ctx->sp[0].misc.p;
+                a.sp_nacc = (int*)(a.sp_sse + ntraj);
+                d_ovf = a.sp_nacc + ntraj;
+                a.ovf_count = d_ovf;
+                CU_TRY(ctx, cudaMemsetAsync(d_ovf, 0, sizeof(int), ctx->stream));
+            }
         }
-        for (long long b0 = 0; b0 < nblocks; b0 += per_launch, ++n_launch) {
+        for (long long b0 = 0; b0 < nblocks; b0 += per_launch) {
             a.blk0 = (int)b0;
             const long long nb = nblocks - b0 < per_launch ? nblocks - b0 : per_launch;
-            kern<<<(unsigned)nb, B, smem, ctx->stream>>>(a);
-            CU_TRY(ctx, cudaGetLastError());
+            if (two) {
+                SupArgs f = a;                       // forward solve: loss, records, residuals, step counts; no gradient rows
+                f.partials = nullptr; f.g_theta = nullptr;
+                k_main<<<(unsigned)nb, B, smem_loss, ctx->stream>>>(f);
+                CU_TRY(ctx, cudaGetLastError());
+                SupArgs g = a;                       // adjoint sweep: gradient rows (and the sse column), d/d theta
+                g.counters = nullptr; g.sse_out = nullptr;
+                k_adj<<<(unsigned)nb, B, smem_grad, ctx->stream>>>(g);
+                CU_TRY(ctx, cudaGetLastError());
+                n_launch += 2;
+            } else {
+                k_main<<<(unsigned)nb, B, grad ? smem_grad : smem_loss, ctx->stream>>>(a);
+                CU_TRY(ctx, cudaGetLastError());
+                ++n_launch;
+            }
+        }
+        if (two) {
+            CU_TRY(ctx, cudaMemcpyAsync(&h_ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_ovf == 0) break;                   // otherwise: once more through the fused kernel, which replays long solves
         }
     }
     {

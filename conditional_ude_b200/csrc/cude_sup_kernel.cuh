@@ -47,6 +47,11 @@ struct SupArgs {
     double* ring;               // GRAD: step records of this launch's blocks, [gridDim.x][SUP_REC_CAP][SUP_REC_ROWS][B] (coalesced rows)
     int blk0;                   // this launch covers blocks blk0 .. blk0 + gridDim.x - 1 of the batch (the host cuts a batch into
                                 // launches whose rings fit its scratch budget)
+    // two-kernel form of the gradient (MODE 2 = forward solve leaving records, MODE 3 = adjoint sweep over them):
+    double* res_g;              // [gridDim.x][3 M][B] weighted residuals of the launch's blocks
+    int* sp_nacc;               // [N x S] accepted steps (0: failed)
+    double* sp_sse;             // [N x S] sse (Inf: failed)
+    int* ovf_count;             // trajectories with more than SUP_REC_CAP accepted steps: the host redoes the call with the fused kernel
 };
 
 template <int DEPTH_, int WIDTH_>
@@ -180,6 +185,7 @@ __device__ __forceinline__ void sup_nn_backward(const double* __restrict__ sW, c
 }
 
 __host__ __device__ inline size_t sup_smem_doubles(int P, int NACC, int M, int B, bool grad, int spb = 0) {
+    // (grad = the fused gradient kernel and the adjoint kernel of the two-kernel form; the forward kernels need the stage rows only)
     // exp table, weights (one copy per start of the block), per-thread rows: k[7][3] (grad: + 2 rows = record buffer 0) +
     // (grad: record buffer 1 [23] + kb[7][3] + residuals M*3); the accumulators are parked in these rows for the reduction
     // ([NACC][B], then expanded to [P+1][B])
@@ -199,8 +205,25 @@ constexpr int SUP_REC_ROWS = 23;               // a record: k1..k6 [18], t, dt, 
 #define CUDE_SUP_MIN_BLOCKS 2
 #endif
 
-template <class SN, bool GRAD>
-__global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_kernel(const SupArgs A) {
+// MODE 0: loss only.  MODE 1: loss + gradient in one kernel (forward solve, then the adjoint sweep; solves longer than the ring
+// replay the forward pass).  MODE 2 + MODE 3: the same gradient as two kernels — 2 is the loss kernel that also leaves the step
+// records, the weighted residuals, the step count and the sse in global memory (156 registers, 3 blocks per SM instead of the
+// fused kernel's 2 x 255 with spills), 3 walks the records backwards with the fused kernel's sweep and reduction code (no
+// forward-pass state alive: fewer spills).  Trajectories beyond SUP_REC_CAP steps are counted; the host then redoes the call
+// with MODE 1.
+constexpr int SUP_LOSS = 0, SUP_FUSED = 1, SUP_FWD_REC = 2, SUP_ADJ = 3;
+#ifndef CUDE_SUP_SORT_BLOCK
+#define CUDE_SUP_SORT_BLOCK 1
+#endif
+#ifndef CUDE_SUP_FWD_BLOCKS
+#define CUDE_SUP_FWD_BLOCKS 3
+#endif
+template <class SN, int MODE>
+__global__ void __launch_bounds__(128, (MODE == SUP_FUSED || MODE == SUP_ADJ) ? CUDE_SUP_MIN_BLOCKS : (MODE == SUP_FWD_REC ? CUDE_SUP_FWD_BLOCKS : 1))
+cude_sup_kernel(const SupArgs A) {
+    constexpr bool GRAD = (MODE == SUP_FUSED || MODE == SUP_ADJ);     // adjoint sweep + gradient reduction in this kernel
+    constexpr bool FWD = (MODE != SUP_ADJ);                           // forward solve in this kernel
+    constexpr bool REC = (MODE == SUP_FUSED || MODE == SUP_FWD_REC);  // the forward solve leaves step records
     using namespace tab;
     constexpr int W = SN::W, P = SN::P;
     extern __shared__ double smem[];
@@ -220,8 +243,35 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     const unsigned bid = blockIdx.x + (unsigned)A.blk0;
     const long long j0 = (long long)bid * B, ntot = (long long)N * A.n_starts;   // flat mode: first trajectory of the block
     int s_first = 0, nsl = 1;
+    // vt: which of the block's B trajectories this thread works on.  The adjoint kernel of the two-kernel form sorts the
+    // block's trajectories by their number of accepted steps (known from the forward kernel), so that the lanes of a warp
+    // sweep equally many steps (29.4 of 32 lanes were active in natural order); everything that identifies the trajectory
+    // — index, start, weights, record and residual columns, the column its gradient is parked in for the block
+    // reduction — follows vt, the per-thread scratch rows stay with tid.  Results do not depend on the permutation.
+    int vt = tid;
+    if constexpr (MODE == SUP_ADJ && CUDE_SUP_SORT_BLOCK) {
+        __shared__ int sBin[SUP_REC_CAP + 2], sPerm[128];
+        for (int k = tid; k < SUP_REC_CAP + 2; k += B) sBin[k] = 0;
+        __syncthreads();
+        long long jn;                                  // this thread's trajectory in natural order
+        bool an;
+        if (spb > 0) { jn = j0 + tid; an = jn < ntot; }
+        else { const int sn = bid / A.nchunks, in_ = (bid - sn * A.nchunks) * B + tid; an = in_ < N; jn = (long long)sn * N + in_; }
+        int key = 0;
+        if (an) { const int na = A.sp_nacc[jn]; key = na > SUP_REC_CAP ? SUP_REC_CAP + 1 : na; }
+        const int rank = atomicAdd(&sBin[key], 1);
+        __syncthreads();
+        if (tid == 0) {                                // longest sweeps first
+            int o = 0;
+            for (int k = SUP_REC_CAP + 1; k >= 0; --k) { const int c = sBin[k]; sBin[k] = o; o += c; }
+        }
+        __syncthreads();
+        sPerm[sBin[key] + rank] = tid;
+        __syncthreads();
+        vt = sPerm[tid];
+    }
     if (spb > 0) {                                    // flat: B consecutive trajectories, up to spb starts per block
-        const long long jj = j0 + tid;
+        const long long jj = j0 + vt;
         active = jj < ntot;
         s_first = (int)(j0 / N);
         s = active ? (int)(jj / N) : s_first;
@@ -236,7 +286,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     } else {
         s = bid / A.nchunks;
         const int ch = bid - s * A.nchunks;
-        i = ch * B + tid;
+        i = ch * B + vt;
         active = i < N;
         const double* gW = A.neural + (long long)s * A.neural_stride;
         for (int p = tid; p < P; p += B) sWall[p] = gW[p];
@@ -247,7 +297,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     double* const myK = sK + tid;
     double* const myKb = sKb + tid;
     double* const myRes = sRes + tid;
-    double* const myAcc = sK + tid;          // the accumulators' parking rows for the reduction (the stage rows, dead by then)
+    double* const myAcc = sK + vt;           // the accumulators' parking rows for the reduction (the stage rows, dead by then)
     double acc[GRAD ? SN::NACC : 1];         // gradient accumulators (compressed layout): registers
 #pragma unroll
     for (int q = 0; q < (GRAD ? SN::NACC : 1); ++q) acc[q] = 0.0;
@@ -281,7 +331,8 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         // global array with rows [slot][row][tid] — the forward pass writes coalesced rows, the adjoint sweep fetches the next
         // record by cp.async into a shared-memory double buffer while it works on the current one (as a local-memory array the
         // ring was read at the top of every step and waited for: long_scoreboard 0.81 per issue)
-        double* const ringb = GRAD ? A.ring + (size_t)blockIdx.x * SUP_REC_CAP * SUP_REC_ROWS * B + tid : nullptr;
+        double* const ringb = (GRAD || REC) ? A.ring + (size_t)blockIdx.x * SUP_REC_CAP * SUP_REC_ROWS * B + vt : nullptr;
+        double* const resg = (MODE == SUP_FWD_REC || MODE == SUP_ADJ) ? A.res_g + (size_t)blockIdx.x * 3 * M * B + vt : nullptr;
 
         // adjoint carry across replay chunks
         double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0, t_next = tend;
@@ -289,6 +340,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         int stop_at = 0x7fffffff;      // accepted steps the (re)played forward pass runs for
         bool first_pass = true;
         do {
+        if constexpr (FWD) {
         // ---------------- forward pass (first pass: the solve; later passes: replay up to stop_at accepted steps) ----------------
         double u0 = yd[0], u1 = yd[(size_t)N], u2 = yd[(size_t)2 * N];      // u0 = data[:,1,i]
         double t = t0;
@@ -299,6 +351,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
             const double r1 = (u1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
             const double r2 = (u2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
             if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
+            if constexpr (MODE == SUP_FWD_REC) { resg[(iobs * 3) * B] = r0 * A.iscale[0]; resg[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; resg[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
             fsse += m_sumsq(r0, r1, r2);
             ++iobs;
         }
@@ -378,10 +431,12 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
                     const double r1 = (y1 - yd[(size_t)(iobs * 3 + 1) * N]) * A.iscale[1];
                     const double r2 = (y2 - yd[(size_t)(iobs * 3 + 2) * N]) * A.iscale[2];
                     if (GRAD) { myRes[(iobs * 3) * B] = r0 * A.iscale[0]; myRes[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; myRes[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
+                    if constexpr (MODE == SUP_FWD_REC) { resg[(iobs * 3) * B] = r0 * A.iscale[0]; resg[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; resg[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
+            if constexpr (MODE == SUP_FWD_REC) { resg[(iobs * 3) * B] = r0 * A.iscale[0]; resg[(iobs * 3 + 1) * B] = r1 * A.iscale[1]; resg[(iobs * 3 + 2) * B] = r2 * A.iscale[2]; }
                     fsse += m_sumsq(r0, r1, r2);
                     ++iobs;
                 }
-                if (GRAD) {
+                if (REC && (MODE == SUP_FUSED || na < SUP_REC_CAP)) {
                     double* const r = ringb + (size_t)(na % SUP_REC_CAP) * SUP_REC_ROWS * B;
 #pragma unroll
                     for (int q = 0; q < 18; ++q) r[q * B] = myK[q * B];
@@ -403,6 +458,16 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
             sse = failed ? CUDART_INF : fsse;
             nacc = na; nrej = nr;
             stop_at = na;
+        }
+        } else {
+            // adjoint kernel of the two-kernel form: what the forward kernel left behind
+            sse = A.sp_sse[jt];
+            nacc = A.sp_nacc[jt];
+            failed = !(sse - sse == 0.0);
+            if (!failed && nacc > SUP_REC_CAP) { atomicAdd(A.ovf_count, 1); break; }     // the host redoes the call with the fused kernel
+            stop_at = nacc;
+            if (!failed)
+                for (int k = 0; k < 3 * M; ++k) myRes[k * B] = resg[k * B];
         }
         first_pass = false;
         if (!GRAD || failed) break;
@@ -509,6 +574,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         }
 #undef SUP_RHS
     }
+    if constexpr (MODE == SUP_ADJ && CUDE_SUP_SORT_BLOCK) __syncthreads();   // column vt is another thread's scratch until it has finished
     if constexpr (GRAD) {      // park the accumulators in the (dead) stage rows for the reduction below
 #pragma unroll
         for (int q = 0; q < SN::NACC; ++q) myAcc[q * B] = acc[q];
@@ -517,6 +583,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
     if (active) {
         if (A.sse_out) A.sse_out[jt] = sse;
         if (GRAD && A.g_theta) A.g_theta[jt] = failed ? 0.0 : gtheta * A.theta_scale;
+        if constexpr (MODE == SUP_FWD_REC) { A.sp_nacc[jt] = failed ? 0 : nacc; A.sp_sse[jt] = sse; }
     }
     const int lane = tid & 31, wid = tid >> 5, nw = (B + 31) >> 5;
     constexpr int nred = GRAD ? P + 1 : 1;
@@ -525,7 +592,7 @@ __global__ void __launch_bounds__(128, GRAD ? CUDE_SUP_MIN_BLOCKS : 1) cude_sup_
         // its expanded values to [q][tid] (its own column of the — now dead — stage rows), then thread (start, q) sums
         // the start's columns of this block in index order (deterministic) into the start's partial row for this block
         double vals_first = active ? sse : 0.0;
-        double* const myRow = sK + tid;
+        double* const myRow = sK + vt;
         if constexpr (GRAD) {
             double ex[P];
 #pragma unroll 1

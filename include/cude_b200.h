@@ -204,7 +204,9 @@ int cude_sup_population_destroy(cude_sup_population* pop);
  *   loss_out[s] = sum_i sse_i / N + lambda * sum(neural_s .^ 2)   (Inf if a trajectory failed)
  *   g_neural[P x n_starts] (may be NULL), g_theta[n_ind x n_starts] (may be NULL => loss only)
  *   sse_out [n_ind x n_starts] (may be NULL): per-individual scaled SSE
- * Solves with more accepted steps than the kernel's step ring (64) replay the forward pass in chunks: any tolerance works. */
+ * Gradient calls run as two kernels (forward solve leaving step records, then the adjoint sweep over them; opts.split = 1: one
+ * fused kernel, same results bit for bit); a call with a solve of more than 64 accepted steps is redone by the fused kernel,
+ * which replays the forward pass in chunks: any tolerance works. */
 int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop, int depth, int width, const cude_opts* opts,
                        int n_starts, const double* neural, long long neural_stride, const double* theta, double lambda,
                        double* sse_out, double* loss_out, double* g_neural, double* g_theta);

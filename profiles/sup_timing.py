@@ -14,7 +14,9 @@ o = cu.SolverOptions(block=int(sys.argv[2])) if len(sys.argv) > 2 else None     
 nns = sup["neural_0p01"][r.integers(0, 25, S)] + 0.05 * r.standard_normal((S, 67))
 th = r.uniform(-1, 1, (S, 37))
 out = {}
-for name, fn in (("loss", lambda: spop.loss(nns, th, lam=0.01, opts=o)), ("loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01, opts=o))):
+of = cu.SolverOptions(block=int(sys.argv[2]), split=1) if len(sys.argv) > 2 else cu.SolverOptions(split=1)
+for name, fn in (("loss", lambda: spop.loss(nns, th, lam=0.01, opts=o)), ("loss_grad", lambda: spop.loss_grad(nns, th, lam=0.01, opts=o)),
+                 ("loss_grad_fused_kernel", lambda: spop.loss_grad(nns, th, lam=0.01, opts=of))):
     ms = []
     for _ in range(5):
         fn(); ms.append(ctx.stats()["kernel_ms"])

@@ -255,10 +255,21 @@ extern "C" int emu_sup_eval(int n_ind, int n_obs, const double* obs_t, const dou
     blockDim.x = 1; threadIdx.x = 0; gridDim.x = 1;
     std::vector<double> ring((size_t)SUP_REC_CAP * SUP_REC_ROWS, 0.0);     // one "block" of one thread per launch
     a.ring = ring.data();
+    std::vector<double> resg((size_t)3 * M, 0.0), spsse((size_t)nblocks, 0.0);
+    std::vector<int> spnacc((size_t)nblocks + 1, 0);
+    a.res_g = resg.data(); a.sp_sse = spsse.data(); a.sp_nacc = spnacc.data(); a.ovf_count = spnacc.data() + nblocks;
     for (long long b = 0; b < nblocks; ++b) {
         blockIdx.x = 0; a.blk0 = (int)b;
-        if (grad) cude_sup_kernel<SN, true>(a); else cude_sup_kernel<SN, false>(a);
+        if (grad == 2) {            // the two-kernel form: forward solve leaving records, then the adjoint sweep over them
+            SupArgs f = a; f.partials = nullptr; f.g_theta = nullptr;
+            cude_sup_kernel<SN, SUP_FWD_REC>(f);
+            SupArgs g = a; g.counters = nullptr; g.sse_out = nullptr;
+            cude_sup_kernel<SN, SUP_ADJ>(g);
+        }
+        else if (grad) cude_sup_kernel<SN, SUP_FUSED>(a);
+        else cude_sup_kernel<SN, SUP_LOSS>(a);
     }
+    if (counters && grad == 2) counters[2] += (unsigned long long)spnacc[nblocks] << 32;     // overflow count in the high word of n_fail
     if (grad && g_neural_traj)
         for (long long b = 0; b < nblocks; ++b)
             for (int p = 0; p < SN::P; ++p) g_neural_traj[b * SN::P + p] = partials[b * prow_stride * (SN::P + 1) + 1 + p];

@@ -165,4 +165,4 @@ def emu_sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), scale=
     rc = L.emu_sup_eval(n_ind, n_obs, _dp(ot), _dp(dj), _dp(pt), _dp(sc), float(ot[0]), float(ot[-1]), S, _dp(neural), stride,
                         _dp(theta), abstol, reltol, maxiters, int(grad), _dp(sse), _dp(gn), _dp(gt), cnt)
     assert rc == 0
-    return dict(sse=sse, g_neural=gn, g_theta=gt, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
+    return dict(sse=sse, g_neural=gn, g_theta=gt, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2] & 0xffffffff, n_overflow=cnt[2] >> 32)

@@ -57,6 +57,21 @@ def test_emulated_packed_block_path(sup):
     assert noise_ok(np.abs(e["g_neural"] - g["g_neural"]) / np.abs(g["g_neural"]).max(axis=-1, keepdims=True), 1e-4)
 
 
+def test_emulated_two_kernel_gradient(sup):
+    """The default gradient path as two kernels (grad=2 in the emulation): the loss kernel leaving step records, weighted
+    residuals, step counts and sse in global memory, then the adjoint sweep over them — bit for bit the fused kernel's results
+    (same sweep code, same records); solves beyond the 64-entry record block are only counted (the host redoes those calls)."""
+    data, t = sup["group_data"][:, :, :5], sup["timepoints"]
+    nns, th = _starts(sup, 3)
+    th = th[:, :5]
+    f = emu_wrap.emu_sup_eval(data, t, nns, th)
+    e = emu_wrap.emu_sup_eval(data, t, nns, th, grad=2)
+    assert e["n_overflow"] == 0 and (e["n_acc"], e["n_rej"]) == (f["n_acc"], f["n_rej"])
+    assert all(np.array_equal(e[k], f[k]) for k in ("sse", "g_neural", "g_theta"))
+    e = emu_wrap.emu_sup_eval(data, t, nns[:1], th[:1], grad=2, abstol=1e-10, reltol=1e-8)
+    assert e["n_overflow"] == 5
+
+
 def test_emulated_step_ring_replay(sup, tmp_path):
     """The gradient pass keeps a ring of accepted-step records and replays the forward pass in chunks when a solve has more
     steps than the ring (round 1 returned Inf beyond 512 steps).  Rebuilt with a 4-entry ring, the ~25-step solves need
