@@ -592,6 +592,13 @@ static void trace_dump() {
     }
     g_trace.clear();
 }
+// second-stage reduction of the partial rows: a warp per (start, q) striding over many rows, or a thread per (start, q) for few
+static void reduce_partials(cudaStream_t st, const double* partials, int nrows, int n_starts, int np1, int nred, double* sums) {
+    const long long n = (long long)n_starts * np1;
+    if (nrows <= 16) cude_reduce_partials_few<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partials, nrows, n_starts, np1, nred, sums);
+    else cude_reduce_partials<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(partials, nrows, n_starts, np1, nred, sums);
+}
+
 static int sm_count(cude_ctx* ctx) {
     if (!ctx->sm_count) CU_TRY(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
     return CUDE_OK;
@@ -1073,10 +1080,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
             const int wpb = 8;
             cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);
         } else {
-            const int wpb = 8;
-            const long long nwarps = (long long)n_starts * np1;
-            cude_reduce_partials<<<(unsigned)((nwarps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-                d_partials, nchunks * (B / 32), n_starts, np1, want_neural_grad ? np1 : 1, d_sums_out);
+            reduce_partials(ctx->stream, d_partials, nchunks * (B / 32), n_starts, np1, want_neural_grad ? np1 : 1, d_sums_out);
         }
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
@@ -1480,10 +1484,7 @@ extern "C" int cude_sup_loss_grad(cude_ctx* ctx, const cude_sup_population* pop,
         }
     }
     {
-        const int wpb = 8;
-        const long long nwarps = (long long)n_starts * np1;
-        cude_reduce_partials<<<(unsigned)((nwarps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-            (const double*)ctx->partials.p, nchunks * nw, n_starts, np1, grad ? np1 : 1, (double*)ctx->sums.p);
+        reduce_partials(ctx->stream, (const double*)ctx->partials.p, nchunks * nw, n_starts, np1, grad ? np1 : 1, (double*)ctx->sums.p);
         CU_TRY(ctx, cudaGetLastError());
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -1099,6 +1099,21 @@ __global__ void cude_reduce_partials(const double* __restrict__ partials, int nc
     if (lane == 0) sums[(size_t)s * np1 + q] = v;
 }
 
+// The same for a few rows per start (small populations x many starts: the suppression example's 10 000 starts x 2 rows took
+// 108 us with a warp per (start, q)): one thread per (start, q), rows in order, consecutive threads on consecutive q.
+__global__ void cude_reduce_partials_few(const double* __restrict__ partials, int nchunks, int n_starts, int np1,
+                                         int nred, double* __restrict__ sums) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n_starts * np1) return;
+    const int s = (int)(g / np1), q = (int)(g - (long long)s * np1);
+    double v = 0.0;
+    if (q < nred) {
+        const double* base = partials + (size_t)s * nchunks * np1 + q;
+        for (int c = 0; c < nchunks; ++c) v += base[(size_t)c * np1];
+    }
+    sums[g] = v;
+}
+
 // flat mode: per-start sse sums from the per-trajectory sse array (loss-only / beta-only calls)
 __global__ void cude_sum_sse(const double* __restrict__ sse, int n_ind, int n_starts, int np1, double* __restrict__ sums) {
     const int warps_per_block = blockDim.x >> 5;
