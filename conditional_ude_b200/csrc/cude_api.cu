@@ -43,6 +43,9 @@ struct DevBuf {
 #ifndef CUDE_SUP_PACK_DEFAULT
 #define CUDE_SUP_PACK_DEFAULT 1            // small suppression populations run several whole starts per 128-thread block (0: one start per block)
 #endif
+#ifndef CUDE_FLAT_IMAJOR_MIN_STARTS
+#define CUDE_FLAT_IMAJOR_MIN_STARTS 4096
+#endif
 #ifndef CUDE_SUP_TWO_KERNEL
 #define CUDE_SUP_TWO_KERNEL 1               // suppression gradient as forward-with-records + adjoint kernels (opts.split = 1: the fused kernel)
 #endif
@@ -109,6 +112,7 @@ struct cude_population {
     mutable long long bal_calls = 0;     // balanced calls since (re)allocation
     mutable void* bal_temp = nullptr;
     mutable size_t bal_temp_bytes = 0;
+    bool ragged = false;                 // individuals differ in their knot count or time span (e.g. Ohashi + Fujita): see a.flat
 };
 
 static thread_local std::string g_err;
@@ -314,6 +318,7 @@ extern "C" int cude_population_create(cude_ctx* ctx, int n_ind,
     double* hk2 = hk1 + N;
     double* hc0 = hk2 + N;
     double* hcv = hc0 + N;
+    bool ragged = false;
     for (size_t i = 0; i < N; ++i) {
         const int nk = n_knots[i], no = n_obs[i];
         if (nk < 2 || nk > max_knots || no < 0 || no > max_obs) return fail(ctx, CUDE_EINVAL, "cude_population_create: n_knots/n_obs out of range");
@@ -329,6 +334,7 @@ extern "C" int cude_population_create(cude_ctx* ctx, int n_ind,
             }
         }
         const double t0 = knot_t[i * K], t1 = knot_t[i * K + nk - 1];
+        if (nk != n_knots[0] || t0 != knot_t[0] || t1 != knot_t[n_knots[0] - 1]) ragged = true;
         for (int k = 0; k < max_obs; ++k) {
             const int kk = k < no ? k : (no > 0 ? no - 1 : 0);
             hot[k * N + i] = no > 0 ? obs_t[i * M + kk] : 0.0;
@@ -344,6 +350,7 @@ extern "C" int cude_population_create(cude_ctx* ctx, int n_ind,
     }
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cude_population* pop = new (std::nothrow) cude_population();
+    if (pop) pop->ragged = ragged;
     if (!pop) return fail(ctx, CUDE_ENOMEM, "out of host memory");
     pop->ctx = ctx; pop->n_ind = n_ind; pop->max_knots = max_knots; pop->max_obs = max_obs;
     cudaError_t e;
@@ -1028,7 +1035,10 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     a.neural_stride = neural_stride;
     a.cond = d_cond;
     a.abstol = o.abstol; a.reltol = o.reltol; a.maxiters = o.maxiters;
-    a.flat = flat ? 1 : 0;
+    // shared network, flat indexing: individual-major warps (32 starts of one individual per warp, cude_kernels.cuh) when the
+    // individuals differ in length (ragged population: config 2, 0.81 -> 0.56 ms) or the starts are dense (profile grids of
+    // >= 4096 points: 1.68 -> 1.57 ms; a 1000-point grid over 25 units of log beta is better off start-major: 0.21 vs 0.24 ms)
+    a.flat = !flat ? 0 : (((pop->ragged && n_starts >= 32) || n_starts >= CUDE_FLAT_IMAJOR_MIN_STARTS) ? 2 : 1);
     a.nchunks = nchunks;
     a.cond_scale = cond_scale;
     a.sse_out = d_sse;

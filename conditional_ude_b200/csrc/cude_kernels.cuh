@@ -516,10 +516,14 @@ __device__ __forceinline__ void cude_eval_block(const EvalArgs& A, const unsigne
     int i, s;
     bool active;
     if (A.flat) {
-        j = (long long)bid * B + tid;
-        active = j < (long long)N * A.n_starts;
-        i = active ? (int)(j % N) : 0;
-        s = active ? (int)(j / N) : 0;
+        // flat indexing over the [S x N] batch of one shared network.  flat = 2: individual-major — the 32 lanes of a warp are 32
+        // starts of ONE individual, i.e. the same glucose curve and time span, so they take nearly the same number of steps
+        // (start-major warps mix individuals: 22.8 of 32 lanes active on the ragged Ohashi + Fujita population of config 2)
+        const long long jf = (long long)bid * B + tid;
+        active = jf < (long long)N * A.n_starts;
+        if (A.flat == 2) { i = active ? (int)(jf / A.n_starts) : 0; s = active ? (int)(jf - (long long)i * A.n_starts) : 0; }
+        else { i = active ? (int)(jf % N) : 0; s = active ? (int)(jf / N) : 0; }
+        j = (long long)s * N + i;
     } else {
         // chunk-major block order: the blocks resident at any time cover a few chunks of individuals x all starts, so the
         // population data of a chunk is read from HBM once and served from L2 to the other starts (start-major order
