@@ -155,6 +155,35 @@ def test_gpu_loss_and_gradient_match_oracle(sup):
 
 
 @pytest.mark.gpu
+def test_gpu_two_kernel_gradient_equals_the_fused_kernel(sup):
+    """The default gradient path (forward kernel leaving records + adjoint kernel with its block-local sort by step count)
+    against the fused kernel (opts.split = 1): per-trajectory sse and d/d theta bit for bit, with flat indexing (37
+    individuals) and with one start per block row (300 individuals: the tile geometry, where per-start rows are summed by
+    warp shuffles in whatever order the sort left, hence 1e-13); a call with solves beyond the 64-record block falls back to
+    the fused kernel by itself."""
+    data, t = sup["group_data"], sup["timepoints"]
+    rng = np.random.default_rng(5)
+    nns = sup["neural_0p01"][rng.integers(0, 25, 40)] + 0.02 * rng.standard_normal((40, 67))
+    for d in (data, np.concatenate([data] * 9, axis=2)[:, :, :300]):
+        n = d.shape[2]
+        th = rng.uniform(-1, 1, (40, n))
+        pop = cu.SuppressionPopulation(d, t)
+        a = pop.loss_grad(nns, th, 0.01, return_sse=True)
+        la = pop.ctx.stats()["launches"]
+        f = pop.loss_grad(nns, th, 0.01, opts=cu.SolverOptions(split=1), return_sse=True)
+        assert la == 3 and pop.ctx.stats()["launches"] == 2
+        assert np.array_equal(a[3], f[3]) and np.array_equal(a[2], f[2])
+        assert relmax(a[0], f[0]) < 1e-14 and relmax(a[1], f[1]) < 1e-12
+    tight = cu.SolverOptions(abstol=1e-10, reltol=1e-7)
+    th = rng.uniform(-1, 1, (4, 37))
+    pop = cu.SuppressionPopulation(data, t)
+    a = pop.loss_grad(nns[:4], th, 0.01, opts=tight, return_sse=True)
+    assert pop.ctx.stats()["launches"] == 4                                    # 2 (two-kernel attempt) + 1 (fused) + reduction
+    f = pop.loss_grad(nns[:4], th, 0.01, opts=cu.SolverOptions(abstol=1e-10, reltol=1e-7, split=1), return_sse=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, f))
+
+
+@pytest.mark.gpu
 def test_gpu_small_scratch_budget_cuts_the_batch_into_launches(sup, monkeypatch):
     """The step rings of a gradient launch live in global scratch; a batch whose rings exceed the budget is cut into several
     launches over block ranges (here: 8 MB = 5 blocks per launch, 58 blocks) — same results bit for bit."""
