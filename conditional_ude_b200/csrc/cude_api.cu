@@ -915,11 +915,12 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
 // ---- latency form of loss + full gradient: one warp per trajectory (cude_warp.cuh), fused-kernel fallback for solves longer
 // than WARP_CAP accepted steps, per-start reduction of the trajectory rows ----
 typedef void (*warp_kernel_t)(const WarpArgs);
+static bool smem_fits_warp(int P, int K, int M) { return sizeof(double) * warp_smem_doubles(P, K, M) <= (size_t)200 * 1024; }
 static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B, int nchunks, eval_kernel_t fused, size_t smem_fused,
                     double* d_sums_out, int* launches) {
     const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
     warp_kernel_t kw = nullptr;
-    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>> : nullptr);
+    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>, true> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>, true> : nullptr);
     if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     const size_t ntraj = (size_t)N * S, nblk = (size_t)S * nchunks;
     int rc;
@@ -954,6 +955,32 @@ static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B
     *launches += 2;
     if (d_sums_out) {
         cude_warp_reduce<<<(unsigned)S, RED_T, 0, st>>>(w.rows, N, (const double*)set.part.p, w.blkflag, nchunks, nw, np1, d_sums_out);
+        CU_TRY(ctx, cudaGetLastError());
+        ++*launches;
+    }
+    return CUDE_OK;
+}
+
+// the forward pass alone in the latency form (loss-only calls of small batches): per-trajectory sse, then the per-start sums
+static int run_warp_loss(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, double* d_sse, double* d_sums_out, int* launches) {
+    const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts;
+    warp_kernel_t kw = nullptr;
+    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>, false> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>, false> : nullptr);
+    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
+    const size_t ntraj = (size_t)N * S;
+    WarpArgs w{};
+    w.pop = a.pop; w.n_starts = S; w.neural = a.neural; w.neural_stride = a.neural_stride; w.cond = a.cond;
+    w.abstol = a.abstol; w.reltol = a.reltol; w.maxiters = a.maxiters; w.cond_scale = a.cond_scale;
+    w.sse_out = d_sse; w.counters = a.counters;
+    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs);
+    int rc;
+    if ((rc = prep_kernel(ctx, (const void*)kw, 32 * WARP_TPB, smem_w))) return rc;
+    kw<<<(unsigned)((ntraj + WARP_TPB - 1) / WARP_TPB), 32 * WARP_TPB, smem_w, ctx->stream>>>(w);
+    CU_TRY(ctx, cudaGetLastError());
+    ++*launches;
+    if (d_sums_out) {
+        const int wpb = 8;
+        cude_sum_sse<<<(S + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, S, np1, d_sums_out);
         CU_TRY(ctx, cudaGetLastError());
         ++*launches;
     }
@@ -1065,6 +1092,12 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
     // the latency form (one warp per trajectory): on request (opts.balance = 4) or automatically for small batches
     const bool use_warp = !use_split && !use_exact && adj && !flat && !mixed && !fbwd && want_neural_grad && d_g_cond && !bal &&
                           (o.balance == 4 || (o.balance == 0 && ntraj <= CUDE_WARP_MAX_TRAJ));
+    const bool use_warp_loss = !grad && !mixed && !d_yhat && smem_fits_warp(P, K, M) &&
+                               (o.balance == 4 || (o.balance == 0 && ntraj <= CUDE_WARP_MAX_TRAJ));
+    if (use_warp_loss && !d_sse && d_sums_out) {
+        if ((rc = ensure(ctx, ctx->scratch, (size_t)ntraj * sizeof(double)))) return rc;
+        d_sse = (double*)ctx->scratch.p;
+    }
     if (ctx->chunk_mode != 2) CU_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (d_sums_out && (flat || !want_neural_grad))
         CU_TRY(ctx, cudaMemsetAsync(d_sums_out, 0, (size_t)np1 * n_starts * sizeof(double), ctx->stream));
@@ -1075,6 +1108,8 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
         if ((rc = run_split(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
     } else if (use_exact) {
         if ((rc = run_exact(ctx, net, a, B, nchunks, fbwd, wc, n_w, kern, smem, d_sums_out, &launches))) return rc;
+    } else if (use_warp_loss && d_sse) {
+        if ((rc = run_warp_loss(ctx, net, a, d_sse, d_sums_out, &launches))) return rc;
     } else if (use_warp) {
         // (fallback through the shared-memory-weights instantiation: no constant-memory upload on the latency path)
         if ((rc = run_warp(ctx, net, a, B, nchunks, select_kernel(net, true, false, false, false, false), smem, d_sums_out, &launches))) return rc;
@@ -1085,7 +1120,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
         if (wc && (rc = wconst_used(ctx))) return rc;
         launches = 1;
     }
-    if (d_sums_out && !use_split && !use_exact && !use_warp) {
+    if (d_sums_out && !use_split && !use_exact && !use_warp && !(use_warp_loss && d_sse)) {
         if (flat) {
             const int wpb = 8;
             cude_sum_sse<<<(n_starts + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_sse, N, n_starts, np1, d_sums_out);

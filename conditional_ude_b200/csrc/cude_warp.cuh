@@ -57,7 +57,9 @@ __host__ __device__ inline size_t warp_per_warp_doubles(int P, int K, int M) {
 __host__ __device__ inline size_t warp_smem_doubles(int P, int K, int M) { return (size_t)256 + WARP_TPB * warp_per_warp_doubles(P, K, M); }
 
 #if !defined(CUDE_HOST_EMU) || defined(CUDE_HOST_EMU_WARP)      // the host emulation of this kernel needs 32 cooperating lanes (tests/emu/emu_warp.cpp)
-template <class NS>
+// GRAD = false: the forward pass only (loss-only calls of small batches, e.g. the 2 x N solves of a SAEM Metropolis step):
+// sse_out[j] per trajectory, no records, no rows.
+template <class NS, bool GRAD = true>
 __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpArgs A) {
     using namespace tab;
     constexpr int W = NS::W, P = NS::P, PP = (P + 1) & ~1;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
                 ++iobs;
                 next_ot = (iobs < nobs) ? sOt[iobs] : CUDART_INF;
             }
-            if (na < WARP_CAP) {
+            if (GRAD && na < WARP_CAP) {
                 if (lane == 0) { rTH[2 * na] = t; rTH[2 * na + 1] = dt; }
                 if (lane < 5) rDG[5 * na + lane] = dg;
             }
@@ -254,8 +256,18 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
     if (ret == 0 && iobs < nobs) ret = 3;
     const bool failed = (ret != 0);
     const double sse = failed ? CUDART_INF : fsse;
-    const bool overflow = !failed && na > WARP_CAP;
+    const bool overflow = GRAD && !failed && na > WARP_CAP;
     __syncwarp();
+    if constexpr (!GRAD) {
+        if (lane == 0) {
+            A.sse_out[j] = sse;
+            if (A.counters) {
+                atomicAdd(&A.counters[0], (unsigned long long)na);
+                atomicAdd(&A.counters[1], (unsigned long long)nr);
+                if (failed) atomicAdd(&A.counters[2], 1ull);
+            }
+        }
+    } else {
 
     double acc[NS::NACC];
 #pragma unroll
@@ -374,6 +386,7 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
             if (failed) atomicAdd(&A.counters[2], 1ull);
         }
     }
+    }   // GRAD
 }
 
 #endif

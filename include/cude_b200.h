@@ -63,7 +63,8 @@ typedef struct {
     int balance;   /* lane balance of loss + full-gradient calls with per-start networks (a warp runs to its slowest lane and the
                     * trajectories of a start take 17-26 steps, so 12 % of the lane-cycles idle in natural order):
                     * 0 (default) = automatic:
-                    *     - calls of <= 4096 trajectories use the WARP-PER-TRAJECTORY latency kernel (mode 4);
+                    *     - calls of <= 4096 trajectories use the WARP-PER-TRAJECTORY latency kernel (mode 4; loss-only calls of that
+                    *       size its forward half);
                     *     - populations of >= 32768 individuals use the TWO-KERNEL gradient (mode 2);
                     *     - everything else the fused kernel (mode 3);
                     * 1 = fused kernel, each start's individuals regrouped by the step counts of an EARLIER call on this

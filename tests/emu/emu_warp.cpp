@@ -69,7 +69,7 @@ using namespace cude;
 // g_cond[N x S], ovf[N x S] (-1: more than WARP_CAP accepted steps — the fused kernel's on the device), counters[3].
 extern "C" int emu_warp_eval(int n_ind, int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
                              int max_obs, const int* n_obs, const double* obs_t, const double* obs_y, const double* kin, const double* cov,
-                             int n_in, int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters,
+                             int n_in, int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters, int grad,
                              double* sse, double* rows, double* g_cond, int* ovf, unsigned long long* counters) {
     const size_t N = n_ind, K = max_knots, M = max_obs, S = n_starts, NT = N * S;
     std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N), cv(N, 0.0);
@@ -107,7 +107,8 @@ extern "C" int emu_warp_eval(int n_ind, int max_knots, const int* n_knots, const
         for (int t = 0; t < T; ++t)
             th.emplace_back([&, t] {
                 threadIdx.x = t;
-                if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>>(a); else cude_warp_kernel<NetShape<3, 2, 4>>(a);
+                if (!grad) { if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, false>(a); else cude_warp_kernel<NetShape<3, 2, 4>, false>(a); }
+                else if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, true>(a); else cude_warp_kernel<NetShape<3, 2, 4>, true>(a);
             });
         for (auto& x : th) x.join();
     }

@@ -287,6 +287,8 @@ def test_warp_per_trajectory_kernel_with_host_threads_as_lanes(fx):
         assert np.array_equal(w["sse"], f["sse"]) and np.array_equal(w["row_sse"], f["sse"])
         assert relmax(w["g_cond"], f["g_cond"]) < 1e-12 and relmax(w["g_neural"], f["g_neural"]) < 1e-12
         assert (w["n_acc"], w["n_rej"], w["n_fail"]) == (f["n_acc"], f["n_rej"], f["n_fail"])
+    wl = emu_wrap.emu_warp_eval(pk, neural, cond, grad=False)                            # the forward pass alone (loss-only calls)
+    assert np.array_equal(wl["sse"], emu_wrap.emu_eval(pk, neural, cond)["sse"]) and wl["n_acc"] == emu_wrap.emu_eval(pk, neural, cond)["n_acc"]
     bad = cond.copy(); bad[1, 2] = np.nan
     w = emu_wrap.emu_warp_eval(pk, neural, bad)
     assert np.isinf(w["sse"][1, 2]) and w["g_cond"][1, 2] == 0 and np.all(w["g_neural"][1, 2] == 0) and w["n_fail"] == 1

@@ -502,6 +502,12 @@ def test_warp_per_trajectory_latency_kernel(fx, ctx):
     r = oracle.OraclePopulation(pk).eval(neural, cond, grad_mode=0, **DET)
     w = pop.loss_grad(neural, cond, opts=SolverOptions(balance=4, **DET), mean=False, return_sse=True)
     assert relmax(w[3], r["sse"]) < 1e-10 and relmax(w[1], r["g_neural"].sum(axis=1)) < 1e-9 and relmax(w[2], r["g_cond"]) < 1e-9
+    # loss-only calls of small batches take the forward half of the same kernel: per-start networks and one shared network
+    for nn_, cd in ((neural, cond), (neural[0], cond)):
+        a = pop.loss(nn_, cd, return_sse=True)                                    # automatic: warp kernel
+        assert ctx.stats()["launches"] == 2
+        b = pop.loss(nn_, cd, opts=SolverOptions(balance=3), return_sse=True)
+        assert np.array_equal(a[1], b[1]) and relmax(a[0], b[0]) < 1e-14
     bad = cond.copy(); bad[2, 5] = np.nan
     w = pop.loss_grad(neural, bad, opts=SolverOptions(balance=4))
     f = pop.loss_grad(neural, bad, opts=SolverOptions(balance=3))
