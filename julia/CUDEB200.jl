@@ -331,4 +331,117 @@ function likelihood_profile(β, nn, pop::Population, lower_bound, upper_bound, s
     sse[2:end] ./ (2 * sigma^2), sse[1] / (2 * sigma^2), parameter_values
 end
 
+"""
+    simulate(pop, neural, cond; opts) -> yhat[M × N × S]
+
+`solve(model.problem, p=θ, saveat=timepoints, save_idxs=1)` (src/parameter-estimation.jl:59) for every (individual, start):
+the model's plasma c-peptide at the observation times (`NaN` beyond an individual's last observation and for failed solves) —
+what the scripts plot against the data (c-peptide/02-conditional.jl:170).  `pop.max_obs` rows.
+"""
+function simulate(pop::Population, neural::AbstractVecOrMat{Float64}, cond::AbstractMatrix{Float64}, max_obs::Integer; opts=CudeOpts())
+    S = size(cond, 2)
+    yhat = Array{Float64,3}(undef, max_obs, pop.n, S)
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    check(ccall((:cude_simulate, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                pop.ctx.handle, pop.handle, pop.net, opts, S, neural, stride, cond, yhat, C_NULL), pop.ctx.handle)
+    yhat
+end
+
+# --- device-resident `_optimize` (src/parameter-estimation.jl:170-183) for all selected starts of `train` (:374-376) -------------
+mutable struct CudeTrainOpts
+    adam_iters::Cint
+    adam_lr::Cdouble
+    adam_beta1::Cdouble
+    adam_beta2::Cdouble
+    adam_eps::Cdouble
+    lbfgs_iters::Cint
+    lbfgs_m::Cint
+    g_tol::Cdouble
+    c1::Cdouble
+    rho_hi::Cdouble
+    rho_lo::Cdouble
+    ls_maxiter::Cint
+    check_every::Cint
+    CudeTrainOpts() = new()
+end
+function train_opts(; adam_iters=1000, adam_lr=1e-2, lbfgs_iters=1000)
+    t = CudeTrainOpts()
+    ccall((:cude_train_default_opts, libcude), Cvoid, (Ref{CudeTrainOpts},), t)
+    t.adam_iters = adam_iters; t.adam_lr = adam_lr; t.lbfgs_iters = lbfgs_iters
+    t
+end
+
+"""
+    train_starts!(pop, neural, cond; adam_iters, adam_lr, lbfgs_iters, opts) -> (objective[S], lbfgs_iterations[S], status[S], evaluations)
+
+Adam, then L-BFGS with BackTracking, for the `S` columns of `neural[P × S]` / `cond[N × S]` in lock-step on the device
+(`cude_train`); the matrices hold the solutions on return.  Replaces the per-start `_optimize` calls of `train` (:374-376).
+"""
+function train_starts!(pop::Population, neural::Matrix{Float64}, cond::Matrix{Float64}; adam_iters=1000, adam_lr=1e-2,
+                       lbfgs_iters=1000, opts=CudeOpts())
+    S = size(cond, 2)
+    size(neural) == (pop.nparams, S) && size(cond, 1) == pop.n || error("train_starts!: neural must be P × S and cond N × S")
+    obj = Vector{Float64}(undef, S); iters = zeros(Cint, S); status = zeros(Cint, S); evals = Ref{Cint}(0)
+    t = train_opts(; adam_iters, adam_lr, lbfgs_iters)
+    check(ccall((:cude_train, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CudeNet}, Ref{CudeOpts}, Ref{CudeTrainOpts}, Cint, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ref{Cint}),
+                pop.ctx.handle, pop.handle, pop.net, opts, t, S, neural, cond, obj, iters, status, evals), pop.ctx.handle)
+    obj, Int.(iters), Int.(status), Int(evals[])
+end
+
+# --- the suppression example (suppression/src/suppression_model.jl) ------------------------------------------------------------------
+"""
+Device image of the suppression example's data: `data[3, n_obs, n_ind]` as `group_data` in suppression/suppression.jl:18-24
+(u0 of individual i = `data[:, 1, i]`, :99-104), `timepoints`, `p_true = [p1, p2, p3]`; `scale` defaults to the mean over
+individuals of the per-state maxima (:125).
+"""
+mutable struct SuppressionPopulation
+    handle::Ptr{Cvoid}
+    ctx::Context
+    n::Int
+    depth::Int
+    width::Int
+    nparams::Int
+end
+function SuppressionPopulation(data::Array{Float64,3}, timepoints::AbstractVector; p_true=[0.4, 0.9, 0.3], scale=nothing,
+                               depth::Integer=5, width::Integer=3, ctx::Context=context())
+    size(data, 1) == 3 || error("SuppressionPopulation: data must be 3 × n_obs × n_ind")
+    t = collect(Float64, timepoints)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    sc = scale === nothing ? C_NULL : collect(Float64, scale)
+    check(ccall((:cude_sup_population_create, libcude), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(data, 3), size(data, 2), t, data, collect(Float64, p_true), sc, t[1], t[end], h), ctx.handle)
+    P = width * 5 + (depth - 1) * width * (width + 1) + width + 1        # chain(4 -> depth × width -> 1)
+    pop = SuppressionPopulation(h[], ctx, size(data, 3), depth, width, P)
+    finalizer(x -> ccall((:cude_sup_population_destroy, libcude), Cint, (Ptr{Cvoid},), x.handle), pop)
+    pop
+end
+
+"""
+    suppression_loss_grad(pop, neural, theta, lambda; opts, grad=true) -> (loss[S], g_neural[P × S], g_theta[N × S])
+
+`suppression_loss(p, (prob, data, timepoints, λ))` (suppression_model.jl:117-130) and its `AutoForwardDiff()` gradient
+(:155-156) for `S` parameter sets at once: `neural` is `P` (shared) or `P × S`, `theta` is `N × S`.
+"""
+function suppression_loss_grad(pop::SuppressionPopulation, neural::AbstractVecOrMat{Float64}, theta::AbstractMatrix{Float64},
+                               lambda::Real; opts=CudeOpts(), grad::Bool=true)
+    S = size(theta, 2)
+    l = Vector{Float64}(undef, S)
+    gn = grad ? Matrix{Float64}(undef, pop.nparams, S) : nothing
+    gt = grad ? Matrix{Float64}(undef, pop.n, S) : nothing
+    stride = ndims(neural) == 1 ? 0 : size(neural, 1)
+    check(ccall((:cude_sup_loss_grad, libcude), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ref{CudeOpts}, Cint, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}, Cdouble,
+                 Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                pop.ctx.handle, pop.handle, pop.depth, pop.width, opts, S, neural, stride, theta, Float64(lambda),
+                C_NULL, l, gn === nothing ? C_NULL : gn, gt === nothing ? C_NULL : gt), pop.ctx.handle)
+    l, gn, gt
+end
+# the reference's own signature: p = ComponentArray(neural = …, theta = …), args = (pop, data, timepoints, λ)
+suppression_loss(p, (pop, _, _, λ)::Tuple{SuppressionPopulation,Any,Any,Real}) =
+    suppression_loss_grad(pop, collect(Float64, p.neural), reshape(collect(Float64, p.theta), :, 1), λ; grad=false)[1][1]
+
 end # module
