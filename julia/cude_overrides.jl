@@ -9,6 +9,7 @@
 #   loss(θ, (model, timepoints, cpeptide_data, neural_network_parameters))     :93
 #   loss(θ, (models, timepoints, cpeptide_data))                               :126
 #   likelihood_profile(β, nn, model, timepoints, cpeptide_data, lb, ub, σ)     src/likelihood-profiles.jl:4
+#   suppression_loss(p, (prob, individual_data, timepoints, λ))                suppression/src/suppression_model.jl:117
 # so that `train` (:211, :272, :340), `train_with_sigma` (:290), `evaluate_model` (:406) and the scripts run unmodified on
 # the GPU.  The reference differentiates with `OptimizationFunction(loss, AutoForwardDiff())` (:231, :281, :299, :370):
 # ForwardDiff calls `loss` with dual numbers, which cannot cross a `ccall`.  The methods below therefore accept duals,
@@ -73,4 +74,28 @@ end
 function likelihood_profile(β, neural_network_parameters, model, timepoints, cpeptide_data, lower_bound, upper_bound, sigma; steps=1000)
     pop = CUDEB200.cached_population(model, timepoints, reshape(cpeptide_data, 1, :))
     CUDEB200.likelihood_profile(β, neural_network_parameters, pop, lower_bound, upper_bound, sigma; steps)
+end
+
+# --- suppression example: suppression/src/suppression_model.jl:117 --------------------------------------------------------
+# Include after suppression/src/suppression_model.jl.  `prob` carries `ude_lsup!(du,u,p,t)`, a global method that closes over
+# nothing readable (suppression.jl:19), so the true kinetic parameters and the network shape of the script are stated here;
+# set them before the first call if your script differs (suppression.jl:17-19: depth 5, width 3, p_true = [0.4, 0.9, 0.3]).
+const SUPPRESSION_P_TRUE = Ref([0.4, 0.9, 0.3])
+const SUPPRESSION_NET = Ref((depth = 5, width = 3))
+const _sup_pop_cache = IdDict{Any,Any}()
+function _suppression_population(individual_data, timepoints)
+    get!(_sup_pop_cache, individual_data) do
+        CUDEB200.SuppressionPopulation(Array{Float64,3}(individual_data), collect(Float64, timepoints);
+                                       p_true = SUPPRESSION_P_TRUE[], depth = SUPPRESSION_NET[].depth, width = SUPPRESSION_NET[].width)
+    end
+end
+function suppression_loss(p, (prob, individual_data, timepoints, λ))
+    pop = _suppression_population(individual_data, timepoints)
+    neural, theta = vec(_primal(p.neural)), vec(_primal(p.theta))
+    if eltype(p) <: Dual                     # OptimizationFunction(suppression_loss, AutoForwardDiff()), :155-156
+        l, gn, gt = CUDEB200.suppression_loss_grad(pop, neural, reshape(theta, :, 1), λ)
+        # the gradient in the order of the dual inputs gathered below: theta, then neural
+        return _lift(l[1], vcat(vec(gt), vec(gn)), vcat(vec(collect(p.theta)), vec(collect(p.neural))))
+    end
+    CUDEB200.suppression_loss_grad(pop, neural, reshape(theta, :, 1), λ; grad=false)[1][1]
 end
