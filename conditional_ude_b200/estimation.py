@@ -36,7 +36,7 @@ def initial_parameters(*args, rng=None):
     if len(args) == 2:
         chain, n_initials = args
         rng = rng or np.random.default_rng()
-        return [chain.init_params(rng) for _ in range(n_initials)]
+        return list(chain.init_params_batch(rng, int(n_initials)))       # rows of one [n x P] draw
     n_models, lb, ub, n_initials = args[:4]
     rng = args[4] if len(args) > 4 else (rng or np.random.default_rng())
     # LatinHypercubeSample: one point per stratum in every dimension, strata permuted independently

@@ -70,6 +70,17 @@ class Chain:
             n_in = n_out
         return np.concatenate(out)
 
+    def init_params_batch(self, rng, n):
+        """n Glorot-normal weight vectors at once, [n x n_params] (one normal draw per layer for all n networks; the multi-start
+        `train` draws 25 000 — a Python loop over init_params took 0.14 s of its 0.39 s)."""
+        out, n_in = [], self.input_dims
+        for n_out in [self.width] * self.depth + [1]:
+            sigma = math.sqrt(2.0 / (n_in + n_out))
+            out.append(rng.normal(0.0, sigma, size=(n, n_out * n_in)))
+            out.append(np.zeros((n, n_out)))
+            n_in = n_out
+        return np.concatenate(out, axis=1)
+
 
 def chain(*args, input_dims=2, output_dims=1, output_activation=softplus):
     """chain(width, depth, act) | chain(widths, act) | chain(widths, acts); src/neural-network.jl:42,85,105.
