@@ -49,8 +49,12 @@ struct DevBuf {
 #ifndef CUDE_SUP_TWO_KERNEL
 #define CUDE_SUP_TWO_KERNEL 1               // suppression gradient as forward-with-records + adjoint kernels (opts.split = 1: the fused kernel)
 #endif
+#ifndef CUDE_WARP32_MAX_TRAJ
+#define CUDE_WARP32_MAX_TRAJ 512            // largest call that gives a whole warp to each trajectory; above, 8 lanes (kernel ms, 32 / 8 lanes / fused:
+                                            // 57 trajectories 0.066 / 0.074 / 0.196, 1425: 0.091 / 0.079 / 0.213, 3990: 0.211 / 0.100 / 0.234, 11 400: 0.500 / 0.216 / 0.238)
+#endif
 #ifndef CUDE_WARP_MAX_TRAJ
-#define CUDE_WARP_MAX_TRAJ 4096             // opts.balance = 0 (automatic): loss + full-gradient calls of at most this many trajectories take the
+#define CUDE_WARP_MAX_TRAJ 8192             // opts.balance = 0 (automatic): loss + full-gradient calls of at most this many trajectories take the
 #endif                                      // warp-per-trajectory latency kernel (cude_warp.cuh): 1776 warps are resident at a time (3 blocks of 4 per SM), a wave takes ~55 us against ~210 us for the fused kernel
 #ifndef CUDE_EXACT_MIN_IND
 #define CUDE_EXACT_MIN_IND 32768            // opts.balance = 0 (automatic): populations of at least this many individuals take the two-kernel
@@ -915,14 +919,30 @@ static int run_exact(cude_ctx* ctx, const cude_net* net, EvalArgs a, int B, int 
 // ---- latency form of loss + full gradient: one warp per trajectory (cude_warp.cuh), fused-kernel fallback for solves longer
 // than WARP_CAP accepted steps, per-start reduction of the trajectory rows ----
 typedef void (*warp_kernel_t)(const WarpArgs);
-static bool smem_fits_warp(int P, int K, int M) { return sizeof(double) * warp_smem_doubles(P, K, M) <= (size_t)200 * 1024; }
+typedef void (*warp_kernel_t)(const WarpArgs);
+static bool smem_fits_warp(int P, int K, int M) { return sizeof(double) * warp_smem_doubles(P, K, M, 8) <= (size_t)200 * 1024; }
+// lanes per trajectory of the latency kernels: 32 for the smallest batches (one trajectory per warp: nothing but its own
+// latency), 8 above (four trajectories per warp: a quarter of the repeated state arithmetic, four times the trajectories per wave)
+static int warp_lanes(size_t ntraj) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("CUDE_WARP_LANES"); forced = e ? atoi(e) : 0; }
+    if (forced == 8 || forced == 32) return forced;
+    return ntraj <= CUDE_WARP32_MAX_TRAJ ? 32 : 8;
+}
+template <bool GRAD>
+static warp_kernel_t select_warp_kernel(const cude_net* net, int G) {
+    if (!(net->depth == 2 && net->width == 4)) return nullptr;
+    if (net->n_in == 2) return G == 8 ? cude_warp_kernel<NetShape<2, 2, 4>, GRAD, 8> : cude_warp_kernel<NetShape<2, 2, 4>, GRAD, 32>;
+    if (net->n_in == 3) return G == 8 ? cude_warp_kernel<NetShape<3, 2, 4>, GRAD, 8> : cude_warp_kernel<NetShape<3, 2, 4>, GRAD, 32>;
+    return nullptr;
+}
 static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B, int nchunks, eval_kernel_t fused, size_t smem_fused,
                     double* d_sums_out, int* launches) {
     const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts, nw = B / 32;
-    warp_kernel_t kw = nullptr;
-    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>, true> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>, true> : nullptr);
-    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     const size_t ntraj = (size_t)N * S, nblk = (size_t)S * nchunks;
+    const int G = warp_lanes(ntraj), tpb = WARP_TPB * (32 / G);           // lanes per trajectory, trajectories per block
+    warp_kernel_t kw = select_warp_kernel<true>(net, G);
+    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     int rc;
     if ((rc = sm_count(ctx))) return rc;
     cude_ctx::SplitSet& set = ctx->sp[0];
@@ -938,13 +958,13 @@ static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B
     w.sse_out = a.sse_out; w.g_cond = a.g_cond; w.rows = (double*)ctx->partials.p; w.counters = a.counters;
     w.ovf = (int*)(misc + o_ovf); w.blkflag = (int*)(misc + o_flag); w.blkcount = w.blkflag + nblk; w.blklist = (int*)(misc + o_list);
     w.fb_block = B; w.nchunks = nchunks;
-    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs);
+    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs, G);
     if (smem_w > 200 * 1024) return fail(ctx, CUDE_EINVAL, "cude_eval_dev: too many knots / observations for the warp kernel");
     if ((rc = prep_kernel(ctx, (const void*)kw, 32 * WARP_TPB, smem_w))) return rc;
     if ((rc = prep_kernel(ctx, (const void*)fused, B, smem_fused))) return rc;
     cudaStream_t st = ctx->stream;
     CU_TRY(ctx, cudaMemsetAsync(w.blkflag, 0, (nblk + 1) * sizeof(int), st));
-    kw<<<(unsigned)((ntraj + WARP_TPB - 1) / WARP_TPB), 32 * WARP_TPB, smem_w, st>>>(w);
+    kw<<<(unsigned)((ntraj + tpb - 1) / tpb), 32 * WARP_TPB, smem_w, st>>>(w);
     CU_TRY(ctx, cudaGetLastError());
     EvalArgs f = a;                               // trajectories beyond WARP_CAP steps: the fused kernel on the flagged blocks
     f.partials = (double*)set.part.p; f.only_flag = w.ovf; f.sp_blkflag = w.blkflag; f.sp_blklist = w.blklist; f.sp_blkcount = w.blkcount;
@@ -964,18 +984,18 @@ static int run_warp(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, int B
 // the forward pass alone in the latency form (loss-only calls of small batches): per-trajectory sse, then the per-start sums
 static int run_warp_loss(cude_ctx* ctx, const cude_net* net, const EvalArgs& a, double* d_sse, double* d_sums_out, int* launches) {
     const int P = cude_net_nparams(net), np1 = P + 1, N = a.pop.n_ind, S = a.n_starts;
-    warp_kernel_t kw = nullptr;
-    if (net->depth == 2 && net->width == 4) kw = net->n_in == 2 ? cude_warp_kernel<NetShape<2, 2, 4>, false> : (net->n_in == 3 ? cude_warp_kernel<NetShape<3, 2, 4>, false> : nullptr);
-    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     const size_t ntraj = (size_t)N * S;
+    const int G = warp_lanes(ntraj), tpb = WARP_TPB * (32 / G);
+    warp_kernel_t kw = select_warp_kernel<false>(net, G);
+    if (!kw) return fail(ctx, CUDE_EUNSUPPORTED, "cude_eval_dev: network shape not compiled in");
     WarpArgs w{};
     w.pop = a.pop; w.n_starts = S; w.neural = a.neural; w.neural_stride = a.neural_stride; w.cond = a.cond;
     w.abstol = a.abstol; w.reltol = a.reltol; w.maxiters = a.maxiters; w.cond_scale = a.cond_scale;
     w.sse_out = d_sse; w.counters = a.counters;
-    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs);
+    const size_t smem_w = sizeof(double) * warp_smem_doubles(P, a.pop.max_knots, a.pop.max_obs, G);
     int rc;
     if ((rc = prep_kernel(ctx, (const void*)kw, 32 * WARP_TPB, smem_w))) return rc;
-    kw<<<(unsigned)((ntraj + WARP_TPB - 1) / WARP_TPB), 32 * WARP_TPB, smem_w, ctx->stream>>>(w);
+    kw<<<(unsigned)((ntraj + tpb - 1) / tpb), 32 * WARP_TPB, smem_w, ctx->stream>>>(w);
     CU_TRY(ctx, cudaGetLastError());
     ++*launches;
     if (d_sums_out) {

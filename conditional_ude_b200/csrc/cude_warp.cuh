@@ -28,7 +28,7 @@ namespace cude {
 #define CUDE_WARP_CAP 64
 #endif
 constexpr int WARP_CAP = CUDE_WARP_CAP;
-constexpr int WARP_TPB = 4;            // trajectories (= warps) per block
+constexpr int WARP_TPB = 4;            // warps per block (32 / G trajectories each)
 
 struct WarpArgs {
     PopDev pop;
@@ -54,18 +54,26 @@ struct WarpArgs {
 __host__ __device__ inline size_t warp_per_warp_doubles(int P, int K, int M) {
     return (size_t)((P + 1) & ~1) + (size_t)3 * K + (size_t)3 * M + (size_t)12 * WARP_CAP;
 }
-__host__ __device__ inline size_t warp_smem_doubles(int P, int K, int M) { return (size_t)256 + WARP_TPB * warp_per_warp_doubles(P, K, M); }
+__host__ __device__ inline size_t warp_smem_doubles(int P, int K, int M, int G = 32) {
+    return (size_t)256 + (size_t)WARP_TPB * (32 / G) * warp_per_warp_doubles(P, K, M);
+}
 
 #if !defined(CUDE_HOST_EMU) || defined(CUDE_HOST_EMU_WARP)      // the host emulation of this kernel needs 32 cooperating lanes (tests/emu/emu_warp.cpp)
 // GRAD = false: the forward pass only (loss-only calls of small batches, e.g. the 2 x N solves of a SAEM Metropolis step):
 // sse_out[j] per trajectory, no records, no rows.
-template <class NS, bool GRAD = true>
+// G = lanes per trajectory (32, 16 or 8): with G < 32 a warp carries 32 / G trajectories side by side — the groups run the same
+// code on their own data and may diverge from each other (step counts, accept / reject); every shuffle and warp barrier names
+// only the group's lanes.  Fewer lanes repeat the state arithmetic, so more trajectories fit a wave; the adjoint's (step, node)
+// evaluations take 32 / G times as many rounds.
+template <class NS, bool GRAD = true, int G = 32>
 __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpArgs A) {
     using namespace tab;
-    constexpr int W = NS::W, P = NS::P, PP = (P + 1) & ~1;
-    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(G == 32 || G == 16 || G == 8, "lanes per trajectory");
+    constexpr int W = NS::W, P = NS::P, PP = (P + 1) & ~1, TPW = 32 / G;
     extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & (G - 1);                 // lane within the trajectory's group
+    const int wid = (threadIdx.x >> 5) * TPW + ((threadIdx.x & 31) / G);     // trajectory slot within the block
+    const unsigned FULL = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));   // the group's lanes
     const int N = A.pop.n_ind, K = A.pop.max_knots, M = A.pop.max_obs;
     double* const sTab = smem;
     double* const sWs = smem + 256 + (size_t)wid * warp_per_warp_doubles(P, K, M);
@@ -80,22 +88,22 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
     double* const rW = rDG + 5 * WARP_CAP;             // [WARP_CAP][5]  node weights of the adjoint
 
     for (int p = threadIdx.x; p < 256; p += blockDim.x) sTab[p] = EXP_TAB256[p];
-    const long long j = (long long)blockIdx.x * WARP_TPB + wid;
+    const long long j = (long long)blockIdx.x * (WARP_TPB * TPW) + wid;
     const bool active = j < (long long)N * A.n_starts;                    // warp-uniform
     int s = 0, i = 0, nk = 2, nobs = 0;
     if (active) {
         s = (int)(j / N);
         i = (int)(j - (long long)s * N);
         const double* gW = A.neural + (long long)s * A.neural_stride;
-        for (int p = lane; p < P; p += 32) sWs[p] = gW[p];
+        for (int p = lane; p < P; p += G) sWs[p] = gW[p];
         nk = A.pop.n_knots[i];
-        for (int k = lane; k < nk; k += 32) {
+        for (int k = lane; k < nk; k += G) {
             sKt[k] = A.pop.knot_t[(size_t)k * N + i];
             sKg[k] = A.pop.knot_g[(size_t)k * N + i];
             if (k < nk - 1) sSl[k] = A.pop.slope[(size_t)k * N + i];
         }
         nobs = A.pop.n_obs[i];
-        for (int k = lane; k < nobs; k += 32) {
+        for (int k = lane; k < nobs; k += G) {
             sOt[k] = A.pop.obs_t[(size_t)k * N + i];
             sOy[k] = A.pop.obs_y[(size_t)k * N + i];
         }
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
         t_softplus_d(mlp_zout<NS>(sW, sTab, c, dg), sTab, spq, ddq);
         double sp[5];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) sp[q] = __shfl_sync(FULL, spq, q);
+        for (int q = 0; q < 5; ++q) sp[q] = __shfl_sync(FULL, spq, q, G);
         if (init) {
             init = false;
             nn0 = sp[0];
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
     const bool failed = (ret != 0);
     const double sse = failed ? CUDART_INF : fsse;
     const bool overflow = GRAD && !failed && na > WARP_CAP;
-    __syncwarp();
+    __syncwarp(FULL);
     if constexpr (!GRAD) {
         if (lane == 0) {
             A.sse_out[j] = sse;
@@ -340,16 +348,16 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
             lam0 = ub0; lam1 = ub1;
             t_next = tn;
         }
-        __syncwarp();
+        __syncwarp(FULL);
         // =================== adjoint, part 2: the (step, node) network evaluations spread over the lanes ===================
-        for (int p = lane; p < 5 * na; p += 32) mlp_backward<NS, double>(sW, sTab, c, rDG[p], rW[p], acc);
+        for (int p = lane; p < 5 * na; p += G) mlp_backward<NS, double>(sW, sTab, c, rDG[p], rW[p], acc);
         // the NN([0; beta]) term (c-peptide-models.jl:91): one node at dG = 0 with weight -sum(w), on the least loaded lane
-        if (lane == 31) mlp_backward<NS, double>(sW, sTab, c, 0.0, -wsum, acc);
+        if (lane == G - 1) mlp_backward<NS, double>(sW, sTab, c, 0.0, -wsum, acc);
 #pragma unroll
         for (int k = 0; k < NS::NACC; ++k) {
             double v = acc[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, G);
             acc[k] = v;
         }
         double db = 0.0;
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(32 * WARP_TPB, 3) cude_warp_kernel(const WarpA
         else if (NS::NIN > 2 && p < 3 * W) v = acc[W + (p - 2 * W)] * covv;
         else if (p < NS::L1) v = acc[W + (p - NS::NIN * W)];
         else v = acc[2 * W + (p - NS::L1)];
-        if (lane == ((p + 1) & 31)) row[p + 1] = v;
+        if (lane == ((p + 1) & (G - 1))) row[p + 1] = v;
     }
     if (lane == 0) {
         if (A.sse_out) A.sse_out[j] = sse;

@@ -63,8 +63,8 @@ typedef struct {
     int balance;   /* lane balance of loss + full-gradient calls with per-start networks (a warp runs to its slowest lane and the
                     * trajectories of a start take 17-26 steps, so 12 % of the lane-cycles idle in natural order):
                     * 0 (default) = automatic:
-                    *     - calls of <= 4096 trajectories use the WARP-PER-TRAJECTORY latency kernel (mode 4; loss-only calls of that
-                    *       size its forward half);
+                    *     - calls of <= 8192 trajectories use the WARP-PER-TRAJECTORY latency kernel (mode 4: a whole warp per trajectory
+                    *       up to 512 trajectories, 8 lanes per trajectory above; loss-only calls of that size its forward half);
                     *     - populations of >= 32768 individuals use the TWO-KERNEL gradient (mode 2);
                     *     - everything else the fused kernel (mode 3);
                     * 1 = fused kernel, each start's individuals regrouped by the step counts of an EARLIER call on this
@@ -75,7 +75,7 @@ typedef struct {
                     *     group of starts, the library sizes the groups to min(64 GB, 40 % of the free memory));
                     * 3 = the fused kernel (one thread per trajectory, forward solve + adjoint sweep) in natural order;
                     * 4 = one warp per trajectory (small batches: config 1, the selected starts of `train`): the 5 network nodes
-                    *     of a step on 5 lanes, the adjoint's (step, node) evaluations spread over the 32 lanes — 0.06-0.09 ms
+                    *     of a step on 5 lanes, the adjoint's (step, node) evaluations spread over the trajectory's 32 (or 8) lanes — 0.06-0.08 ms
                     *     instead of 0.2 ms per evaluation of 57-1425 trajectories.
                     * Per-trajectory sse is bitwise the same in every mode, d/d cond in modes 0-3 (mode 4: to 1e-13); the
                     * per-start sums differ only in summation order and are run-to-run deterministic in modes 0, 2, 3 and 4. */

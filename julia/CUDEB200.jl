@@ -36,7 +36,7 @@ struct CudeOpts
     maxiters::Cint
     precision::Cint
     block::Cint
-    balance::Cint     # 0: automatic (<= 4096 trajectories: warp per trajectory; >= 32768 individuals: two-kernel gradient; else fused kernel); 1: history regrouping; 2 / 3 / 4: force two-kernel / fused / warp-per-trajectory (include/cude_b200.h)
+    balance::Cint     # 0: automatic (<= 8192 trajectories: warp per trajectory; >= 32768 individuals: two-kernel gradient; else fused kernel); 1: history regrouping; 2 / 3 / 4: force two-kernel / fused / warp-per-trajectory (include/cude_b200.h)
     split::Cint       # 2: split gradient pipeline instead of the fused adjoint kernel (include/cude_b200.h)
 end
 CudeOpts(; abstol=1e-6, reltol=1e-3, maxiters=1_000_000, precision=0, balance=0, split=0) =

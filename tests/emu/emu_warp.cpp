@@ -32,30 +32,35 @@ struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 
 struct Barrier {
-    std::mutex m; std::condition_variable cv; int n = 0, count = 0; unsigned gen = 0;
-    void wait() {
+    std::mutex m; std::condition_variable cv; int count = 0; unsigned gen = 0;
+    void wait(int n) {
         std::unique_lock<std::mutex> lk(m);
         const unsigned g = gen;
         if (++count == n) { count = 0; ++gen; cv.notify_all(); }
         else cv.wait(lk, [&] { return gen != g; });
     }
 };
-static Barrier g_block_bar, g_warp_bar[4];
+// a warp's lanes cooperate in groups of `width` (= lanes per trajectory, 32 / 16 / 8): one barrier per (warp, group)
+static Barrier g_block_bar, g_group_bar[4][4];
 static unsigned long long g_slot[4][32];
-static inline void __syncthreads() { g_block_bar.wait(); }
-static inline void __syncwarp() { g_warp_bar[threadIdx.x >> 5].wait(); }
-template <class T> static inline T emu_shfl(T v, int src) {
+static int g_block_threads = 128;
+static inline void __syncthreads() { g_block_bar.wait(g_block_threads); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) {
+    const int width = __builtin_popcount(mask), gi = __builtin_ctz(mask) / width;
+    g_group_bar[threadIdx.x >> 5][gi].wait(width);
+}
+template <class T> static inline T emu_shfl(T v, int src_lane, int width) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, gi = l / width;
     unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
     g_slot[w][l] = raw;
-    g_warp_bar[w].wait();
-    raw = g_slot[w][src & 31];
-    g_warp_bar[w].wait();
+    g_group_bar[w][gi].wait(width);
+    raw = g_slot[w][gi * width + (src_lane & (width - 1))];
+    g_group_bar[w][gi].wait(width);
     T r; memcpy(&r, &raw, sizeof(T)); return r;
 }
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_shfl(v, (threadIdx.x & 31) ^ o); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) { return emu_shfl(v, src, width); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o, int width = 32) { return emu_shfl(v, ((threadIdx.x & 31) & (width - 1)) ^ o, width); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
@@ -69,7 +74,7 @@ using namespace cude;
 // g_cond[N x S], ovf[N x S] (-1: more than WARP_CAP accepted steps — the fused kernel's on the device), counters[3].
 extern "C" int emu_warp_eval(int n_ind, int max_knots, const int* n_knots, const double* knot_t, const double* knot_g,
                              int max_obs, const int* n_obs, const double* obs_t, const double* obs_y, const double* kin, const double* cov,
-                             int n_in, int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters, int grad,
+                             int n_in, int n_starts, const double* neural, const double* cond, double abstol, double reltol, int maxiters, int grad, int lanes,
                              double* sse, double* rows, double* g_cond, int* ovf, unsigned long long* counters) {
     const size_t N = n_ind, K = max_knots, M = max_obs, S = n_starts, NT = N * S;
     std::vector<double> kt(K * N), kg(K * N), sl(K * N, 0.0), ot(M * N), oy(M * N), k0(N), k1(N), k2(N), c0(N), cv(N, 0.0);
@@ -96,19 +101,24 @@ extern "C" int emu_warp_eval(int n_ind, int max_knots, const int* n_knots, const
     std::vector<int> flags(NT + 1, 0), list(NT, 0);
     a.blkflag = flags.data(); a.blkcount = flags.data() + NT; a.blklist = list.data();
     a.fb_block = 1; a.nchunks = n_ind;
-    if (warp_smem_doubles(P, max_knots, max_obs) > (size_t)(1 << 16)) return 1;
-    const int T = 32 * WARP_TPB;
-    blockDim.x = T; gridDim.x = (int)((NT + WARP_TPB - 1) / WARP_TPB);
-    g_block_bar.n = T;
-    for (int w = 0; w < WARP_TPB; ++w) g_warp_bar[w].n = 32;
+    if (lanes != 32 && lanes != 8) return 3;
+    if (warp_smem_doubles(P, max_knots, max_obs, lanes) > (size_t)(1 << 16)) return 1;
+    const int T = 32 * WARP_TPB, tpb = WARP_TPB * (32 / lanes);
+    blockDim.x = T; gridDim.x = (int)((NT + tpb - 1) / tpb);
+    g_block_threads = T;
     for (int b = 0; b < gridDim.x; ++b) {
         blockIdx.x = b;
         std::vector<std::thread> th;
         for (int t = 0; t < T; ++t)
             th.emplace_back([&, t] {
                 threadIdx.x = t;
-                if (!grad) { if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, false>(a); else cude_warp_kernel<NetShape<3, 2, 4>, false>(a); }
-                else if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, true>(a); else cude_warp_kernel<NetShape<3, 2, 4>, true>(a);
+                if (lanes == 8) {
+                    if (!grad) { if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, false, 8>(a); else cude_warp_kernel<NetShape<3, 2, 4>, false, 8>(a); }
+                    else if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, true, 8>(a); else cude_warp_kernel<NetShape<3, 2, 4>, true, 8>(a);
+                } else {
+                    if (!grad) { if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, false, 32>(a); else cude_warp_kernel<NetShape<3, 2, 4>, false, 32>(a); }
+                    else if (n_in == 2) cude_warp_kernel<NetShape<2, 2, 4>, true, 32>(a); else cude_warp_kernel<NetShape<3, 2, 4>, true, 32>(a);
+                }
             });
         for (auto& x : th) x.join();
     }

@@ -117,12 +117,12 @@ def build_warp():
     return LIB_WARP
 
 
-def emu_warp_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, grad=True):
+def emu_warp_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=100000, grad=True, lanes=32):
     """The warp-per-trajectory kernel (csrc/cude_warp.cuh) with every CUDA thread as a host thread (tests/emu/emu_warp.cpp).
     Returns dict(sse[S,N], g_neural[S,N,P], g_cond[S,N], overflow[S,N] bool, n_acc, n_rej, n_fail)."""
     L = C.CDLL(build_warp())
     L.emu_warp_eval.argtypes = [C.c_int, C.c_int, _I, _D, _D, C.c_int, _I, _D, _D, _D, _D, C.c_int, C.c_int, _D, _D,
-                                C.c_double, C.c_double, C.c_int, C.c_int, _D, _D, _D, _I, C.POINTER(C.c_ulonglong)]
+                                C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _D, _D, _D, _I, C.POINTER(C.c_ulonglong)]
     ch = packed["chain"]
     N, P = int(packed["n_ind"]), ch.n_params
     a = {k: np.ascontiguousarray(packed[k], dtype=np.float64) for k in ("knot_t", "knot_g", "obs_t", "obs_y", "kin")}
@@ -138,7 +138,7 @@ def emu_warp_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=10000
     cnt = (C.c_ulonglong * 3)()
     rc = L.emu_warp_eval(N, int(packed["max_knots"]), nk.ctypes.data_as(_I), _dp(a["knot_t"]), _dp(a["knot_g"]),
                          int(packed["max_obs"]), no.ctypes.data_as(_I), _dp(a["obs_t"]), _dp(a["obs_y"]), _dp(a["kin"]), _dp(cov),
-                         ch.input_dims, S, _dp(neural), _dp(cond), abstol, reltol, maxiters, int(grad), _dp(sse), _dp(rows), _dp(gc),
+                         ch.input_dims, S, _dp(neural), _dp(cond), abstol, reltol, maxiters, int(grad), int(lanes), _dp(sse), _dp(rows), _dp(gc),
                          ovf.ctypes.data_as(_I), cnt)
     assert rc == 0, rc
     return dict(sse=sse, row_sse=rows[:, :, 0], g_neural=rows[:, :, 1:], g_cond=gc, overflow=ovf < 0, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])

@@ -280,17 +280,17 @@ def test_warp_per_trajectory_kernel_with_host_threads_as_lanes(fx):
     pk = cu.pack_models([models[i] for i in pick], [ts[i] for i in pick], [ys[i] for i in pick])
     rng = np.random.default_rng(8)
     neural, cond = random_starts(rng, pk["chain"], len(pick), 2)
-    for o in (dict(), DET):
-        f = emu_wrap.emu_eval(pk, neural, cond, **o)
+    for o in (dict(), DET, dict(lanes=8)):                                                # lanes=8: four trajectories per warp
+        f = emu_wrap.emu_eval(pk, neural, cond, **{k: v for k, v in o.items() if k != "lanes"})
         w = emu_wrap.emu_warp_eval(pk, neural, cond, **o)
         assert not w["overflow"].any()
         assert np.array_equal(w["sse"], f["sse"]) and np.array_equal(w["row_sse"], f["sse"])
         assert relmax(w["g_cond"], f["g_cond"]) < 1e-12 and relmax(w["g_neural"], f["g_neural"]) < 1e-12
         assert (w["n_acc"], w["n_rej"], w["n_fail"]) == (f["n_acc"], f["n_rej"], f["n_fail"])
-    wl = emu_wrap.emu_warp_eval(pk, neural, cond, grad=False)                            # the forward pass alone (loss-only calls)
+    wl = emu_wrap.emu_warp_eval(pk, neural, cond, grad=False, lanes=8)                   # the forward pass alone (loss-only calls)
     assert np.array_equal(wl["sse"], emu_wrap.emu_eval(pk, neural, cond)["sse"]) and wl["n_acc"] == emu_wrap.emu_eval(pk, neural, cond)["n_acc"]
     bad = cond.copy(); bad[1, 2] = np.nan
-    w = emu_wrap.emu_warp_eval(pk, neural, bad)
+    w = emu_wrap.emu_warp_eval(pk, neural, bad, lanes=8)
     assert np.isinf(w["sse"][1, 2]) and w["g_cond"][1, 2] == 0 and np.all(w["g_neural"][1, 2] == 0) and w["n_fail"] == 1
     w = emu_wrap.emu_warp_eval(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)      # every solve beyond 64 steps
     f = emu_wrap.emu_eval(pk, neural[:1], cond[:1], abstol=1e-10, reltol=1e-8)
