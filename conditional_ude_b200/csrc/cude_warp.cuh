@@ -1,11 +1,11 @@
 // =====================================================================================
-// cude_warp.cuh — the LATENCY form of loss + gradient: one WARP per trajectory.
+// cude_warp.cuh — the LATENCY form of loss + gradient: one WARP (or a group of 8 lanes) per trajectory.
 //
 // Small batches — config 1 (57 individuals, stored weights), the 25 selected starts of `train`
 // (reference src/parameter-estimation.jl:374-376: 1425 trajectories per optimiser iteration) — leave most of the GPU idle
 // with one thread per trajectory, and what the caller waits for is the latency of one thread walking ~20 adaptive steps and
-// their adjoint: ~100 sequential network evaluations forward, ~100 forward + backward in the sweep.  Here the 32 lanes of
-// a warp share one trajectory:
+// their adjoint: ~100 sequential network evaluations forward, ~100 forward + backward in the sweep.  Here the G lanes of
+// a group (G = 32: a whole warp, calls of up to 512 trajectories; G = 8: four trajectories per warp, up to 8192) share one trajectory:
 //   forward  every lane carries the state redundantly (uniform control flow, no divergence); lane q % 5 evaluates the
 //            network at node q of the step (the production term does not depend on the state, so the 5 nodes of a step
 //            are independent), 5 shuffles hand the values round, the stage arithmetic is the fused kernel's
