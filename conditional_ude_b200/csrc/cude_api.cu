@@ -924,8 +924,7 @@ static bool smem_fits_warp(int P, int K, int M) { return sizeof(double) * warp_s
 // lanes per trajectory of the latency kernels: 32 for the smallest batches (one trajectory per warp: nothing but its own
 // latency), 8 above (four trajectories per warp: a quarter of the repeated state arithmetic, four times the trajectories per wave)
 static int warp_lanes(size_t ntraj) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("CUDE_WARP_LANES"); forced = e ? atoi(e) : 0; }
+    static const int forced = [] { const char* e = getenv("CUDE_WARP_LANES"); return e ? atoi(e) : 0; }();   // tuning override, read once
     if (forced == 8 || forced == 32) return forced;
     return ntraj <= CUDE_WARP32_MAX_TRAJ ? 32 : 8;
 }
