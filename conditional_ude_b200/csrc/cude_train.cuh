@@ -44,7 +44,10 @@ struct TrainArgs {
 };
 enum { SC_FX = 0, SC_FPREV, SC_ALPHA, SC_APREV, SC_DPHI0, SC_BESTF, SC_N };
 enum { IC_NH = 0, IC_HEAD, IC_ITERS, IC_LS, IC_STATUS, IC_N };       // status: 0 active, 1 converged, 2 line search failed, 3 maxiters
-constexpr int TRAIN_T = 128;
+#ifndef CUDE_TRAIN_T
+#define CUDE_TRAIN_T 128
+#endif
+constexpr int TRAIN_T = CUDE_TRAIN_T;      // threads per start (the host emulation runs 64: two warps still exercise the cross-warp sums)
 
 __device__ __forceinline__ double train_block_sum(double v, double* sh) {
     // sum over the block, result in every thread (deterministic: fixed tree)

@@ -9,10 +9,11 @@ sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os
 import numpy as np
 import test_emu_kernel as T
 import test_suppression_kernel as S
+import test_emu_train as R
 fx = dict(np.load(os.path.join(HERE, "..", "golden", "cpeptide_fixtures.npz")))
 sup = dict(np.load(os.path.join(HERE, "..", "golden", "suppression_fixtures.npz")))
 n = 0
-for mod, arg in ((T, fx), (S, sup)):
+for mod, arg in ((T, fx), (S, sup), (R, None)):
     for name in sorted(dir(mod)):
         f = getattr(mod, name)
         if not name.startswith("test_") or not callable(f) or "gpu" in name:

@@ -144,6 +144,47 @@ def emu_warp_eval(packed, neural, cond, abstol=1e-6, reltol=1e-3, maxiters=10000
     return dict(sse=sse, row_sse=rows[:, :, 0], g_neural=rows[:, :, 1:], g_cond=gc, overflow=ovf < 0, n_acc=cnt[0], n_rej=cnt[1], n_fail=cnt[2])
 
 
+LIB_TRAIN = os.path.join(_HERE, "libcude_emu_train_san.so" if _SAN else "libcude_emu_train.so")
+
+
+def build_train():
+    src = [os.path.join(_HERE, "emu_train.cpp"), os.path.join(_HERE, "emu_threads.h"),
+           os.path.join(_HERE, "..", "..", "conditional_ude_b200", "csrc", "cude_train.cuh")]
+    if not os.path.exists(LIB_TRAIN) or os.path.getmtime(LIB_TRAIN) < max(os.path.getmtime(s) for s in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DCUDE_TRAIN_T=64"] +
+                              (["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if _SAN else []) +
+                              ["-o", LIB_TRAIN, src[0]])
+    return LIB_TRAIN
+
+
+def emu_train(fg, x0, n_neural, adam_iters=0, adam_lr=1e-2, lbfgs_iters=0, lbfgs_m=10, g_tol=1e-8, c1=1e-4, rho_hi=0.5, rho_lo=0.1,
+              ls_maxiter=50, check_every=16):
+    """The device-resident optimisers of cude_train (csrc/cude_train.cuh) with every CUDA thread as a host thread and the
+    library's host loop restated in tests/emu/emu_train.cpp.  fg(x[S, D]) -> (f[S], g[S, D]); the first n_neural columns play
+    the network part.  Returns (x[S, D], objective[S], lbfgs_iterations[S], status[S], evaluations)."""
+    L = C.CDLL(build_train())
+    x = np.array(x0, dtype=np.float64, order="C")
+    S, D = x.shape
+    CB = C.CFUNCTYPE(None, _D, _D, _D)
+
+    def cb(px, pf, pg):
+        f, g = fg(np.ctypeslib.as_array(px, shape=(S, D)).copy())
+        np.ctypeslib.as_array(pf, shape=(S,))[:] = f
+        np.ctypeslib.as_array(pg, shape=(S, D))[:] = g
+
+    L.emu_train.argtypes = [C.c_int, C.c_int, C.c_int, CB, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                            C.c_double, C.c_int, C.c_int, _D, _D, _I, _I, _I]
+    obj = np.empty(S)
+    iters = np.zeros(S, dtype=np.int32)
+    status = np.zeros(S, dtype=np.int32)
+    ev = C.c_int(0)
+    rc = L.emu_train(S, int(n_neural), D - int(n_neural), CB(cb), int(adam_iters), float(adam_lr), int(lbfgs_iters), int(lbfgs_m),
+                     g_tol, c1, rho_hi, rho_lo, int(ls_maxiter), int(check_every), _dp(x), _dp(obj), iters.ctypes.data_as(_I),
+                     status.ctypes.data_as(_I), C.byref(ev))
+    assert rc == 0
+    return x, obj, iters, status, ev.value
+
+
 def emu_sup_eval(data, timepoints, neural, theta, p_true=(0.4, 0.9, 0.3), scale=None, abstol=1e-6, reltol=1e-3,
                  maxiters=100000, grad=True):
     """Suppression variant through the host-compiled kernel source; same conventions as oracle.sup_eval."""
