@@ -1110,6 +1110,7 @@ static int eval_dev_impl(cude_ctx* ctx, const cude_population* pop, const cude_n
                            (o.balance == 2 || (o.balance == 0 && N >= CUDE_EXACT_MIN_IND));
     // the latency form (one warp per trajectory): on request (opts.balance = 4) or automatically for small batches
     const bool use_warp = !use_split && !use_exact && adj && !flat && !mixed && !fbwd && want_neural_grad && d_g_cond && !bal &&
+                          smem_fits_warp(P, K, M) &&     // very long knot / observation lists: the thread-per-trajectory kernels
                           (o.balance == 4 || (o.balance == 0 && ntraj <= CUDE_WARP_MAX_TRAJ));
     const bool use_warp_loss = !grad && !mixed && !d_yhat && smem_fits_warp(P, K, M) &&
                                (o.balance == 4 || (o.balance == 0 && ntraj <= CUDE_WARP_MAX_TRAJ));
